@@ -1,0 +1,636 @@
+// abc_capi.cu -- the C ABI of libabcb200.so (include/abc_b200.h): context, buffers, host<->device
+// staging and kernel sequencing.  No CPU fallback anywhere: every compute entry point needs a device.
+#include <algorithm>
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <numeric>
+#include <vector>
+
+#include "abc_common.cuh"
+#include "abc_internal.h"
+
+#define ABC_VERSION 100
+
+static thread_local char g_err[1024] = "";
+
+void abc_set_error(const char* fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+}
+
+extern "C" const char* abc_last_error(void) { return g_err; }
+extern "C" int abc_version(void) { return ABC_VERSION; }
+
+extern "C" int abc_device_count(void) {
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; }
+    return n;
+}
+
+extern "C" int abc_n_params(int m) { return (m >= 1 && m <= 2) ? 5 : (m >= 3 && m <= 5) ? 9 : -1; }
+
+extern "C" const char* abc_model_name(int m) {
+    static const char* names[5] = {"const", "const_const", "kon", "alpha", "gamma"};
+    return (m >= 1 && m <= 5) ? names[m - 1] : nullptr;
+}
+
+template <typename T>
+struct DevBuf {
+    T* p = nullptr;
+    size_t cap = 0;
+    int ensure(size_t n) {
+        if (n <= cap) return ABC_OK;
+        if (p) cudaFree(p);
+        p = nullptr; cap = 0;
+        cudaError_t e = cudaMalloc((void**)&p, n * sizeof(T));
+        if (e != cudaSuccess) {
+            abc_set_error("cudaMalloc(%zu bytes) failed: %s", n * sizeof(T), cudaGetErrorString(e));
+            cudaGetLastError();
+            return ABC_ERR_NOMEM;
+        }
+        cap = n;
+        return ABC_OK;
+    }
+    void release() { if (p) cudaFree(p); p = nullptr; cap = 0; }
+};
+
+struct abc_ctx {
+    int device = 0, sm_count = 0;
+    cudaStream_t stream = nullptr;
+    cudaEvent_t ev[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
+    // design
+    bool has_design = false;
+    abc_design_t design;
+    std::vector<uint32_t> beta_q32;
+    int32_t beta_off[11];
+    double beta_mean[10], beta_m2[10], beta_var[10];
+    DevBuf<uint32_t> d_beta;
+    DevBuf<double> d_age_dist;
+    DevBuf<double> d_beta_mom;   // [30]: mean, m2, var for the 10 groups
+    // data statistics
+    bool has_data = false;
+    int32_t G = 0;
+    DevBuf<double> d_d, d_den;
+    // simulate work buffers
+    DevBuf<double> d_theta, d_stats, d_moments;
+    DevBuf<AbcRates> d_rates;
+    DevBuf<unsigned long long> d_sums, d_counters;
+    DevBuf<unsigned int> d_work;
+    DevBuf<uint32_t> d_cells;
+    // score work buffers
+    DevBuf<double> d_sstats, d_err;
+    DevBuf<unsigned long long> d_counts, d_acc_count;
+    DevBuf<int32_t> d_acc_gene;
+    DevBuf<long long> d_acc_particle;
+    DevBuf<double> d_acc_err;
+    int64_t acc_capacity = 0;
+    int64_t launches = 0;
+    abc_counters_t last;
+};
+
+#define CTX_GUARD(ctx)                                                       \
+    if (!(ctx)) { abc_set_error("null context"); return ABC_ERR_ARG; }       \
+    ABC_CUDA_CHECK(cudaSetDevice((ctx)->device))
+
+extern "C" int abc_create(int device, abc_ctx_t** out) {
+    if (!out) { abc_set_error("abc_create: out is NULL"); return ABC_ERR_ARG; }
+    *out = nullptr;
+    int n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    if (e != cudaSuccess || n == 0) {
+        abc_set_error("no CUDA device available (%s); libabcb200 has no CPU fallback",
+                      e != cudaSuccess ? cudaGetErrorString(e) : "device count 0");
+        cudaGetLastError();
+        return ABC_ERR_CUDA;
+    }
+    if (device < 0 || device >= n) { abc_set_error("device %d out of range [0,%d)", device, n); return ABC_ERR_ARG; }
+    ABC_CUDA_CHECK(cudaSetDevice(device));
+    abc_ctx* c = new (std::nothrow) abc_ctx();
+    if (!c) { abc_set_error("out of host memory"); return ABC_ERR_NOMEM; }
+    c->device = device;
+    cudaDeviceProp prop;
+    ABC_CUDA_CHECK(cudaGetDeviceProperties(&prop, device));
+    c->sm_count = prop.multiProcessorCount;
+    ABC_CUDA_CHECK(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+    for (int i = 0; i < 5; ++i) ABC_CUDA_CHECK(cudaEventCreate(&c->ev[i]));
+    memset(&c->last, 0, sizeof(c->last));
+    memset(&c->design, 0, sizeof(c->design));
+    int rc = c->d_counters.ensure(8);
+    if (rc == ABC_OK) rc = c->d_work.ensure(1);
+    if (rc == ABC_OK) rc = c->d_acc_count.ensure(1);
+    if (rc != ABC_OK) { delete c; return rc; }
+    ABC_CUDA_CHECK(cudaMemset(c->d_acc_count.p, 0, sizeof(unsigned long long)));
+    *out = c;
+    return ABC_OK;
+}
+
+extern "C" int abc_destroy(abc_ctx_t* c) {
+    if (!c) return ABC_OK;
+    cudaSetDevice(c->device);
+    cudaStreamSynchronize(c->stream);
+    c->d_beta.release(); c->d_age_dist.release(); c->d_beta_mom.release(); c->d_d.release(); c->d_den.release();
+    c->d_theta.release(); c->d_stats.release(); c->d_moments.release(); c->d_rates.release();
+    c->d_sums.release(); c->d_counters.release(); c->d_work.release(); c->d_cells.release();
+    c->d_sstats.release(); c->d_err.release(); c->d_counts.release(); c->d_acc_count.release();
+    c->d_acc_gene.release(); c->d_acc_particle.release(); c->d_acc_err.release();
+    for (int i = 0; i < 5; ++i) if (c->ev[i]) cudaEventDestroy(c->ev[i]);
+    if (c->stream) cudaStreamDestroy(c->stream);
+    delete c;
+    return ABC_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+extern "C" int abc_set_design(abc_ctx_t* c, const abc_design_t* d) {
+    CTX_GUARD(c);
+    if (!d) { abc_set_error("abc_set_design: design is NULL"); return ABC_ERR_ARG; }
+    if (!(d->cycle > 0.0)) { abc_set_error("cycle must be > 0"); return ABC_ERR_ARG; }
+    for (int a = 0; a < ABC_NAGE; ++a)
+        if (!(d->agevec[a] > 0.0 && d->agevec[a] < d->cycle)) {
+            abc_set_error("agevec[%d] = %g must lie in (0, cycle)", a, d->agevec[a]);
+            return ABC_ERR_ARG;
+        }
+    for (int j = 0; j < ABC_NCOND; ++j)
+        if (!(d->pulse[j] >= 0.0 && d->chase[j] >= 0.0)) { abc_set_error("pulse/chase must be >= 0"); return ABC_ERR_ARG; }
+    if (d->sim_kind != ABC_SIM_SSA && d->sim_kind != ABC_SIM_ODE) { abc_set_error("unknown sim_kind %d", d->sim_kind); return ABC_ERR_ARG; }
+    if (d->sim_kind == ABC_SIM_SSA) {
+        if (d->n_cells < 2 || d->n_cells > (1 << 20)) { abc_set_error("n_cells must be in [2, 2^20]"); return ABC_ERR_ARG; }
+        if (d->n_pre_cycles < 0 || d->n_pre_cycles > 15) { abc_set_error("n_pre_cycles must be in [0, 15]"); return ABC_ERR_ARG; }
+        // the label window must start inside the simulated time span
+        for (int j = 0; j < ABC_NCOND; ++j)
+            for (int a = 0; a < ABC_NAGE; ++a)
+                if (d->agevec[a] - d->pulse[j] - d->chase[j] < -(double)d->n_pre_cycles * d->cycle) {
+                    abc_set_error("n_pre_cycles too small for pulse+chase of condition %d", j + 1);
+                    return ABC_ERR_ARG;
+                }
+    }
+    c->design = *d;
+    c->beta_q32.clear();
+    for (int g = 0; g < 11; ++g) c->beta_off[g] = 0;
+    if (d->downsampling) {
+        const double* bl[2] = {d->betas_pulse, d->betas_chase};
+        const int32_t* cl[2] = {d->cluster_pulse, d->cluster_chase};
+        const int32_t nn[2] = {d->n_pulse, d->n_chase};
+        for (int s = 0; s < 2; ++s) {
+            if (!bl[s] || !cl[s] || nn[s] <= 0) { abc_set_error("downsampling requires beta lists and cluster ids"); return ABC_ERR_ARG; }
+            for (int k = 1; k <= ABC_NAGE; ++k) {
+                const int grp = s * ABC_NAGE + (k - 1);
+                c->beta_off[grp] = (int32_t)c->beta_q32.size();
+                double sum = 0.0, sum2 = 0.0;
+                long cnt = 0;
+                for (int i = 0; i < nn[s]; ++i) {
+                    if (cl[s][i] != k) continue;
+                    const double b = bl[s][i];
+                    if (!(b >= 0.0 && b <= 1.0)) { abc_set_error("capture efficiency %g outside [0,1]", b); return ABC_ERR_ARG; }
+                    double q = std::floor(b * 4294967296.0 + 0.5);
+                    c->beta_q32.push_back(q >= 4294967295.0 ? 0xFFFFFFFFu : (uint32_t)q);
+                    sum += b; sum2 += b * b; cnt++;
+                }
+                if (cnt < 2) { abc_set_error("age cluster %d of the %s cells has < 2 capture efficiencies", k, s ? "chase" : "pulse"); return ABC_ERR_ARG; }
+                // model.jl:229-234: mean(beta), mean(beta.^2), var(beta) (corrected)
+                const double mu = sum / (double)cnt;
+                double ss = 0.0;
+                for (int i = 0; i < nn[s]; ++i) if (cl[s][i] == k) ss += (bl[s][i] - mu) * (bl[s][i] - mu);
+                c->beta_mean[grp] = mu; c->beta_m2[grp] = sum2 / (double)cnt; c->beta_var[grp] = ss / (double)(cnt - 1);
+            }
+        }
+        c->beta_off[10] = (int32_t)c->beta_q32.size();
+        int rc = c->d_beta.ensure(c->beta_q32.size());
+        if (rc != ABC_OK) return rc;
+        ABC_CUDA_CHECK(cudaMemcpy(c->d_beta.p, c->beta_q32.data(), c->beta_q32.size() * sizeof(uint32_t), cudaMemcpyHostToDevice));
+        double bm[30];
+        for (int g = 0; g < 10; ++g) { bm[g] = c->beta_mean[g]; bm[10 + g] = c->beta_m2[g]; bm[20 + g] = c->beta_var[g]; }
+        rc = c->d_beta_mom.ensure(30);
+        if (rc != ABC_OK) return rc;
+        ABC_CUDA_CHECK(cudaMemcpy(c->d_beta_mom.p, bm, sizeof(bm), cudaMemcpyHostToDevice));
+    } else {
+        int rc = c->d_beta.ensure(1);
+        if (rc != ABC_OK) return rc;
+    }
+    c->design.betas_pulse = c->design.betas_chase = nullptr;   // not retained
+    c->design.cluster_pulse = c->design.cluster_chase = nullptr;
+    int rc = c->d_age_dist.ensure(ABC_NAGE * ABC_NCOND);
+    if (rc != ABC_OK) return rc;
+    ABC_CUDA_CHECK(cudaMemcpy(c->d_age_dist.p, d->age_dist, sizeof(double) * ABC_NAGE * ABC_NCOND, cudaMemcpyHostToDevice));
+    c->has_design = true;
+    return ABC_OK;
+}
+
+extern "C" int abc_set_data(abc_ctx_t* c, const double* d, const double* se, int32_t G) {
+    CTX_GUARD(c);
+    if (!d || !se || G <= 0) { abc_set_error("abc_set_data: bad arguments"); return ABC_ERR_ARG; }
+    const size_t n = (size_t)G * ABC_NSTATS;
+    int rc = c->d_d.ensure(n);
+    if (rc == ABC_OK) rc = c->d_den.ensure(n);
+    DevBuf<double> d_se;
+    if (rc == ABC_OK) rc = d_se.ensure(n);
+    if (rc == ABC_OK) rc = c->d_counts.ensure((size_t)G);
+    if (rc != ABC_OK) { d_se.release(); return rc; }
+    ABC_CUDA_CHECK(cudaMemcpy(c->d_d.p, d, n * sizeof(double), cudaMemcpyHostToDevice));
+    ABC_CUDA_CHECK(cudaMemcpy(d_se.p, se, n * sizeof(double), cudaMemcpyHostToDevice));
+    rc = abc_launch_prepare_data(c->d_d.p, d_se.p, G, c->d_den.p, nullptr, c->stream);
+    c->launches++;
+    if (rc == ABC_OK) {
+        cudaError_t e = cudaStreamSynchronize(c->stream);
+        if (e != cudaSuccess) { abc_set_error("prepare_data failed: %s", cudaGetErrorString(e)); rc = ABC_ERR_CUDA; }
+    }
+    d_se.release();
+    if (rc != ABC_OK) return rc;
+    ABC_CUDA_CHECK(cudaMemset(c->d_counts.p, 0, (size_t)G * sizeof(unsigned long long)));
+    ABC_CUDA_CHECK(cudaMemset(c->d_acc_count.p, 0, sizeof(unsigned long long)));
+    c->G = G;
+    c->has_data = true;
+    return ABC_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+static int check_model(int m) {
+    if (m < 1 || m > 5) { abc_set_error("model index m = %d must be in 1..5", m); return ABC_ERR_ARG; }
+    return ABC_OK;
+}
+
+extern "C" int abc_fix_params(abc_ctx_t* c, int m, int64_t n, int64_t offset, uint64_t seed, double* theta) {
+    CTX_GUARD(c);
+    int rc = check_model(m);
+    if (rc != ABC_OK) return rc;
+    if (n < 0 || (n > 0 && !theta)) { abc_set_error("abc_fix_params: bad arguments"); return ABC_ERR_ARG; }
+    if (n == 0) return ABC_OK;
+    const int P = abc_n_params(m);
+    rc = c->d_theta.ensure((size_t)n * P);
+    if (rc != ABC_OK) return rc;
+    rc = abc_launch_prior(c->d_theta.p, m, n, offset, seed, c->stream);
+    c->launches++;
+    if (rc != ABC_OK) return rc;
+    ABC_CUDA_CHECK(cudaMemcpyAsync(theta, c->d_theta.p, (size_t)n * P * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+    ABC_CUDA_CHECK(cudaStreamSynchronize(c->stream));
+    return ABC_OK;
+}
+
+static AbcSsaParams make_ssa_params(const abc_ctx* c, int m, int64_t n, int64_t offset, uint64_t seed) {
+    AbcSsaParams p;
+    memset(&p, 0, sizeof(p));
+    p.n_particles = n; p.particle_offset = offset;
+    p.seed_lo = (uint32_t)seed; p.seed_hi = (uint32_t)(seed >> 32);
+    p.m = m; p.scaling = (m != 2) ? 1 : 0;
+    p.n_cells = c->design.n_cells;
+    p.chunks = (c->design.n_cells + 31) / 32;
+    p.n_pre = c->design.n_pre_cycles;
+    p.downsampling = c->design.downsampling;
+    p.single_readout = -1;
+    p.cycle = c->design.cycle;
+    for (int a = 0; a < 5; ++a) p.agevec[a] = c->design.agevec[a];
+    for (int j = 0; j < 11; ++j) { p.pulse[j] = c->design.pulse[j]; p.chase[j] = c->design.chase[j]; p.beta_off[j] = c->beta_off[j]; }
+    return p;
+}
+
+// device-side pipeline: (prior) -> rates -> SSA -> moments -> statistics, all on `st`
+static int simulate_device(abc_ctx* c, int m, int64_t n, int64_t offset, uint64_t seed, int prior_supplied,
+                           double* d_theta, double* d_stats, double* d_moments_out, cudaStream_t st) {
+    int rc = ABC_OK;
+    if (!c->has_design) { abc_set_error("abc_set_design has not been called"); return ABC_ERR_STATE; }
+    if (c->design.sim_kind != ABC_SIM_SSA) { abc_set_error("sim_kind ABC_SIM_ODE is not available in this build"); return ABC_ERR_STATE; }
+    if (!prior_supplied) {
+        rc = abc_launch_prior(d_theta, m, n, offset, seed, st);
+        c->launches++;
+        if (rc != ABC_OK) return rc;
+    }
+    if ((rc = c->d_rates.ensure((size_t)n)) != ABC_OK) return rc;
+    if ((rc = c->d_sums.ensure((size_t)n * ABC_NREAD * 5)) != ABC_OK) return rc;
+    double* d_mom = d_moments_out;
+    if (!d_mom) {
+        if ((rc = c->d_moments.ensure((size_t)n * ABC_NREAD * 5)) != ABC_OK) return rc;
+        d_mom = c->d_moments.p;
+    }
+    if ((rc = abc_launch_rates(d_theta, m, n, c->d_rates.p, st)) != ABC_OK) return rc;
+    c->launches++;
+    ABC_CUDA_CHECK(cudaMemsetAsync(c->d_sums.p, 0, (size_t)n * ABC_NREAD * 5 * sizeof(unsigned long long), st));
+    ABC_CUDA_CHECK(cudaMemsetAsync(c->d_counters.p, 0, 8 * sizeof(unsigned long long), st));
+    AbcSsaParams prm = make_ssa_params(c, m, n, offset, seed);
+    ABC_CUDA_CHECK(cudaEventRecord(c->ev[0], st));
+    if ((rc = abc_launch_ssa(c->d_rates.p, prm, c->d_beta.p, c->d_sums.p, c->d_counters.p, c->d_work.p, nullptr, 0,
+                             c->sm_count, st)) != ABC_OK) return rc;
+    c->launches++;
+    ABC_CUDA_CHECK(cudaEventRecord(c->ev[1], st));
+    if ((rc = abc_launch_moments_from_sums(c->d_sums.p, n, c->design.n_cells, d_mom, st)) != ABC_OK) return rc;
+    c->launches++;
+    if (d_stats) {
+        if ((rc = abc_launch_summary_stats(d_mom, c->d_age_dist.p, n, d_stats, st)) != ABC_OK) return rc;
+        c->launches++;
+    }
+    ABC_CUDA_CHECK(cudaEventRecord(c->ev[2], st));
+    return ABC_OK;
+}
+
+static int read_counters(abc_ctx* c, int64_t n, abc_counters_t* out, bool accumulate) {
+    unsigned long long h[8];
+    ABC_CUDA_CHECK(cudaMemcpy(h, c->d_counters.p, sizeof(h), cudaMemcpyDeviceToHost));
+    float ms_sim = 0.f, ms_st = 0.f;
+    if (cudaEventElapsedTime(&ms_sim, c->ev[0], c->ev[1]) != cudaSuccess) cudaGetLastError();
+    if (cudaEventElapsedTime(&ms_st, c->ev[1], c->ev[2]) != cudaSuccess) cudaGetLastError();
+    abc_counters_t r;
+    memset(&r, 0, sizeof(r));
+    r.n_particles = (uint64_t)n; r.n_lineages = h[0]; r.n_events = h[1]; r.n_draws = h[2];
+    r.ms_simulate = ms_sim; r.ms_stats = ms_st;
+    if (accumulate) {
+        c->last.n_particles += r.n_particles; c->last.n_lineages += r.n_lineages; c->last.n_events += r.n_events;
+        c->last.n_draws += r.n_draws; c->last.ms_simulate += r.ms_simulate; c->last.ms_stats += r.ms_stats;
+    } else {
+        double keep = c->last.ms_score;
+        c->last = r;
+        c->last.ms_score = keep;
+    }
+    if (out) *out = c->last;
+    return ABC_OK;
+}
+
+#define SIM_CHUNK (1 << 17)
+
+extern "C" int abc_simulate(abc_ctx_t* c, int m, int64_t n, int64_t offset, uint64_t seed, int prior_supplied,
+                            double* theta, double* stats, abc_counters_t* counters) {
+    CTX_GUARD(c);
+    int rc = check_model(m);
+    if (rc != ABC_OK) return rc;
+    if (n < 0 || (n > 0 && (!theta || !stats))) { abc_set_error("abc_simulate: bad arguments"); return ABC_ERR_ARG; }
+    const int P = abc_n_params(m);
+    memset(&c->last, 0, sizeof(c->last));
+    for (int64_t b0 = 0; b0 < n; b0 += SIM_CHUNK) {
+        const int64_t nb = std::min<int64_t>(SIM_CHUNK, n - b0);
+        if ((rc = c->d_theta.ensure((size_t)nb * P)) != ABC_OK) return rc;
+        if ((rc = c->d_stats.ensure((size_t)nb * ABC_NSTATS)) != ABC_OK) return rc;
+        if (prior_supplied)
+            ABC_CUDA_CHECK(cudaMemcpyAsync(c->d_theta.p, theta + b0 * P, (size_t)nb * P * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+        rc = simulate_device(c, m, nb, offset + b0, seed, prior_supplied, c->d_theta.p, c->d_stats.p, nullptr, c->stream);
+        if (rc != ABC_OK) return rc;
+        if (!prior_supplied)
+            ABC_CUDA_CHECK(cudaMemcpyAsync(theta + b0 * P, c->d_theta.p, (size_t)nb * P * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+        ABC_CUDA_CHECK(cudaMemcpyAsync(stats + b0 * ABC_NSTATS, c->d_stats.p, (size_t)nb * ABC_NSTATS * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+        ABC_CUDA_CHECK(cudaStreamSynchronize(c->stream));
+        if ((rc = read_counters(c, nb, nullptr, true)) != ABC_OK) return rc;
+    }
+    if (counters) *counters = c->last;
+    return ABC_OK;
+}
+
+extern "C" int abc_simulate_moments(abc_ctx_t* c, int m, int64_t n, int64_t offset, uint64_t seed,
+                                    const double* theta, double* moments, abc_counters_t* counters) {
+    CTX_GUARD(c);
+    int rc = check_model(m);
+    if (rc != ABC_OK) return rc;
+    if (n < 0 || (n > 0 && (!theta || !moments))) { abc_set_error("abc_simulate_moments: bad arguments"); return ABC_ERR_ARG; }
+    const int P = abc_n_params(m);
+    memset(&c->last, 0, sizeof(c->last));
+    for (int64_t b0 = 0; b0 < n; b0 += SIM_CHUNK) {
+        const int64_t nb = std::min<int64_t>(SIM_CHUNK, n - b0);
+        if ((rc = c->d_theta.ensure((size_t)nb * P)) != ABC_OK) return rc;
+        if ((rc = c->d_moments.ensure((size_t)nb * ABC_NREAD * 5)) != ABC_OK) return rc;
+        ABC_CUDA_CHECK(cudaMemcpyAsync(c->d_theta.p, theta + b0 * P, (size_t)nb * P * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+        rc = simulate_device(c, m, nb, offset + b0, seed, 1, c->d_theta.p, nullptr, c->d_moments.p, c->stream);
+        if (rc != ABC_OK) return rc;
+        ABC_CUDA_CHECK(cudaMemcpyAsync(moments + b0 * ABC_NREAD * 5, c->d_moments.p, (size_t)nb * ABC_NREAD * 5 * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+        ABC_CUDA_CHECK(cudaStreamSynchronize(c->stream));
+        if ((rc = read_counters(c, nb, nullptr, true)) != ABC_OK) return rc;
+    }
+    if (counters) *counters = c->last;
+    return ABC_OK;
+}
+
+extern "C" int abc_ssa_cells(abc_ctx_t* c, int m, const double* theta, int64_t particle_index, uint64_t seed,
+                             int cond, int age, int exact_math, uint32_t* counts) {
+    CTX_GUARD(c);
+    int rc = check_model(m);
+    if (rc != ABC_OK) return rc;
+    if (!c->has_design) { abc_set_error("abc_set_design has not been called"); return ABC_ERR_STATE; }
+    if (!theta || !counts || cond < 0 || cond >= ABC_NCOND || age < 0 || age >= ABC_NAGE) { abc_set_error("abc_ssa_cells: bad arguments"); return ABC_ERR_ARG; }
+    const int P = abc_n_params(m);
+    const int nc = c->design.n_cells;
+    if ((rc = c->d_theta.ensure((size_t)P)) != ABC_OK) return rc;
+    if ((rc = c->d_rates.ensure(1)) != ABC_OK) return rc;
+    if ((rc = c->d_cells.ensure((size_t)4 * nc)) != ABC_OK) return rc;
+    ABC_CUDA_CHECK(cudaMemcpyAsync(c->d_theta.p, theta, P * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+    if ((rc = abc_launch_rates(c->d_theta.p, m, 1, c->d_rates.p, c->stream)) != ABC_OK) return rc;
+    ABC_CUDA_CHECK(cudaMemsetAsync(c->d_counters.p, 0, 8 * sizeof(unsigned long long), c->stream));
+    AbcSsaParams prm = make_ssa_params(c, m, 1, particle_index, seed);
+    prm.single_readout = cond * ABC_NAGE + age;
+    rc = abc_launch_ssa(c->d_rates.p, prm, c->d_beta.p, nullptr, c->d_counters.p, c->d_work.p, c->d_cells.p, exact_math,
+                        c->sm_count, c->stream);
+    c->launches += 2;
+    if (rc != ABC_OK) return rc;
+    ABC_CUDA_CHECK(cudaMemcpyAsync(counts, c->d_cells.p, (size_t)4 * nc * sizeof(uint32_t), cudaMemcpyDeviceToHost, c->stream));
+    ABC_CUDA_CHECK(cudaStreamSynchronize(c->stream));
+    return ABC_OK;
+}
+
+extern "C" int abc_summary_stats(abc_ctx_t* c, const double* moments, int64_t n, double* stats) {
+    CTX_GUARD(c);
+    if (!c->has_design) { abc_set_error("abc_set_design has not been called"); return ABC_ERR_STATE; }
+    if (n < 0 || (n > 0 && (!moments || !stats))) { abc_set_error("abc_summary_stats: bad arguments"); return ABC_ERR_ARG; }
+    if (n == 0) return ABC_OK;
+    int rc;
+    if ((rc = c->d_moments.ensure((size_t)n * ABC_NREAD * 5)) != ABC_OK) return rc;
+    if ((rc = c->d_stats.ensure((size_t)n * ABC_NSTATS)) != ABC_OK) return rc;
+    ABC_CUDA_CHECK(cudaMemcpyAsync(c->d_moments.p, moments, (size_t)n * ABC_NREAD * 5 * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+    if ((rc = abc_launch_summary_stats(c->d_moments.p, c->d_age_dist.p, n, c->d_stats.p, c->stream)) != ABC_OK) return rc;
+    c->launches++;
+    ABC_CUDA_CHECK(cudaMemcpyAsync(stats, c->d_stats.p, (size_t)n * ABC_NSTATS * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+    ABC_CUDA_CHECK(cudaStreamSynchronize(c->stream));
+    return ABC_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+static int ensure_accept(abc_ctx* c, int64_t want) {
+    if (c->acc_capacity >= want) return ABC_OK;
+    if (c->acc_capacity > 0) {
+        // growing would drop tuples already stored: only allowed while empty
+        unsigned long long cnt = 0;
+        ABC_CUDA_CHECK(cudaMemcpy(&cnt, c->d_acc_count.p, sizeof(cnt), cudaMemcpyDeviceToHost));
+        if (cnt != 0) return ABC_OK;
+    }
+    int rc;
+    if ((rc = c->d_acc_gene.ensure((size_t)want)) != ABC_OK) return rc;
+    if ((rc = c->d_acc_particle.ensure((size_t)want)) != ABC_OK) return rc;
+    if ((rc = c->d_acc_err.ensure((size_t)want)) != ABC_OK) return rc;
+    c->acc_capacity = want;
+    return ABC_OK;
+}
+
+static int64_t default_accept_capacity(int64_t n, int G) {
+    // generous: 2 % of the pairs of this call, at least 1 Mi tuples, at most 256 Mi
+    double w = 0.02 * (double)n * (double)G;
+    int64_t cap = (int64_t)w;
+    if (cap < (1 << 20)) cap = 1 << 20;
+    if (cap > (1ll << 28)) cap = 1ll << 28;
+    return cap;
+}
+
+static int score_device(abc_ctx* c, const double* d_stats, int64_t n, int64_t offset, double eps, int layout,
+                        double* d_err, cudaStream_t st) {
+    if (!c->has_data) { abc_set_error("abc_set_data has not been called"); return ABC_ERR_STATE; }
+    if (layout != ABC_ERR_NONE && layout != ABC_ERR_GENE_MAJOR && layout != ABC_ERR_PARTICLE_MAJOR) {
+        abc_set_error("unknown err_layout %d", layout);
+        return ABC_ERR_ARG;
+    }
+    int rc = ensure_accept(c, default_accept_capacity(n, c->G));
+    if (rc != ABC_OK) return rc;
+    AbcScoreArgs a;
+    a.stats = d_stats; a.d = c->d_d.p; a.den = c->d_den.p; a.rden = nullptr;
+    a.n = n; a.G = c->G; a.particle_offset = offset; a.eps = eps;
+    a.err_layout = layout; a.err = (layout == ABC_ERR_NONE) ? nullptr : d_err;
+    a.counts = c->d_counts.p; a.acc_count = c->d_acc_count.p; a.acc_capacity = c->acc_capacity;
+    a.acc_gene = c->d_acc_gene.p; a.acc_particle = c->d_acc_particle.p; a.acc_err = c->d_acc_err.p;
+    ABC_CUDA_CHECK(cudaEventRecord(c->ev[3], st));
+    rc = abc_launch_score(a, c->sm_count, st);
+    c->launches++;
+    ABC_CUDA_CHECK(cudaEventRecord(c->ev[4], st));
+    return rc;
+}
+
+extern "C" int abc_score(abc_ctx_t* c, const double* stats, int64_t n, int64_t offset, double eps, int layout,
+                         double* err, int64_t* counts, abc_counters_t* counters) {
+    CTX_GUARD(c);
+    if (!c->has_data) { abc_set_error("abc_set_data has not been called"); return ABC_ERR_STATE; }
+    if (n < 0 || (n > 0 && !stats) || (layout != ABC_ERR_NONE && n > 0 && !err)) { abc_set_error("abc_score: bad arguments"); return ABC_ERR_ARG; }
+    const int G = c->G;
+    int rc;
+    // chunk so that the device copy of the error matrix stays below ~8 GB
+    int64_t chunk = (layout == ABC_ERR_NONE) ? (1ll << 22) : std::max<int64_t>(1024, (int64_t)(8.0e9 / (8.0 * G)));
+    double ms_total = 0.0;
+    for (int64_t b0 = 0; b0 < n; b0 += chunk) {
+        const int64_t nb = std::min<int64_t>(chunk, n - b0);
+        if ((rc = c->d_sstats.ensure((size_t)nb * ABC_NSTATS)) != ABC_OK) return rc;
+        if (layout != ABC_ERR_NONE && (rc = c->d_err.ensure((size_t)nb * G)) != ABC_OK) return rc;
+        ABC_CUDA_CHECK(cudaMemcpyAsync(c->d_sstats.p, stats + b0 * ABC_NSTATS, (size_t)nb * ABC_NSTATS * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+        rc = score_device(c, c->d_sstats.p, nb, offset + b0, eps, layout, c->d_err.p, c->stream);
+        if (rc != ABC_OK) return rc;
+        if (layout == ABC_ERR_PARTICLE_MAJOR) {
+            ABC_CUDA_CHECK(cudaMemcpyAsync(err + b0 * G, c->d_err.p, (size_t)nb * G * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+        } else if (layout == ABC_ERR_GENE_MAJOR) {
+            ABC_CUDA_CHECK(cudaMemcpy2DAsync(err + b0, (size_t)n * sizeof(double), c->d_err.p, (size_t)nb * sizeof(double),
+                                             (size_t)nb * sizeof(double), (size_t)G, cudaMemcpyDeviceToHost, c->stream));
+        }
+        ABC_CUDA_CHECK(cudaStreamSynchronize(c->stream));
+        float ms = 0.f;
+        if (cudaEventElapsedTime(&ms, c->ev[3], c->ev[4]) != cudaSuccess) cudaGetLastError();
+        ms_total += ms;
+    }
+    c->last.ms_score = ms_total;
+    unsigned long long total = 0;
+    ABC_CUDA_CHECK(cudaMemcpy(&total, c->d_acc_count.p, sizeof(total), cudaMemcpyDeviceToHost));
+    if ((int64_t)total > c->acc_capacity) {
+        abc_set_error("accepted-tuple buffer overflow: %llu accepted pairs > capacity %lld; lower eps or score in smaller batches",
+                      total, (long long)c->acc_capacity);
+        return ABC_ERR_NOMEM;
+    }
+    if (counts) {
+        std::vector<unsigned long long> h((size_t)G);
+        ABC_CUDA_CHECK(cudaMemcpy(h.data(), c->d_counts.p, (size_t)G * sizeof(unsigned long long), cudaMemcpyDeviceToHost));
+        for (int g = 0; g < G; ++g) counts[g] = (int64_t)h[g];
+    }
+    if (counters) *counters = c->last;
+    return ABC_OK;
+}
+
+extern "C" int64_t abc_accept_total(abc_ctx_t* c) {
+    if (!c) return -1;
+    if (cudaSetDevice(c->device) != cudaSuccess) return -1;
+    unsigned long long total = 0;
+    cudaStreamSynchronize(c->stream);
+    if (cudaMemcpy(&total, c->d_acc_count.p, sizeof(total), cudaMemcpyDeviceToHost) != cudaSuccess) return -1;
+    return (int64_t)total;
+}
+
+extern "C" int abc_accept_reset(abc_ctx_t* c) {
+    CTX_GUARD(c);
+    ABC_CUDA_CHECK(cudaStreamSynchronize(c->stream));
+    ABC_CUDA_CHECK(cudaMemset(c->d_acc_count.p, 0, sizeof(unsigned long long)));
+    if (c->G > 0) ABC_CUDA_CHECK(cudaMemset(c->d_counts.p, 0, (size_t)c->G * sizeof(unsigned long long)));
+    return ABC_OK;
+}
+
+static int fetch_tuples(abc_ctx* c, std::vector<int32_t>& g, std::vector<long long>& p, std::vector<double>& e) {
+    ABC_CUDA_CHECK(cudaStreamSynchronize(c->stream));
+    unsigned long long total = 0;
+    ABC_CUDA_CHECK(cudaMemcpy(&total, c->d_acc_count.p, sizeof(total), cudaMemcpyDeviceToHost));
+    if ((int64_t)total > c->acc_capacity) { abc_set_error("accepted-tuple buffer overflowed"); return ABC_ERR_NOMEM; }
+    g.resize(total); p.resize(total); e.resize(total);
+    if (total) {
+        ABC_CUDA_CHECK(cudaMemcpy(g.data(), c->d_acc_gene.p, total * sizeof(int32_t), cudaMemcpyDeviceToHost));
+        ABC_CUDA_CHECK(cudaMemcpy(p.data(), c->d_acc_particle.p, total * sizeof(long long), cudaMemcpyDeviceToHost));
+        ABC_CUDA_CHECK(cudaMemcpy(e.data(), c->d_acc_err.p, total * sizeof(double), cudaMemcpyDeviceToHost));
+    }
+    return ABC_OK;
+}
+
+extern "C" int abc_accept_tuples(abc_ctx_t* c, int32_t* gene, int64_t* particle, double* err) {
+    CTX_GUARD(c);
+    std::vector<int32_t> g; std::vector<long long> p; std::vector<double> e;
+    int rc = fetch_tuples(c, g, p, e);
+    if (rc != ABC_OK) return rc;
+    for (size_t k = 0; k < g.size(); ++k) {
+        if (gene) gene[k] = g[k];
+        if (particle) particle[k] = (int64_t)p[k];
+        if (err) err[k] = e[k];
+    }
+    return ABC_OK;
+}
+
+extern "C" int abc_accept_fetch(abc_ctx_t* c, int64_t* offsets, int64_t* idx, double* errs) {
+    CTX_GUARD(c);
+    if (!c->has_data || !offsets) { abc_set_error("abc_accept_fetch: bad state/arguments"); return ABC_ERR_ARG; }
+    std::vector<int32_t> g; std::vector<long long> p; std::vector<double> e;
+    int rc = fetch_tuples(c, g, p, e);
+    if (rc != ABC_OK) return rc;
+    const size_t total = g.size();
+    std::vector<size_t> ord(total);
+    std::iota(ord.begin(), ord.end(), (size_t)0);
+    // per gene: ascending error, ties by ascending particle index == v[sortperm(err[v])] (stable)
+    std::sort(ord.begin(), ord.end(), [&](size_t a, size_t b) {
+        if (g[a] != g[b]) return g[a] < g[b];
+        if (e[a] != e[b]) return e[a] < e[b];
+        return p[a] < p[b];
+    });
+    for (int k = 0; k <= c->G; ++k) offsets[k] = 0;
+    for (size_t k = 0; k < total; ++k) offsets[g[k] + 1] += 1;
+    for (int k = 0; k < c->G; ++k) offsets[k + 1] += offsets[k];
+    for (size_t k = 0; k < total; ++k) {
+        if (idx) idx[k] = (int64_t)p[ord[k]];
+        if (errs) errs[k] = e[ord[k]];
+    }
+    return ABC_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+extern "C" int abc_simulate_dev(abc_ctx_t* c, int m, int64_t n, int64_t offset, uint64_t seed, int prior_supplied,
+                                double* d_theta, double* d_stats, void* stream) {
+    CTX_GUARD(c);
+    int rc = check_model(m);
+    if (rc != ABC_OK) return rc;
+    if (n <= 0 || !d_theta || !d_stats) { abc_set_error("abc_simulate_dev: bad arguments"); return ABC_ERR_ARG; }
+    cudaStream_t st = stream ? (cudaStream_t)stream : c->stream;
+    return simulate_device(c, m, n, offset, seed, prior_supplied, d_theta, d_stats, nullptr, st);
+}
+
+extern "C" int abc_score_dev(abc_ctx_t* c, const double* d_stats, int64_t n, int64_t offset, double eps, int layout,
+                             double* d_err, void* stream) {
+    CTX_GUARD(c);
+    if (n <= 0 || !d_stats || (layout != ABC_ERR_NONE && !d_err)) { abc_set_error("abc_score_dev: bad arguments"); return ABC_ERR_ARG; }
+    cudaStream_t st = stream ? (cudaStream_t)stream : c->stream;
+    return score_device(c, d_stats, n, offset, eps, layout, d_err, st);
+}
+
+extern "C" int abc_counters(abc_ctx_t* c, abc_counters_t* out) {
+    CTX_GUARD(c);
+    if (!out) { abc_set_error("abc_counters: out is NULL"); return ABC_ERR_ARG; }
+    ABC_CUDA_CHECK(cudaDeviceSynchronize());
+    int rc = read_counters(c, 0, nullptr, false);
+    if (rc != ABC_OK) return rc;
+    float ms = 0.f;
+    if (cudaEventElapsedTime(&ms, c->ev[3], c->ev[4]) == cudaSuccess) c->last.ms_score = ms; else cudaGetLastError();
+    *out = c->last;
+    return ABC_OK;
+}
+
+extern "C" int64_t abc_launch_count(abc_ctx_t* c) { return c ? c->launches : -1; }

@@ -1,0 +1,67 @@
+// abc_internal.h -- launcher declarations shared by the .cu files of libabcb200.so (not installed)
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include "../../include/abc_b200.h"
+
+void abc_set_error(const char* fmt, ...);
+
+// per-particle linear-scale rates of the CME; 24 words = 96 B
+struct AbcRates {
+    float kon[5], koff[5], alpha[5], gamma[5];
+    float lam;          // labelling efficiency 10^theta_lambda clamped to [0,1]
+    uint32_t pon_thr;   // floor(P_on * 2^32): initial gene state threshold
+    float pad0, pad1;
+};
+
+struct AbcSsaParams {
+    int64_t  n_particles;      // particles in this launch
+    int64_t  particle_offset;  // global index of the first one (Philox key part)
+    uint32_t seed_lo, seed_hi;
+    int32_t  m;                // model 1..5
+    int32_t  scaling;          // m != 2
+    int32_t  n_cells;
+    int32_t  chunks;           // ceil(n_cells / 32)
+    int32_t  n_pre;            // complete cycles before the read-out cycle
+    int32_t  downsampling;
+    int32_t  single_readout;   // >= 0: debug mode, simulate only this read-out of particle 0
+    double   cycle;
+    double   agevec[5];
+    double   pulse[11];
+    double   chase[11];
+    int32_t  beta_off[11];     // offsets into beta_q32: pulse clusters 1..5, chase clusters 1..5
+};
+
+// device buffers produced by the simulate stage
+//   sums:     [particle][55][5] uint64  (sum u, sum l, sum u^2, sum u*l, sum l^2 over the cells)
+//   counters: [4] uint64 (lineages, events, draws, spare)
+int abc_launch_rates(const double* d_theta, int m, int64_t n, AbcRates* d_rates, cudaStream_t st);
+int abc_launch_prior(double* d_theta, int m, int64_t n, int64_t offset, uint64_t seed, cudaStream_t st);
+int abc_launch_ssa(const AbcRates* d_rates, const AbcSsaParams& prm, const uint32_t* d_beta_q32,
+                   unsigned long long* d_sums, unsigned long long* d_counters, unsigned int* d_work,
+                   uint32_t* d_cells_out, int exact_math, int sm_count, cudaStream_t st);
+int abc_launch_moments_from_sums(const unsigned long long* d_sums, int64_t n, int n_cells, double* d_moments,
+                                 cudaStream_t st);
+int abc_launch_summary_stats(const double* d_moments, const double* d_age_dist, int64_t n, double* d_stats,
+                             cudaStream_t st);
+
+// scoring
+int abc_launch_prepare_data(const double* d_d, const double* d_se, int G, double* d_den, double* d_rden,
+                            cudaStream_t st);
+struct AbcScoreArgs {
+    const double* stats;   // [n][53]
+    const double* d;       // [G][53]
+    const double* den;     // [G][53]
+    const double* rden;    // [G][53]
+    int64_t n;
+    int32_t G;
+    int64_t particle_offset;
+    double  eps;
+    int32_t err_layout;
+    double* err;           // nullable
+    unsigned long long* counts;       // [G]
+    unsigned long long* acc_count;    // [1] running number of accepted tuples
+    int64_t acc_capacity;
+    int32_t* acc_gene; long long* acc_particle; double* acc_err;
+};
+int abc_launch_score(const AbcScoreArgs& a, int sm_count, cudaStream_t st);

@@ -1,0 +1,550 @@
+// abc_ssa.cu -- Gillespie direct-method SSA of the 5 transcription models, capture-efficiency
+// thinning, per read-out moment sums, and the 53 summary statistics.  sm_100a.
+//
+// The stochastic process is the CME whose moments scripts/model.jl:74-86 (f), :98-111
+// (periodic_boundary) and :221-239 (downsample) describe -- SURVEY.md section 8a-CME:
+//   state (g in {0,1}, U, L);  off->on kon(t)(1-g);  on->off koff*g;  U birth alpha(t)(1-lam(t))g;
+//   L birth alpha(t)lam(t)g;  U death gamma(t)U;  L death gamma(t)L;
+//   alpha(t) = 10^theta_alpha(step) * (1 + scaling*mod(t,cycle)/cycle)      (model.jl:1-27)
+//   lam(t) = 10^theta_lambda on [age-pulse-chase, age-chase], else 0            (model.jl:58-64, :183)
+//   at every multiple of the cycle: U <- Bin(U,1/2), L <- Bin(L,1/2)            (model.jl:98-111)
+//   read-out at t = age, then U' ~ Bin(U,beta), L' ~ Bin(L,beta), beta drawn from the empirical
+//   capture efficiencies of the (pulse|chase, age cluster) group                (model.jl:221-239)
+//
+// Mapping: one thread per cell lineage, one warp per 32 cells of one (particle, condition, age)
+// read-out, persistent CTAs pulling (particle, read-out, chunk) items from a global atomic queue.
+// The piecewise-constant rate schedule of the read-out is staged per warp in shared memory.
+// Random numbers: Philox4x32-10, counter = (block index, particle lo, particle hi, tag(cell, read-out,
+// model)), key = seed: results do not depend on the launch geometry or on the number of GPUs.
+#include "abc_common.cuh"
+#include "abc_internal.h"
+
+// ------------------------------------------------------------------------------------------------
+// explicit-rounding float helpers: the file is compiled with -fmad=false, FMAs are explicit
+__device__ __forceinline__ float f_add(float a, float b) { return __fadd_rn(a, b); }
+__device__ __forceinline__ float f_mul(float a, float b) { return __fmul_rn(a, b); }
+__device__ __forceinline__ float f_fma(float a, float b, float c) { return __fmaf_rn(a, b, c); }
+
+// deterministic natural log for u in (0, 1]: IEEE ops only (bit-reproducible on the CPU)
+__device__ __forceinline__ float log_det(float u) {
+    uint32_t ix = __float_as_uint(u) - 0x3f3504f3u;
+    int e = (int)ix >> 23;
+    float mnt = __uint_as_float((ix & 0x007fffffu) + 0x3f3504f3u);
+    float f = f_add(mnt, -1.0f);
+    float s = __fdiv_rn(f, f_add(2.0f, f));
+    float z = f_mul(s, s);
+    float p = f_fma(z, 1.0f / 9.0f, 1.0f / 7.0f);
+    p = f_fma(z, p, 1.0f / 5.0f);
+    p = f_fma(z, p, 1.0f / 3.0f);
+    p = f_fma(z, p, 1.0f);
+    float l1p = f_mul(f_add(s, s), p);
+    return f_fma((float)e, 0.693147182464599609375f, l1p);
+}
+
+template <bool EXACT>
+__device__ __forceinline__ float exp_variate(uint32_t w) {
+    // u in (0,1]: (w + 0.5) * 2^-32
+    float u = f_fma((float)w, 2.3283064365386963e-10f, 1.1641532182693481e-10f);
+    if (EXACT) {
+        return -log_det(u);
+    } else {
+        return f_mul(__log2f(u), -0.693147182464599609375f);
+    }
+}
+
+template <bool EXACT>
+__device__ __forceinline__ float wait_time(float c0, float c1, float E) {
+    // solve c0*tau + c1*tau^2/2 = E for tau >= 0 (linear-in-time total propensity)
+    float disc = f_fma(f_add(c1, c1), E, f_mul(c0, c0));
+    float E2 = f_add(E, E);
+    if (EXACT) {
+        return __fdiv_rn(E2, f_add(c0, __fsqrt_rn(disc)));
+    } else {
+        float r;
+        asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(disc));
+        return __fdividef(E2, f_add(c0, r));
+    }
+}
+
+// one sub-interval of the rate schedule: constant kon, koff, gamma, lam; alpha(x) = A0 + A1*x
+struct Seg {
+    float len, kon, koff, A0;
+    float A1, gam, lamf, pad;
+};
+
+#define SSA_MAX_CYCLES 16
+#define SSA_SEG_PER_CYCLE 7
+#define SSA_WARPS 8
+
+struct WarpTable {
+    Seg seg[SSA_MAX_CYCLES][SSA_SEG_PER_CYCLE];
+    int n_ent[SSA_MAX_CYCLES];
+};
+
+struct Lineage {
+    uint32_t U, L;
+    int g;
+    uint32_t ctr;          // next Philox block index
+    uint32_t c1, c2, c3, k0, k1;
+    uint32_t n_events, n_draws;
+};
+
+__device__ __forceinline__ uint4 next_block(Lineage& s) {
+    uint4 b = philox4x32_10(s.ctr, s.c1, s.c2, s.c3, s.k0, s.k1);
+    s.ctr += 1u;
+    return b;
+}
+
+__device__ __forceinline__ uint32_t next_word(WordSrc& ws, Lineage& s) {
+    if (ws.avail == 0) {
+        uint4 b = next_block(s);
+        ws.w0 = b.x; ws.w1 = b.y; ws.w2 = b.z; ws.w3 = b.w;
+        ws.avail = 4;
+    }
+    uint32_t r = ws.w0;
+    ws.w0 = ws.w1; ws.w1 = ws.w2; ws.w2 = ws.w3;
+    ws.avail -= 1;
+    return r;
+}
+
+// Binomial(n, 1/2): the number of set bits among n fresh random bits
+__device__ __forceinline__ uint32_t binhalf(uint32_t n, WordSrc& ws, Lineage& s) {
+    uint32_t cnt = 0;
+    while (n >= 32u) { cnt += __popc(next_word(ws, s)); n -= 32u; }
+    if (n > 0u) cnt += __popc(next_word(ws, s) & ((1u << n) - 1u));
+    return cnt;
+}
+
+// Binomial(n, B / 2^32), exact: every molecule's uniform is compared with B bit by bit (MSB first);
+// at each level the undecided molecules split Bin(m, 1/2).
+__device__ __forceinline__ uint32_t binom_q32(uint32_t n, uint32_t B, WordSrc& ws, Lineage& s) {
+    uint32_t m = n, acc = 0;
+    for (int bit = 31; bit >= 0 && m > 0u; --bit) {
+        uint32_t h = binhalf(m, ws, s);
+        if ((B >> bit) & 1u) { acc += h; m -= h; }
+        else m = h;
+    }
+    return acc;
+}
+
+// one event draw.  returns true if the sub-interval boundary was crossed (no reaction fired).
+template <bool EXACT>
+__device__ __forceinline__ bool ssa_step(Lineage& s, float& x, const Seg& sg, uint32_t wt, uint32_t wc) {
+    const bool on = (s.g != 0);
+    const float asw = on ? sg.koff : sg.kon;
+    const float n = (float)(s.U + s.L);
+    const float ad = f_mul(sg.gam, n);
+    const float ab = on ? f_fma(sg.A1, x, sg.A0) : 0.0f;
+    const float c1 = on ? sg.A1 : 0.0f;
+    const float base = f_add(asw, ad);
+    const float c0 = f_add(base, ab);
+    const float E = exp_variate<EXACT>(wt);
+    const float tau = wait_time<EXACT>(c0, c1, E);
+    const float xn = f_add(x, tau);
+    s.n_draws += 1u;
+    if (!(xn < sg.len)) return true;
+    x = xn;
+    const float abn = on ? f_fma(sg.A1, xn, sg.A0) : 0.0f;
+    const float tot = f_add(base, abn);
+    const float rs = f_mul(f_mul((float)wc, 2.3283064365386963e-10f), tot);
+    const float rb = f_mul(f_mul((float)(~wc), 2.3283064365386963e-10f), tot);
+    const bool sw = rs < asw;
+    const bool birth = !sw && ((rb < abn) || (n == 0.0f));
+    const bool death = !sw && !birth;
+    const bool lab = birth && (rb < f_mul(sg.lamf, abn));
+    const float rd = f_add(rs, -asw);
+    const bool dU = ((rd < f_mul(sg.gam, (float)s.U)) || (s.L == 0u)) && (s.U > 0u);
+    s.g ^= (int)sw;
+    s.U += (uint32_t)(birth && !lab);
+    s.L += (uint32_t)lab;
+    s.U -= (uint32_t)(death && dU);
+    s.L -= (uint32_t)(death && !dU);
+    s.n_events += 1u;
+    return false;
+}
+
+__device__ __forceinline__ unsigned long long warp_sum_u64(unsigned long long v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+
+// build the schedule of one read-out: lane c builds cycle c
+__device__ __forceinline__ void build_table(WarpTable& tab, const AbcRates& r, const AbcSsaParams& prm,
+                                            int cond, int age_i, int lane) {
+    const int c = lane;
+    if (c <= prm.n_pre) {
+        const double cycle = prm.cycle;
+        const double age = prm.agevec[age_i];
+        const double tl0 = age - prm.pulse[cond] - prm.chase[cond];
+        const double tl1 = age - prm.chase[cond];
+        const double Tc = (double)(c - prm.n_pre) * cycle;
+        const double cyc_end = (c == prm.n_pre) ? age : cycle;
+        const double l0 = tl0 - Tc, l1 = tl1 - Tc;
+        const double step_len = cycle / 5.0;
+        const double sc = prm.scaling ? 1.0 : 0.0;
+        double pos = 0.0;
+        int k = 0, n = 0;
+        while (pos < cyc_end && n < SSA_SEG_PER_CYCLE) {
+            double step_end = (double)(k + 1) * step_len;
+            double nxt = step_end < cyc_end ? step_end : cyc_end;
+            if (l0 > pos && l0 < nxt) nxt = l0;
+            if (l1 > pos && l1 < nxt) nxt = l1;
+            const double mid = 0.5 * (pos + nxt);
+            const bool lab = (mid >= l0) && (mid <= l1);
+            Seg sg;
+            sg.len = (float)(nxt - pos);
+            sg.kon = r.kon[k];
+            sg.koff = r.koff[k];
+            sg.gam = r.gamma[k];
+            sg.A0 = (float)((double)r.alpha[k] * (1.0 + sc * pos / cycle));
+            sg.A1 = (float)((double)r.alpha[k] * sc / cycle);
+            sg.lamf = lab ? r.lam : 0.0f;
+            sg.pad = 0.0f;
+            tab.seg[c][n] = sg;
+            n += 1;
+            pos = nxt;
+            if (!(pos < step_end)) k += 1;
+            if (k > 4) k = 4;
+        }
+        tab.n_ent[c] = n;
+    }
+}
+
+template <bool EXACT>
+__global__ void __launch_bounds__(SSA_WARPS * 32)
+abc_ssa_kernel(const AbcRates* __restrict__ rates, const AbcSsaParams prm, const uint32_t* __restrict__ beta_q32,
+               unsigned long long* __restrict__ sums, unsigned long long* __restrict__ counters,
+               unsigned int* __restrict__ work, uint32_t* __restrict__ cells_out) {
+    __shared__ WarpTable tabs[SSA_WARPS];
+    __shared__ AbcRates srates[SSA_WARPS];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    WarpTable& tab = tabs[warp];
+    const unsigned long long per_particle = (unsigned long long)ABC_NREAD * prm.chunks;
+    const unsigned long long total = (prm.single_readout >= 0)
+                                         ? (unsigned long long)prm.chunks
+                                         : (unsigned long long)prm.n_particles * per_particle;
+    unsigned long long acc_lineages = 0, acc_events = 0, acc_draws = 0;
+
+    for (;;) {
+        unsigned int item = 0;
+        if (lane == 0) item = atomicAdd(work, 1u);
+        item = __shfl_sync(0xffffffffu, item, 0);
+        if ((unsigned long long)item >= total) break;
+        long long p;
+        int readout, chunk;
+        if (prm.single_readout >= 0) {
+            p = 0; readout = prm.single_readout; chunk = (int)item;
+        } else {
+            p = (long long)(item / per_particle);
+            unsigned int rem = (unsigned int)(item % per_particle);
+            readout = (int)(rem / prm.chunks);
+            chunk = (int)(rem % prm.chunks);
+        }
+        const int cond = readout / ABC_NAGE, age_i = readout % ABC_NAGE;
+
+        // stage this particle's rates and the read-out's schedule in shared memory
+        __syncwarp();
+        if (lane < 24) ((uint32_t*)&srates[warp])[lane] = ((const uint32_t*)&rates[p])[lane];
+        __syncwarp();
+        build_table(tab, srates[warp], prm, cond, age_i, lane);
+        __syncwarp();
+
+        const int cell = chunk * 32 + lane;
+        const bool live = cell < prm.n_cells;
+        const unsigned long long gp = (unsigned long long)(prm.particle_offset + p);
+        Lineage s;
+        s.c1 = (uint32_t)gp; s.c2 = (uint32_t)(gp >> 32);
+        s.c3 = abc_tag((uint32_t)cell, (uint32_t)readout, (uint32_t)prm.m, ABC_DOM_SSA);
+        s.k0 = prm.seed_lo; s.k1 = prm.seed_hi;
+        s.ctr = 0u; s.U = 0u; s.L = 0u; s.g = 0; s.n_events = 0u; s.n_draws = 0u;
+        uint32_t Ud = 0u, Ld = 0u;
+
+        if (live) {
+            {   // initial gene state ~ Bernoulli(P_on)
+                uint4 b = next_block(s);
+                s.g = (b.x < srates[warp].pon_thr) ? 1 : 0;
+            }
+            for (int c = 0; c <= prm.n_pre; ++c) {
+                const int n_ent = tab.n_ent[c];
+                int e = 0;
+                float x = 0.0f;
+                Seg sg = tab.seg[c][0];
+                while (e < n_ent) {
+                    const uint4 b = next_block(s);
+                    if (ssa_step<EXACT>(s, x, sg, b.x, b.y)) {
+                        e += 1; x = 0.0f;
+                        if (e < n_ent) sg = tab.seg[c][e];
+                    }
+                    if (e < n_ent) {
+                        if (ssa_step<EXACT>(s, x, sg, b.z, b.w)) {
+                            e += 1; x = 0.0f;
+                            if (e < n_ent) sg = tab.seg[c][e];
+                        }
+                    }
+                }
+                if (c < prm.n_pre) {   // cell division: binomial partitioning, gene state kept
+                    WordSrc ws; ws.avail = 0;
+                    s.U = binhalf(s.U, ws, s);
+                    s.L = binhalf(s.L, ws, s);
+                }
+            }
+            Ud = s.U; Ld = s.L;
+            if (prm.downsampling) {
+                WordSrc ws; ws.avail = 0;
+                const int grp = (cond < 6 ? 0 : ABC_NAGE) + age_i;
+                const uint32_t off = (uint32_t)prm.beta_off[grp];
+                const uint32_t cnt = (uint32_t)prm.beta_off[grp + 1] - off;
+                const uint32_t B = beta_q32[off + __umulhi(next_word(ws, s), cnt)];
+                Ud = binom_q32(s.U, B, ws, s);
+                Ld = binom_q32(s.L, B, ws, s);
+            }
+            if (cells_out != nullptr) {
+                cells_out[0 * prm.n_cells + cell] = s.U;
+                cells_out[1 * prm.n_cells + cell] = s.L;
+                cells_out[2 * prm.n_cells + cell] = Ud;
+                cells_out[3 * prm.n_cells + cell] = Ld;
+            }
+        }
+        __syncwarp();
+        // per read-out moment sums (exact integers: order independent => deterministic)
+        const unsigned long long u = Ud, l = Ld;
+        unsigned long long su = warp_sum_u64(u), sl = warp_sum_u64(l);
+        unsigned long long suu = warp_sum_u64(u * u), sul = warp_sum_u64(u * l), sll = warp_sum_u64(l * l);
+        if (lane == 0 && sums != nullptr) {
+            unsigned long long* dst = sums + ((unsigned long long)p * ABC_NREAD + readout) * 5ull;
+            atomicAdd(dst + 0, su); atomicAdd(dst + 1, sl); atomicAdd(dst + 2, suu);
+            atomicAdd(dst + 3, sul); atomicAdd(dst + 4, sll);
+        }
+        acc_lineages += live ? 1ull : 0ull;
+        acc_events += s.n_events;
+        acc_draws += s.n_draws;
+    }
+    acc_lineages = warp_sum_u64(acc_lineages);
+    acc_events = warp_sum_u64(acc_events);
+    acc_draws = warp_sum_u64(acc_draws);
+    if (lane == 0) {
+        atomicAdd(counters + 0, acc_lineages);
+        atomicAdd(counters + 1, acc_events);
+        atomicAdd(counters + 2, acc_draws);
+    }
+}
+
+int abc_launch_ssa(const AbcRates* d_rates, const AbcSsaParams& prm, const uint32_t* d_beta_q32,
+                   unsigned long long* d_sums, unsigned long long* d_counters, unsigned int* d_work,
+                   uint32_t* d_cells_out, int exact_math, int sm_count, cudaStream_t st) {
+    if (prm.n_pre + 1 > SSA_MAX_CYCLES) {
+        abc_set_error("n_pre_cycles must be <= %d", SSA_MAX_CYCLES - 1);
+        return ABC_ERR_ARG;
+    }
+    ABC_CUDA_CHECK(cudaMemsetAsync(d_work, 0, sizeof(unsigned int), st));
+    int per_sm = 0;
+    if (exact_math) {
+        ABC_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, abc_ssa_kernel<true>, SSA_WARPS * 32, 0));
+    } else {
+        ABC_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, abc_ssa_kernel<false>, SSA_WARPS * 32, 0));
+    }
+    if (per_sm < 1) per_sm = 1;
+    unsigned long long items = (prm.single_readout >= 0) ? (unsigned long long)prm.chunks
+                               : (unsigned long long)prm.n_particles * ABC_NREAD * prm.chunks;
+    if (items > 0xFFFFFFF0ull - 65536ull) {
+        abc_set_error("too many work items in one SSA launch (%llu); split the batch", items);
+        return ABC_ERR_ARG;
+    }
+    unsigned long long want = (items + SSA_WARPS - 1) / SSA_WARPS;
+    unsigned long long grid = (unsigned long long)sm_count * per_sm;
+    if (grid > want) grid = want;
+    if (grid < 1) grid = 1;
+    if (exact_math)
+        abc_ssa_kernel<true><<<(unsigned)grid, SSA_WARPS * 32, 0, st>>>(d_rates, prm, d_beta_q32, d_sums, d_counters, d_work, d_cells_out);
+    else
+        abc_ssa_kernel<false><<<(unsigned)grid, SSA_WARPS * 32, 0, st>>>(d_rates, prm, d_beta_q32, d_sums, d_counters, d_work, d_cells_out);
+    ABC_CUDA_CHECK(cudaGetLastError());
+    return ABC_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// theta (log10, [n][P]) -> linear float rates.  vary_map of model.jl:30-43 / abc_simulation.jl:82-85.
+__global__ void abc_rates_kernel(const double* __restrict__ theta, int m, long long n, AbcRates* __restrict__ out) {
+    long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const int P = (m <= 2) ? 5 : 9;
+    const double* th = theta + i * P;
+    const int vary = (m == 3) ? 0 : (m == 4) ? 2 : (m == 5) ? 3 : -1;
+    AbcRates r;
+    int k = 0;
+    float* dst[4] = {r.kon, r.koff, r.alpha, r.gamma};
+    for (int q = 0; q < 4; ++q) {
+        if (q == vary) {
+            for (int j = 0; j < 5; ++j) dst[q][j] = (float)abc_exp10_det(th[k + j]);
+            k += 5;
+        } else {
+            float v = (float)abc_exp10_det(th[k]);
+            for (int j = 0; j < 5; ++j) dst[q][j] = v;
+            k += 1;
+        }
+    }
+    double lam = abc_exp10_det(th[k]);
+    if (!(lam <= 1.0)) lam = 1.0;
+    if (!(lam >= 0.0)) lam = 0.0;
+    r.lam = (float)lam;
+    // gene state at the start of the first simulated cycle ~ stationary of the last rate step
+    double kon = (double)r.kon[4], koff = (double)r.koff[4];
+    double pon = kon / (kon + koff);
+    double thr = pon * 4294967296.0;
+    r.pon_thr = (thr >= 4294967295.0) ? 0xFFFFFFFFu : (thr > 0.0 ? (uint32_t)thr : 0u);
+    r.pad0 = 0.0f; r.pad1 = 0.0f;
+    out[i] = r;
+}
+
+int abc_launch_rates(const double* d_theta, int m, int64_t n, AbcRates* d_rates, cudaStream_t st) {
+    if (n <= 0) return ABC_OK;
+    int threads = 128;
+    long long blocks = (n + threads - 1) / threads;
+    abc_rates_kernel<<<(unsigned)blocks, threads, 0, st>>>(d_theta, m, (long long)n, d_rates);
+    ABC_CUDA_CHECK(cudaGetLastError());
+    return ABC_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// P1: fix_params (abc_simulation.jl:3-11): log10 kon,koff,alpha ~ U(-3,3), gamma ~ U(-3,2), lambda ~ U(-0.7,0)
+__global__ void abc_prior_kernel(double* __restrict__ theta, int m, long long n, long long offset,
+                                 uint32_t k0, uint32_t k1) {
+    long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const int P = (m <= 2) ? 5 : 9;
+    const int vary = (m == 3) ? 0 : (m == 4) ? 2 : (m == 5) ? 3 : -1;
+    const unsigned long long gp = (unsigned long long)(offset + i);
+    const uint32_t tag = abc_tag(0u, 0u, (uint32_t)m, ABC_DOM_PRIOR);
+    double lo[ABC_MAXP], hi[ABC_MAXP];
+    int k = 0;
+    for (int q = 0; q < 4; ++q) {
+        int len = (q == vary) ? 5 : 1;
+        for (int j = 0; j < len; ++j) { lo[k] = -3.0; hi[k] = (q == 3) ? 2.0 : 3.0; k++; }
+    }
+    lo[k] = -0.7; hi[k] = 0.0;
+    for (int b = 0; b * 2 < P; ++b) {
+        uint4 w = philox4x32_10((uint32_t)b, (uint32_t)gp, (uint32_t)(gp >> 32), tag, k0, k1);
+        // 53-bit uniforms in [0,1)
+        double u0 = (double)(((unsigned long long)(w.x >> 5) << 26) | (unsigned long long)(w.y >> 6)) * (1.0 / 9007199254740992.0);
+        double u1 = (double)(((unsigned long long)(w.z >> 5) << 26) | (unsigned long long)(w.w >> 6)) * (1.0 / 9007199254740992.0);
+        int j0 = 2 * b, j1 = 2 * b + 1;
+        theta[i * P + j0] = abc_fma(hi[j0] - lo[j0], u0, lo[j0]);
+        if (j1 < P) theta[i * P + j1] = abc_fma(hi[j1] - lo[j1], u1, lo[j1]);
+    }
+}
+
+int abc_launch_prior(double* d_theta, int m, int64_t n, int64_t offset, uint64_t seed, cudaStream_t st) {
+    if (n <= 0) return ABC_OK;
+    int threads = 128;
+    long long blocks = (n + threads - 1) / threads;
+    abc_prior_kernel<<<(unsigned)blocks, threads, 0, st>>>(d_theta, m, (long long)n, (long long)offset,
+                                                          (uint32_t)seed, (uint32_t)(seed >> 32));
+    ABC_CUDA_CHECK(cudaGetLastError());
+    return ABC_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// integer sums -> sample moments per (particle, read-out): mean_u, mean_l, var_u, cov_ul, var_l
+// (corrected, n-1, like var()/cov() of scripts/data_summary_statistics.jl:117-121)
+__device__ __forceinline__ double u128_to_double(unsigned __int128 v) {
+    unsigned long long hi = (unsigned long long)(v >> 64), lo = (unsigned long long)v;
+    return __dadd_rn(__dmul_rn((double)hi, 18446744073709551616.0), (double)lo);
+}
+
+__global__ void abc_moments_kernel(const unsigned long long* __restrict__ sums, long long n_items, int n_cells,
+                                   double* __restrict__ mom) {
+    long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n_items) return;
+    const unsigned long long* s = sums + i * 5;
+    const unsigned long long su = s[0], sl = s[1], suu = s[2], sul = s[3], sll = s[4];
+    const unsigned __int128 N = (unsigned __int128)(unsigned long long)n_cells;
+    const double dn = (double)n_cells;
+    const double dnn = __dmul_rn(dn, (double)(n_cells - 1));
+    unsigned __int128 a, b;
+    double* o = mom + i * 5;
+    o[0] = __ddiv_rn((double)su, dn);
+    o[1] = __ddiv_rn((double)sl, dn);
+    a = N * suu; b = (unsigned __int128)su * su;
+    o[2] = __ddiv_rn(u128_to_double(a - b), dnn);
+    a = N * sul; b = (unsigned __int128)su * sl;
+    o[3] = (a >= b) ? __ddiv_rn(u128_to_double(a - b), dnn) : -__ddiv_rn(u128_to_double(b - a), dnn);
+    a = N * sll; b = (unsigned __int128)sl * sl;
+    o[4] = __ddiv_rn(u128_to_double(a - b), dnn);
+}
+
+int abc_launch_moments_from_sums(const unsigned long long* d_sums, int64_t n, int n_cells, double* d_moments,
+                                 cudaStream_t st) {
+    long long items = (long long)n * ABC_NREAD;
+    if (items <= 0) return ABC_OK;
+    int threads = 128;
+    long long blocks = (items + threads - 1) / threads;
+    abc_moments_kernel<<<(unsigned)blocks, threads, 0, st>>>(d_sums, items, n_cells, d_moments);
+    ABC_CUDA_CHECK(cudaGetLastError());
+    return ABC_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// S1: the 53 summary statistics of abc_sim (abc_simulation.jl:23-46) with weighted_cov
+// (data_summary_statistics.jl:179-181).  FP64, explicit rounding, the reference's operation order.
+__device__ __forceinline__ double d_add(double a, double b) { return __dadd_rn(a, b); }
+__device__ __forceinline__ double d_mul(double a, double b) { return __dmul_rn(a, b); }
+
+__device__ __forceinline__ double wsum5(const double* w, const double* x) {
+    double s = 0.0;
+#pragma unroll
+    for (int i = 0; i < 5; ++i) s = d_add(s, d_mul(w[i], x[i]));
+    return s;
+}
+__device__ __forceinline__ double wcov5(const double* x, const double* y, const double* w) {
+    const double mx = wsum5(w, x), my = wsum5(w, y);
+    double s = 0.0;
+#pragma unroll
+    for (int i = 0; i < 5; ++i) s = d_add(s, d_mul(w[i], d_mul(d_add(x[i], -mx), d_add(y[i], -my))));
+    return s;
+}
+
+__global__ void abc_stats_kernel(const double* __restrict__ mom, const double* __restrict__ age_dist, long long n,
+                                 double* __restrict__ stats) {
+    long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const double* mp = mom + i * (ABC_NREAD * 5);
+    double* st = stats + i * ABC_NSTATS;
+    for (int j = 0; j < ABC_NCOND; ++j) {
+        double w[5], c[5][5];
+#pragma unroll
+        for (int a = 0; a < 5; ++a) {
+            w[a] = age_dist[j * 5 + a];
+#pragma unroll
+            for (int q = 0; q < 5; ++q) c[q][a] = mp[(j * 5 + a) * 5 + q];
+        }
+        const double s1 = wsum5(w, c[0]), s2 = wsum5(w, c[1]);
+        st[20 + j] = __ddiv_rn(s2, d_add(s1, s2));
+        const double v1 = d_add(wsum5(w, c[2]), wcov5(c[0], c[0], w));
+        const double v2 = d_add(wsum5(w, c[4]), wcov5(c[1], c[1], w));
+        const double stds = __dsqrt_rn(fabs(d_mul(v1, v2)));
+        st[31 + j] = __ddiv_rn(wsum5(w, c[3]), stds);
+        st[42 + j] = __ddiv_rn(wcov5(c[0], c[1], w), stds);
+        if (j == 5 || j == 6) {
+            double* mo = st + (j == 5 ? 0 : 10);
+            double* ff = st + (j == 5 ? 5 : 15);
+#pragma unroll
+            for (int a = 0; a < 5; ++a) {
+                const double tot = d_add(c[0][a], c[1][a]);
+                const double eps = (tot == 0.0) ? 0.0001 : 0.0;
+                mo[a] = tot;
+                ff[a] = __ddiv_rn(d_add(d_add(c[2][a], d_mul(2.0, c[3][a])), c[4][a]), d_add(tot, eps));
+            }
+        }
+    }
+}
+
+int abc_launch_summary_stats(const double* d_moments, const double* d_age_dist, int64_t n, double* d_stats,
+                             cudaStream_t st) {
+    if (n <= 0) return ABC_OK;
+    int threads = 64;
+    long long blocks = (n + threads - 1) / threads;
+    abc_stats_kernel<<<(unsigned)blocks, threads, 0, st>>>(d_moments, d_age_dist, (long long)n, d_stats);
+    ABC_CUDA_CHECK(cudaGetLastError());
+    return ABC_OK;
+}

@@ -1,0 +1,172 @@
+"""AbcEngine: one libabcb200 context on one GPU, numpy in / numpy out.
+
+Thin wrapper over the C ABI (include/abc_b200.h) -- what the Julia host does with ``ccall``.  All
+arithmetic happens in the CUDA library; this module only allocates host arrays and passes pointers.
+Array conventions follow the Julia host: a Julia ``P x n`` column-major matrix is a numpy ``(n, P)``
+C-contiguous array.
+"""
+import ctypes
+
+import numpy as np
+
+from . import _lib
+from .design import Design
+from .model import _check_m, n_params
+
+
+class AbcEngine:
+    def __init__(self, device=0):
+        self._lib = _lib.load()
+        self._ctx = ctypes.c_void_p()
+        _lib.check(self._lib.abc_create(int(device), ctypes.byref(self._ctx)))
+        self.device = int(device)
+        self.design = None
+        self.n_genes = 0
+
+    def close(self):
+        if getattr(self, "_ctx", None) is not None and self._ctx:
+            self._lib.abc_destroy(self._ctx)
+            self._ctx = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        self.close()
+
+    # ---- configuration ---------------------------------------------------------------------
+    def set_design(self, design: Design):
+        cd, keep = design.to_c()
+        _lib.check(self._lib.abc_set_design(self._ctx, ctypes.byref(cd)))
+        del keep
+        self.design = design
+
+    def set_data(self, d, se):
+        """d, se: (G, 53) in the order pulse_mean, pulse_ff, chase_mean, chase_ff, ratio, mean_corr, corr_mean"""
+        d = np.ascontiguousarray(d, dtype=np.float64)
+        se = np.ascontiguousarray(se, dtype=np.float64)
+        assert d.ndim == 2 and d.shape[1] == _lib.NSTATS and d.shape == se.shape
+        _lib.check(self._lib.abc_set_data(self._ctx, _lib.ptr(d), _lib.ptr(se), d.shape[0]))
+        self.n_genes = d.shape[0]
+
+    # ---- P1 ----------------------------------------------------------------------------------
+    def fix_params(self, m, n, particle_offset=0, seed=20240229):
+        """fix_params(vary_map, N) (abc_simulation.jl:3-11) -> (n, P) log10 parameters"""
+        P = n_params(_check_m(m))
+        theta = np.empty((int(n), P), dtype=np.float64)
+        _lib.check(self._lib.abc_fix_params(self._ctx, m, int(n), int(particle_offset), int(seed), _lib.ptr(theta)))
+        return theta
+
+    # ---- M1-M10 + S1 ---------------------------------------------------------------------------
+    def simulate(self, m, n_trials=None, theta=None, particle_offset=0, seed=20240229):
+        """abc_sim over a batch.  theta=None draws the prior.  Returns (theta (n,P), stats (n,53), counters)"""
+        P = n_params(_check_m(m))
+        if theta is None:
+            n = int(n_trials)
+            theta = np.empty((n, P), dtype=np.float64)
+            supplied = 0
+        else:
+            theta = np.ascontiguousarray(theta, dtype=np.float64).reshape(-1, P)
+            n = theta.shape[0]
+            supplied = 1
+        stats = np.empty((n, _lib.NSTATS), dtype=np.float64)
+        cnt = _lib.AbcCounters()
+        _lib.check(self._lib.abc_simulate(self._ctx, m, n, int(particle_offset), int(seed), supplied,
+                                          _lib.ptr(theta), _lib.ptr(stats), ctypes.byref(cnt)))
+        return theta, stats, cnt.as_dict()
+
+    def simulate_moments(self, m, theta, particle_offset=0, seed=20240229):
+        """per (condition, age) moments: (n, 11, 5, 5) [mean_u, mean_l, var_u, cov_ul, var_l]"""
+        P = n_params(_check_m(m))
+        theta = np.ascontiguousarray(theta, dtype=np.float64).reshape(-1, P)
+        n = theta.shape[0]
+        mom = np.empty((n, _lib.NCOND, _lib.NAGE, 5), dtype=np.float64)
+        cnt = _lib.AbcCounters()
+        _lib.check(self._lib.abc_simulate_moments(self._ctx, m, n, int(particle_offset), int(seed),
+                                                  _lib.ptr(theta), _lib.ptr(mom), ctypes.byref(cnt)))
+        return mom, cnt.as_dict()
+
+    def ssa_cells(self, m, theta, particle_index, cond, age, seed=20240229, exact_math=False):
+        """per-cell counts of one read-out: (4, n_cells) uint32 rows U, L (before thinning), U', L'"""
+        P = n_params(_check_m(m))
+        theta = np.ascontiguousarray(theta, dtype=np.float64).reshape(P)
+        out = np.empty((4, self.design.n_cells), dtype=np.uint32)
+        _lib.check(self._lib.abc_ssa_cells(self._ctx, m, _lib.ptr(theta), int(particle_index), int(seed),
+                                           int(cond), int(age), int(bool(exact_math)), _lib.ptr(out)))
+        return out
+
+    def summary_stats(self, moments):
+        """S1 (abc_simulation.jl:23-46): (n, 11, 5, 5) moments -> (n, 53)"""
+        mom = np.ascontiguousarray(moments, dtype=np.float64).reshape(-1, _lib.NCOND, _lib.NAGE, 5)
+        stats = np.empty((mom.shape[0], _lib.NSTATS), dtype=np.float64)
+        _lib.check(self._lib.abc_summary_stats(self._ctx, _lib.ptr(mom), mom.shape[0], _lib.ptr(stats)))
+        return stats
+
+    # ---- E2/E3 + A1 ------------------------------------------------------------------------------
+    def accept_reset(self):
+        _lib.check(self._lib.abc_accept_reset(self._ctx))
+
+    def score(self, stats, eps=4.8, particle_offset=0, err_layout=_lib.ERR_PARTICLE_MAJOR, want_counts=True):
+        """compute_trunc_errors + eps-acceptance.  Returns (err or None, counts or None, counters).
+        err is (n, G) for ERR_PARTICLE_MAJOR (rows of error_<model>.txt) or (G, n) for ERR_GENE_MAJOR."""
+        stats = np.ascontiguousarray(stats, dtype=np.float64).reshape(-1, _lib.NSTATS)
+        n, G = stats.shape[0], self.n_genes
+        err = None
+        if err_layout == _lib.ERR_PARTICLE_MAJOR:
+            err = np.empty((n, G), dtype=np.float64)
+        elif err_layout == _lib.ERR_GENE_MAJOR:
+            err = np.empty((G, n), dtype=np.float64)
+        counts = np.zeros(G, dtype=np.int64) if want_counts else None
+        cnt = _lib.AbcCounters()
+        _lib.check(self._lib.abc_score(self._ctx, _lib.ptr(stats), n, int(particle_offset), float(eps), int(err_layout),
+                                       _lib.ptr(err), _lib.ptr(counts), ctypes.byref(cnt)))
+        return err, counts, cnt.as_dict()
+
+    def accept_total(self):
+        t = self._lib.abc_accept_total(self._ctx)
+        if t < 0:
+            raise _lib.AbcError("abc_accept_total failed")
+        return int(t)
+
+    def accept_fetch(self):
+        """CSR (offsets (G+1,), idx (total,) 1-based sorted by (err, idx) per gene, errs (total,))"""
+        total = self.accept_total()
+        offsets = np.zeros(self.n_genes + 1, dtype=np.int64)
+        idx = np.empty(total, dtype=np.int64)
+        errs = np.empty(total, dtype=np.float64)
+        _lib.check(self._lib.abc_accept_fetch(self._ctx, _lib.ptr(offsets), _lib.ptr(idx), _lib.ptr(errs)))
+        return offsets, idx, errs
+
+    def accept_tuples(self):
+        total = self.accept_total()
+        gene = np.empty(total, dtype=np.int32)
+        part = np.empty(total, dtype=np.int64)
+        errs = np.empty(total, dtype=np.float64)
+        _lib.check(self._lib.abc_accept_tuples(self._ctx, _lib.ptr(gene), _lib.ptr(part), _lib.ptr(errs)))
+        return gene, part, errs
+
+    # ---- device-resident variants (raw device pointers, e.g. torch tensors' data_ptr()) -----------
+    def simulate_dev(self, m, n, d_theta_ptr, d_stats_ptr, particle_offset=0, seed=20240229, prior_supplied=False,
+                     stream=None):
+        _lib.check(self._lib.abc_simulate_dev(self._ctx, _check_m(m), int(n), int(particle_offset), int(seed),
+                                              int(bool(prior_supplied)), ctypes.c_void_p(d_theta_ptr),
+                                              ctypes.c_void_p(d_stats_ptr), ctypes.c_void_p(stream or 0)))
+
+    def score_dev(self, d_stats_ptr, n, eps=4.8, particle_offset=0, err_layout=_lib.ERR_NONE, d_err_ptr=0, stream=None):
+        _lib.check(self._lib.abc_score_dev(self._ctx, ctypes.c_void_p(d_stats_ptr), int(n), int(particle_offset),
+                                           float(eps), int(err_layout), ctypes.c_void_p(d_err_ptr or 0),
+                                           ctypes.c_void_p(stream or 0)))
+
+    def counters(self):
+        cnt = _lib.AbcCounters()
+        _lib.check(self._lib.abc_counters(self._ctx, ctypes.byref(cnt)))
+        return cnt.as_dict()
+
+    def launch_count(self):
+        return int(self._lib.abc_launch_count(self._ctx))

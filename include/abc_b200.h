@@ -1,0 +1,165 @@
+/*
+ * abc_b200.h -- C ABI of libabcb200.so: the B200-native ABC simulate -> summarise -> score -> accept
+ * hot path of pthomaslab/abc_inference_transcription.
+ *
+ * The reference has no FFI; its boundary is script level (Julia globals m, n_trials, submit and
+ * `include`d scripts).  Each entry point below names the reference code it replaces.  A Julia host
+ * binds these with  ccall((:abc_simulate, "libabcb200"), Cint, (...), ...)  -- see INTEGRATION.md.
+ *
+ * Conventions
+ *   - every function returns 0 on success, a negative abc_status_t otherwise; the message is in
+ *     abc_last_error() (thread local).  No C++ exception crosses this boundary.
+ *   - all host buffers are caller owned, column-major Julia arrays map as documented per argument,
+ *     and must stay alive for the duration of the (blocking) call.
+ *   - the library owns all device memory.  There is NO CPU fallback: without a CUDA device every
+ *     compute entry point fails with ABC_ERR_CUDA.
+ *   - particle indices in outputs are 1-based (Julia), everything else is 0-based.
+ *   - calls on one context are not re-entrant; use one context per GPU / per host thread.
+ */
+#ifndef ABC_B200_H
+#define ABC_B200_H
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define ABC_NAGE   5    /* n_age_clusters            scripts/load_process_data.jl:68 */
+#define ABC_NCOND  11   /* labelling conditions      scripts/abc_simulation.jl:65    */
+#define ABC_NSTATS 53   /* 4*5 + 3*11                scripts/compute_errors.jl:51    */
+#define ABC_NMODELS 5   /* const, const_const, kon, alpha, gamma   abc_simulation.jl:82 */
+#define ABC_MAXP   9    /* parameters per particle: 5 (m=1,2) or 9 (m=3,4,5) */
+
+typedef enum {
+    ABC_OK = 0,
+    ABC_ERR_ARG = -1,      /* bad argument (NULL, out of range model index, ...) */
+    ABC_ERR_CUDA = -2,     /* CUDA runtime error or no device */
+    ABC_ERR_STATE = -3,    /* design / data statistics not set yet */
+    ABC_ERR_NOMEM = -4
+} abc_status_t;
+
+typedef struct abc_ctx abc_ctx_t;
+
+/* simulator selection for abc_simulate */
+#define ABC_SIM_SSA 0      /* Gillespie direct-method SSA (the north-star path) */
+#define ABC_SIM_ODE 1      /* moment ODEs, what scripts/model.jl actually integrates (model.jl:74-96) */
+
+/* Experimental design: the globals scripts/abc_simulation.jl:65-79 builds plus the data-derived
+ * globals of scripts/load_process_data.jl:59-83 (age, pulse_idx, chase_idx, age_id_distribution)
+ * and data/capture_efficiencies.txt, which abc_sim() receives as arguments (abc_simulation.jl:13-14). */
+typedef struct {
+    double  cycle;                       /* 20.0                                abc_simulation.jl:72 */
+    double  t0;                          /* -3*cycle (moment-ODE path only)     abc_simulation.jl:73 */
+    double  agevec[ABC_NAGE];            /* tau_ .* cycle                       abc_simulation.jl:74 */
+    double  pulse[ABC_NCOND];            /* condition_id[:,1]                   abc_simulation.jl:65 */
+    double  chase[ABC_NCOND];            /* condition_id[:,2] */
+    double  age_dist[ABC_NAGE * ABC_NCOND]; /* age_id_distribution, Julia 5x11 column-major, used AS GIVEN */
+    double  iv[9];                       /* ODE path initial moments            abc_simulation.jl:70-71 */
+    int32_t downsampling;                /* 1: apply capture efficiencies       abc_simulation.jl:79 */
+    int32_t n_cells;                     /* SSA: cells per (condition, age) read-out (>= 2) */
+    int32_t n_pre_cycles;                /* SSA: complete cell cycles simulated before the read-out cycle */
+    int32_t sim_kind;                    /* ABC_SIM_SSA or ABC_SIM_ODE */
+    /* capture efficiencies betas[pulse_idx], age[pulse_idx] and betas[chase_idx], age[chase_idx]
+     * (abc_simulation.jl:24,36); cluster ids are 1..5 */
+    const double*  betas_pulse;
+    const int32_t* cluster_pulse;
+    int32_t        n_pulse;
+    const double*  betas_chase;
+    const int32_t* cluster_chase;
+    int32_t        n_chase;
+    /* ODE path integrator tolerances (CVODE defaults of the reference: 1e-3 / 1e-6) */
+    double  ode_rtol, ode_atol;
+} abc_design_t;
+
+/* run counters (metrics row) */
+typedef struct {
+    uint64_t n_particles;
+    uint64_t n_lineages;     /* SSA cell lineages simulated */
+    uint64_t n_events;       /* SSA reaction events fired */
+    uint64_t n_draws;        /* SSA event draws (events + discarded draws at breakpoints) */
+    uint64_t n_ode_steps;    /* ODE path: accepted integrator steps */
+    double   ms_simulate;    /* device time of the simulate kernels (CUDA events) */
+    double   ms_stats;
+    double   ms_score;
+} abc_counters_t;
+
+/* ---- lifetime ---------------------------------------------------------------------------- */
+int  abc_create(int device, abc_ctx_t** ctx);
+int  abc_destroy(abc_ctx_t* ctx);
+const char* abc_last_error(void);
+int  abc_version(void);
+int  abc_device_count(void);
+/* number of parameters of model m in 1..5: length(vary_map) flattened; model.jl:30-43 */
+int  abc_n_params(int m);
+/* the reference's model_name table, abc_simulation.jl:82 */
+const char* abc_model_name(int m);
+
+/* ---- configuration ----------------------------------------------------------------------- */
+/* replaces the globals consumed by abc_sim(), abc_simulation.jl:13-14, 65-79 */
+int  abc_set_design(abc_ctx_t* ctx, const abc_design_t* design);
+/* data-side summary statistics and bootstrap SEs: the 14 matrices compute_trunc_errors receives
+ * (compute_errors.jl:45-49), concatenated per gene in the order pulse_mean[5], pulse_ff[5],
+ * chase_mean[5], chase_ff[5], ratio[11], mean_corr[11], corr_mean[11].
+ * d, se: Julia 53 x G column-major (gene contiguous). */
+int  abc_set_data(abc_ctx_t* ctx, const double* d, const double* se, int32_t n_genes);
+
+/* ---- P1: prior draws, fix_params(vary_map, N)  abc_simulation.jl:3-11 ---------------------- */
+/* theta: Julia P x n column-major (one particle's P values contiguous), log10 units, column order
+ * [kon..., koff, alpha..., gamma..., lambda].  Counter-based: draw i depends only on
+ * (seed, m, particle_offset + i). */
+int  abc_fix_params(abc_ctx_t* ctx, int m, int64_t n, int64_t particle_offset, uint64_t seed, double* theta);
+
+/* ---- M1-M10 + S1: abc_sim() over a batch  abc_simulation.jl:13-46, 88-97 -------------------- */
+/* prior_supplied == 0: theta is an output (drawn as abc_fix_params would); != 0: theta is an input.
+ * stats: Julia 53 x n column-major, order as in abc_set_data.  counters may be NULL. */
+int  abc_simulate(abc_ctx_t* ctx, int m, int64_t n_trials, int64_t particle_offset, uint64_t seed,
+                  int prior_supplied, double* theta, double* stats, abc_counters_t* counters);
+/* per (condition, age) moments behind the statistics (after optional downsampling):
+ * moments: Julia 5 x 5 x 11 x n column-major = [particle][cond][age][mean_u,mean_l,var_u,cov_ul,var_l];
+ * with downsampling == 0 and sim_kind == ABC_SIM_ODE this is run_part_sim(), recover_statistics.jl:1-11 */
+int  abc_simulate_moments(abc_ctx_t* ctx, int m, int64_t n, int64_t particle_offset, uint64_t seed,
+                          const double* theta, double* moments, abc_counters_t* counters);
+/* SSA debug/parity hook: the per-cell counts of one read-out.  counts: 4 x n_cells uint32
+ * (U, L before thinning, U', L' after), for particle_index (global), condition j, age a (0-based). */
+int  abc_ssa_cells(abc_ctx_t* ctx, int m, const double* theta, int64_t particle_index, uint64_t seed,
+                   int cond, int age, int exact_math, uint32_t* counts);
+
+/* ---- S1 alone: the 53 statistics from moments  abc_simulation.jl:23-46 --------------------- */
+int  abc_summary_stats(abc_ctx_t* ctx, const double* moments, int64_t n, double* stats);
+
+/* ---- E2/E3 + A1: compute_trunc_errors and the eps-acceptance  compute_errors.jl:30-70,
+ *      accepted_particles.jl:10-32 ----------------------------------------------------------- */
+#define ABC_ERR_NONE         0  /* do not materialise the error matrix (fused acceptance only) */
+#define ABC_ERR_GENE_MAJOR   1  /* err[g*n + i]: one column per gene like the .jdf (process_error_files.jl:3-7) */
+#define ABC_ERR_PARTICLE_MAJOR 2 /* err[i*G + g]: one row per particle like error_<model>.txt (compute_errors.jl:66-68) */
+/* stats: 53 x n column-major.  eps: acceptance threshold (4.8, accepted_particles.jl:10).
+ * err: NULL or n*G doubles in err_layout.  counts: NULL or G int64 (accepted per gene).
+ * The accepted set is kept in the context for abc_accept_fetch. */
+int  abc_score(abc_ctx_t* ctx, const double* stats, int64_t n, int64_t particle_offset, double eps,
+               int err_layout, double* err, int64_t* counts, abc_counters_t* counters);
+/* number of accepted (gene, particle) pairs of the last abc_score call(s) since abc_accept_reset */
+int64_t abc_accept_total(abc_ctx_t* ctx);
+int  abc_accept_reset(abc_ctx_t* ctx);
+/* CSR of accepted particles: offsets[G+1]; idx[total] 1-based global particle indices sorted per gene
+ * by (error ascending, index ascending) == v[sortperm(err[v])], accepted_particles.jl:20-24;
+ * errs (nullable) the matching error values.  A gene with offsets[g+1]==offsets[g] is the
+ * reference's "0" line (accepted_particles.jl:27-29). */
+int  abc_accept_fetch(abc_ctx_t* ctx, int64_t* offsets, int64_t* idx, double* errs);
+/* unsorted accepted tuples (for multi-GPU gathers): gene int32, particle int64 (1-based global), err double */
+int  abc_accept_tuples(abc_ctx_t* ctx, int32_t* gene, int64_t* particle, double* err);
+
+/* ---- device-resident variants (inputs/outputs are device pointers on the context's device;
+ *      stream is a cudaStream_t passed as void*, NULL = default stream; asynchronous) ---------- */
+int  abc_simulate_dev(abc_ctx_t* ctx, int m, int64_t n, int64_t particle_offset, uint64_t seed,
+                      int prior_supplied, double* d_theta, double* d_stats, void* stream);
+int  abc_score_dev(abc_ctx_t* ctx, const double* d_stats, int64_t n, int64_t particle_offset, double eps,
+                   int err_layout, double* d_err, void* stream);
+/* device counters of the last *_dev launches (synchronises the stream) */
+int  abc_counters(abc_ctx_t* ctx, abc_counters_t* counters);
+/* how many kernels this library has launched on the context since creation */
+int64_t abc_launch_count(abc_ctx_t* ctx);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,204 @@
+"""ctypes access to the CPU test oracle (oracle/liboracle.so).  TEST INFRASTRUCTURE ONLY: imported by
+tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs, never by the product."""
+import ctypes
+import os
+import subprocess
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ORACLE_DIR = os.path.join(ROOT, "oracle")
+LIB = os.path.join(ORACLE_DIR, "liboracle.so")
+
+NAGE, NCOND, NSTATS = 5, 11, 53
+PULSE = [0.25, 0.5, 0.75, 1, 2, 3, 22, 22, 22, 22, 22]
+CHASE = [0, 0, 0, 0, 0, 0, 0, 1, 2, 4, 6]
+MATH_LIBM, MATH_DET = 0, 1
+
+
+class OrcDesign(ctypes.Structure):
+    _fields_ = [("cycle", ctypes.c_double), ("t0", ctypes.c_double), ("agevec", ctypes.c_double * 5),
+                ("pulse", ctypes.c_double * 11), ("chase", ctypes.c_double * 11), ("age_dist", ctypes.c_double * 55),
+                ("iv", ctypes.c_double * 9), ("downsampling", ctypes.c_int),
+                ("beta_mean", ctypes.c_double * 10), ("beta_m2", ctypes.c_double * 10), ("beta_var", ctypes.c_double * 10),
+                ("rtol", ctypes.c_double), ("atol", ctypes.c_double)]
+
+
+class OrcSsaDesign(ctypes.Structure):
+    _fields_ = [("cycle", ctypes.c_double), ("agevec", ctypes.c_double * 5), ("pulse", ctypes.c_double * 11),
+                ("chase", ctypes.c_double * 11), ("n_cells", ctypes.c_int), ("n_pre", ctypes.c_int),
+                ("downsampling", ctypes.c_int), ("beta_q32", ctypes.c_void_p), ("beta_off", ctypes.c_int * 11)]
+
+
+_lib = None
+
+
+def build(force=False):
+    if force or not os.path.exists(LIB) or any(
+            os.path.getmtime(os.path.join(ORACLE_DIR, f)) > os.path.getmtime(LIB)
+            for f in os.listdir(ORACLE_DIR) if f.endswith((".c", ".h"))):
+        subprocess.check_call(["make", "-C", ORACLE_DIR, "-B", "liboracle.so"], stdout=subprocess.DEVNULL)
+    return LIB
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        build()
+        _lib = ctypes.CDLL(LIB)
+        _lib.orc_run_sim.restype = ctypes.c_int
+        _lib.orc_run_part_sim.restype = ctypes.c_int
+        _lib.orc_transient_phase.restype = ctypes.c_int
+        _lib.orc_model.restype = ctypes.c_long
+        _lib.orc_accept_gene.restype = ctypes.c_int64
+        _lib.orc_nlsqerror_part.restype = ctypes.c_double
+        _lib.orc_weighted_cov.restype = ctypes.c_double
+        _lib.orc_size_scaling.restype = ctypes.c_double
+        _lib.orc_labelling.restype = ctypes.c_double
+        _lib.orc_exp10_det.restype = ctypes.c_double
+        _lib.orc_exp10_det.argtypes = [ctypes.c_double]
+        _lib.orc_size_scaling.argtypes = [ctypes.c_double, ctypes.c_double]
+        _lib.orc_labelling.argtypes = [ctypes.c_double] * 4
+    return _lib
+
+
+def _p(a):
+    return a.ctypes.data_as(ctypes.c_void_p)
+
+
+def beta_moments(betas, clusters):
+    betas = np.ascontiguousarray(betas, dtype=np.float64)
+    clusters = np.ascontiguousarray(clusters, dtype=np.int32)
+    bm, b2, bv = np.zeros(5), np.zeros(5), np.zeros(5)
+    lib().orc_beta_moments(_p(betas), _p(clusters), len(betas), _p(bm), _p(b2), _p(bv))
+    return bm, b2, bv
+
+
+def make_design(age_dist=None, iv_index=1, downsampling=False, betas=None, rtol=1e-8, atol=None):
+    """betas = (betas_pulse, age_pulse, betas_chase, age_chase) when downsampling"""
+    d = OrcDesign()
+    d.cycle, d.t0 = 20.0, -60.0
+    d.agevec[:] = [2, 6, 10, 14, 18]
+    d.pulse[:] = PULSE
+    d.chase[:] = CHASE
+    ad = np.full((5, 11), 0.2) if age_dist is None else np.asarray(age_dist, dtype=np.float64)
+    d.age_dist[:] = list(ad.T.reshape(-1))
+    iv = [0.0] * 9
+    iv[iv_index] = 0.5
+    d.iv[:] = iv
+    d.downsampling = int(downsampling)
+    d.rtol = rtol
+    d.atol = rtol * 1e-3 if atol is None else atol
+    if downsampling:
+        bp, ap, bc, ac = betas
+        for s, (b, cl) in enumerate([(bp, ap), (bc, ac)]):
+            bm, b2, bv = beta_moments(b, cl)
+            for k in range(5):
+                d.beta_mean[s * 5 + k], d.beta_m2[s * 5 + k], d.beta_var[s * 5 + k] = bm[k], b2[k], bv[k]
+    return d
+
+
+def make_ssa_design(n_cells, n_pre, downsampling, betas=None):
+    """returns (OrcSsaDesign, keepalive)"""
+    sd = OrcSsaDesign()
+    sd.cycle = 20.0
+    sd.agevec[:] = [2, 6, 10, 14, 18]
+    sd.pulse[:] = PULSE
+    sd.chase[:] = CHASE
+    sd.n_cells, sd.n_pre, sd.downsampling = int(n_cells), int(n_pre), int(downsampling)
+    keep = None
+    if downsampling:
+        bp, ap, bc, ac = betas
+        q = np.zeros(len(bp) + len(bc), dtype=np.uint32)
+        off = np.zeros(6, dtype=np.int32)
+        b = np.ascontiguousarray(bp, dtype=np.float64)
+        c = np.ascontiguousarray(ap, dtype=np.int32)
+        lib().orc_quantise_betas(_p(b), _p(c), len(b), _p(q), _p(off))
+        for k in range(6):
+            sd.beta_off[k] = int(off[k])
+        q2 = q[len(bp):]
+        b = np.ascontiguousarray(bc, dtype=np.float64)
+        c = np.ascontiguousarray(ac, dtype=np.int32)
+        lib().orc_quantise_betas(_p(b), _p(c), len(b), _p(q2), _p(off))
+        for k in range(6):
+            sd.beta_off[5 + k] = int(off[k]) + len(bp)
+        sd.beta_q32 = q.ctypes.data
+        keep = q
+    return sd, keep
+
+
+def run_part_sim(theta, m, design):
+    theta = np.ascontiguousarray(theta, dtype=np.float64)
+    out = np.zeros(275)
+    k = lib().orc_run_part_sim(_p(theta), int(m), ctypes.byref(design), _p(out))
+    return out.reshape(11, 5, 5), k
+
+
+def run_sim(theta, m, design):
+    theta = np.ascontiguousarray(theta, dtype=np.float64)
+    stats, mom = np.zeros(53), np.zeros(275)
+    lib().orc_run_sim(_p(theta), int(m), ctypes.byref(design), _p(stats), _p(mom))
+    return stats, mom.reshape(11, 5, 5)
+
+
+def summary_stats(moments, age_dist):
+    mom = np.ascontiguousarray(moments, dtype=np.float64).reshape(-1, 275)
+    ad = np.ascontiguousarray(np.asarray(age_dist, dtype=np.float64).T.reshape(-1))
+    out = np.zeros((mom.shape[0], 53))
+    for i in range(mom.shape[0]):
+        lib().orc_summary_stats(_p(mom[i]), _p(ad), _p(out[i]))
+    return out
+
+
+def compute_trunc_errors(stats, d, se):
+    stats = np.ascontiguousarray(stats, dtype=np.float64).reshape(-1, 53)
+    d = np.ascontiguousarray(d, dtype=np.float64)
+    se = np.ascontiguousarray(se, dtype=np.float64)
+    err = np.zeros((stats.shape[0], d.shape[0]))
+    lib().orc_compute_trunc_errors(_p(stats), ctypes.c_int64(stats.shape[0]), _p(d), _p(se), d.shape[0], _p(err))
+    return err
+
+
+def accept_gene(err_col, eps):
+    err_col = np.ascontiguousarray(err_col, dtype=np.float64)
+    idx = np.zeros(len(err_col), dtype=np.int64)
+    n = lib().orc_accept_gene(_p(err_col), ctypes.c_int64(len(err_col)), ctypes.c_int64(1), ctypes.c_double(eps), _p(idx))
+    return idx[:n]
+
+
+def prior(m, particle, seed, P):
+    th = np.zeros(P)
+    lib().orc_prior(int(m), ctypes.c_int64(particle), ctypes.c_uint64(seed), _p(th))
+    return th
+
+
+def ssa_readout(theta, m, sd, particle, seed, cond, age, math_mode=MATH_DET):
+    theta = np.ascontiguousarray(theta, dtype=np.float64)
+    counts = np.zeros((4, sd.n_cells), dtype=np.uint32)
+    ev = ctypes.c_uint64(0)
+    lib().orc_ssa_readout(_p(theta), int(m), ctypes.byref(sd), ctypes.c_int64(particle), ctypes.c_uint64(seed),
+                          int(cond), int(age), int(math_mode), _p(counts), ctypes.byref(ev))
+    return counts, ev.value
+
+
+def ssa_moments(theta, m, sd, particle, seed, math_mode=MATH_DET):
+    theta = np.ascontiguousarray(theta, dtype=np.float64)
+    mom = np.zeros(275)
+    ev = ctypes.c_uint64(0)
+    lib().orc_ssa_moments(_p(theta), int(m), ctypes.byref(sd), ctypes.c_int64(particle), ctypes.c_uint64(seed),
+                          int(math_mode), _p(mom), ctypes.byref(ev))
+    return mom.reshape(11, 5, 5), ev.value
+
+
+def philox(ctr, key):
+    c = np.array(ctr, dtype=np.uint32)
+    k = np.array(key, dtype=np.uint32)
+    out = np.zeros(4, dtype=np.uint32)
+    # static inline in the header: exercised through orc_prior / the SSA; a tiny shim is compiled on demand
+    shim = os.path.join(ORACLE_DIR, "_philox_shim.so")
+    if not os.path.exists(shim):
+        src = '#include "oracle_philox.h"\nvoid shim(const uint32_t* c, const uint32_t* k, uint32_t* o){orc_philox4x32_10(c,k,o);}\n'
+        subprocess.run(["gcc", "-O2", "-fPIC", "-shared", "-I", ORACLE_DIR, "-x", "c", "-", "-o", shim],
+                       input=src.encode(), check=True)
+    ctypes.CDLL(shim).shim(_p(c), _p(k), _p(out))
+    return out
