@@ -79,6 +79,8 @@ SYMBOLS = {
     "abc_simulate_dev": (ctypes.c_int, [_vp, ctypes.c_int, ctypes.c_int64, ctypes.c_int64, ctypes.c_uint64,
                                         ctypes.c_int, _vp, _vp, _vp]),
     "abc_score_dev": (ctypes.c_int, [_vp, _vp, ctypes.c_int64, ctypes.c_int64, ctypes.c_double, ctypes.c_int, _vp, _vp]),
+    "abc_counts_dev": (ctypes.c_int, [_vp, _vp, _vp]),
+    "abc_accept_tuples_dev": (ctypes.c_int, [_vp, _vp, _vp, _vp, ctypes.c_int64, _vp]),
     "abc_counters": (ctypes.c_int, [_vp, ctypes.POINTER(AbcCounters)]),
     "abc_launch_count": (ctypes.c_int64, [_vp]),
 }

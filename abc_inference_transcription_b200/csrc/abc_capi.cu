@@ -621,6 +621,32 @@ extern "C" int abc_score_dev(abc_ctx_t* c, const double* d_stats, int64_t n, int
     return score_device(c, d_stats, n, offset, eps, layout, d_err, st);
 }
 
+extern "C" int abc_counts_dev(abc_ctx_t* c, int64_t* d_counts, void* stream) {
+    CTX_GUARD(c);
+    if (!c->has_data || !d_counts) { abc_set_error("abc_counts_dev: bad state/arguments"); return ABC_ERR_ARG; }
+    cudaStream_t st = stream ? (cudaStream_t)stream : c->stream;
+    ABC_CUDA_CHECK(cudaMemcpyAsync(d_counts, c->d_counts.p, (size_t)c->G * sizeof(int64_t), cudaMemcpyDeviceToDevice, st));
+    return ABC_OK;
+}
+
+extern "C" int abc_accept_tuples_dev(abc_ctx_t* c, int32_t* d_gene, int64_t* d_particle, double* d_err,
+                                     int64_t capacity, void* stream) {
+    CTX_GUARD(c);
+    if (!d_gene || !d_particle || !d_err || capacity < 0) { abc_set_error("abc_accept_tuples_dev: bad arguments"); return ABC_ERR_ARG; }
+    cudaStream_t st = stream ? (cudaStream_t)stream : c->stream;
+    ABC_CUDA_CHECK(cudaStreamSynchronize(st));
+    unsigned long long total = 0;
+    ABC_CUDA_CHECK(cudaMemcpy(&total, c->d_acc_count.p, sizeof(total), cudaMemcpyDeviceToHost));
+    if ((int64_t)total > c->acc_capacity) { abc_set_error("accepted-tuple buffer overflowed"); return ABC_ERR_NOMEM; }
+    size_t k = (size_t)std::min<int64_t>((int64_t)total, capacity);
+    if (k) {
+        ABC_CUDA_CHECK(cudaMemcpyAsync(d_gene, c->d_acc_gene.p, k * sizeof(int32_t), cudaMemcpyDeviceToDevice, st));
+        ABC_CUDA_CHECK(cudaMemcpyAsync(d_particle, c->d_acc_particle.p, k * sizeof(long long), cudaMemcpyDeviceToDevice, st));
+        ABC_CUDA_CHECK(cudaMemcpyAsync(d_err, c->d_acc_err.p, k * sizeof(double), cudaMemcpyDeviceToDevice, st));
+    }
+    return ABC_OK;
+}
+
 extern "C" int abc_counters(abc_ctx_t* c, abc_counters_t* out) {
     CTX_GUARD(c);
     if (!out) { abc_set_error("abc_counters: out is NULL"); return ABC_ERR_ARG; }

@@ -163,6 +163,13 @@ class AbcEngine:
                                            float(eps), int(err_layout), ctypes.c_void_p(d_err_ptr or 0),
                                            ctypes.c_void_p(stream or 0)))
 
+    def counts_dev(self, d_counts_ptr, stream=None):
+        _lib.check(self._lib.abc_counts_dev(self._ctx, ctypes.c_void_p(d_counts_ptr), ctypes.c_void_p(stream or 0)))
+
+    def accept_tuples_dev(self, d_gene_ptr, d_particle_ptr, d_err_ptr, capacity, stream=None):
+        _lib.check(self._lib.abc_accept_tuples_dev(self._ctx, ctypes.c_void_p(d_gene_ptr), ctypes.c_void_p(d_particle_ptr),
+                                                   ctypes.c_void_p(d_err_ptr), int(capacity), ctypes.c_void_p(stream or 0)))
+
     def counters(self):
         cnt = _lib.AbcCounters()
         _lib.check(self._lib.abc_counters(self._ctx, ctypes.byref(cnt)))

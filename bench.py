@@ -1,0 +1,338 @@
+#!/usr/bin/env python
+"""bench.py -- ABC particles simulated + scored per second (BASELINE.json metric).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference]
+
+A step is one pass of the hot path over one batch of synthetic prior draws: for each of the 5 models,
+B particles are drawn (Philox, keyed by the global particle index), simulated with the SSA, reduced to the
+53 summary statistics, scored against the 3419 real genes and eps-accepted.  Workload = BASELINE configs[1]
+("all 5 models on 1xB200"), streamed in batches; N > 1 shards the particle range over ranks (weak scaling)
+and gathers the per-gene acceptance counts and accepted tuples with NCCL.
+
+`value`  : whole-job particles/s with inputs resident in HBM (abc_*_dev entry points, CUDA events).
+`e2e`    : the same through the host-buffer C ABI a Julia host calls (abc_simulate + abc_score with the
+           error matrix and the accepted lists copied back), wall clock around synchronous calls.
+`--impl reference` times the reference's own CPU algorithm (moment ODEs -> 53 statistics -> errors ->
+acceptance; oracle port, the Julia/Sundials original cannot run here) on all host cores.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+GOLD = os.path.join(ROOT, "tests", "golden")
+
+METRIC = "abc_particles_simulated_and_scored_per_s"
+UNIT = "particles/s"
+SEED = 20240229
+EPS = 4.8
+NOMINAL_INSTR_PER_EVENT = 64.0       # algorithmic lane-instructions per SSA event
+ALG_BYTES_PER_PARTICLE_SCORE = 27776  # 424 B read + G*8 B written, G = 3419
+
+
+def load_inputs():
+    betas = np.load(os.path.join(GOLD, "ref_betas.npy"))
+    z = np.load(os.path.join(GOLD, "ref_summary_stats.npz"))
+    return betas, z["d"], z["se"]
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        with open(p) as f:
+            j = json.load(f)
+        return {"hbm_gbs": j.get("hbm_gbs", 6650.0), "sm_max_mhz": j.get("sm_max_mhz", 1965.0), "src": "measured"}
+    return {"hbm_gbs": 6650.0, "sm_max_mhz": 1965.0, "src": "fallback"}
+
+
+class ClockSampler(threading.Thread):
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)"""
+
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index, self.rows, self.stop_flag = index, [], False
+
+    def run(self):
+        q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+             "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+             "clocks_event_reasons.sw_power_cap")
+        while not self.stop_flag:
+            try:
+                out = subprocess.run(["nvidia-smi", f"--id={self.index}", f"--query-gpu={q}", "--format=csv,noheader,nounits"],
+                                     capture_output=True, text=True, timeout=5).stdout.strip()
+                if out:
+                    self.rows.append([x.strip() for x in out.split(",")])
+            except Exception:
+                pass
+            time.sleep(0.2)
+
+    def summary(self):
+        if not self.rows:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["unavailable"]}
+        sm = sorted(float(r[0]) for r in self.rows if r[0].replace(".", "").isdigit())
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = [n for k, n in enumerate(names) if any(len(r) > 3 + k and r[3 + k] == "Active" for r in self.rows)]
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": float(self.rows[0][1]), "reasons": reasons,
+                "samples": len(self.rows)}
+
+
+# ------------------------------------------------------------------------------------------------
+def cpu_reference_sample(n_particles, threads, rtol=1e-3, atol=1e-6, seed=SEED):
+    """The reference's CPU path on a bounded sample: prior draw -> moment ODEs (run_sim, CVODE-like
+    tolerances) -> 53 statistics -> errors vs all genes -> acceptance.  Oracle port, `threads` host threads
+    (the C calls release the GIL)."""
+    import oracle
+    from concurrent.futures import ThreadPoolExecutor
+    from abc_inference_transcription_b200 import n_params, split_betas
+    betas, d, se = load_inputs()
+    od = oracle.make_design(iv_index=1, downsampling=True, betas=split_betas(betas), rtol=rtol, atol=atol)
+    oracle.lib()
+    jobs = [(1 + (i % 5), i) for i in range(n_particles)]
+
+    def one(job):
+        m, i = job
+        th = oracle.prior(m, i, seed, n_params(m))
+        st, _ = oracle.run_sim(th, m, od)
+        err = oracle.compute_trunc_errors(st[None, :], d, se)
+        return int((err <= EPS).sum())
+
+    t0 = time.perf_counter()
+    with ThreadPoolExecutor(max_workers=threads) as ex:
+        acc = sum(ex.map(one, jobs))
+    dt = time.perf_counter() - t0
+    return n_particles / dt, dt, acc
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    cores = os.cpu_count() or 1
+    n = args.ref_particles
+    vals = []
+    for _ in range(args.warmup):
+        cpu_reference_sample(max(cores, n // 4), cores)
+    t_all = 0.0
+    for _ in range(args.steps):
+        v, dt, _ = cpu_reference_sample(n, cores)
+        vals.append(v)
+        t_all += dt
+    value = n * args.steps / t_all
+    sample = f"{n} prior particles/step over the 5 models (moment-ODE port rtol 1e-3/atol 1e-6 + score vs 3419 genes)"
+    line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": 1e3 * t_all / args.steps, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": workload_config(args),
+            "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+            "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0,
+            "note": "reference algorithm = CVODE moment ODEs (scripts/model.jl:89-96); Julia+Sundials cannot run here, "
+                    "timed is the C restatement oracle/abc_oracle.c on all host threads"}
+    print(json.dumps(line), flush=True)
+
+
+def workload_config(args):
+    return {"workload": "BASELINE configs[1]: all 5 models, prior draws streamed in batches, SSA + 53 statistics + "
+                        "error scoring vs 3419 genes + eps=4.8 acceptance",
+            "models": 5, "particles_per_model_per_step_per_gpu": args.batch, "n_cells_per_readout": args.n_cells,
+            "n_pre_cycles": args.n_pre, "readouts": 55, "genes": 3419, "eps": EPS, "seed": SEED,
+            "l2": "flushed between steps (256 MiB write)", "lineages": "independent per (condition, age, cell)"}
+
+
+# ------------------------------------------------------------------------------------------------
+def run_b200(args):
+    import torch
+    import torch.distributed as dist
+    from abc_inference_transcription_b200 import AbcEngine, ERR_PARTICLE_MAJOR, n_params, synthetic_design
+    from abc_inference_transcription_b200.dist import gather_acceptance
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    dev = torch.device("cuda", local)
+    betas, d, se = load_inputs()
+    G = d.shape[0]
+    B = args.batch
+    eng = AbcEngine(local)
+    eng.set_design(synthetic_design(betas, n_cells=args.n_cells, n_pre_cycles=args.n_pre))
+    eng.set_data(d, se)
+
+    stream = torch.cuda.current_stream().cuda_stream
+    th_dev = [torch.empty((B, n_params(m)), dtype=torch.float64, device=dev) for m in range(1, 6)]
+    st_dev = torch.empty((B, 53), dtype=torch.float64, device=dev)
+    err_dev = torch.empty((B, G), dtype=torch.float64, device=dev)
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+    counts_dev = torch.zeros(G, dtype=torch.int64, device=dev)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def offset_of(step, m):
+        # global particle index: disjoint ranges per (step, rank); the same index in different models is a
+        # different Philox stream (the model is part of the counter)
+        return (step * world + rank) * B
+
+    sim_ms, score_ms, events, draws = [], [], 0, 0
+
+    def device_step(step, timed):
+        nonlocal events, draws
+        eng.accept_reset()
+        for m in range(1, 6):
+            eng.simulate_dev(m, B, th_dev[m - 1].data_ptr(), st_dev.data_ptr(), particle_offset=offset_of(step, m),
+                             seed=SEED, prior_supplied=False, stream=stream)
+            eng.score_dev(st_dev.data_ptr(), B, eps=EPS, particle_offset=offset_of(step, m),
+                          err_layout=ERR_PARTICLE_MAJOR, d_err_ptr=err_dev.data_ptr(), stream=stream)
+            if timed:
+                c = eng.counters()       # synchronises; device time of this model's kernels
+                sim_ms.append(c["ms_simulate"]); score_ms.append(c["ms_score"])
+                events += c["n_events"]; draws += c["n_draws"]
+        if world > 1:
+            eng.counts_dev(counts_dev.data_ptr(), stream=stream)
+            dist.all_reduce(counts_dev)
+
+    # ---- device-resident timing ---------------------------------------------------------------
+    for w in range(args.warmup):
+        device_step(w, False)
+        flush.fill_(w & 0xFF)
+    barrier()
+    launches0 = eng.launch_count()
+    sampler = ClockSampler(local)
+    sampler.start()
+    step_ms = []
+    for k in range(args.steps):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        barrier()
+        e0.record()
+        device_step(args.warmup + k, True)
+        e1.record()
+        barrier()
+        step_ms.append(e0.elapsed_time(e1))
+        flush.fill_(k & 0xFF)           # L2 flush between timed iterations (outside the timed region)
+    sampler.stop_flag = True
+    launches = eng.launch_count() - launches0
+    t_dev = sum(step_ms) / 1e3
+    t = torch.tensor([t_dev], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    t_dev = float(t.item())
+    particles = 5 * B * world * args.steps
+    value = particles / t_dev
+
+    # ---- end to end through the host-buffer C ABI ----------------------------------------------
+    h2d = d2h = 0
+    barrier()
+    t0 = time.perf_counter()
+    for k in range(args.steps):
+        eng.accept_reset()
+        for m in range(1, 6):
+            off = offset_of(args.warmup + k, m)
+            theta, stats, _ = eng.simulate(m, n_trials=B, particle_offset=off, seed=SEED)
+            err, counts, _ = eng.score(stats, eps=EPS, particle_offset=off, err_layout=ERR_PARTICLE_MAJOR)
+            h2d += stats.nbytes
+            d2h += theta.nbytes + stats.nbytes + err.nbytes + counts.nbytes
+        res = gather_acceptance(eng, world, dev)     # NCCL: all-reduce counts, gather accepted tuples
+        d2h += res["bytes_d2h"]
+    barrier()
+    t_e2e = time.perf_counter() - t0
+    te = torch.tensor([t_e2e], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(te, op=dist.ReduceOp.MAX)
+    t_e2e = float(te.item())
+    e2e_value = particles / t_e2e
+
+    if rank == 0:
+        pk = peaks()
+        peak_instr = 148 * 128 * pk["sm_max_mhz"] * 1e6 / 1e12        # T lane-instr/s at max clock
+        ssa_s = sum(sim_ms) / 1e3
+        ev_per_s = events / ssa_s if ssa_s > 0 else 0.0
+        achieved = ev_per_s * NOMINAL_INSTR_PER_EVENT / 1e12
+        sc_s = sum(score_ms) / 1e3
+        sc_gbs = (5 * B * args.steps) * ALG_BYTES_PER_PARTICLE_SCORE / sc_s / 1e9 if sc_s > 0 else 0.0
+        line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+                "ms_per_step": 1e3 * t_dev / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+                "dtype": "f32 (SSA propensities/times) + u32 counts + f64 (statistics, scoring)", "data": "synthetic",
+                "config": workload_config(args),
+                "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d // args.steps,
+                        "d2h_bytes_per_step": d2h // args.steps},
+                "gpu_launches": int(launches),
+                "clocks": sampler.summary(),
+                "roofline": {"kernel": "abc_ssa_kernel<false>", "bound": "issue", "achieved": achieved, "peak": peak_instr,
+                             "unit": "Tlane-instr/s", "frac": achieved / peak_instr, "traffic": None,
+                             "events_per_s": ev_per_s, "events": int(events), "draws": int(draws),
+                             "nominal_instr_per_event": NOMINAL_INSTR_PER_EVENT,
+                             "peak_src": f"148 SM x 128 lanes x sm_max_mhz ({pk['src']})",
+                             "share_of_step": ssa_s / t_dev if t_dev > 0 else None},
+                "roofline_score": {"kernel": "abc_score_kernel", "bound": "hbm", "achieved": sc_gbs, "peak": pk["hbm_gbs"],
+                                   "unit": "GB/s", "frac": sc_gbs / pk["hbm_gbs"], "traffic": None,
+                                   "peak_src": pk["src"], "share_of_step": sc_s / t_dev if t_dev > 0 else None}}
+        if world == 1 and not args.no_cpu:
+            cores = os.cpu_count() or 1
+            v, dt, _ = cpu_reference_sample(args.ref_particles, cores)
+            line["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": cores, "kind": "port",
+                                    "sample": f"{args.ref_particles} prior particles over the 5 models, reference algorithm "
+                                              f"(moment-ODE port, rtol 1e-3) + scoring, {dt:.1f} s"}
+            line["cpu_baseline_ssa"] = cpu_ssa_sample(cores, args)
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def cpu_ssa_sample(cores, args):
+    """same SSA workload on the host cores (oracle SSA port), bounded: a few read-outs of a few particles"""
+    import oracle
+    from concurrent.futures import ThreadPoolExecutor
+    from abc_inference_transcription_b200 import n_params, split_betas
+    betas, _, _ = load_inputs()
+    sd, keep = oracle.make_ssa_design(args.n_cells, args.n_pre, True, split_betas(betas))
+    jobs = [(1 + (i % 5), i, (7 * i) % 11, (3 * i) % 5) for i in range(4 * cores)]
+
+    def one(job):
+        m, i, c, a = job
+        th = oracle.prior(m, i, SEED, n_params(m))
+        _, ev = oracle.ssa_readout(th, m, sd, i, SEED, c, a, oracle.MATH_LIBM)
+        return ev
+
+    t0 = time.perf_counter()
+    with ThreadPoolExecutor(max_workers=cores) as ex:
+        ev = sum(ex.map(one, jobs))
+    dt = time.perf_counter() - t0
+    readouts_per_s = len(jobs) / dt
+    return {"value": readouts_per_s / 55.0, "unit": UNIT, "cores": cores, "kind": "port",
+            "events_per_s": ev / dt,
+            "sample": f"{len(jobs)} read-outs ({args.n_cells} cells each) of prior particles, oracle SSA, {dt:.1f} s; "
+                      "particles/s = read-outs/s / 55"}
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=3)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--batch", type=int, default=256, help="particles per model per step per GPU")
+    ap.add_argument("--n-cells", type=int, default=96)
+    ap.add_argument("--n-pre", type=int, default=10)
+    ap.add_argument("--ref-particles", type=int, default=1600)
+    ap.add_argument("--no-cpu", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_b200(args)
+
+
+if __name__ == "__main__":
+    main()

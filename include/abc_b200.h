@@ -154,6 +154,12 @@ int  abc_simulate_dev(abc_ctx_t* ctx, int m, int64_t n, int64_t particle_offset,
                       int prior_supplied, double* d_theta, double* d_stats, void* stream);
 int  abc_score_dev(abc_ctx_t* ctx, const double* d_stats, int64_t n, int64_t particle_offset, double eps,
                    int err_layout, double* d_err, void* stream);
+/* device-side exports for multi-GPU gathers (torch.distributed / NCCL work on the caller's tensors):
+ * copy the per-gene accepted counts (G int64) / the unsorted accepted tuples into caller device
+ * buffers on `stream`.  abc_accept_tuples_dev copies min(total, capacity) tuples. */
+int  abc_counts_dev(abc_ctx_t* ctx, int64_t* d_counts, void* stream);
+int  abc_accept_tuples_dev(abc_ctx_t* ctx, int32_t* d_gene, int64_t* d_particle, double* d_err, int64_t capacity,
+                           void* stream);
 /* device counters of the last *_dev launches (synchronises the stream) */
 int  abc_counters(abc_ctx_t* ctx, abc_counters_t* counters);
 /* how many kernels this library has launched on the context since creation */

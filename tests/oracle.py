@@ -202,3 +202,16 @@ def philox(ctr, key):
                        input=src.encode(), check=True)
     ctypes.CDLL(shim).shim(_p(c), _p(k), _p(out))
     return out
+
+
+def same_bits(a, b):
+    """bit-exact equality of float64 arrays; NaNs must sit in the same places (payload/sign of a NaN is
+    not defined by IEEE-754 arithmetic and differs between x86 and the GPU)"""
+    a = np.ascontiguousarray(a, dtype=np.float64)
+    b = np.ascontiguousarray(b, dtype=np.float64)
+    if a.shape != b.shape:
+        return False
+    na, nb = np.isnan(a), np.isnan(b)
+    if not np.array_equal(na, nb):
+        return False
+    return np.array_equal(a.view(np.uint64)[~na], b.view(np.uint64)[~nb])
