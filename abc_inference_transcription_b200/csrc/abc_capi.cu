@@ -82,6 +82,9 @@ struct abc_ctx {
     DevBuf<unsigned long long> d_sums, d_counters;
     DevBuf<unsigned int> d_work;
     DevBuf<uint32_t> d_cells;
+    DevBuf<unsigned int> d_keys_in, d_keys_out;
+    DevBuf<int> d_idx_in, d_order;
+    DevBuf<unsigned char> d_sort_tmp;
     // score work buffers
     DevBuf<double> d_sstats, d_err;
     DevBuf<unsigned long long> d_counts, d_acc_count;
@@ -135,6 +138,7 @@ extern "C" int abc_destroy(abc_ctx_t* c) {
     cudaStreamSynchronize(c->stream);
     c->d_beta.release(); c->d_age_dist.release(); c->d_beta_mom.release(); c->d_d.release(); c->d_den.release();
     c->d_theta.release(); c->d_stats.release(); c->d_moments.release(); c->d_rates.release();
+    c->d_keys_in.release(); c->d_keys_out.release(); c->d_idx_in.release(); c->d_order.release(); c->d_sort_tmp.release();
     c->d_sums.release(); c->d_counters.release(); c->d_work.release(); c->d_cells.release();
     c->d_sstats.release(); c->d_err.release(); c->d_counts.release(); c->d_acc_count.release();
     c->d_acc_gene.release(); c->d_acc_particle.release(); c->d_acc_err.release();
@@ -307,11 +311,25 @@ static int simulate_device(abc_ctx* c, int m, int64_t n, int64_t offset, uint64_
     }
     if ((rc = abc_launch_rates(d_theta, m, n, c->d_rates.p, st)) != ABC_OK) return rc;
     c->launches++;
+    // longest-processing-time-first order of the particles (scheduling only, results are order independent)
+    const int* d_order = nullptr;
+    if (n >= 64 && n < (1ll << 31)) {
+        const size_t tmp = abc_order_temp_bytes((int)n);
+        if ((rc = c->d_keys_in.ensure((size_t)n)) != ABC_OK) return rc;
+        if ((rc = c->d_keys_out.ensure((size_t)n)) != ABC_OK) return rc;
+        if ((rc = c->d_idx_in.ensure((size_t)n)) != ABC_OK) return rc;
+        if ((rc = c->d_order.ensure((size_t)n)) != ABC_OK) return rc;
+        if ((rc = c->d_sort_tmp.ensure(tmp)) != ABC_OK) return rc;
+        if ((rc = abc_launch_order(c->d_rates.p, (int)n, c->d_keys_in.p, c->d_keys_out.p, c->d_idx_in.p, c->d_order.p,
+                                   c->d_sort_tmp.p, tmp, st)) != ABC_OK) return rc;
+        c->launches += 2;
+        d_order = c->d_order.p;
+    }
     ABC_CUDA_CHECK(cudaMemsetAsync(c->d_sums.p, 0, (size_t)n * ABC_NREAD * 5 * sizeof(unsigned long long), st));
     ABC_CUDA_CHECK(cudaMemsetAsync(c->d_counters.p, 0, 8 * sizeof(unsigned long long), st));
     AbcSsaParams prm = make_ssa_params(c, m, n, offset, seed);
     ABC_CUDA_CHECK(cudaEventRecord(c->ev[0], st));
-    if ((rc = abc_launch_ssa(c->d_rates.p, prm, c->d_beta.p, c->d_sums.p, c->d_counters.p, c->d_work.p, nullptr, 0,
+    if ((rc = abc_launch_ssa(c->d_rates.p, prm, c->d_beta.p, c->d_sums.p, c->d_counters.p, c->d_work.p, nullptr, d_order, 0,
                              c->sm_count, st)) != ABC_OK) return rc;
     c->launches++;
     ABC_CUDA_CHECK(cudaEventRecord(c->ev[1], st));
@@ -415,7 +433,7 @@ extern "C" int abc_ssa_cells(abc_ctx_t* c, int m, const double* theta, int64_t p
     ABC_CUDA_CHECK(cudaMemsetAsync(c->d_counters.p, 0, 8 * sizeof(unsigned long long), c->stream));
     AbcSsaParams prm = make_ssa_params(c, m, 1, particle_index, seed);
     prm.single_readout = cond * ABC_NAGE + age;
-    rc = abc_launch_ssa(c->d_rates.p, prm, c->d_beta.p, nullptr, c->d_counters.p, c->d_work.p, c->d_cells.p, exact_math,
+    rc = abc_launch_ssa(c->d_rates.p, prm, c->d_beta.p, nullptr, c->d_counters.p, c->d_work.p, c->d_cells.p, nullptr, exact_math,
                         c->sm_count, c->stream);
     c->launches += 2;
     if (rc != ABC_OK) return rc;

@@ -11,7 +11,7 @@ struct AbcRates {
     float kon[5], koff[5], alpha[5], gamma[5];
     float lam;          // labelling efficiency 10^theta_lambda clamped to [0,1]
     uint32_t pon_thr;   // floor(P_on * 2^32): initial gene state threshold
-    float pad0, pad1;
+    float pad0, pad1;   // pad0 = predicted events per hour (scheduling hint only)
 };
 
 struct AbcSsaParams {
@@ -39,7 +39,10 @@ int abc_launch_rates(const double* d_theta, int m, int64_t n, AbcRates* d_rates,
 int abc_launch_prior(double* d_theta, int m, int64_t n, int64_t offset, uint64_t seed, cudaStream_t st);
 int abc_launch_ssa(const AbcRates* d_rates, const AbcSsaParams& prm, const uint32_t* d_beta_q32,
                    unsigned long long* d_sums, unsigned long long* d_counters, unsigned int* d_work,
-                   uint32_t* d_cells_out, int exact_math, int sm_count, cudaStream_t st);
+                   uint32_t* d_cells_out, const int* d_order, int exact_math, int sm_count, cudaStream_t st);
+size_t abc_order_temp_bytes(int n);
+int abc_launch_order(const AbcRates* d_rates, int n, unsigned int* d_keys_in, unsigned int* d_keys_out, int* d_idx_in,
+                     int* d_order, void* d_temp, size_t temp_bytes, cudaStream_t st);
 int abc_launch_moments_from_sums(const unsigned long long* d_sums, int64_t n, int n_cells, double* d_moments,
                                  cudaStream_t st);
 int abc_launch_summary_stats(const double* d_moments, const double* d_age_dist, int64_t n, double* d_stats,

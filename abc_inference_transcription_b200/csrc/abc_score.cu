@@ -11,9 +11,12 @@
 // computed once by abc_prepare_data_kernel with the same operation order.
 //
 // Early exit: every term is >= 0 or NaN and rounding is monotone, so once the running
-// total of completed groups exceeds 10.0 the final value is exactly 10.0.  A warp leaves a gene as
-// soon as ALL its lanes are past 10.0; a NaN lane never satisfies (err > 10.0) and is evaluated in
-// full, so NaN propagation is unchanged.
+// total of completed groups exceeds 10.0 the final value is exactly 10.0 -- unless a later term is
+// NaN, which the reference lets through unclipped.  A NaN term can only come from a NaN statistic of
+// the particle (then the particle's whole row is NaN: every gene uses all 53 statistics) or from
+// non-finite data of the gene.  So: particles with a NaN statistic are answered NaN directly, genes
+// with non-finite data are evaluated in full, and otherwise a warp leaves a gene as soon as ALL its
+// lanes are past 10.0.
 //
 // Mapping: one thread per particle (its 53 statistics live in registers), genes streamed through
 // shared memory in tiles (broadcast reads), results staged per tile and written as full 128-byte
@@ -63,8 +66,14 @@ abc_score_kernel(const AbcScoreArgs a) {
     __shared__ double sh_d[SC_GT][ABC_NSTATS];
     __shared__ double sh_den[SC_GT][ABC_NSTATS];
     __shared__ double sh_err[SC_GT][SC_THREADS + 1];
+    __shared__ int sh_bad[SC_GT];
     const int tid = threadIdx.x, lane = tid & 31;
     const long long n_tiles = (a.n + SC_THREADS - 1) / SC_THREADS;
+    // blockIdx.y owns a contiguous range of gene tiles
+    const int n_gtiles = (a.G + SC_GT - 1) / SC_GT;
+    const int gt_per = (n_gtiles + gridDim.y - 1) / gridDim.y;
+    const int g_lo = min(a.G, (int)blockIdx.y * gt_per * SC_GT);
+    const int g_hi = min(a.G, g_lo + gt_per * SC_GT);
 
     for (long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
         const long long i0 = tile * SC_THREADS;
@@ -76,31 +85,41 @@ abc_score_kernel(const AbcScoreArgs a) {
 #pragma unroll
             for (int t = 0; t < ABC_NSTATS; ++t) s[t] = sp[t];
         }
-        for (int g0 = 0; g0 < a.G; g0 += SC_GT) {
-            const int gt = min(SC_GT, a.G - g0);
+        bool rnan = false;
+#pragma unroll
+        for (int t = 0; t < ABC_NSTATS; ++t) rnan = rnan || (s[t] != s[t]);
+        for (int g0 = g_lo; g0 < g_hi; g0 += SC_GT) {
+            const int gt = min(SC_GT, g_hi - g0);
+            __syncthreads();
+            if (tid < SC_GT) sh_bad[tid] = 0;
             __syncthreads();
             for (int k = tid; k < gt * ABC_NSTATS; k += SC_THREADS) {
-                (&sh_d[0][0])[k] = a.d[(long long)g0 * ABC_NSTATS + k];
-                (&sh_den[0][0])[k] = a.den[(long long)g0 * ABC_NSTATS + k];
+                const double dv = a.d[(long long)g0 * ABC_NSTATS + k];
+                const double nv = a.den[(long long)g0 * ABC_NSTATS + k];
+                (&sh_d[0][0])[k] = dv;
+                (&sh_den[0][0])[k] = nv;
+                // non-finite data (x - x != 0 for Inf and NaN): no early exit for this gene
+                if (__dadd_rn(dv, -dv) != 0.0 || __dadd_rn(nv, -nv) != 0.0) sh_bad[k / ABC_NSTATS] = 1;
             }
             __syncthreads();
             for (int gg = 0; gg < gt; ++gg) {
                 const double* gd = sh_d[gg];
                 const double* gden = sh_den[gg];
+                const bool gbad = sh_bad[gg] != 0;       // warp uniform
                 double err = 0.0;
                 // group order and sizes: compute_errors.jl:55-61
                 err = __dadd_rn(err, group_err<0, 5>(s, gd, gden));
-                if (!__all_sync(0xffffffffu, err > 10.0)) {
+                if (gbad || !__all_sync(0xffffffffu, rnan || err > 10.0)) {
                     err = __dadd_rn(err, group_err<5, 10>(s, gd, gden));
-                    if (!__all_sync(0xffffffffu, err > 10.0)) {
+                    if (gbad || !__all_sync(0xffffffffu, rnan || err > 10.0)) {
                         err = __dadd_rn(err, group_err<10, 15>(s, gd, gden));
-                        if (!__all_sync(0xffffffffu, err > 10.0)) {
+                        if (gbad || !__all_sync(0xffffffffu, rnan || err > 10.0)) {
                             err = __dadd_rn(err, group_err<15, 20>(s, gd, gden));
-                            if (!__all_sync(0xffffffffu, err > 10.0)) {
+                            if (gbad || !__all_sync(0xffffffffu, rnan || err > 10.0)) {
                                 err = __dadd_rn(err, group_err<20, 31>(s, gd, gden));
-                                if (!__all_sync(0xffffffffu, err > 10.0)) {
+                                if (gbad || !__all_sync(0xffffffffu, rnan || err > 10.0)) {
                                     err = __dadd_rn(err, group_err<31, 42>(s, gd, gden));
-                                    if (!__all_sync(0xffffffffu, err > 10.0)) {
+                                    if (gbad || !__all_sync(0xffffffffu, rnan || err > 10.0)) {
                                         err = __dadd_rn(err, group_err<42, 53>(s, gd, gden));
                                     }
                                 }
@@ -109,6 +128,7 @@ abc_score_kernel(const AbcScoreArgs a) {
                     }
                 }
                 if (err > 10.0) err = 10.0;
+                if (rnan) err = __longlong_as_double(0x7ff8000000000000ll);
                 sh_err[gg][tid] = err;
                 // fused threshold acceptance (accepted_particles.jl:20): err <= eps, NaN never accepted
                 const bool acc = live && (err <= a.eps);
@@ -156,9 +176,15 @@ int abc_launch_score(const AbcScoreArgs& a, int sm_count, cudaStream_t st) {
     int per_sm = 0;
     ABC_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, abc_score_kernel, SC_THREADS, 0));
     if (per_sm < 1) per_sm = 1;
-    long long grid = (long long)sm_count * per_sm;
-    if (grid > n_tiles) grid = n_tiles;
-    abc_score_kernel<<<(unsigned)grid, SC_THREADS, 0, st>>>(a);
+    long long gx = (long long)sm_count * per_sm;
+    if (gx > n_tiles) gx = n_tiles;
+    // small batches: split the genes over blockIdx.y so that the grid still fills the chip
+    const int n_gtiles = (a.G + SC_GT - 1) / SC_GT;
+    long long gy = (4ll * sm_count * per_sm + gx - 1) / gx;
+    if (gy > n_gtiles) gy = n_gtiles;
+    if (gy > 65535) gy = 65535;
+    if (gy < 1) gy = 1;
+    abc_score_kernel<<<dim3((unsigned)gx, (unsigned)gy), SC_THREADS, 0, st>>>(a);
     ABC_CUDA_CHECK(cudaGetLastError());
     return ABC_OK;
 }

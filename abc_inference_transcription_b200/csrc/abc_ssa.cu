@@ -18,6 +18,7 @@
 // model)), key = seed: results do not depend on the launch geometry or on the number of GPUs.
 #include "abc_common.cuh"
 #include "abc_internal.h"
+#include <cub/cub.cuh>
 
 // ------------------------------------------------------------------------------------------------
 // explicit-rounding float helpers: the file is compiled with -fmad=false, FMAs are explicit
@@ -48,7 +49,9 @@ __device__ __forceinline__ float exp_variate(uint32_t w) {
     if (EXACT) {
         return -log_det(u);
     } else {
-        return f_mul(__log2f(u), -0.693147182464599609375f);
+        float l;
+        asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(l) : "f"(u));
+        return f_mul(l, -0.693147182464599609375f);
     }
 }
 
@@ -60,9 +63,10 @@ __device__ __forceinline__ float wait_time(float c0, float c1, float E) {
     if (EXACT) {
         return __fdiv_rn(E2, f_add(c0, __fsqrt_rn(disc)));
     } else {
-        float r;
+        float r, q;
         asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(disc));
-        return __fdividef(E2, f_add(c0, r));
+        asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(q) : "f"(f_add(c0, r)));
+        return f_mul(E2, q);
     }
 }
 
@@ -82,11 +86,11 @@ struct WarpTable {
 };
 
 struct Lineage {
-    uint32_t U, L;
+    float U, L;            // molecule counts, exact in binary32 (< 2^24)
     int g;
     uint32_t ctr;          // next Philox block index
     uint32_t c1, c2, c3, k0, k1;
-    uint32_t n_events, n_draws;
+    uint32_t n_events;
 };
 
 __device__ __forceinline__ uint4 next_block(Lineage& s) {
@@ -132,7 +136,7 @@ template <bool EXACT>
 __device__ __forceinline__ bool ssa_step(Lineage& s, float& x, const Seg& sg, uint32_t wt, uint32_t wc) {
     const bool on = (s.g != 0);
     const float asw = on ? sg.koff : sg.kon;
-    const float n = (float)(s.U + s.L);
+    const float n = f_add(s.U, s.L);
     const float ad = f_mul(sg.gam, n);
     const float ab = on ? f_fma(sg.A1, x, sg.A0) : 0.0f;
     const float c1 = on ? sg.A1 : 0.0f;
@@ -141,7 +145,6 @@ __device__ __forceinline__ bool ssa_step(Lineage& s, float& x, const Seg& sg, ui
     const float E = exp_variate<EXACT>(wt);
     const float tau = wait_time<EXACT>(c0, c1, E);
     const float xn = f_add(x, tau);
-    s.n_draws += 1u;
     if (!(xn < sg.len)) return true;
     x = xn;
     const float abn = on ? f_fma(sg.A1, xn, sg.A0) : 0.0f;
@@ -153,12 +156,12 @@ __device__ __forceinline__ bool ssa_step(Lineage& s, float& x, const Seg& sg, ui
     const bool death = !sw && !birth;
     const bool lab = birth && (rb < f_mul(sg.lamf, abn));
     const float rd = f_add(rs, -asw);
-    const bool dU = ((rd < f_mul(sg.gam, (float)s.U)) || (s.L == 0u)) && (s.U > 0u);
+    const bool dU = (rd < f_mul(sg.gam, s.U)) || (s.L == 0.0f);
     s.g ^= (int)sw;
-    s.U += (uint32_t)(birth && !lab);
-    s.L += (uint32_t)lab;
-    s.U -= (uint32_t)(death && dU);
-    s.L -= (uint32_t)(death && !dU);
+    const float dUv = (birth && !lab) ? 1.0f : ((death && dU) ? -1.0f : 0.0f);
+    const float dLv = lab ? 1.0f : ((death && !dU) ? -1.0f : 0.0f);
+    s.U = f_add(s.U, dUv);
+    s.L = f_add(s.L, dLv);
     s.n_events += 1u;
     return false;
 }
@@ -215,7 +218,7 @@ template <bool EXACT>
 __global__ void __launch_bounds__(SSA_WARPS * 32)
 abc_ssa_kernel(const AbcRates* __restrict__ rates, const AbcSsaParams prm, const uint32_t* __restrict__ beta_q32,
                unsigned long long* __restrict__ sums, unsigned long long* __restrict__ counters,
-               unsigned int* __restrict__ work, uint32_t* __restrict__ cells_out) {
+               unsigned int* __restrict__ work, uint32_t* __restrict__ cells_out, const int* __restrict__ order) {
     __shared__ WarpTable tabs[SSA_WARPS];
     __shared__ AbcRates srates[SSA_WARPS];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -237,6 +240,7 @@ abc_ssa_kernel(const AbcRates* __restrict__ rates, const AbcSsaParams prm, const
             p = 0; readout = prm.single_readout; chunk = (int)item;
         } else {
             p = (long long)(item / per_particle);
+            if (order != nullptr) p = order[p];      // heaviest predicted particles first
             unsigned int rem = (unsigned int)(item % per_particle);
             readout = (int)(rem / prm.chunks);
             chunk = (int)(rem % prm.chunks);
@@ -257,8 +261,8 @@ abc_ssa_kernel(const AbcRates* __restrict__ rates, const AbcSsaParams prm, const
         s.c1 = (uint32_t)gp; s.c2 = (uint32_t)(gp >> 32);
         s.c3 = abc_tag((uint32_t)cell, (uint32_t)readout, (uint32_t)prm.m, ABC_DOM_SSA);
         s.k0 = prm.seed_lo; s.k1 = prm.seed_hi;
-        s.ctr = 0u; s.U = 0u; s.L = 0u; s.g = 0; s.n_events = 0u; s.n_draws = 0u;
-        uint32_t Ud = 0u, Ld = 0u;
+        s.ctr = 0u; s.U = 0.0f; s.L = 0.0f; s.g = 0; s.n_events = 0u;
+        uint32_t Ud = 0u, Ld = 0u, n_cross = 0u;
 
         if (live) {
             {   // initial gene state ~ Bernoulli(P_on)
@@ -267,6 +271,7 @@ abc_ssa_kernel(const AbcRates* __restrict__ rates, const AbcSsaParams prm, const
             }
             for (int c = 0; c <= prm.n_pre; ++c) {
                 const int n_ent = tab.n_ent[c];
+                n_cross += (uint32_t)n_ent;
                 int e = 0;
                 float x = 0.0f;
                 Seg sg = tab.seg[c][0];
@@ -285,23 +290,24 @@ abc_ssa_kernel(const AbcRates* __restrict__ rates, const AbcSsaParams prm, const
                 }
                 if (c < prm.n_pre) {   // cell division: binomial partitioning, gene state kept
                     WordSrc ws; ws.avail = 0;
-                    s.U = binhalf(s.U, ws, s);
-                    s.L = binhalf(s.L, ws, s);
+                    s.U = (float)binhalf((uint32_t)s.U, ws, s);
+                    s.L = (float)binhalf((uint32_t)s.L, ws, s);
                 }
             }
-            Ud = s.U; Ld = s.L;
+            const uint32_t Uc = (uint32_t)s.U, Lc = (uint32_t)s.L;
+            Ud = Uc; Ld = Lc;
             if (prm.downsampling) {
                 WordSrc ws; ws.avail = 0;
                 const int grp = (cond < 6 ? 0 : ABC_NAGE) + age_i;
                 const uint32_t off = (uint32_t)prm.beta_off[grp];
                 const uint32_t cnt = (uint32_t)prm.beta_off[grp + 1] - off;
                 const uint32_t B = beta_q32[off + __umulhi(next_word(ws, s), cnt)];
-                Ud = binom_q32(s.U, B, ws, s);
-                Ld = binom_q32(s.L, B, ws, s);
+                Ud = binom_q32(Uc, B, ws, s);
+                Ld = binom_q32(Lc, B, ws, s);
             }
             if (cells_out != nullptr) {
-                cells_out[0 * prm.n_cells + cell] = s.U;
-                cells_out[1 * prm.n_cells + cell] = s.L;
+                cells_out[0 * prm.n_cells + cell] = Uc;
+                cells_out[1 * prm.n_cells + cell] = Lc;
                 cells_out[2 * prm.n_cells + cell] = Ud;
                 cells_out[3 * prm.n_cells + cell] = Ld;
             }
@@ -318,7 +324,7 @@ abc_ssa_kernel(const AbcRates* __restrict__ rates, const AbcSsaParams prm, const
         }
         acc_lineages += live ? 1ull : 0ull;
         acc_events += s.n_events;
-        acc_draws += s.n_draws;
+        acc_draws += (unsigned long long)s.n_events + n_cross;
     }
     acc_lineages = warp_sum_u64(acc_lineages);
     acc_events = warp_sum_u64(acc_events);
@@ -332,7 +338,7 @@ abc_ssa_kernel(const AbcRates* __restrict__ rates, const AbcSsaParams prm, const
 
 int abc_launch_ssa(const AbcRates* d_rates, const AbcSsaParams& prm, const uint32_t* d_beta_q32,
                    unsigned long long* d_sums, unsigned long long* d_counters, unsigned int* d_work,
-                   uint32_t* d_cells_out, int exact_math, int sm_count, cudaStream_t st) {
+                   uint32_t* d_cells_out, const int* d_order, int exact_math, int sm_count, cudaStream_t st) {
     if (prm.n_pre + 1 > SSA_MAX_CYCLES) {
         abc_set_error("n_pre_cycles must be <= %d", SSA_MAX_CYCLES - 1);
         return ABC_ERR_ARG;
@@ -356,9 +362,9 @@ int abc_launch_ssa(const AbcRates* d_rates, const AbcSsaParams& prm, const uint3
     if (grid > want) grid = want;
     if (grid < 1) grid = 1;
     if (exact_math)
-        abc_ssa_kernel<true><<<(unsigned)grid, SSA_WARPS * 32, 0, st>>>(d_rates, prm, d_beta_q32, d_sums, d_counters, d_work, d_cells_out);
+        abc_ssa_kernel<true><<<(unsigned)grid, SSA_WARPS * 32, 0, st>>>(d_rates, prm, d_beta_q32, d_sums, d_counters, d_work, d_cells_out, d_order);
     else
-        abc_ssa_kernel<false><<<(unsigned)grid, SSA_WARPS * 32, 0, st>>>(d_rates, prm, d_beta_q32, d_sums, d_counters, d_work, d_cells_out);
+        abc_ssa_kernel<false><<<(unsigned)grid, SSA_WARPS * 32, 0, st>>>(d_rates, prm, d_beta_q32, d_sums, d_counters, d_work, d_cells_out, d_order);
     ABC_CUDA_CHECK(cudaGetLastError());
     return ABC_OK;
 }
@@ -393,8 +399,44 @@ __global__ void abc_rates_kernel(const double* __restrict__ theta, int m, long l
     double pon = kon / (kon + koff);
     double thr = pon * 4294967296.0;
     r.pon_thr = (thr >= 4294967295.0) ? 0xFFFFFFFFu : (thr > 0.0 ? (uint32_t)thr : 0u);
-    r.pad0 = 0.0f; r.pad1 = 0.0f;
+    // predicted SSA events per simulated hour (switching + births + deaths), used only to schedule the
+    // heaviest particles first (longest-processing-time order); it never influences a result
+    float cost = 0.0f;
+    for (int j = 0; j < 5; ++j) {
+        const float s2 = r.kon[j] + r.koff[j];
+        const float sw = 2.0f * r.kon[j] * r.koff[j] / s2;
+        const float br = r.alpha[j] * (m != 2 ? 1.5f : 1.0f) * r.kon[j] / s2;
+        cost += 0.2f * (sw + 2.0f * br);
+    }
+    r.pad0 = (cost == cost && cost > 0.0f) ? cost : 0.0f;
+    r.pad1 = 0.0f;
     out[i] = r;
+}
+
+// particle order by predicted cost, descending (CUB radix sort on the float bit patterns; plumbing only)
+__global__ void abc_cost_keys_kernel(const AbcRates* __restrict__ rates, int n, unsigned int* __restrict__ keys,
+                                     int* __restrict__ idx) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    keys[i] = __float_as_uint(rates[i].pad0);
+    idx[i] = i;
+}
+
+size_t abc_order_temp_bytes(int n) {
+    size_t bytes = 0;
+    cub::DeviceRadixSort::SortPairsDescending(nullptr, bytes, (const unsigned int*)nullptr, (unsigned int*)nullptr,
+                                              (const int*)nullptr, (int*)nullptr, n);
+    return bytes;
+}
+
+int abc_launch_order(const AbcRates* d_rates, int n, unsigned int* d_keys_in, unsigned int* d_keys_out, int* d_idx_in,
+                     int* d_order, void* d_temp, size_t temp_bytes, cudaStream_t st) {
+    if (n <= 0) return ABC_OK;
+    abc_cost_keys_kernel<<<(n + 255) / 256, 256, 0, st>>>(d_rates, n, d_keys_in, d_idx_in);
+    ABC_CUDA_CHECK(cudaGetLastError());
+    ABC_CUDA_CHECK(cub::DeviceRadixSort::SortPairsDescending(d_temp, temp_bytes, d_keys_in, d_keys_out, d_idx_in, d_order,
+                                                             n, 0, 32, st));
+    return ABC_OK;
 }
 
 int abc_launch_rates(const double* d_theta, int m, int64_t n, AbcRates* d_rates, cudaStream_t st) {

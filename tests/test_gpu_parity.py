@@ -102,6 +102,35 @@ def test_score_special_values(eng, data_stats):
     assert np.array_equal(counts, (ref <= 4.8).sum(0))
 
 
+def test_score_late_nan_defeats_early_exit(eng, data_stats):
+    """a NaN in the LAST group must give NaN even when the first groups already exceed 10 for every lane
+    of the warp (the reference does not clip NaN, compute_errors.jl:62-64)"""
+    d, se = data_stats
+    rng = np.random.default_rng(22)
+    s = d[rng.integers(0, d.shape[0], 256)] * 1e3       # wildly off: every pair saturates in group 1
+    s[17, 52] = np.nan
+    s[40, 31] = np.nan
+    s[41, 45] = np.inf
+    ref = oracle.compute_trunc_errors(s, d, se)
+    assert np.isnan(ref[17]).all() and np.isnan(ref[40]).all() and (ref[41] == 10.0).all() and (ref[0] == 10.0).all()
+    eng.accept_reset()
+    err, counts, _ = eng.score(s, eps=4.8, err_layout=ERR_PARTICLE_MAJOR)
+    assert oracle.same_bits(err, ref)
+    assert counts.sum() == 0
+    # non-finite DATA of a gene: that gene's column is evaluated in full
+    d2, se2 = d.copy(), se.copy()
+    d2[5, 50] = np.nan
+    se2[9, 44] = np.inf
+    eng.set_data(d2, se2)
+    try:
+        err2, _, _ = eng.score(s, eps=4.8, err_layout=ERR_PARTICLE_MAJOR)
+    finally:
+        eng.set_data(d, se)
+    ref2 = oracle.compute_trunc_errors(s, d2, se2)
+    assert np.isnan(ref2[:, 5]).all()
+    assert oracle.same_bits(err2, ref2)
+
+
 def test_accept_lists_match_reference_order(eng, data_stats):
     """v[sortperm(err[v])] per gene, 1-based, stable; empty -> the '0' line (accepted_particles.jl:19-30)"""
     d, se = data_stats
