@@ -1,0 +1,52 @@
+"""GPU test of the host-side mirror end to end: run(m, n_trials, submit) -> simulation files -> load_s_data ->
+compute_trunc_errors -> error file -> accepted particles file, each stage checked against the oracle."""
+import os
+
+import numpy as np
+import pytest
+
+import oracle
+from abc_inference_transcription_b200 import AbcEngine, abc_simulation, accepted_particles, compute_errors, synthetic_design
+from abc_inference_transcription_b200.jlfmt import readdlm
+
+pytestmark = pytest.mark.gpu
+GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+
+
+def test_wrapper_section_2_and_3(tmp_path):
+    betas = np.load(os.path.join(GOLD, "ref_betas.npy"))
+    z = np.load(os.path.join(GOLD, "ref_summary_stats.npz"))
+    d, se = z["d"][:300], z["se"][:300]
+    root = str(tmp_path)
+    with AbcEngine(0) as eng:
+        eng.set_design(synthetic_design(betas, n_cells=32, n_pre_cycles=8))
+        # wrapper.jl:59-66: m = 3; n_trials = 40; submit = 2
+        m, n_trials, submit = 3, 40, 2
+        tot = abc_simulation.run(eng, m, n_trials, submit=submit, root=root, seed=9, batch=16)
+        assert tot["n_particles"] == 40
+        sim = os.path.join(root, "data", "simulations")
+        assert readdlm(os.path.join(sim, "kon", "progress_kon_2.txt")).ravel().tolist() == [16, 32, 40]
+        sets = readdlm(os.path.join(sim, "kon", "sets_kon_2.txt"))
+        assert sets.shape == (40, 9)
+        # the batches are windows of one global particle stream: submit 2 covers particles [40, 80)
+        assert oracle.same_bits(sets, eng.fix_params(m, 40, particle_offset=40, seed=9))
+        parts = compute_errors.load_s_data(sim, "kon", "_2.txt")
+        stats = compute_errors.pack_stats(*parts)
+        _, direct, _ = eng.simulate(m, theta=sets, particle_offset=40, seed=9)
+        assert oracle.same_bits(stats, direct)                 # text round trip is bit exact
+        # wrapper.jl:72-81
+        cols = [d[:, 0:5], se[:, 0:5], d[:, 5:10], se[:, 5:10], d[:, 10:15], se[:, 10:15], d[:, 15:20], se[:, 15:20],
+                d[:, 20:31], se[:, 20:31], d[:, 31:42], se[:, 31:42], d[:, 42:53], se[:, 42:53]]
+        probe = np.concatenate([stats, d[:10] * 1.02])         # a few particles that do get accepted
+        pp = [probe[:, 0:5], probe[:, 5:10], probe[:, 10:15], probe[:, 15:20], probe[:, 20:31], probe[:, 31:42], probe[:, 42:53]]
+        eng.accept_reset()
+        err = compute_errors.compute_trunc_errors(eng, *cols, *pp, "kon", out_dir=os.path.join(root, "errors"))
+        ref = oracle.compute_trunc_errors(probe, d, se)
+        assert oracle.same_bits(err, ref)
+        assert oracle.same_bits(readdlm(os.path.join(root, "errors", "error_kon.txt")), ref)
+        offsets, idx = accepted_particles.accepted_from_engine(eng)
+        accepted_particles.write_particles(root, "kon", offsets, idx)
+        lines = accepted_particles.read_particles(os.path.join(root, "data", "posteriors", "particles_kon.txt"))
+        assert len(lines) == 300 and sum(len(v) for v in lines) > 0
+        for g in range(300):
+            assert np.array_equal(lines[g], oracle.accept_gene(ref[:, g], 4.8))

@@ -1,0 +1,94 @@
+"""CPU tests of the host-side mirror: model tables, Julia text formats, file layouts (no GPU, no compute)."""
+import os
+
+import numpy as np
+import pytest
+
+from abc_inference_transcription_b200 import get_vary_map, model_name, n_params, prior_bounds, scaling_for, vary_map_for
+from abc_inference_transcription_b200 import abc_simulation, accepted_particles, compute_errors
+from abc_inference_transcription_b200.dist import csr_from_tuples, shard_range
+from abc_inference_transcription_b200.jlfmt import jl_float, readdlm, writedlm_rows
+
+
+def test_model_tables_match_reference():
+    assert [model_name(m) for m in range(1, 6)] == ["const", "const_const", "kon", "alpha", "gamma"]
+    assert get_vary_map([0, 0, 0, 0], 5) == [1, 2, 3, 4]                       # model.jl:30-43
+    assert get_vary_map([1, 0, 0, 0], 5) == [[1, 2, 3, 4, 5], 6, 7, 8]
+    assert vary_map_for(5) == [1, 2, 3, [4, 5, 6, 7, 8]]
+    assert [scaling_for(m) for m in range(1, 6)] == [1, 0, 1, 1, 1]            # abc_simulation.jl:85
+    assert [n_params(m) for m in range(1, 6)] == [5, 5, 9, 9, 9]
+    lo, hi = prior_bounds(5)
+    assert list(lo) == [-3, -3, -3, -3, -3, -3, -3, -3, -0.7] and list(hi) == [3, 3, 3, 2, 2, 2, 2, 2, 0]
+    with pytest.raises(ValueError):
+        model_name(6)
+
+
+@pytest.mark.parametrize("x,want", [(1.0, "1.0"), (0.1, "0.1"), (1e-5, "1.0e-5"), (0.0001, "0.0001"), (1e6, "1.0e6"),
+                                    (123456.0, "123456.0"), (2.056424836200255, "2.056424836200255"), (10.0, "10.0"),
+                                    (float("nan"), "NaN"), (float("-inf"), "-Inf"), (-1.5e-7, "-1.5e-7")])
+def test_julia_float_text(x, want):
+    assert jl_float(x) == want
+
+
+def test_text_roundtrip_is_bit_exact(tmp_path):
+    rng = np.random.default_rng(0)
+    a = np.concatenate([rng.lognormal(0, 5, (50, 11)), [[np.nan, np.inf, -np.inf, 0.0, 10.0, 4.8, 1e-300, 1e300, 5e-324, -0.0, 1 / 3]]])
+    p = tmp_path / "a.txt"
+    with open(p, "w") as fh:
+        writedlm_rows(fh, a)
+    b = readdlm(str(p))
+    assert np.array_equal(np.isnan(a), np.isnan(b))
+    assert np.array_equal(a[~np.isnan(a)].view(np.uint64), b[~np.isnan(b)].view(np.uint64))
+
+
+def test_simulation_file_layout_roundtrip(tmp_path):
+    """write_stats -> load_s_data recovers the 7 matrices (abc_simulation.jl:47-61 <-> compute_errors.jl:17-28)"""
+    rng = np.random.default_rng(1)
+    stats = rng.lognormal(0, 1, (7, 53))
+    abc_simulation.write_stats(str(tmp_path), "kon", 3, stats[:4])
+    abc_simulation.write_stats(str(tmp_path), "kon", 3, stats[4:])           # append mode like the reference
+    d = tmp_path / "data" / "simulations" / "kon"
+    assert sorted(os.listdir(d)) == ["s_chase_kon_3.txt", "s_corr_mean_kon_3.txt", "s_mean_corr_kon_3.txt",
+                                     "s_pulse_kon_3.txt", "s_ratios_kon_3.txt"]
+    assert len(open(d / "s_pulse_kon_3.txt").read().splitlines()) == 14      # 2 rows per particle
+    parts = compute_errors.load_s_data(str(tmp_path / "data" / "simulations"), "kon", "_3.txt")
+    assert [p.shape for p in parts] == [(7, 5)] * 4 + [(7, 11)] * 3
+    assert np.array_equal(compute_errors.pack_stats(*parts), stats)
+    raw = compute_errors.readdlm(str(d / "s_pulse_kon_3.txt"))
+    assert np.array_equal(compute_errors.get_mean_subset(raw), stats[:, 0:5])
+    assert np.array_equal(compute_errors.get_ff_subset(raw), stats[:, 5:10])
+
+
+def test_particles_file_layout(tmp_path):
+    offsets = np.array([0, 2, 2, 5])
+    idx = np.array([7, 3, 1, 9, 4])
+    accepted_particles.write_particles(str(tmp_path), "const", offsets, idx)
+    text = open(tmp_path / "data" / "posteriors" / "particles_const.txt").read()
+    assert text == "7\t3\n0\n1\t9\t4\n"                                       # accepted_particles.jl:23-30
+    got = accepted_particles.read_particles(str(tmp_path / "data" / "posteriors" / "particles_const.txt"))
+    assert [list(v) for v in got] == [[7, 3], [], [1, 9, 4]]
+
+
+def test_error_column_store(tmp_path):
+    err = np.arange(12.0).reshape(4, 3)
+    with open(tmp_path / "error_const.txt", "w") as fh:
+        writedlm_rows(fh, err)
+    shapes = compute_errors.process_error_files(str(tmp_path), str(tmp_path / "cols"), model_names=("const",))
+    assert shapes == {"const": (3, 4)}
+    assert np.array_equal(compute_errors.load_error_column(str(tmp_path / "cols"), "const", 2), err[:, 1])
+
+
+def test_shard_range_partitions_exactly():
+    for n, w in [(10, 3), (5_000_000, 8), (7, 8), (0, 2)]:
+        r = [shard_range(n, k, w) for k in range(w)]
+        assert r[0][0] == 0 and r[-1][1] == n
+        assert all(r[k][1] == r[k + 1][0] for k in range(w - 1))
+        assert max(b - a for a, b in r) - min(b - a for a, b in r) <= 1
+
+
+def test_csr_from_tuples_order():
+    gene = np.array([2, 0, 2, 0, 2], dtype=np.int32)
+    part = np.array([5, 9, 3, 1, 8], dtype=np.int64)
+    err = np.array([1.0, 2.0, 1.0, 2.0, 0.5])
+    off, idx, e = csr_from_tuples(gene, part, err, 4)
+    assert list(off) == [0, 2, 2, 5, 5] and list(idx) == [1, 9, 8, 3, 5] and list(e) == [2.0, 2.0, 0.5, 1.0, 1.0]
