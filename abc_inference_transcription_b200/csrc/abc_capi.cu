@@ -77,7 +77,7 @@ struct abc_ctx {
     int32_t G = 0;
     DevBuf<double> d_d, d_den;
     // simulate work buffers
-    DevBuf<double> d_theta, d_stats, d_moments;
+    DevBuf<double> d_theta, d_stats, d_moments, d_ss_iv;
     DevBuf<AbcRates> d_rates;
     DevBuf<unsigned long long> d_sums, d_counters;
     DevBuf<unsigned int> d_work;
@@ -137,7 +137,7 @@ extern "C" int abc_destroy(abc_ctx_t* c) {
     cudaSetDevice(c->device);
     cudaStreamSynchronize(c->stream);
     c->d_beta.release(); c->d_age_dist.release(); c->d_beta_mom.release(); c->d_d.release(); c->d_den.release();
-    c->d_theta.release(); c->d_stats.release(); c->d_moments.release(); c->d_rates.release();
+    c->d_theta.release(); c->d_stats.release(); c->d_moments.release(); c->d_ss_iv.release(); c->d_rates.release();
     c->d_keys_in.release(); c->d_keys_out.release(); c->d_idx_in.release(); c->d_order.release(); c->d_sort_tmp.release();
     c->d_sums.release(); c->d_counters.release(); c->d_work.release(); c->d_cells.release();
     c->d_sstats.release(); c->d_err.release(); c->d_counts.release(); c->d_acc_count.release();
@@ -296,11 +296,30 @@ static int simulate_device(abc_ctx* c, int m, int64_t n, int64_t offset, uint64_
                            double* d_theta, double* d_stats, double* d_moments_out, cudaStream_t st) {
     int rc = ABC_OK;
     if (!c->has_design) { abc_set_error("abc_set_design has not been called"); return ABC_ERR_STATE; }
-    if (c->design.sim_kind != ABC_SIM_SSA) { abc_set_error("sim_kind ABC_SIM_ODE is not available in this build"); return ABC_ERR_STATE; }
     if (!prior_supplied) {
         rc = abc_launch_prior(d_theta, m, n, offset, seed, st);
         c->launches++;
         if (rc != ABC_OK) return rc;
+    }
+    if (c->design.sim_kind == ABC_SIM_ODE) {
+        // what scripts/model.jl integrates: moment ODEs -> (downsample) -> moments -> statistics
+        double* d_mom_ode = d_moments_out;
+        if (!d_mom_ode) {
+            if ((rc = c->d_moments.ensure((size_t)n * ABC_NREAD * 5)) != ABC_OK) return rc;
+            d_mom_ode = c->d_moments.p;
+        }
+        if ((rc = c->d_ss_iv.ensure((size_t)n * 9)) != ABC_OK) return rc;
+        ABC_CUDA_CHECK(cudaMemsetAsync(c->d_counters.p, 0, 8 * sizeof(unsigned long long), st));
+        ABC_CUDA_CHECK(cudaEventRecord(c->ev[0], st));
+        if ((rc = abc_launch_ode(d_theta, c->design, m, n, c->d_beta_mom.p, c->d_ss_iv.p, d_mom_ode, c->d_counters.p, st)) != ABC_OK) return rc;
+        c->launches += 2;
+        ABC_CUDA_CHECK(cudaEventRecord(c->ev[1], st));
+        if (d_stats) {
+            if ((rc = abc_launch_summary_stats(d_mom_ode, c->d_age_dist.p, n, d_stats, st)) != ABC_OK) return rc;
+            c->launches++;
+        }
+        ABC_CUDA_CHECK(cudaEventRecord(c->ev[2], st));
+        return ABC_OK;
     }
     if ((rc = c->d_rates.ensure((size_t)n)) != ABC_OK) return rc;
     if ((rc = c->d_sums.ensure((size_t)n * ABC_NREAD * 5)) != ABC_OK) return rc;
@@ -351,11 +370,11 @@ static int read_counters(abc_ctx* c, int64_t n, abc_counters_t* out, bool accumu
     if (cudaEventElapsedTime(&ms_st, c->ev[1], c->ev[2]) != cudaSuccess) cudaGetLastError();
     abc_counters_t r;
     memset(&r, 0, sizeof(r));
-    r.n_particles = (uint64_t)n; r.n_lineages = h[0]; r.n_events = h[1]; r.n_draws = h[2];
+    r.n_particles = (uint64_t)n; r.n_lineages = h[0]; r.n_events = h[1]; r.n_draws = h[2]; r.n_ode_steps = h[4];
     r.ms_simulate = ms_sim; r.ms_stats = ms_st;
     if (accumulate) {
         c->last.n_particles += r.n_particles; c->last.n_lineages += r.n_lineages; c->last.n_events += r.n_events;
-        c->last.n_draws += r.n_draws; c->last.ms_simulate += r.ms_simulate; c->last.ms_stats += r.ms_stats;
+        c->last.n_draws += r.n_draws; c->last.n_ode_steps += r.n_ode_steps; c->last.ms_simulate += r.ms_simulate; c->last.ms_stats += r.ms_stats;
     } else {
         double keep = c->last.ms_score;
         c->last = r;
@@ -422,6 +441,7 @@ extern "C" int abc_ssa_cells(abc_ctx_t* c, int m, const double* theta, int64_t p
     int rc = check_model(m);
     if (rc != ABC_OK) return rc;
     if (!c->has_design) { abc_set_error("abc_set_design has not been called"); return ABC_ERR_STATE; }
+    if (c->design.sim_kind != ABC_SIM_SSA) { abc_set_error("abc_ssa_cells needs sim_kind == ABC_SIM_SSA"); return ABC_ERR_STATE; }
     if (!theta || !counts || cond < 0 || cond >= ABC_NCOND || age < 0 || age >= ABC_NAGE) { abc_set_error("abc_ssa_cells: bad arguments"); return ABC_ERR_ARG; }
     const int P = abc_n_params(m);
     const int nc = c->design.n_cells;

@@ -1,0 +1,64 @@
+"""GPU tests of the device moment-ODE path (sim_kind = ABC_SIM_ODE): the computation scripts/model.jl performs,
+checked against the reference's shipped recovered_statistics and against the CPU oracle."""
+import os
+
+import numpy as np
+import pytest
+
+import oracle
+from abc_inference_transcription_b200 import AbcEngine, SIM_ODE, split_betas, synthetic_design
+
+pytestmark = pytest.mark.gpu
+GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+MODELS = ["const", "const_const", "kon", "alpha", "gamma"]
+
+
+@pytest.fixture(scope="module")
+def betas():
+    return np.load(os.path.join(GOLD, "ref_betas.npy"))
+
+
+def test_device_odes_reproduce_reference_recovered_statistics(betas):
+    """run_part_sim (recover_statistics.jl:1-11: iv[1] = 1/2, no downsampling) on every shipped MAP row of the
+    fixture: same tolerance as the oracle-vs-golden test (the goldens carry CVODE 1e-3 noise), and the device
+    path agrees with the tight-tolerance oracle to 1e-4."""
+    maps = np.load(os.path.join(GOLD, "ref_map_sets.npz"))
+    rec = np.load(os.path.join(GOLD, "ref_recovered.npz"))
+    des = synthetic_design(betas, sim_kind=SIM_ODE, downsampling=False, iv=np.array([0.5, 0, 0, 0, 0, 0, 0, 0, 0.0]),
+                           ode_rtol=1e-7, ode_atol=1e-10)
+    od = oracle.make_design(iv_index=0, downsampling=False, rtol=1e-9)
+    with AbcEngine(0) as eng:
+        eng.set_design(des)
+        for m, name in enumerate(MODELS, start=1):
+            rows, gold = rec[f"rows_{name}"], rec[f"moments_{name}"]
+            theta = maps[f"theta_{name}"][rows]
+            mom, cnt = eng.simulate_moments(m, theta)
+            assert cnt["n_ode_steps"] > 0
+            rel = np.abs(mom - gold) / np.maximum(np.abs(gold), 1e-4)
+            assert np.median(rel) < 1e-3, (name, np.median(rel))
+            assert (rel < 2e-2).mean() > 0.97, (name, (rel < 2e-2).mean())
+            assert rel.max() < 0.2, (name, rel.max())
+            for i in range(0, len(theta), max(1, len(theta) // 6)):
+                want, _ = oracle.run_part_sim(theta[i], m, od)
+                r2 = np.abs(mom[i] - want) / np.maximum(np.abs(want), 1e-6)
+                assert r2.max() < 1e-4, (name, i, r2.max())
+
+
+@pytest.mark.parametrize("m", [1, 2, 3, 4, 5])
+def test_device_ode_statistics_match_oracle_run_sim(betas, m):
+    """abc_sim through the ODE path with downsampling: 53 statistics vs the oracle's run_sim on prior draws"""
+    bt = split_betas(betas)
+    des = synthetic_design(betas, sim_kind=SIM_ODE, ode_rtol=1e-7, ode_atol=1e-10)
+    od = oracle.make_design(iv_index=1, downsampling=True, betas=bt, rtol=1e-9)
+    with AbcEngine(0) as eng:
+        eng.set_design(des)
+        theta, stats, cnt = eng.simulate(m, n_trials=40, particle_offset=500, seed=3)
+        # S1 on the device's own moments is bit exact
+        mom, _ = eng.simulate_moments(m, theta, particle_offset=500, seed=3)
+        assert oracle.same_bits(stats, oracle.summary_stats(mom, des.age_dist))
+        for i in range(0, 40, 5):
+            want, wmom = oracle.run_sim(theta[i], m, od)
+            assert np.allclose(mom[i], wmom, rtol=2e-4, atol=1e-9), (i, np.abs(mom[i] - wmom).max())
+            ok = np.isfinite(want)
+            assert np.array_equal(np.isfinite(stats[i]), ok)
+            assert np.allclose(stats[i][ok], want[ok], rtol=2e-3, atol=1e-6), (i, np.abs(stats[i][ok] - want[ok]).max())
