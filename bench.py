@@ -253,6 +253,8 @@ def run_b200(args):
     t_e2e = float(te.item())
     e2e_value = particles / t_e2e
 
+    ode = run_ode_path(args, eng_cls=AbcEngine, betas=betas, d=d, se=se, dev=dev, world=world, rank=rank, local=local,
+                       barrier=barrier)
     if rank == 0:
         pk = peaks()
         peak_instr = 148 * 128 * pk["sm_max_mhz"] * 1e6 / 1e12        # T lane-instr/s at max clock
@@ -278,6 +280,7 @@ def run_b200(args):
                 "roofline_score": {"kernel": "abc_score_kernel", "bound": "hbm", "achieved": sc_gbs, "peak": pk["hbm_gbs"],
                                    "unit": "GB/s", "frac": sc_gbs / pk["hbm_gbs"], "traffic": None,
                                    "peak_src": pk["src"], "share_of_step": sc_s / t_dev if t_dev > 0 else None}}
+        line["ode_path"] = ode
         if world == 1 and not args.no_cpu:
             cores = os.cpu_count() or 1
             v, dt, _ = cpu_reference_sample(args.ref_particles, cores)
@@ -288,6 +291,61 @@ def run_b200(args):
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
+
+
+def run_ode_path(args, eng_cls, betas, d, se, dev, world, rank, local, barrier):
+    """Same step with sim_kind = ABC_SIM_ODE: the moment-ODE computation the reference's CPU path performs
+    (scripts/model.jl), on the device.  Reported next to the SSA headline, never instead of it."""
+    import torch
+    import torch.distributed as dist
+    from abc_inference_transcription_b200 import ERR_PARTICLE_MAJOR, SIM_ODE, n_params, synthetic_design
+    B = args.ode_batch
+    G = d.shape[0]
+    eng = eng_cls(local)
+    eng.set_design(synthetic_design(betas, sim_kind=SIM_ODE))
+    eng.set_data(d, se)
+    stream = torch.cuda.current_stream().cuda_stream
+    th_dev = [torch.empty((B, n_params(m)), dtype=torch.float64, device=dev) for m in range(1, 6)]
+    st_dev = torch.empty((B, 53), dtype=torch.float64, device=dev)
+    err_dev = torch.empty((B, G), dtype=torch.float64, device=dev)
+    steps = max(1, args.steps)
+
+    def dev_step(k):
+        eng.accept_reset()
+        for m in range(1, 6):
+            off = (k * world + rank) * B
+            eng.simulate_dev(m, B, th_dev[m - 1].data_ptr(), st_dev.data_ptr(), particle_offset=off, seed=SEED, stream=stream)
+            eng.score_dev(st_dev.data_ptr(), B, eps=EPS, particle_offset=off, err_layout=ERR_PARTICLE_MAJOR,
+                          d_err_ptr=err_dev.data_ptr(), stream=stream)
+
+    dev_step(0)
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for k in range(steps):
+        dev_step(1 + k)
+    e1.record()
+    barrier()
+    t_dev = e0.elapsed_time(e1) / 1e3
+    ode_steps = eng.counters()["n_ode_steps"]
+    t0 = time.perf_counter()
+    for k in range(steps):
+        eng.accept_reset()
+        for m in range(1, 6):
+            off = ((1 + k) * world + rank) * B
+            theta, stats, _ = eng.simulate(m, n_trials=B, particle_offset=off, seed=SEED)
+            err, counts, _ = eng.score(stats, eps=EPS, particle_offset=off, err_layout=ERR_PARTICLE_MAJOR)
+        eng.accept_fetch()
+    barrier()
+    t_e2e = time.perf_counter() - t0
+    tt = torch.tensor([t_dev, t_e2e], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+    n = 5 * B * world * steps
+    eng.close()
+    return {"sim_kind": "moment ODEs on device (Radau IIA, rtol 1e-6)", "value": n / float(tt[0]), "unit": UNIT,
+            "e2e": n / float(tt[1]), "particles_per_model_per_step_per_gpu": B, "steps": steps,
+            "ode_steps_last_launch": int(ode_steps)}
 
 
 def cpu_ssa_sample(cores, args):
@@ -322,9 +380,10 @@ def main():
     ap.add_argument("--steps", type=int, default=3)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--batch", type=int, default=256, help="particles per model per step per GPU")
+    ap.add_argument("--batch", type=int, default=1024, help="particles per model per step per GPU")
     ap.add_argument("--n-cells", type=int, default=96)
     ap.add_argument("--n-pre", type=int, default=10)
+    ap.add_argument("--ode-batch", type=int, default=8192, help="particles per model per step for the ODE-path line")
     ap.add_argument("--ref-particles", type=int, default=1600)
     ap.add_argument("--no-cpu", action="store_true")
     args = ap.parse_args()

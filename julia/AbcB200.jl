@@ -1,0 +1,112 @@
+# AbcB200.jl -- thin ccall binding of libabcb200.so (include/abc_b200.h) for the reference's Julia host.
+#
+# NOT EXECUTED IN THE BUILD CONTAINER (no Julia toolchain there, SURVEY R7); the same symbols are exercised
+# through ctypes by abc_inference_transcription_b200/_lib.py and tests/.  No CUDA.jl, no codegen: every call is
+# a plain ccall with Julia-owned column-major arrays.
+module AbcB200
+
+const LIB = get(ENV, "ABCB200_LIB", joinpath(@__DIR__, "..", "abc_inference_transcription_b200", "libabcb200.so"))
+
+const SIM_SSA = Cint(0); const SIM_ODE = Cint(1)
+const ERR_NONE = Cint(0); const ERR_GENE_MAJOR = Cint(1); const ERR_PARTICLE_MAJOR = Cint(2)
+
+# mirrors abc_design_t field by field (isbits: passed by Ref)
+struct Design
+    cycle::Cdouble; t0::Cdouble
+    agevec::NTuple{5,Cdouble}
+    pulse::NTuple{11,Cdouble}; chase::NTuple{11,Cdouble}
+    age_dist::NTuple{55,Cdouble}          # vec(age_dist::Matrix 5x11), column-major, used as given
+    iv::NTuple{9,Cdouble}
+    downsampling::Cint; n_cells::Cint; n_pre_cycles::Cint; sim_kind::Cint
+    betas_pulse::Ptr{Cdouble}; cluster_pulse::Ptr{Cint}; n_pulse::Cint
+    betas_chase::Ptr{Cdouble}; cluster_chase::Ptr{Cint}; n_chase::Cint
+    ode_rtol::Cdouble; ode_atol::Cdouble
+end
+
+struct Counters
+    n_particles::UInt64; n_lineages::UInt64; n_events::UInt64; n_draws::UInt64; n_ode_steps::UInt64
+    ms_simulate::Cdouble; ms_stats::Cdouble; ms_score::Cdouble
+end
+
+mutable struct Context
+    ptr::Ptr{Cvoid}
+    n_genes::Int
+end
+
+last_error() = unsafe_string(ccall((:abc_last_error, LIB), Cstring, ()))
+check(rc) = rc == 0 ? nothing : error("libabcb200 error $rc: $(last_error())")
+
+function Context(device::Integer=0)
+    p = Ref{Ptr{Cvoid}}(C_NULL)
+    check(ccall((:abc_create, LIB), Cint, (Cint, Ref{Ptr{Cvoid}}), device, p))
+    ctx = Context(p[], 0)
+    finalizer(c -> ccall((:abc_destroy, LIB), Cint, (Ptr{Cvoid},), c.ptr), ctx)
+    return ctx
+end
+
+n_params(m) = Int(ccall((:abc_n_params, LIB), Cint, (Cint,), m))
+
+"""set_design(ctx; ...) -- the globals abc_sim receives (abc_simulation.jl:13-14, 65-79)"""
+function set_design(ctx::Context; cycle=20.0, t0=-3cycle, agevec, pulsevec, chasevec, age_dist::Matrix{Float64},
+                    iv=[0.0, 0.5, 0, 0, 0, 0, 0, 0, 0], downsampling=true, betas::Vector{Float64}, age::Vector{<:Integer},
+                    pulse_idx::Vector{Int}, chase_idx::Vector{Int}, n_cells=96, n_pre_cycles=10, sim_kind=SIM_SSA,
+                    ode_rtol=1e-6, ode_atol=1e-9)
+    bp = betas[pulse_idx]; ap = Cint.(age[pulse_idx]); bc = betas[chase_idx]; ac = Cint.(age[chase_idx])
+    GC.@preserve bp ap bc ac begin
+        d = Design(cycle, t0, Tuple(agevec), Tuple(pulsevec), Tuple(chasevec), Tuple(vec(age_dist)), Tuple(iv),
+                   downsampling, n_cells, n_pre_cycles, sim_kind,
+                   pointer(bp), pointer(ap), length(bp), pointer(bc), pointer(ac), length(bc), ode_rtol, ode_atol)
+        check(ccall((:abc_set_design, LIB), Cint, (Ptr{Cvoid}, Ref{Design}), ctx.ptr, d))
+    end
+end
+
+"""set_data(ctx, d, se): d, se are 53 x G (rows: pulse_mean, pulse_ff, chase_mean, chase_ff, ratio, mean_corr, corr_mean)"""
+function set_data(ctx::Context, d::Matrix{Float64}, se::Matrix{Float64})
+    @assert size(d) == size(se) && size(d, 1) == 53
+    check(ccall((:abc_set_data, LIB), Cint, (Ptr{Cvoid}, Ptr{Cdouble}, Ptr{Cdouble}, Cint), ctx.ptr, d, se, size(d, 2)))
+    ctx.n_genes = size(d, 2)
+end
+
+"""fix_params(ctx, m, N; particle_offset, seed) -> P x N matrix (transpose it to get the reference's N x P)"""
+function fix_params(ctx::Context, m, N; particle_offset=0, seed=UInt64(20240229))
+    θ = Matrix{Float64}(undef, n_params(m), N)
+    check(ccall((:abc_fix_params, LIB), Cint, (Ptr{Cvoid}, Cint, Int64, Int64, UInt64, Ptr{Cdouble}),
+                ctx.ptr, m, N, particle_offset, seed, θ))
+    return θ
+end
+
+"""simulate(ctx, m, n_trials) -> (θ P x n, stats 53 x n, counters): the trial loop of abc_simulation.jl:88-97"""
+function simulate(ctx::Context, m, n_trials; particle_offset=0, seed=UInt64(20240229), theta=nothing)
+    θ = theta === nothing ? Matrix{Float64}(undef, n_params(m), n_trials) : theta
+    stats = Matrix{Float64}(undef, 53, size(θ, 2))
+    c = Ref{Counters}()
+    check(ccall((:abc_simulate, LIB), Cint,
+                (Ptr{Cvoid}, Cint, Int64, Int64, UInt64, Cint, Ptr{Cdouble}, Ptr{Cdouble}, Ref{Counters}),
+                ctx.ptr, m, size(θ, 2), particle_offset, seed, theta === nothing ? 0 : 1, θ, stats, c))
+    return θ, stats, c[]
+end
+
+accept_reset(ctx::Context) = check(ccall((:abc_accept_reset, LIB), Cint, (Ptr{Cvoid},), ctx.ptr))
+
+"""score(ctx, stats; eps, layout) -> (err, counts).  ERR_PARTICLE_MAJOR: err is G x n (column i = row i of
+error_<model>.txt); ERR_GENE_MAJOR: n x G (column g = JDF column x<g>)."""
+function score(ctx::Context, stats::Matrix{Float64}; eps=4.8, particle_offset=0, layout=ERR_PARTICLE_MAJOR)
+    n, G = size(stats, 2), ctx.n_genes
+    err = layout == ERR_NONE ? Matrix{Float64}(undef, 0, 0) :
+          layout == ERR_PARTICLE_MAJOR ? Matrix{Float64}(undef, G, n) : Matrix{Float64}(undef, n, G)
+    counts = Vector{Int64}(undef, G)
+    check(ccall((:abc_score, LIB), Cint,
+                (Ptr{Cvoid}, Ptr{Cdouble}, Int64, Int64, Cdouble, Cint, Ptr{Cdouble}, Ptr{Int64}, Ptr{Cvoid}),
+                ctx.ptr, stats, n, particle_offset, eps, layout, layout == ERR_NONE ? C_NULL : pointer(err), counts, C_NULL))
+    return err, counts
+end
+
+"""accept_fetch(ctx) -> (offsets G+1, idx): idx[offsets[g]+1 : offsets[g+1]] == v[sortperm(err[v])] of gene g"""
+function accept_fetch(ctx::Context)
+    total = ccall((:abc_accept_total, LIB), Int64, (Ptr{Cvoid},), ctx.ptr)
+    offsets = Vector{Int64}(undef, ctx.n_genes + 1); idx = Vector{Int64}(undef, total); errs = Vector{Float64}(undef, total)
+    check(ccall((:abc_accept_fetch, LIB), Cint, (Ptr{Cvoid}, Ptr{Int64}, Ptr{Int64}, Ptr{Cdouble}), ctx.ptr, offsets, idx, errs))
+    return offsets, idx, errs
+end
+
+end # module

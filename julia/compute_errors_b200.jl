@@ -1,0 +1,27 @@
+# compute_errors_b200.jl -- drop-in for compute_errors.jl + process_error_files.jl + accepted_particles.jl
+# (wrapper.jl:72-81).  Keeps `m` / `model_name`, reads the simulation files with the reference's own
+# load_s_data, writes error_<model>.txt rows, the JDF column store and data/posteriors/particles_<model>.txt.
+# NOT EXECUTED IN THE BUILD CONTAINER (no Julia there).
+using DelimitedFiles, DataFrames, JDF
+include(joinpath(@__DIR__, "AbcB200.jl"))
+include("scripts/compute_errors.jl")     # only for load_s_data / get_mean_subset / get_ff_subset (compute_errors.jl:1-28)
+
+d  = permutedims(hcat(pulse_mean, pulse_ff, chase_mean, chase_ff, ratio_data, mean_corr_data, corr_mean_data))       # 53 x G
+se = permutedims(hcat(pulse_mean_se, pulse_ff_se, chase_mean_se, chase_ff_se, ratio_se, mean_corr_se, corr_mean_se))
+ctx = AbcB200.Context(0)
+AbcB200.set_data(ctx, d, se)
+
+s_pulse_mean,s_pulse_ff,s_chase_mean,s_chase_ff,s_ratios,s_mean_corr,s_corr_mean = load_s_data("data/simulations/",model_name,".txt")
+stats = permutedims(hcat(s_pulse_mean,s_pulse_ff,s_chase_mean,s_chase_ff,s_ratios,s_mean_corr,s_corr_mean))           # 53 x M
+
+ε = 4.8                                                                                      # accepted_particles.jl:10
+AbcB200.accept_reset(ctx)
+@time err, counts = AbcB200.score(ctx, stats; eps=ε, layout=AbcB200.ERR_GENE_MAJOR)          # M x G, column g == x<g>
+JDF.save("data/errors/error_"*model_name*".jdf", DataFrame(err, :auto))                      # process_error_files.jl:5-6
+offsets, idx, _ = AbcB200.accept_fetch(ctx)
+open("data/posteriors/particles_"*model_name*".txt", "a") do io                              # accepted_particles.jl:23-30
+    for g in 1:length(counts)
+        v = idx[offsets[g]+1:offsets[g+1]]
+        writedlm(io, isempty(v) ? [0] : reshape(v, 1, :))
+    end
+end
