@@ -81,6 +81,7 @@ SYMBOLS = {
     "abc_score_dev": (ctypes.c_int, [_vp, _vp, ctypes.c_int64, ctypes.c_int64, ctypes.c_double, ctypes.c_int, _vp, _vp]),
     "abc_counts_dev": (ctypes.c_int, [_vp, _vp, _vp]),
     "abc_accept_tuples_dev": (ctypes.c_int, [_vp, _vp, _vp, _vp, ctypes.c_int64, _vp]),
+    "abc_set_option": (ctypes.c_int, [_vp, ctypes.c_char_p, ctypes.c_int64]),
     "abc_counters": (ctypes.c_int, [_vp, ctypes.POINTER(AbcCounters)]),
     "abc_launch_count": (ctypes.c_int64, [_vp]),
 }

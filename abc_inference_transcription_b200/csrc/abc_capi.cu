@@ -76,6 +76,8 @@ struct abc_ctx {
     bool has_data = false;
     int32_t G = 0;
     DevBuf<double> d_d, d_den;
+    DevBuf<float2> d_fbw, d_fa;
+    int force_reference_score = 0;
     // simulate work buffers
     DevBuf<double> d_theta, d_stats, d_moments, d_ss_iv;
     DevBuf<AbcRates> d_rates;
@@ -136,7 +138,7 @@ extern "C" int abc_destroy(abc_ctx_t* c) {
     if (!c) return ABC_OK;
     cudaSetDevice(c->device);
     cudaStreamSynchronize(c->stream);
-    c->d_beta.release(); c->d_age_dist.release(); c->d_beta_mom.release(); c->d_d.release(); c->d_den.release();
+    c->d_beta.release(); c->d_age_dist.release(); c->d_beta_mom.release(); c->d_d.release(); c->d_den.release(); c->d_fbw.release(); c->d_fa.release();
     c->d_theta.release(); c->d_stats.release(); c->d_moments.release(); c->d_ss_iv.release(); c->d_rates.release();
     c->d_keys_in.release(); c->d_keys_out.release(); c->d_idx_in.release(); c->d_order.release(); c->d_sort_tmp.release();
     c->d_sums.release(); c->d_counters.release(); c->d_work.release(); c->d_cells.release();
@@ -230,14 +232,16 @@ extern "C" int abc_set_data(abc_ctx_t* c, const double* d, const double* se, int
     const size_t n = (size_t)G * ABC_NSTATS;
     int rc = c->d_d.ensure(n);
     if (rc == ABC_OK) rc = c->d_den.ensure(n);
+    if (rc == ABC_OK) rc = c->d_fbw.ensure(n);
+    if (rc == ABC_OK) rc = c->d_fa.ensure((size_t)G);
     DevBuf<double> d_se;
     if (rc == ABC_OK) rc = d_se.ensure(n);
     if (rc == ABC_OK) rc = c->d_counts.ensure((size_t)G);
     if (rc != ABC_OK) { d_se.release(); return rc; }
     ABC_CUDA_CHECK(cudaMemcpy(c->d_d.p, d, n * sizeof(double), cudaMemcpyHostToDevice));
     ABC_CUDA_CHECK(cudaMemcpy(d_se.p, se, n * sizeof(double), cudaMemcpyHostToDevice));
-    rc = abc_launch_prepare_data(c->d_d.p, d_se.p, G, c->d_den.p, nullptr, c->stream);
-    c->launches++;
+    rc = abc_launch_prepare_data(c->d_d.p, d_se.p, G, c->d_den.p, c->d_fbw.p, c->d_fa.p, c->stream);
+    c->launches += 2;
     if (rc == ABC_OK) {
         cudaError_t e = cudaStreamSynchronize(c->stream);
         if (e != cudaSuccess) { abc_set_error("prepare_data failed: %s", cudaGetErrorString(e)); rc = ABC_ERR_CUDA; }
@@ -514,7 +518,8 @@ static int score_device(abc_ctx* c, const double* d_stats, int64_t n, int64_t of
     int rc = ensure_accept(c, default_accept_capacity(n, c->G));
     if (rc != ABC_OK) return rc;
     AbcScoreArgs a;
-    a.stats = d_stats; a.d = c->d_d.p; a.den = c->d_den.p; a.rden = nullptr;
+    a.stats = d_stats; a.d = c->d_d.p; a.den = c->d_den.p; a.fbw = c->d_fbw.p; a.fa = c->d_fa.p;
+    a.force_reference_kernel = c->force_reference_score;
     a.n = n; a.G = c->G; a.particle_offset = offset; a.eps = eps;
     a.err_layout = layout; a.err = (layout == ABC_ERR_NONE) ? nullptr : d_err;
     a.counts = c->d_counts.p; a.acc_count = c->d_acc_count.p; a.acc_capacity = c->acc_capacity;
@@ -683,6 +688,14 @@ extern "C" int abc_accept_tuples_dev(abc_ctx_t* c, int32_t* d_gene, int64_t* d_p
         ABC_CUDA_CHECK(cudaMemcpyAsync(d_err, c->d_acc_err.p, k * sizeof(double), cudaMemcpyDeviceToDevice, st));
     }
     return ABC_OK;
+}
+
+extern "C" int abc_set_option(abc_ctx_t* c, const char* name, int64_t value) {
+    CTX_GUARD(c);
+    if (!name) { abc_set_error("abc_set_option: name is NULL"); return ABC_ERR_ARG; }
+    if (strcmp(name, "score_reference_kernel") == 0) { c->force_reference_score = value ? 1 : 0; return ABC_OK; }
+    abc_set_error("abc_set_option: unknown option '%s'", name);
+    return ABC_ERR_ARG;
 }
 
 extern "C" int abc_counters(abc_ctx_t* c, abc_counters_t* out) {

@@ -53,13 +53,15 @@ int abc_launch_ode(const double* d_theta, const abc_design_t& des, int m, int64_
                    double* d_ss_iv, double* d_moments, unsigned long long* d_counters, cudaStream_t st);
 
 // scoring
-int abc_launch_prepare_data(const double* d_d, const double* d_se, int G, double* d_den, double* d_rden,
+int abc_launch_prepare_data(const double* d_d, const double* d_se, int G, double* d_den, float2* d_fbw, float2* d_fa,
                             cudaStream_t st);
 struct AbcScoreArgs {
     const double* stats;   // [n][53]
     const double* d;       // [G][53]
     const double* den;     // [G][53]
-    const double* rden;    // [G][53]
+    const float2* fbw;     // [G][53] FP32 pre-filter constants (2 w d, w), w = 1/(53 den)
+    const float2* fa;      // [G] (sum_{t<15} w d^2, sum_{t>=15} w d^2)
+    int32_t force_reference_kernel;   // 1: always use the plain FP64 kernel (abc_score_kernel)
     int64_t n;
     int32_t G;
     int64_t particle_offset;

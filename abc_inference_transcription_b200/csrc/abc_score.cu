@@ -38,12 +38,35 @@ __global__ void abc_prepare_data_kernel(const double* __restrict__ d, const doub
     den[i] = __dadd_rn(__dadd_rn(__dmul_rn(si, si), __dmul_rn(sig2, __dmul_rn(di, di))), eps);
 }
 
-int abc_launch_prepare_data(const double* d_d, const double* d_se, int G, double* d_den, double* d_rden,
+// FP32 pre-filter constants (see abc_score2_kernel): with w = 1/(53 den),
+//   sum_t w (d-s)^2 = sum_t w d^2 - sum_t (2 w d) s + sum_t w s^2
+// fbw[g][t] = (2 w d, w); fa[g] = (sum_{t<15} w d^2, sum_{t>=15} w d^2).  A gene whose data is not finite
+// or badly scaled gets NaN constants, which sends all its pairs to the exact path.
+#define SC2_T1 15   // terms of stage 1: groups pulse_mean, pulse_ff, chase_mean
+__global__ void abc_prepare_filter_kernel(const double* __restrict__ d, const double* __restrict__ den, int G,
+                                          float2* __restrict__ fbw, float2* __restrict__ fa) {
+    const int g = blockIdx.x * blockDim.x + threadIdx.x;
+    if (g >= G) return;
+    double a1 = 0.0, a2 = 0.0;
+    bool bad = false;
+    for (int t = 0; t < ABC_NSTATS; ++t) {
+        const double dv = d[(long long)g * ABC_NSTATS + t], nv = den[(long long)g * ABC_NSTATS + t];
+        if (!(nv >= 1e-30 && nv <= 1e30) || !(fabs(dv) <= 1e15)) bad = true;
+        const double w = 1.0 / (53.0 * nv);
+        fbw[(long long)g * ABC_NSTATS + t] = make_float2((float)(2.0 * w * dv), (float)w);
+        if (t < SC2_T1) a1 += w * dv * dv; else a2 += w * dv * dv;
+    }
+    const float nanf_ = __int_as_float(0x7fc00000);
+    fa[g] = bad ? make_float2(nanf_, nanf_) : make_float2((float)a1, (float)a2);
+}
+
+int abc_launch_prepare_data(const double* d_d, const double* d_se, int G, double* d_den, float2* d_fbw, float2* d_fa,
                             cudaStream_t st) {
-    (void)d_rden;
     long long n = (long long)G * ABC_NSTATS;
     if (n <= 0) return ABC_OK;
     abc_prepare_data_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(d_d, d_se, n, d_den);
+    ABC_CUDA_CHECK(cudaGetLastError());
+    abc_prepare_filter_kernel<<<(G + 127) / 128, 128, 0, st>>>(d_d, d_den, G, d_fbw, d_fa);
     ABC_CUDA_CHECK(cudaGetLastError());
     return ABC_OK;
 }
@@ -170,8 +193,225 @@ abc_score_kernel(const AbcScoreArgs a) {
     }
 }
 
+
+// ------------------------------------------------------------------------------------------------
+// abc_score2_kernel: three-stage scoring for eps < 10 (the reference's eps is 4.8).
+//   stage 1 (all pairs, FP32): rigorous lower bound of the first 15 terms; "surely > 10" pairs are answered
+//            10.0 at once (91 % of prior-particle x gene pairs on the real data), the rest are queued;
+//   stage 2 (queued pairs, FP32, compacted): lower bound over all 53 terms; survivors (1.7 %) are queued;
+//   stage 3 (queued pairs, FP64, compacted): the exact reference arithmetic (same code as abc_score_kernel).
+// Soundness of the bound: every term is >= 0, so any partial sum bounds the total from below; the FP32
+// evaluation of the expanded form differs from the exact partial sum by < 1e-3 + 1e-5 * p (w d^2 <= 1/(53 sigma^2)
+// = 1.89 bounds the cancelling magnitudes; |s| >> |d| makes the sum huge and the error relative), so
+// p32 > 10.01 implies the exact total exceeds 10.0, which the reference clips to exactly 10.0.  NaN or Inf in
+// p32 never satisfies the test and falls through to the exact path; particles with a NaN statistic are
+// answered NaN directly (every gene uses all 53 statistics, compute_errors.jl:58-64).
+#define SC2_THREADS 128
+#define SC2_PPT 2
+#define SC2_TILE (SC2_THREADS * SC2_PPT)
+#define SC2_GT 32
+#define SC2_SUB 4
+#define SC2_Q1 2048
+#define SC2_Q2 2048
+#define SC2_SURE 10.01f
+
+struct Score2Smem {
+    float2 bw[SC2_GT][SC2_T1];
+    float a1[SC2_GT];
+    unsigned int q1_id[SC2_Q1];
+    float q1_p[SC2_Q1];
+    unsigned int q2_id[SC2_Q2];
+    unsigned int mask[SC2_GT][SC2_TILE / 32 + 1];
+    unsigned char rownan[SC2_TILE];
+    int q1n, q2n;
+};
+
+__device__ __forceinline__ double exact_pair_error(const double* __restrict__ sp, const double* __restrict__ gd,
+                                                   const double* __restrict__ gden) {
+    // compute_errors.jl:30-43, 55-64: the reference's operation order, explicit rounding
+    const int off[8] = {0, 5, 10, 15, 20, 31, 42, 53};
+    double err = 0.0;
+#pragma unroll
+    for (int l = 0; l < 7; ++l) {
+        double e = 0.0;
+        for (int t = off[l]; t < off[l + 1]; ++t) {
+            const double diff = __dadd_rn(gd[t], -sp[t]);
+            e = __dadd_rn(e, __ddiv_rn(__dmul_rn(diff, diff), gden[t]));
+        }
+        err = __dadd_rn(err, __ddiv_rn(e, 53.0));
+    }
+    return (err > 10.0) ? 10.0 : err;
+}
+
+__device__ __forceinline__ void score2_store(const AbcScoreArgs& a, long long i, int g, double v) {
+    if (a.err == nullptr) return;
+    if (a.err_layout == ABC_ERR_GENE_MAJOR) a.err[(long long)g * a.n + i] = v;
+    else a.err[i * (long long)a.G + g] = v;
+}
+
+__device__ void score2_drain(const AbcScoreArgs& a, Score2Smem& sm, const float2* __restrict__ fbw,
+                             const float2* __restrict__ fa, long long i0, int g0) {
+    __syncthreads();
+    const int n1 = sm.q1n;
+    // stage 2: FP32 lower bound over the remaining 38 terms, one queued pair per thread
+    for (int e = threadIdx.x; e < n1; e += SC2_THREADS) {
+        const unsigned int id = sm.q1_id[e];
+        const int g = g0 + (int)(id >> 16);
+        const long long i = i0 + (long long)(id & 0xffffu);
+        const double* sp = a.stats + i * ABC_NSTATS;
+        const float2* bw = fbw + (long long)g * ABC_NSTATS;
+        float p = sm.q1_p[e] + fa[g].y;
+#pragma unroll 2
+        for (int t = SC2_T1; t < ABC_NSTATS; ++t) {
+            const float sv = (float)sp[t];
+            const float2 c = bw[t];
+            p = __fmaf_rn(-c.x, sv, p);
+            p = __fmaf_rn(c.y, __fmul_rn(sv, sv), p);
+        }
+        if (p > SC2_SURE) score2_store(a, i, g, 10.0);
+        else sm.q2_id[atomicAdd(&sm.q2n, 1)] = id;
+    }
+    __syncthreads();
+    const int n2 = sm.q2n;
+    // stage 3: exact FP64, one surviving pair per thread; fused eps-acceptance
+    for (int e = threadIdx.x; e < n2; e += SC2_THREADS) {
+        const unsigned int id = sm.q2_id[e];
+        const int g = g0 + (int)(id >> 16);
+        const long long i = i0 + (long long)(id & 0xffffu);
+        const double err = exact_pair_error(a.stats + i * ABC_NSTATS, a.d + (long long)g * ABC_NSTATS,
+                                            a.den + (long long)g * ABC_NSTATS);
+        score2_store(a, i, g, err);
+        if (err <= a.eps) {
+            const unsigned long long slot = atomicAdd(a.acc_count, 1ull);
+            atomicAdd(a.counts + g, 1ull);
+            if ((long long)slot < a.acc_capacity) {
+                a.acc_gene[slot] = g;
+                a.acc_particle[slot] = a.particle_offset + i + 1;
+                a.acc_err[slot] = err;
+            }
+        }
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) { sm.q1n = 0; sm.q2n = 0; }
+    __syncthreads();
+}
+
+__global__ void __launch_bounds__(SC2_THREADS)
+abc_score2_kernel(const AbcScoreArgs a, const float2* __restrict__ fbw, const float2* __restrict__ fa) {
+    __shared__ Score2Smem sm;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const long long n_tiles = (a.n + SC2_TILE - 1) / SC2_TILE;
+    const int n_gtiles = (a.G + SC2_GT - 1) / SC2_GT;
+    const int gt_per = (n_gtiles + gridDim.y - 1) / gridDim.y;
+    const int g_lo = min(a.G, (int)blockIdx.y * gt_per * SC2_GT);
+    const int g_hi = min(a.G, g_lo + gt_per * SC2_GT);
+    const double qnan = __longlong_as_double(0x7ff8000000000000ll);
+    if (tid == 0) { sm.q1n = 0; sm.q2n = 0; }
+
+    for (long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+        const long long i0 = tile * SC2_TILE;
+        float s[SC2_PPT][SC2_T1], s2[SC2_PPT][SC2_T1];
+        bool live[SC2_PPT], rnan[SC2_PPT];
+        __syncthreads();
+#pragma unroll
+        for (int pp = 0; pp < SC2_PPT; ++pp) {
+            const long long i = i0 + pp * SC2_THREADS + tid;
+            live[pp] = i < a.n;
+            const double* sp = a.stats + (live[pp] ? i : (a.n - 1)) * ABC_NSTATS;
+            bool nn = false;
+            for (int t = SC2_T1; t < ABC_NSTATS; ++t) nn = nn || (sp[t] != sp[t]);
+#pragma unroll
+            for (int t = 0; t < SC2_T1; ++t) {
+                const double v = sp[t];
+                nn = nn || (v != v);
+                s[pp][t] = (float)v;
+                s2[pp][t] = __fmul_rn(s[pp][t], s[pp][t]);
+            }
+            rnan[pp] = nn;
+            sm.rownan[pp * SC2_THREADS + tid] = nn ? 1 : 0;
+        }
+        for (int g0 = g_lo; g0 < g_hi; g0 += SC2_GT) {
+            const int gt = min(SC2_GT, g_hi - g0);
+            __syncthreads();
+            for (int k = tid; k < gt * SC2_T1; k += SC2_THREADS)
+                sm.bw[k / SC2_T1][k % SC2_T1] = fbw[(long long)(g0 + k / SC2_T1) * ABC_NSTATS + (k % SC2_T1)];
+            if (tid < gt) sm.a1[tid] = fa[g0 + tid].x;
+            __syncthreads();
+            for (int gs = 0; gs < gt; gs += SC2_SUB) {
+                if (sm.q1n > SC2_Q1 - SC2_SUB * SC2_TILE) score2_drain(a, sm, fbw, fa, i0, g0);   // block uniform
+                const int ge = min(gt, gs + SC2_SUB);
+                for (int gg = gs; gg < ge; ++gg) {
+                    float p[SC2_PPT];
+#pragma unroll
+                    for (int pp = 0; pp < SC2_PPT; ++pp) p[pp] = sm.a1[gg];
+#pragma unroll
+                    for (int t = 0; t < SC2_T1; ++t) {
+                        const float2 c = sm.bw[gg][t];
+#pragma unroll
+                        for (int pp = 0; pp < SC2_PPT; ++pp) {
+                            p[pp] = __fmaf_rn(-c.x, s[pp][t], p[pp]);
+                            p[pp] = __fmaf_rn(c.y, s2[pp][t], p[pp]);
+                        }
+                    }
+#pragma unroll
+                    for (int pp = 0; pp < SC2_PPT; ++pp) {
+                        const bool sure = rnan[pp] || (p[pp] > SC2_SURE);
+                        const unsigned int bal = __ballot_sync(0xffffffffu, sure);
+                        if (a.err != nullptr) {
+                            if (a.err_layout == ABC_ERR_GENE_MAJOR) {
+                                if (sure && live[pp])
+                                    a.err[(long long)(g0 + gg) * a.n + i0 + pp * SC2_THREADS + tid] = rnan[pp] ? qnan : 10.0;
+                            } else if (lane == 0) {
+                                sm.mask[gg][pp * (SC2_THREADS / 32) + warp] = bal;
+                            }
+                        }
+                        const unsigned int need = __ballot_sync(0xffffffffu, !sure && live[pp]);
+                        if (need != 0u) {
+                            int base = 0;
+                            if (lane == 0) base = atomicAdd(&sm.q1n, __popc(need));
+                            base = __shfl_sync(0xffffffffu, base, 0);
+                            if (!sure && live[pp]) {
+                                const int slot = base + __popc(need & ((1u << lane) - 1u));
+                                sm.q1_id[slot] = ((unsigned int)gg << 16) | (unsigned int)(pp * SC2_THREADS + tid);
+                                sm.q1_p[slot] = p[pp];
+                            }
+                        }
+                    }
+                }
+                __syncthreads();
+            }
+            // particle-major: write the "sure" values of this gene tile as contiguous row segments
+            if (a.err != nullptr && a.err_layout == ABC_ERR_PARTICLE_MAJOR) {
+                for (int r = warp; r < SC2_TILE; r += SC2_THREADS / 32) {
+                    const long long i = i0 + r;
+                    if (i >= a.n) break;
+                    if (lane < gt && ((sm.mask[lane][r >> 5] >> (r & 31)) & 1u))
+                        a.err[i * (long long)a.G + g0 + lane] = sm.rownan[r] ? qnan : 10.0;
+                }
+            }
+            score2_drain(a, sm, fbw, fa, i0, g0);
+        }
+    }
+}
+
 int abc_launch_score(const AbcScoreArgs& a, int sm_count, cudaStream_t st) {
     if (a.n <= 0 || a.G <= 0) return ABC_OK;
+    if (a.fbw != nullptr && a.fa != nullptr && a.eps < 10.0 && !a.force_reference_kernel) {
+        const long long nt = (a.n + SC2_TILE - 1) / SC2_TILE;
+        int per = 0;
+        ABC_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per, abc_score2_kernel, SC2_THREADS, 0));
+        if (per < 1) per = 1;
+        long long gx2 = (long long)sm_count * per;
+        if (gx2 > nt) gx2 = nt;
+        const int ngt = (a.G + SC2_GT - 1) / SC2_GT;
+        long long gy2 = (4ll * sm_count * per + gx2 - 1) / gx2;
+        if (gy2 > ngt) gy2 = ngt;
+        if (gy2 > 65535) gy2 = 65535;
+        if (gy2 < 1) gy2 = 1;
+        abc_score2_kernel<<<dim3((unsigned)gx2, (unsigned)gy2), SC2_THREADS, 0, st>>>(a, a.fbw, a.fa);
+        ABC_CUDA_CHECK(cudaGetLastError());
+        return ABC_OK;
+    }
     long long n_tiles = (a.n + SC_THREADS - 1) / SC_THREADS;
     int per_sm = 0;
     ABC_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, abc_score_kernel, SC_THREADS, 0));

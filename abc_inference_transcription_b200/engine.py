@@ -170,6 +170,9 @@ class AbcEngine:
         _lib.check(self._lib.abc_accept_tuples_dev(self._ctx, ctypes.c_void_p(d_gene_ptr), ctypes.c_void_p(d_particle_ptr),
                                                    ctypes.c_void_p(d_err_ptr), int(capacity), ctypes.c_void_p(stream or 0)))
 
+    def set_option(self, name, value):
+        _lib.check(self._lib.abc_set_option(self._ctx, name.encode(), int(value)))
+
     def counters(self):
         cnt = _lib.AbcCounters()
         _lib.check(self._lib.abc_counters(self._ctx, ctypes.byref(cnt)))

@@ -160,6 +160,9 @@ int  abc_score_dev(abc_ctx_t* ctx, const double* d_stats, int64_t n, int64_t par
 int  abc_counts_dev(abc_ctx_t* ctx, int64_t* d_counts, void* stream);
 int  abc_accept_tuples_dev(abc_ctx_t* ctx, int32_t* d_gene, int64_t* d_particle, double* d_err, int64_t capacity,
                            void* stream);
+/* tuning / diagnostics switches.  "score_reference_kernel" = 1: score with the plain FP64 kernel (every pair
+ * evaluated in full) instead of the three-stage kernel; results are bit-identical either way. */
+int  abc_set_option(abc_ctx_t* ctx, const char* name, int64_t value);
 /* device counters of the last *_dev launches (synchronises the stream) */
 int  abc_counters(abc_ctx_t* ctx, abc_counters_t* counters);
 /* how many kernels this library has launched on the context since creation */

@@ -159,6 +159,56 @@ def test_accept_lists_match_reference_order(eng, data_stats):
     assert np.array_equal(o2, offsets) and np.array_equal(i2, idx)
 
 
+def test_score_kernels_agree_and_eps_above_clip(eng, data_stats):
+    """three-stage kernel == plain FP64 kernel == oracle; eps >= 10 (accepts the clipped pairs) takes the plain path"""
+    d, se = data_stats
+    rng = np.random.default_rng(8)
+    s = synth_stats(rng, d, 600)
+    s[5, 3] = np.nan
+    ref = oracle.compute_trunc_errors(s, d, se)
+    got = {}
+    for flag in (0, 1):
+        eng.set_option("score_reference_kernel", flag)
+        eng.accept_reset()
+        err, counts, _ = eng.score(s, eps=4.8, err_layout=ERR_GENE_MAJOR)
+        off, idx, errs = eng.accept_fetch()
+        got[flag] = (err, counts, off, idx)
+        assert oracle.same_bits(err, ref.T)
+    eng.set_option("score_reference_kernel", 0)
+    assert all(np.array_equal(a, b) for a, b in zip(got[0][1:], got[1][1:]))
+    eng.accept_reset()
+    err, counts, _ = eng.score(s[:40], eps=10.0, err_layout=ERR_PARTICLE_MAJOR)
+    assert oracle.same_bits(err, ref[:40])
+    assert np.array_equal(counts, (ref[:40] <= 10.0).sum(0)) and counts.sum() > 40 * 3000
+    off, idx, _ = eng.accept_fetch()
+    for g in (0, 1711, 3418):
+        assert np.array_equal(idx[off[g]:off[g + 1]], oracle.accept_gene(ref[:40, g], 10.0))
+
+
+def test_score_near_matches_fill_the_queues(eng, data_stats):
+    """every particle close to the data of every gene of a small gene set: nothing is 'surely > 10', so all
+    pairs travel through both queues (queue drains mid-tile are exercised)"""
+    d, se = data_stats
+    rng = np.random.default_rng(9)
+    sub = slice(100, 164)
+    eng.set_data(np.tile(d[100:101], (64, 1)) * np.exp(rng.normal(0, 0.01, (64, 53))), np.tile(se[100:101], (64, 1)))
+    try:
+        dd = np.tile(d[100:101], (64, 1)) * np.exp(np.random.default_rng(9).normal(0, 0.01, (64, 53)))
+        ss = np.tile(se[100:101], (64, 1))
+        s = d[100] * np.exp(rng.normal(0, 0.05, (1000, 53)))
+        ref = oracle.compute_trunc_errors(s, dd, ss)
+        assert (ref < 10.0).mean() > 0.9
+        eng.accept_reset()
+        err, counts, _ = eng.score(s, eps=4.8, err_layout=ERR_PARTICLE_MAJOR)
+        assert oracle.same_bits(err, ref)
+        assert np.array_equal(counts, (ref <= 4.8).sum(0))
+        off, idx, _ = eng.accept_fetch()
+        for g in range(0, 64, 7):
+            assert np.array_equal(idx[off[g]:off[g + 1]], oracle.accept_gene(ref[:, g], 4.8))
+    finally:
+        eng.set_data(d, se)
+
+
 def test_score_empty_and_small(eng, data_stats):
     d, se = data_stats
     eng.accept_reset()
