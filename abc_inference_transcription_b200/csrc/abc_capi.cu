@@ -77,6 +77,8 @@ struct abc_ctx {
     int32_t G = 0;
     DevBuf<double> d_d, d_den;
     DevBuf<float2> d_fbw, d_fa;
+    DevBuf<float> d_fstats;
+    DevBuf<unsigned char> d_rnan;
     int force_reference_score = 0;
     // simulate work buffers
     DevBuf<double> d_theta, d_stats, d_moments, d_ss_iv;
@@ -138,7 +140,7 @@ extern "C" int abc_destroy(abc_ctx_t* c) {
     if (!c) return ABC_OK;
     cudaSetDevice(c->device);
     cudaStreamSynchronize(c->stream);
-    c->d_beta.release(); c->d_age_dist.release(); c->d_beta_mom.release(); c->d_d.release(); c->d_den.release(); c->d_fbw.release(); c->d_fa.release();
+    c->d_beta.release(); c->d_age_dist.release(); c->d_beta_mom.release(); c->d_d.release(); c->d_den.release(); c->d_fbw.release(); c->d_fa.release(); c->d_fstats.release(); c->d_rnan.release();
     c->d_theta.release(); c->d_stats.release(); c->d_moments.release(); c->d_ss_iv.release(); c->d_rates.release();
     c->d_keys_in.release(); c->d_keys_out.release(); c->d_idx_in.release(); c->d_order.release(); c->d_sort_tmp.release();
     c->d_sums.release(); c->d_counters.release(); c->d_work.release(); c->d_cells.release();
@@ -524,7 +526,15 @@ static int score_device(abc_ctx* c, const double* d_stats, int64_t n, int64_t of
     a.err_layout = layout; a.err = (layout == ABC_ERR_NONE) ? nullptr : d_err;
     a.counts = c->d_counts.p; a.acc_count = c->d_acc_count.p; a.acc_capacity = c->acc_capacity;
     a.acc_gene = c->d_acc_gene.p; a.acc_particle = c->d_acc_particle.p; a.acc_err = c->d_acc_err.p;
+    a.fstats = nullptr; a.rnan = nullptr;
     ABC_CUDA_CHECK(cudaEventRecord(c->ev[3], st));
+    if (!c->force_reference_score && eps < 10.0) {
+        if ((rc = c->d_fstats.ensure((size_t)n * ABC_NSTATS)) != ABC_OK) return rc;
+        if ((rc = c->d_rnan.ensure((size_t)n)) != ABC_OK) return rc;
+        if ((rc = abc_launch_score_prep(d_stats, n, c->d_fstats.p, c->d_rnan.p, st)) != ABC_OK) return rc;
+        c->launches++;
+        a.fstats = c->d_fstats.p; a.rnan = c->d_rnan.p;
+    }
     rc = abc_launch_score(a, c->sm_count, st);
     c->launches++;
     ABC_CUDA_CHECK(cudaEventRecord(c->ev[4], st));
@@ -652,7 +662,7 @@ extern "C" int abc_simulate_dev(abc_ctx_t* c, int m, int64_t n, int64_t offset, 
     int rc = check_model(m);
     if (rc != ABC_OK) return rc;
     if (n <= 0 || !d_theta || !d_stats) { abc_set_error("abc_simulate_dev: bad arguments"); return ABC_ERR_ARG; }
-    cudaStream_t st = stream ? (cudaStream_t)stream : c->stream;
+    cudaStream_t st = (cudaStream_t)stream;   // NULL = the legacy default stream (torch's default stream)
     return simulate_device(c, m, n, offset, seed, prior_supplied, d_theta, d_stats, nullptr, st);
 }
 
@@ -660,14 +670,14 @@ extern "C" int abc_score_dev(abc_ctx_t* c, const double* d_stats, int64_t n, int
                              double* d_err, void* stream) {
     CTX_GUARD(c);
     if (n <= 0 || !d_stats || (layout != ABC_ERR_NONE && !d_err)) { abc_set_error("abc_score_dev: bad arguments"); return ABC_ERR_ARG; }
-    cudaStream_t st = stream ? (cudaStream_t)stream : c->stream;
+    cudaStream_t st = (cudaStream_t)stream;   // NULL = the legacy default stream (torch's default stream)
     return score_device(c, d_stats, n, offset, eps, layout, d_err, st);
 }
 
 extern "C" int abc_counts_dev(abc_ctx_t* c, int64_t* d_counts, void* stream) {
     CTX_GUARD(c);
     if (!c->has_data || !d_counts) { abc_set_error("abc_counts_dev: bad state/arguments"); return ABC_ERR_ARG; }
-    cudaStream_t st = stream ? (cudaStream_t)stream : c->stream;
+    cudaStream_t st = (cudaStream_t)stream;   // NULL = the legacy default stream (torch's default stream)
     ABC_CUDA_CHECK(cudaMemcpyAsync(d_counts, c->d_counts.p, (size_t)c->G * sizeof(int64_t), cudaMemcpyDeviceToDevice, st));
     return ABC_OK;
 }
@@ -676,7 +686,7 @@ extern "C" int abc_accept_tuples_dev(abc_ctx_t* c, int32_t* d_gene, int64_t* d_p
                                      int64_t capacity, void* stream) {
     CTX_GUARD(c);
     if (!d_gene || !d_particle || !d_err || capacity < 0) { abc_set_error("abc_accept_tuples_dev: bad arguments"); return ABC_ERR_ARG; }
-    cudaStream_t st = stream ? (cudaStream_t)stream : c->stream;
+    cudaStream_t st = (cudaStream_t)stream;   // NULL = the legacy default stream (torch's default stream)
     ABC_CUDA_CHECK(cudaStreamSynchronize(st));
     unsigned long long total = 0;
     ABC_CUDA_CHECK(cudaMemcpy(&total, c->d_acc_count.p, sizeof(total), cudaMemcpyDeviceToHost));

@@ -61,6 +61,8 @@ struct AbcScoreArgs {
     const double* den;     // [G][53]
     const float2* fbw;     // [G][53] FP32 pre-filter constants (2 w d, w), w = 1/(53 den)
     const float2* fa;      // [G] (sum_{t<15} w d^2, sum_{t>=15} w d^2)
+    const float* fstats;   // [n][53] FP32 copy of stats (abc_launch_score_prep)
+    const unsigned char* rnan;   // [n] 1 if the particle has a NaN statistic
     int32_t force_reference_kernel;   // 1: always use the plain FP64 kernel (abc_score_kernel)
     int64_t n;
     int32_t G;
@@ -74,3 +76,4 @@ struct AbcScoreArgs {
     int32_t* acc_gene; long long* acc_particle; double* acc_err;
 };
 int abc_launch_score(const AbcScoreArgs& a, int sm_count, cudaStream_t st);
+int abc_launch_score_prep(const double* d_stats, int64_t n, float* d_fstats, unsigned char* d_rnan, cudaStream_t st);

@@ -207,33 +207,50 @@ abc_score_kernel(const AbcScoreArgs a) {
 // p32 never satisfies the test and falls through to the exact path; particles with a NaN statistic are
 // answered NaN directly (every gene uses all 53 statistics, compute_errors.jl:58-64).
 #define SC2_THREADS 128
+#define SC2_WARPS (SC2_THREADS / 32)
 #define SC2_PPT 2
 #define SC2_TILE (SC2_THREADS * SC2_PPT)
 #define SC2_GT 32
 #define SC2_SUB 4
-#define SC2_Q1 2048
+#define SC2_Q1W 512                      // stage-1 queue entries per warp (warp private: no atomics)
 #define SC2_Q2 2048
 #define SC2_SURE 10.01f
 
 struct Score2Smem {
     float2 bw[SC2_GT][SC2_T1];
     float a1[SC2_GT];
-    unsigned int q1_id[SC2_Q1];
-    float q1_p[SC2_Q1];
+    unsigned int q1_id[SC2_WARPS][SC2_Q1W];
+    float q1_p[SC2_WARPS][SC2_Q1W];
     unsigned int q2_id[SC2_Q2];
     unsigned int mask[SC2_GT][SC2_TILE / 32 + 1];
-    unsigned char rownan[SC2_TILE];
-    int q1n, q2n;
+    int q1cnt[SC2_WARPS];
+    int q2n;
+    int any_nan;
 };
+
+// particle prologue: FP32 copy of the statistics and a per-particle "has a NaN statistic" flag
+__global__ void abc_score_prep_kernel(const double* __restrict__ stats, long long n, float* __restrict__ fstats,
+                                      unsigned char* __restrict__ rnan) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    bool nn = false;
+    for (int t = 0; t < ABC_NSTATS; ++t) {
+        const double v = stats[i * ABC_NSTATS + t];
+        nn = nn || (v != v);
+        fstats[i * ABC_NSTATS + t] = (float)v;
+    }
+    rnan[i] = nn ? 1 : 0;
+}
 
 __device__ __forceinline__ double exact_pair_error(const double* __restrict__ sp, const double* __restrict__ gd,
                                                    const double* __restrict__ gden) {
     // compute_errors.jl:30-43, 55-64: the reference's operation order, explicit rounding
     const int off[8] = {0, 5, 10, 15, 20, 31, 42, 53};
     double err = 0.0;
-#pragma unroll
+#pragma unroll 1
     for (int l = 0; l < 7; ++l) {
         double e = 0.0;
+#pragma unroll 1
         for (int t = off[l]; t < off[l + 1]; ++t) {
             const double diff = __dadd_rn(gd[t], -sp[t]);
             e = __dadd_rn(e, __ddiv_rn(__dmul_rn(diff, diff), gden[t]));
@@ -249,86 +266,114 @@ __device__ __forceinline__ void score2_store(const AbcScoreArgs& a, long long i,
     else a.err[i * (long long)a.G + g] = v;
 }
 
-__device__ void score2_drain(const AbcScoreArgs& a, Score2Smem& sm, const float2* __restrict__ fbw,
-                             const float2* __restrict__ fa, long long i0, int g0) {
-    __syncthreads();
-    const int n1 = sm.q1n;
-    // stage 2: FP32 lower bound over the remaining 38 terms, one queued pair per thread
-    for (int e = threadIdx.x; e < n1; e += SC2_THREADS) {
-        const unsigned int id = sm.q1_id[e];
-        const int g = g0 + (int)(id >> 16);
-        const long long i = i0 + (long long)(id & 0xffffu);
-        const double* sp = a.stats + i * ABC_NSTATS;
-        const float2* bw = fbw + (long long)g * ABC_NSTATS;
-        float p = sm.q1_p[e] + fa[g].y;
-#pragma unroll 2
-        for (int t = SC2_T1; t < ABC_NSTATS; ++t) {
-            const float sv = (float)sp[t];
-            const float2 c = bw[t];
-            p = __fmaf_rn(-c.x, sv, p);
-            p = __fmaf_rn(c.y, __fmul_rn(sv, sv), p);
+// stage 3 on one q2 entry: exact FP64; fused eps-acceptance
+__device__ __forceinline__ void score2_exact_round(const AbcScoreArgs& a, Score2Smem& sm, long long i0, int e) {
+    const unsigned int id = sm.q2_id[e];
+    const int g = (int)(id >> 16);
+    const long long i = i0 + (long long)(id & 0xffffu);
+    const double err = exact_pair_error(a.stats + i * ABC_NSTATS, a.d + (long long)g * ABC_NSTATS,
+                                        a.den + (long long)g * ABC_NSTATS);
+    score2_store(a, i, g, err);
+    if (err <= a.eps) {
+        const unsigned long long slot = atomicAdd(a.acc_count, 1ull);
+        atomicAdd(a.counts + g, 1ull);
+        if ((long long)slot < a.acc_capacity) {
+            a.acc_gene[slot] = g;
+            a.acc_particle[slot] = a.particle_offset + i + 1;
+            a.acc_err[slot] = err;
         }
-        if (p > SC2_SURE) score2_store(a, i, g, 10.0);
-        else sm.q2_id[atomicAdd(&sm.q2n, 1)] = id;
     }
+}
+
+// drain q2: full rounds of SC2_THREADS entries; the remainder stays queued unless `final`
+__device__ void score2_drain_q2(const AbcScoreArgs& a, Score2Smem& sm, long long i0, bool final) {
     __syncthreads();
     const int n2 = sm.q2n;
-    // stage 3: exact FP64, one surviving pair per thread; fused eps-acceptance
-    for (int e = threadIdx.x; e < n2; e += SC2_THREADS) {
-        const unsigned int id = sm.q2_id[e];
-        const int g = g0 + (int)(id >> 16);
-        const long long i = i0 + (long long)(id & 0xffffu);
-        const double err = exact_pair_error(a.stats + i * ABC_NSTATS, a.d + (long long)g * ABC_NSTATS,
-                                            a.den + (long long)g * ABC_NSTATS);
-        score2_store(a, i, g, err);
-        if (err <= a.eps) {
-            const unsigned long long slot = atomicAdd(a.acc_count, 1ull);
-            atomicAdd(a.counts + g, 1ull);
-            if ((long long)slot < a.acc_capacity) {
-                a.acc_gene[slot] = g;
-                a.acc_particle[slot] = a.particle_offset + i + 1;
-                a.acc_err[slot] = err;
-            }
-        }
-    }
+    const int full = final ? n2 : (n2 / SC2_THREADS) * SC2_THREADS;
+    for (int e = threadIdx.x; e < full; e += SC2_THREADS) score2_exact_round(a, sm, i0, e);
     __syncthreads();
-    if (threadIdx.x == 0) { sm.q1n = 0; sm.q2n = 0; }
+    const int rem = n2 - full;
+    unsigned int keep = 0;
+    if ((int)threadIdx.x < rem) keep = sm.q2_id[full + threadIdx.x];
+    __syncthreads();
+    if ((int)threadIdx.x < rem) sm.q2_id[threadIdx.x] = keep;
+    if (threadIdx.x == 0) sm.q2n = rem;
     __syncthreads();
 }
 
-__global__ void __launch_bounds__(SC2_THREADS)
+// drain the warp-private stage-1 queues: stage 2 = FP32 lower bound over the remaining 38 terms, one queued
+// pair per thread.  Callers have published their fill counts in sm.q1cnt and reset their registers.
+__device__ void score2_drain_q1(const AbcScoreArgs& a, Score2Smem& sm, const float2* __restrict__ fbw,
+                                const float2* __restrict__ fa, long long i0, bool final) {
+    __syncthreads();
+    int c0 = sm.q1cnt[0], c1 = c0 + sm.q1cnt[1], c2 = c1 + sm.q1cnt[2], total = c2 + sm.q1cnt[3];
+    for (int base = 0; base < total; base += SC2_THREADS) {
+        if (sm.q2n > SC2_Q2 - SC2_THREADS) score2_drain_q2(a, sm, i0, false);      // block uniform
+        const int e = base + threadIdx.x;
+        if (e < total) {
+            const int w = (e >= c2) ? 3 : (e >= c1) ? 2 : (e >= c0) ? 1 : 0;
+            const int k = e - ((w == 3) ? c2 : (w == 2) ? c1 : (w == 1) ? c0 : 0);
+            const unsigned int id = sm.q1_id[w][k];
+            const int g = (int)(id >> 16);
+            const long long i = i0 + (long long)(id & 0xffffu);
+            const float* sp = a.fstats + i * ABC_NSTATS + SC2_T1;
+            const float2* bw = fbw + (long long)g * ABC_NSTATS + SC2_T1;
+            float p = sm.q1_p[w][k] + fa[g].y;
+#pragma unroll
+            for (int t = 0; t < ABC_NSTATS - SC2_T1; ++t) {
+                const float sv = sp[t];
+                const float2 c = bw[t];
+                p = __fmaf_rn(-c.x, sv, p);
+                p = __fmaf_rn(c.y, __fmul_rn(sv, sv), p);
+            }
+            if (p > SC2_SURE) score2_store(a, i, g, 10.0);
+            else sm.q2_id[atomicAdd(&sm.q2n, 1)] = id;
+        }
+        __syncthreads();
+    }
+    if (threadIdx.x < SC2_WARPS) sm.q1cnt[threadIdx.x] = 0;
+    __syncthreads();
+    if (final) score2_drain_q2(a, sm, i0, true);
+}
+
+__global__ void __launch_bounds__(SC2_THREADS, 4)
 abc_score2_kernel(const AbcScoreArgs a, const float2* __restrict__ fbw, const float2* __restrict__ fa) {
     __shared__ Score2Smem sm;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const unsigned int lt_mask = (1u << lane) - 1u;
     const long long n_tiles = (a.n + SC2_TILE - 1) / SC2_TILE;
     const int n_gtiles = (a.G + SC2_GT - 1) / SC2_GT;
     const int gt_per = (n_gtiles + gridDim.y - 1) / gridDim.y;
     const int g_lo = min(a.G, (int)blockIdx.y * gt_per * SC2_GT);
     const int g_hi = min(a.G, g_lo + gt_per * SC2_GT);
     const double qnan = __longlong_as_double(0x7ff8000000000000ll);
-    if (tid == 0) { sm.q1n = 0; sm.q2n = 0; }
+    const bool pmajor = (a.err != nullptr) && (a.err_layout == ABC_ERR_PARTICLE_MAJOR);
+    const bool gmajor = (a.err != nullptr) && (a.err_layout == ABC_ERR_GENE_MAJOR);
+    if (tid < SC2_WARPS) sm.q1cnt[tid] = 0;
+    if (tid == 0) { sm.q2n = 0; sm.any_nan = 0; }
+    int q1w = 0;                                      // fill of this warp's queue (warp uniform)
 
     for (long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
         const long long i0 = tile * SC2_TILE;
+        const int rows = (int)min((long long)SC2_TILE, a.n - i0);
         float s[SC2_PPT][SC2_T1], s2[SC2_PPT][SC2_T1];
-        bool live[SC2_PPT], rnan[SC2_PPT];
+        bool rnan[SC2_PPT];
+        unsigned int live_bal[SC2_PPT], nan_bal[SC2_PPT];
+        __syncthreads();
+        if (tid == 0) sm.any_nan = 0;
         __syncthreads();
 #pragma unroll
         for (int pp = 0; pp < SC2_PPT; ++pp) {
             const long long i = i0 + pp * SC2_THREADS + tid;
-            live[pp] = i < a.n;
-            const double* sp = a.stats + (live[pp] ? i : (a.n - 1)) * ABC_NSTATS;
-            bool nn = false;
-            for (int t = SC2_T1; t < ABC_NSTATS; ++t) nn = nn || (sp[t] != sp[t]);
+            const bool live = i < a.n;
+            const long long ii = live ? i : (a.n - 1);
+            const float* sp = a.fstats + ii * ABC_NSTATS;
 #pragma unroll
-            for (int t = 0; t < SC2_T1; ++t) {
-                const double v = sp[t];
-                nn = nn || (v != v);
-                s[pp][t] = (float)v;
-                s2[pp][t] = __fmul_rn(s[pp][t], s[pp][t]);
-            }
-            rnan[pp] = nn;
-            sm.rownan[pp * SC2_THREADS + tid] = nn ? 1 : 0;
+            for (int t = 0; t < SC2_T1; ++t) { s[pp][t] = sp[t]; s2[pp][t] = __fmul_rn(s[pp][t], s[pp][t]); }
+            rnan[pp] = a.rnan[ii] != 0;
+            live_bal[pp] = __ballot_sync(0xffffffffu, live);
+            nan_bal[pp] = __ballot_sync(0xffffffffu, rnan[pp] && live);
+            if (nan_bal[pp] != 0u && lane == 0) sm.any_nan = 1;
         }
         for (int g0 = g_lo; g0 < g_hi; g0 += SC2_GT) {
             const int gt = min(SC2_GT, g_hi - g0);
@@ -338,7 +383,6 @@ abc_score2_kernel(const AbcScoreArgs a, const float2* __restrict__ fbw, const fl
             if (tid < gt) sm.a1[tid] = fa[g0 + tid].x;
             __syncthreads();
             for (int gs = 0; gs < gt; gs += SC2_SUB) {
-                if (sm.q1n > SC2_Q1 - SC2_SUB * SC2_TILE) score2_drain(a, sm, fbw, fa, i0, g0);   // block uniform
                 const int ge = min(gt, gs + SC2_SUB);
                 for (int gg = gs; gg < ge; ++gg) {
                     float p[SC2_PPT];
@@ -357,46 +401,66 @@ abc_score2_kernel(const AbcScoreArgs a, const float2* __restrict__ fbw, const fl
                     for (int pp = 0; pp < SC2_PPT; ++pp) {
                         const bool sure = rnan[pp] || (p[pp] > SC2_SURE);
                         const unsigned int bal = __ballot_sync(0xffffffffu, sure);
-                        if (a.err != nullptr) {
-                            if (a.err_layout == ABC_ERR_GENE_MAJOR) {
-                                if (sure && live[pp])
-                                    a.err[(long long)(g0 + gg) * a.n + i0 + pp * SC2_THREADS + tid] = rnan[pp] ? qnan : 10.0;
-                            } else if (lane == 0) {
-                                sm.mask[gg][pp * (SC2_THREADS / 32) + warp] = bal;
-                            }
+                        if (gmajor) {
+                            if (sure && ((live_bal[pp] >> lane) & 1u))
+                                a.err[(long long)(g0 + gg) * a.n + i0 + pp * SC2_THREADS + tid] = rnan[pp] ? qnan : 10.0;
+                        } else if (pmajor && lane == 0) {
+                            sm.mask[gg][pp * SC2_WARPS + warp] = bal;
                         }
-                        const unsigned int need = __ballot_sync(0xffffffffu, !sure && live[pp]);
-                        if (need != 0u) {
-                            int base = 0;
-                            if (lane == 0) base = atomicAdd(&sm.q1n, __popc(need));
-                            base = __shfl_sync(0xffffffffu, base, 0);
-                            if (!sure && live[pp]) {
-                                const int slot = base + __popc(need & ((1u << lane) - 1u));
-                                sm.q1_id[slot] = ((unsigned int)gg << 16) | (unsigned int)(pp * SC2_THREADS + tid);
-                                sm.q1_p[slot] = p[pp];
-                            }
+                        const unsigned int need = ~bal & live_bal[pp];
+                        if (!sure && ((need >> lane) & 1u)) {
+                            const int slot = q1w + __popc(need & lt_mask);
+                            sm.q1_id[warp][slot] = ((unsigned int)(g0 + gg) << 16) | (unsigned int)(pp * SC2_THREADS + tid);
+                            sm.q1_p[warp][slot] = p[pp];
                         }
+                        q1w += __popc(need);
                     }
                 }
-                __syncthreads();
-            }
-            // particle-major: write the "sure" values of this gene tile as contiguous row segments
-            if (a.err != nullptr && a.err_layout == ABC_ERR_PARTICLE_MAJOR) {
-                for (int r = warp; r < SC2_TILE; r += SC2_THREADS / 32) {
-                    const long long i = i0 + r;
-                    if (i >= a.n) break;
-                    if (lane < gt && ((sm.mask[lane][r >> 5] >> (r & 31)) & 1u))
-                        a.err[i * (long long)a.G + g0 + lane] = sm.rownan[r] ? qnan : 10.0;
+                // a sub-batch adds at most SC2_SUB * SC2_PPT * 32 = 256 entries per warp
+                const bool want_drain = __syncthreads_or(q1w > SC2_Q1W - SC2_SUB * SC2_PPT * 32);
+                if (want_drain) {
+                    if (lane == 0) sm.q1cnt[warp] = q1w;
+                    q1w = 0;
+                    score2_drain_q1(a, sm, fbw, fa, i0, false);
                 }
             }
-            score2_drain(a, sm, fbw, fa, i0, g0);
+            // particle-major: the "surely 10.0" values of this gene tile as contiguous row segments
+            if (pmajor) {
+                __syncthreads();
+                unsigned int mw[SC2_TILE / 32];
+#pragma unroll
+                for (int w = 0; w < SC2_TILE / 32; ++w) mw[w] = (lane < gt) ? sm.mask[lane][w] : 0u;
+                double* rowp = a.err + (i0 + warp) * (long long)a.G + g0 + lane;
+#pragma unroll
+                for (int w = 0; w < SC2_TILE / 32; ++w) {
+#pragma unroll
+                    for (int j = 0; j < 32 / SC2_WARPS; ++j) {
+                        const int b = warp + SC2_WARPS * j, r = 32 * w + b;
+                        if (r < rows && ((mw[w] >> b) & 1u)) rowp[(long long)(32 * w + SC2_WARPS * j) * a.G] = 10.0;
+                    }
+                }
+                if (sm.any_nan) {        // rare: rows of particles with a NaN statistic are NaN, not 10.0
+                    for (int r = warp; r < rows; r += SC2_WARPS)
+                        if (a.rnan[i0 + r] && lane < gt) a.err[(i0 + r) * (long long)a.G + g0 + lane] = qnan;
+                }
+            }
         }
+        if (lane == 0) sm.q1cnt[warp] = q1w;
+        q1w = 0;
+        score2_drain_q1(a, sm, fbw, fa, i0, true);      // end of the particle tile: empty both queues
     }
+}
+
+int abc_launch_score_prep(const double* d_stats, int64_t n, float* d_fstats, unsigned char* d_rnan, cudaStream_t st) {
+    if (n <= 0) return ABC_OK;
+    abc_score_prep_kernel<<<(unsigned)((n + 127) / 128), 128, 0, st>>>(d_stats, (long long)n, d_fstats, d_rnan);
+    ABC_CUDA_CHECK(cudaGetLastError());
+    return ABC_OK;
 }
 
 int abc_launch_score(const AbcScoreArgs& a, int sm_count, cudaStream_t st) {
     if (a.n <= 0 || a.G <= 0) return ABC_OK;
-    if (a.fbw != nullptr && a.fa != nullptr && a.eps < 10.0 && !a.force_reference_kernel) {
+    if (a.fbw != nullptr && a.fa != nullptr && a.fstats != nullptr && a.eps < 10.0 && a.G < 65536 && !a.force_reference_kernel) {
         const long long nt = (a.n + SC2_TILE - 1) / SC2_TILE;
         int per = 0;
         ABC_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per, abc_score2_kernel, SC2_THREADS, 0));

@@ -149,7 +149,7 @@ int  abc_accept_fetch(abc_ctx_t* ctx, int64_t* offsets, int64_t* idx, double* er
 int  abc_accept_tuples(abc_ctx_t* ctx, int32_t* gene, int64_t* particle, double* err);
 
 /* ---- device-resident variants (inputs/outputs are device pointers on the context's device;
- *      stream is a cudaStream_t passed as void*, NULL = default stream; asynchronous) ---------- */
+ *      stream is a cudaStream_t passed as void*, NULL = the legacy default stream; asynchronous) ---------- */
 int  abc_simulate_dev(abc_ctx_t* ctx, int m, int64_t n, int64_t particle_offset, uint64_t seed,
                       int prior_supplied, double* d_theta, double* d_stats, void* stream);
 int  abc_score_dev(abc_ctx_t* ctx, const double* d_stats, int64_t n, int64_t particle_offset, double eps,
