@@ -131,15 +131,25 @@ __device__ __forceinline__ uint32_t binom_q32(uint32_t n, uint32_t B, WordSrc& w
     return acc;
 }
 
+// exact "g ? x : 0" / "g ? b : a" on the FMA pipe (integer multiply-add on the bit patterns; g in {0,1}):
+// the ALU pipe (half rate on sm_100) is the busiest pipe of this kernel, selects would add to it
+__device__ __forceinline__ float gate(int g, float x) { return __uint_as_float((uint32_t)g * __float_as_uint(x)); }
+__device__ __forceinline__ float pick(int g, float a, float b) {
+    return __uint_as_float(__float_as_uint(a) + (uint32_t)g * (__float_as_uint(b) - __float_as_uint(a)));
+}
+
 // one event draw.  returns true if the sub-interval boundary was crossed (no reaction fired).
+// Channel layout on [0, tot): switch at the bottom (u*tot < a_sw), death at the top ((1-u)*tot < a_d, U first),
+// birth in between (labelled iff u*tot - a_sw < lam*a_b).  Both ends of the uniform keep full binary32
+// resolution, and an empty death channel (a_d == 0) or an empty species can never be selected.
 template <bool EXACT>
 __device__ __forceinline__ bool ssa_step(Lineage& s, float& x, const Seg& sg, uint32_t wt, uint32_t wc) {
-    const bool on = (s.g != 0);
-    const float asw = on ? sg.koff : sg.kon;
+    const int g = s.g;
+    const float asw = pick(g, sg.kon, sg.koff);
     const float n = f_add(s.U, s.L);
     const float ad = f_mul(sg.gam, n);
-    const float ab = on ? f_fma(sg.A1, x, sg.A0) : 0.0f;
-    const float c1 = on ? sg.A1 : 0.0f;
+    const float ab = gate(g, f_fma(sg.A1, x, sg.A0));
+    const float c1 = gate(g, sg.A1);
     const float base = f_add(asw, ad);
     const float c0 = f_add(base, ab);
     const float E = exp_variate<EXACT>(wt);
@@ -147,21 +157,20 @@ __device__ __forceinline__ bool ssa_step(Lineage& s, float& x, const Seg& sg, ui
     const float xn = f_add(x, tau);
     if (!(xn < sg.len)) return true;
     x = xn;
-    const float abn = on ? f_fma(sg.A1, xn, sg.A0) : 0.0f;
-    const float tot = f_add(base, abn);
-    const float rs = f_mul(f_mul((float)wc, 2.3283064365386963e-10f), tot);
-    const float rb = f_mul(f_mul((float)(~wc), 2.3283064365386963e-10f), tot);
+    const float abn = gate(g, f_fma(sg.A1, xn, sg.A0));
+    const float t32 = f_mul(f_add(base, abn), 2.3283064365386963e-10f);
+    const float rs = f_mul((float)wc, t32);
+    const float rb = f_mul((float)(~wc), t32);
     const bool sw = rs < asw;
-    const bool birth = !sw && ((rb < abn) || (n == 0.0f));
-    const bool death = !sw && !birth;
-    const bool lab = birth && (rb < f_mul(sg.lamf, abn));
-    const float rd = f_add(rs, -asw);
-    const bool dU = (rd < f_mul(sg.gam, s.U)) || (s.L == 0.0f);
-    s.g ^= (int)sw;
-    const float dUv = (birth && !lab) ? 1.0f : ((death && dU) ? -1.0f : 0.0f);
-    const float dLv = lab ? 1.0f : ((death && !dU) ? -1.0f : 0.0f);
-    s.U = f_add(s.U, dUv);
-    s.L = f_add(s.L, dLv);
+    const bool death = !sw && (rb < ad);
+    const bool dU = rb < f_mul(sg.gam, s.U);
+    const bool birth = !sw && !death;
+    const bool lab = birth && (f_add(rs, -asw) < f_mul(sg.lamf, abn));
+    s.g = g ^ (int)sw;
+    if (birth && !lab) s.U = f_add(s.U, 1.0f);
+    if (lab) s.L = f_add(s.L, 1.0f);
+    if (death && dU) s.U = f_add(s.U, -1.0f);
+    if (death && !dU) s.L = f_add(s.L, -1.0f);
     s.n_events += 1u;
     return false;
 }

@@ -177,11 +177,13 @@ static int build_cycle(const rates_t* r, const orc_ssa_design_t* d, int scaling,
 
 typedef struct { uint32_t U, L; int g; uint64_t events; } cell_t;
 
-/* one event draw in sub-interval sg at position *x; returns 1 when the boundary is crossed */
+/* one event draw in sub-interval sg at position *x; returns 1 when the boundary is crossed.
+ * Channel layout on [0, tot): switch at the bottom, death at the top (U first), birth in between
+ * (DESIGN.md 5.3). */
 static int ssa_step(cell_t* s, float* x, const seg_t* sg, uint32_t wt, uint32_t wc, int math_mode) {
     int on = s->g != 0;
     float asw = on ? sg->koff : sg->kon;
-    float n = (float)(s->U + s->L);
+    float n = (float)s->U + (float)s->L;
     float ad = sg->gam * n;
     float ab = on ? fmaf(sg->A1, *x, sg->A0) : 0.0f;
     float c1 = on ? sg->A1 : 0.0f;
@@ -195,15 +197,14 @@ static int ssa_step(cell_t* s, float* x, const seg_t* sg, uint32_t wt, uint32_t 
     if (!(xn < sg->len)) return 1;
     *x = xn;
     float abn = on ? fmaf(sg->A1, xn, sg->A0) : 0.0f;
-    float tot = base + abn;
-    float rs = ((float)wc * 2.3283064365386963e-10f) * tot;
-    float rb = ((float)(~wc) * 2.3283064365386963e-10f) * tot;
+    float t32 = (base + abn) * 2.3283064365386963e-10f;
+    float rs = (float)wc * t32;
+    float rb = (float)(~wc) * t32;
     int sw = rs < asw;
-    int birth = !sw && ((rb < abn) || (n == 0.0f));
-    int death = !sw && !birth;
-    int lab = birth && (rb < sg->lamf * abn);
-    float rd = rs + -asw;
-    int dU = ((rd < sg->gam * (float)s->U) || (s->L == 0u)) && (s->U > 0u);
+    int death = !sw && (rb < ad);
+    int dU = rb < sg->gam * (float)s->U;
+    int birth = !sw && !death;
+    int lab = birth && ((rs + -asw) < sg->lamf * abn);
     if (sw) s->g ^= 1;
     if (birth && !lab) s->U += 1u;
     if (lab) s->L += 1u;

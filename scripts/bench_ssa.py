@@ -1,0 +1,32 @@
+"""SSA-kernel micro-benchmark: one simulate_dev launch per model on a resident batch, events/s from the in-kernel
+counters and the library's CUDA-event timing.  Usage: python scripts/bench_ssa.py [n_particles] [models e.g. 12345] [n_cells] [n_pre]"""
+import os
+import sys
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+from abc_inference_transcription_b200 import AbcEngine, n_params, synthetic_design  # noqa: E402
+
+n = int(sys.argv[1]) if len(sys.argv) > 1 else 2048
+models = [int(c) for c in (sys.argv[2] if len(sys.argv) > 2 else "12345")]
+n_cells = int(sys.argv[3]) if len(sys.argv) > 3 else 96
+n_pre = int(sys.argv[4]) if len(sys.argv) > 4 else 10
+betas = np.load(os.path.join(ROOT, "tests", "golden", "ref_betas.npy"))
+eng = AbcEngine(0)
+eng.set_design(synthetic_design(betas, n_cells=n_cells, n_pre_cycles=n_pre))
+dev = torch.device("cuda", 0)
+st = torch.empty((n, 53), dtype=torch.float64, device=dev)
+tot_ev = tot_ms = 0.0
+for rep in range(2):
+    for m in models:
+        th = torch.empty((n, n_params(m)), dtype=torch.float64, device=dev)
+        eng.simulate_dev(m, n, th.data_ptr(), st.data_ptr(), particle_offset=rep * n, seed=20240229)
+        c = eng.counters()
+        if rep == 1:
+            tot_ev += c["n_events"]; tot_ms += c["ms_simulate"]
+            print(f"m={m} n={n}: {c['ms_simulate']:.1f} ms  {c['n_events']/c['ms_simulate']/1e6:.1f} Gev/s  "
+                  f"{n/c['ms_simulate']*1e3:.0f} particles/s  events/particle {c['n_events']/n:.3g}")
+print(f"total: {tot_ev/tot_ms/1e6:.1f} Gev/s  roofline frac (64 instr/event nominal) {tot_ev/tot_ms*1e3*64/37.225e12:.3f}")
