@@ -80,6 +80,7 @@ struct abc_ctx {
     DevBuf<float> d_fstats;
     DevBuf<unsigned char> d_rnan;
     int force_reference_score = 0;
+    int ssa_hybrid = 1;          // exact telegraph/Poisson burn-in before the label window
     // simulate work buffers
     DevBuf<double> d_theta, d_stats, d_moments, d_ss_iv;
     DevBuf<AbcRates> d_rates;
@@ -291,6 +292,7 @@ static AbcSsaParams make_ssa_params(const abc_ctx* c, int m, int64_t n, int64_t 
     p.n_pre = c->design.n_pre_cycles;
     p.downsampling = c->design.downsampling;
     p.single_readout = -1;
+    p.hybrid = c->ssa_hybrid;
     p.cycle = c->design.cycle;
     for (int a = 0; a < 5; ++a) p.agevec[a] = c->design.agevec[a];
     for (int j = 0; j < 11; ++j) { p.pulse[j] = c->design.pulse[j]; p.chase[j] = c->design.chase[j]; p.beta_off[j] = c->beta_off[j]; }
@@ -704,6 +706,7 @@ extern "C" int abc_set_option(abc_ctx_t* c, const char* name, int64_t value) {
     CTX_GUARD(c);
     if (!name) { abc_set_error("abc_set_option: name is NULL"); return ABC_ERR_ARG; }
     if (strcmp(name, "score_reference_kernel") == 0) { c->force_reference_score = value ? 1 : 0; return ABC_OK; }
+    if (strcmp(name, "ssa_hybrid_burnin") == 0) { c->ssa_hybrid = value ? 1 : 0; return ABC_OK; }
     abc_set_error("abc_set_option: unknown option '%s'", name);
     return ABC_ERR_ARG;
 }

@@ -25,6 +25,7 @@ struct AbcSsaParams {
     int32_t  n_pre;            // complete cycles before the read-out cycle
     int32_t  downsampling;
     int32_t  single_readout;   // >= 0: debug mode, simulate only this read-out of particle 0
+    int32_t  hybrid;           // 1: exact telegraph + Poisson burn-in before the label window (fast-math kernel only)
     double   cycle;
     double   agevec[5];
     double   pulse[11];

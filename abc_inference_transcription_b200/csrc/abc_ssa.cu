@@ -83,6 +83,7 @@ struct Seg {
 struct WarpTable {
     Seg seg[SSA_MAX_CYCLES][SSA_SEG_PER_CYCLE];
     int n_ent[SSA_MAX_CYCLES];
+    int c_star, e_star;     // cycle / entry at which the label window opens (hybrid burn-in hands over here)
 };
 
 struct Lineage {
@@ -175,6 +176,88 @@ __device__ __forceinline__ bool ssa_step(Lineage& s, float& x, const Seg& sg, ui
     return false;
 }
 
+
+// ------------------------------------------------------------------------------------------------
+// Hybrid burn-in (exact).  Before the label window opens the only species are g and U, and the gene switches
+// autonomously (kon, koff do not depend on the mRNA counts).  Conditional on the gene path, transcripts are
+// born as an inhomogeneous Poisson process of rate alpha(t) g(t) and survive independently (death hazard
+// gamma(t), probability 1/2 at every division), so the number alive at time t* is Poisson(Lam) with
+//     Lam(t*) = int alpha(s) g(s) exp(-int_s^t* gamma) 2^-(divisions in (s,t*]) ds .
+// Phase A simulates only the telegraph process with Gillespie's method and integrates Lam in closed form on
+// every constant-g stretch (alpha is linear in time there); at t* it draws U ~ Poisson(Lam), L = 0, and the
+// full direct-method SSA of all six channels takes over.  The law of (g, U) at t* is exactly the one the
+// full SSA would have produced from the same start (U = 0 at the first simulated cycle).
+__device__ __forceinline__ float exp_neg(float z) {      // e^-z, z >= 0
+    float r;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(f_mul(z, -1.4426950408889634f)));
+    return r;
+}
+
+// Lam <- Lam e^{-gam d} + g * int_0^d (a + A1 w) e^{-gam (d - w)} dw
+__device__ __forceinline__ float lam_advance(float lam, int g, float a, float A1, float gam, float d) {
+    const float z = f_mul(gam, d);
+    const float ez = exp_neg(z);
+    // phi1 = (1 - e^-z)/z, psi = (z - 1 + e^-z)/z^2 = (1 - phi1)/z; series below z = 0.25 (cancellation)
+    float p1s = f_fma(z, f_fma(z, f_fma(z, f_fma(z, 1.0f / 120.0f, -1.0f / 24.0f), 1.0f / 6.0f), -0.5f), 1.0f);
+    float pss = f_fma(z, f_fma(z, f_fma(z, f_fma(z, 1.0f / 720.0f, -1.0f / 120.0f), 1.0f / 24.0f), -1.0f / 6.0f), 0.5f);
+    float rz;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(rz) : "f"(z));
+    const float p1d = f_mul(f_add(1.0f, -ez), rz);
+    const float psd = f_mul(f_add(1.0f, -p1d), rz);
+    const bool small = z < 0.25f;
+    const float phi1 = small ? p1s : p1d, psi = small ? pss : psd;
+    const float inc = f_mul(d, f_fma(f_mul(A1, d), psi, f_mul(a, phi1)));
+    return f_fma(lam, ez, gate(g, inc));
+}
+
+// one telegraph draw in sub-interval sg at position x; returns true when the boundary is crossed
+__device__ __forceinline__ bool telegraph_step(Lineage& s, float& x, float& lam, const Seg& sg, uint32_t w) {
+    const int g = s.g;
+    const float asw = pick(g, sg.kon, sg.koff);
+    const float E = exp_variate<false>(w);
+    float q;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(q) : "f"(asw));
+    const float xn = f_fma(E, q, x);
+    const bool crossed = !(xn < sg.len);
+    const float x1 = crossed ? sg.len : xn;
+    lam = lam_advance(lam, g, f_fma(sg.A1, x, sg.A0), sg.A1, sg.gam, f_add(x1, -x));
+    if (crossed) return true;
+    x = xn;
+    s.g = g ^ 1;
+    s.n_events += 1u;
+    return false;
+}
+
+// Poisson(lam): inversion by sequential search below 12, Hoermann's PTRS (1993) above; the rarely taken
+// exact acceptance test runs in FP64.
+__device__ __noinline__ float poisson_draw(float lam, WordSrc& ws, Lineage& s) {
+    if (!(lam > 0.0f)) return 0.0f;
+    if (lam < 12.0f) {
+        const double u = ((double)next_word(ws, s) + 0.5) * 2.3283064365386963e-10;
+        double p = exp(-(double)lam), c = p;
+        int k = 0;
+        while (u > c && k < 200) { k += 1; p *= (double)lam / (double)k; c += p; }
+        return (float)k;
+    }
+    const float slam = sqrtf(lam);
+    const float b = 0.931f + 2.53f * slam;
+    const float a = -0.059f + 0.02483f * b;
+    const float inv_alpha = 1.1239f + 1.1328f / (b - 3.4f);
+    const float vr = 0.9277f - 3.6224f / (b - 2.0f);
+    for (int it = 0; it < 64; ++it) {
+        const float U = f_fma((float)next_word(ws, s), 2.3283064365386963e-10f, -0.5f);
+        const float V = f_fma((float)next_word(ws, s), 2.3283064365386963e-10f, 1.1641532182693481e-10f);
+        const float us = 0.5f - fabsf(U);
+        const float k = floorf((2.0f * a / us + b) * U + lam + 0.43f);
+        if (us >= 0.07f && V <= vr) return k;
+        if (k < 0.0f || (us < 0.013f && V > us)) continue;
+        const double lhs = log((double)V) + log((double)inv_alpha) - log((double)a / ((double)us * (double)us) + (double)b);
+        const double rhs = -(double)lam + (double)k * log((double)lam) - lgamma((double)k + 1.0);
+        if (lhs <= rhs) return k;
+    }
+    return floorf(lam + 0.5f);
+}
+
 __device__ __forceinline__ unsigned long long warp_sum_u64(unsigned long long v) {
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
@@ -213,6 +296,7 @@ __device__ __forceinline__ void build_table(WarpTable& tab, const AbcRates& r, c
             sg.A1 = (float)((double)r.alpha[k] * sc / cycle);
             sg.lamf = lab ? r.lam : 0.0f;
             sg.pad = 0.0f;
+            if (lab && pos == l0) { tab.c_star = c; tab.e_star = n; }
             tab.seg[c][n] = sg;
             n += 1;
             pos = nxt;
@@ -223,8 +307,8 @@ __device__ __forceinline__ void build_table(WarpTable& tab, const AbcRates& r, c
     }
 }
 
-template <bool EXACT>
-__global__ void __launch_bounds__(SSA_WARPS * 32)
+template <bool EXACT, bool HYBRID>
+__global__ void __launch_bounds__(SSA_WARPS * 32, 4)
 abc_ssa_kernel(const AbcRates* __restrict__ rates, const AbcSsaParams prm, const uint32_t* __restrict__ beta_q32,
                unsigned long long* __restrict__ sums, unsigned long long* __restrict__ counters,
                unsigned int* __restrict__ work, uint32_t* __restrict__ cells_out, const int* __restrict__ order) {
@@ -260,7 +344,11 @@ abc_ssa_kernel(const AbcRates* __restrict__ rates, const AbcSsaParams prm, const
         __syncwarp();
         if (lane < 24) ((uint32_t*)&srates[warp])[lane] = ((const uint32_t*)&rates[p])[lane];
         __syncwarp();
+        if (lane == 0) { tab.c_star = -1; tab.e_star = 0; }
+        __syncwarp();
         build_table(tab, srates[warp], prm, cond, age_i, lane);
+        __syncwarp();
+        if (lane == 0 && tab.c_star < 0) { tab.c_star = prm.n_pre; tab.e_star = tab.n_ent[prm.n_pre]; }   // empty window
         __syncwarp();
 
         const int cell = chunk * 32 + lane;
@@ -278,12 +366,38 @@ abc_ssa_kernel(const AbcRates* __restrict__ rates, const AbcSsaParams prm, const
                 uint4 b = next_block(s);
                 s.g = (b.x < srates[warp].pon_thr) ? 1 : 0;
             }
+            const int c_star = HYBRID ? tab.c_star : 0, e_star = HYBRID ? tab.e_star : 0;
+            float lam = 0.0f;                           // Poisson mean of U given the gene path (phase A)
             for (int c = 0; c <= prm.n_pre; ++c) {
                 const int n_ent = tab.n_ent[c];
                 n_cross += (uint32_t)n_ent;
                 int e = 0;
                 float x = 0.0f;
                 Seg sg = tab.seg[c][0];
+                if (HYBRID && c <= c_star) {
+                    // phase A: telegraph process + closed-form Lam, one random word per draw
+                    const int e_end = (c == c_star) ? e_star : n_ent;
+                    while (e < e_end) {
+                        const uint4 b = next_block(s);
+                        const uint32_t w4[4] = {b.x, b.y, b.z, b.w};
+#pragma unroll
+                        for (int j = 0; j < 4; ++j) {
+                            if (e < e_end) {
+                                if (telegraph_step(s, x, lam, sg, w4[j])) {
+                                    e += 1; x = 0.0f;
+                                    if (e < n_ent) sg = tab.seg[c][e];
+                                }
+                            }
+                        }
+                    }
+                    if (c == c_star) {                  // hand over: U ~ Poisson(Lam), L = 0
+                        WordSrc ws; ws.avail = 0;
+                        s.U = poisson_draw(lam, ws, s);
+                    } else {
+                        lam = f_mul(lam, 0.5f);         // division thins a Poisson count to half its mean
+                        continue;
+                    }
+                }
                 while (e < n_ent) {
                     const uint4 b = next_block(s);
                     if (ssa_step<EXACT>(s, x, sg, b.x, b.y)) {
@@ -353,11 +467,14 @@ int abc_launch_ssa(const AbcRates* d_rates, const AbcSsaParams& prm, const uint3
         return ABC_ERR_ARG;
     }
     ABC_CUDA_CHECK(cudaMemsetAsync(d_work, 0, sizeof(unsigned int), st));
+    const bool hybrid = (prm.hybrid != 0) && !exact_math;
     int per_sm = 0;
     if (exact_math) {
-        ABC_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, abc_ssa_kernel<true>, SSA_WARPS * 32, 0));
+        ABC_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, abc_ssa_kernel<true, false>, SSA_WARPS * 32, 0));
+    } else if (hybrid) {
+        ABC_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, abc_ssa_kernel<false, true>, SSA_WARPS * 32, 0));
     } else {
-        ABC_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, abc_ssa_kernel<false>, SSA_WARPS * 32, 0));
+        ABC_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, abc_ssa_kernel<false, false>, SSA_WARPS * 32, 0));
     }
     if (per_sm < 1) per_sm = 1;
     unsigned long long items = (prm.single_readout >= 0) ? (unsigned long long)prm.chunks
@@ -371,9 +488,11 @@ int abc_launch_ssa(const AbcRates* d_rates, const AbcSsaParams& prm, const uint3
     if (grid > want) grid = want;
     if (grid < 1) grid = 1;
     if (exact_math)
-        abc_ssa_kernel<true><<<(unsigned)grid, SSA_WARPS * 32, 0, st>>>(d_rates, prm, d_beta_q32, d_sums, d_counters, d_work, d_cells_out, d_order);
+        abc_ssa_kernel<true, false><<<(unsigned)grid, SSA_WARPS * 32, 0, st>>>(d_rates, prm, d_beta_q32, d_sums, d_counters, d_work, d_cells_out, d_order);
+    else if (hybrid)
+        abc_ssa_kernel<false, true><<<(unsigned)grid, SSA_WARPS * 32, 0, st>>>(d_rates, prm, d_beta_q32, d_sums, d_counters, d_work, d_cells_out, d_order);
     else
-        abc_ssa_kernel<false><<<(unsigned)grid, SSA_WARPS * 32, 0, st>>>(d_rates, prm, d_beta_q32, d_sums, d_counters, d_work, d_cells_out, d_order);
+        abc_ssa_kernel<false, false><<<(unsigned)grid, SSA_WARPS * 32, 0, st>>>(d_rates, prm, d_beta_q32, d_sums, d_counters, d_work, d_cells_out, d_order);
     ABC_CUDA_CHECK(cudaGetLastError());
     return ABC_OK;
 }

@@ -161,7 +161,10 @@ int  abc_counts_dev(abc_ctx_t* ctx, int64_t* d_counts, void* stream);
 int  abc_accept_tuples_dev(abc_ctx_t* ctx, int32_t* d_gene, int64_t* d_particle, double* d_err, int64_t capacity,
                            void* stream);
 /* tuning / diagnostics switches.  "score_reference_kernel" = 1: score with the plain FP64 kernel (every pair
- * evaluated in full) instead of the three-stage kernel; results are bit-identical either way. */
+ * evaluated in full) instead of the three-stage kernel; results are bit-identical either way.
+ * "ssa_hybrid_burnin" = 0: run the full six-channel direct method from the first simulated cycle; 1 (default):
+ * before the label window opens simulate only the gene switch and draw U ~ Poisson(Lam | gene path) at the
+ * window start (exact); the exact_math variant of abc_ssa_cells always uses 0. */
 int  abc_set_option(abc_ctx_t* ctx, const char* name, int64_t value);
 /* device counters of the last *_dev launches (synchronises the stream) */
 int  abc_counters(abc_ctx_t* ctx, abc_counters_t* counters);

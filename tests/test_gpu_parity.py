@@ -289,18 +289,50 @@ def test_ssa_exact_math_is_bit_identical_to_oracle(eng, betas, m, cond, age):
 
 
 def test_ssa_fast_math_statistically_equivalent(eng, betas):
-    """fast (MUFU) variant vs deterministic variant: most lineages identical, marginals pass KS"""
+    """fast (MUFU) variant vs deterministic variant of the SAME algorithm (full direct method from the first
+    cycle): most lineages identical, marginals pass KS"""
     from scipy.stats import ks_2samp
-    with cells_per_readout(eng, 4096):
-        m, cond, age = 1, 7, 2
-        fast = eng.ssa_cells(m, DEMO[m], particle_index=1, cond=cond, age=age, seed=11, exact_math=False)
-        det = eng.ssa_cells(m, DEMO[m], particle_index=1, cond=cond, age=age, seed=11, exact_math=True)
-        other = eng.ssa_cells(m, DEMO[m], particle_index=2, cond=cond, age=age, seed=11, exact_math=True)
+    eng.set_option("ssa_hybrid_burnin", 0)
+    try:
+        with cells_per_readout(eng, 4096):
+            m, cond, age = 1, 7, 2
+            fast = eng.ssa_cells(m, DEMO[m], particle_index=1, cond=cond, age=age, seed=11, exact_math=False)
+            det = eng.ssa_cells(m, DEMO[m], particle_index=1, cond=cond, age=age, seed=11, exact_math=True)
+            other = eng.ssa_cells(m, DEMO[m], particle_index=2, cond=cond, age=age, seed=11, exact_math=True)
+    finally:
+        eng.set_option("ssa_hybrid_burnin", 1)
     same = (fast == det).all(0).mean()
     assert same > 0.5, same
     for row in range(4):
         assert ks_2samp(fast[row], other[row]).pvalue > 1e-4
         assert ks_2samp(det[row], other[row]).pvalue > 1e-4
+
+
+@pytest.mark.parametrize("m,cond,age", [(1, 5, 0), (1, 9, 3), (2, 0, 4), (3, 7, 1), (4, 10, 0), (5, 6, 2), (5, 3, 3)])
+def test_ssa_hybrid_burnin_equals_full_direct_method(eng, betas, m, cond, age):
+    """exact telegraph + Poisson burn-in (default) vs the full six-channel SSA from the first cycle (which is
+    bit-identical to the oracle): two-sample KS on U, L, U', L' and on U+L, plus mean/variance z-scores"""
+    from scipy.stats import ks_2samp
+    n = 16384
+    with cells_per_readout(eng, n):
+        hyb = eng.ssa_cells(m, DEMO[m], particle_index=3, cond=cond, age=age, seed=21, exact_math=False).astype(np.float64)
+        eng.set_option("ssa_hybrid_burnin", 0)
+        try:
+            full = eng.ssa_cells(m, DEMO[m], particle_index=4, cond=cond, age=age, seed=21, exact_math=False).astype(np.float64)
+        finally:
+            eng.set_option("ssa_hybrid_burnin", 1)
+    assert not np.array_equal(hyb, full)
+    rows = [hyb[0], hyb[1], hyb[2], hyb[3], hyb[0] + hyb[1]], [full[0], full[1], full[2], full[3], full[0] + full[1]]
+    for a, b in zip(*rows):
+        assert ks_2samp(a, b).pvalue > 1e-4, (ks_2samp(a, b), a.mean(), b.mean())
+        z = (a.mean() - b.mean()) / np.sqrt(a.var() / n + b.var() / n + 1e-300)
+        assert abs(z) < 4.5, z
+    # the covariance structure (same beta for U and L, shared gene history) is preserved
+    c_h = np.cov(hyb[2], hyb[3])[0, 1]
+    c_f = np.cov(full[2], full[3])[0, 1]
+    pr = (hyb[2] - hyb[2].mean()) * (hyb[3] - hyb[3].mean())
+    qr = (full[2] - full[2].mean()) * (full[3] - full[3].mean())
+    assert abs(c_h - c_f) / np.sqrt(pr.var() / n + qr.var() / n + 1e-300) < 4.5
 
 
 @pytest.mark.parametrize("m", [1, 3, 5])

@@ -92,3 +92,26 @@ def test_csr_from_tuples_order():
     err = np.array([1.0, 2.0, 1.0, 2.0, 0.5])
     off, idx, e = csr_from_tuples(gene, part, err, 4)
     assert list(off) == [0, 2, 2, 5, 5] and list(idx) == [1, 9, 8, 3, 5] and list(e) == [2.0, 2.0, 0.5, 1.0, 1.0]
+
+
+def test_model_probs_and_posterior_summaries():
+    from abc_inference_transcription_b200 import posteriors
+    rng = np.random.default_rng(0)
+    p, lb, ub = posteriors.get_model_probs([30, 10], rng=rng)
+    assert np.allclose(p, [0.75, 0.25]) and (lb <= p).all() and (p <= ub).all() and ub[0] <= 1.0
+    assert all((x == 0).all() for x in posteriors.get_model_probs([0, 0]))
+    counts = np.array([[5, 0, 0, 2], [0, 0, 0, 1], [0, 0, 3, 1], [0, 0, 0, 0], [0, 0, 1, 0]])
+    prob, lb, ub = posteriors.model_probs_for_genes(counts, [[0, 1], [2, 3, 4]], rng=rng)
+    assert prob[0].tolist() == [1.0, 0.0] and prob[1].tolist() == [0.0, 0.0] and prob[2].tolist() == [0.0, 1.0]
+    assert np.allclose(prob[3], [0.75, 0.25])                        # model_probs.jl:42-54
+    sets = np.arange(40.0).reshape(10, 4)
+    offsets, idx = np.array([0, 3, 3, 5]), np.array([7, 2, 9, 1, 4])
+    assert posteriors.get_n_particles(offsets).tolist() == [3, 0, 2]
+    m = posteriors.get_posterior_estimate(sets, offsets, idx, [1, 3], "map")
+    assert np.array_equal(m, sets[[6, 0]])                           # first accepted index, 1-based (posterior_kinetics.jl:14)
+    mean = posteriors.get_posterior_estimate(sets, offsets, idx, [1], "mean")
+    assert np.allclose(mean[0], sets[[6, 1, 8]].mean(0))
+    lbs, ubs = posteriors.get_posterior_ci(sets, offsets, idx, [1], 0.95)
+    assert np.allclose(ubs[0], np.quantile(sets[[6, 1, 8]], 0.95, axis=0)) and (lbs <= ubs).all()
+    with pytest.raises(ValueError):
+        posteriors.get_posterior_estimate(sets, offsets, idx, [2], "map")
