@@ -144,7 +144,8 @@ def workload_config(args):
                         "error scoring vs 3419 genes + eps=4.8 acceptance",
             "models": 5, "particles_per_model_per_step_per_gpu": args.batch, "n_cells_per_readout": args.n_cells,
             "n_pre_cycles": args.n_pre, "readouts": 55, "genes": 3419, "eps": EPS, "seed": SEED,
-            "l2": "flushed between steps (256 MiB write)", "lineages": "independent per (condition, age, cell)"}
+            "l2": "flushed between steps (256 MiB write)", "lineages": "independent per (condition, age, cell)",
+            "ssa": "direct method; exact telegraph+Poisson burn-in before the label window (ssa_hybrid_burnin=1)"}
 
 
 # ------------------------------------------------------------------------------------------------
@@ -272,6 +273,23 @@ def run_b200(args):
             score_big_ms.append(e0.elapsed_time(e1))
     score_big_s = sum(score_big_ms) / len(score_big_ms) / 1e3
     del big_err, big_stats
+    # ---- the same SSA without the hybrid burn-in (all six channels from the first cycle), small batch ----
+    eng.set_option("ssa_hybrid_burnin", 0)
+    nfd = min(B, 1024)
+    full_direct = {}
+    ev_fd = ms_fd = 0.0
+    for rep in range(2):
+        for m in range(1, 6):
+            eng.simulate_dev(m, nfd, th_dev[m - 1].data_ptr(), st_dev.data_ptr(), particle_offset=rep * nfd, seed=SEED,
+                             prior_supplied=False, stream=stream)
+            c = eng.counters()
+            if rep == 1:
+                ev_fd += c["n_events"]; ms_fd += c["ms_simulate"]
+    eng.set_option("ssa_hybrid_burnin", 1)
+    full_direct = {"particles_per_s": 5 * nfd / (ms_fd / 1e3), "events_per_s": ev_fd / (ms_fd / 1e3),
+                   "events_per_particle": ev_fd / (5 * nfd), "particles_per_model": nfd,
+                   "frac_of_issue_roofline_nominal64": ev_fd / (ms_fd / 1e3) * NOMINAL_INSTR_PER_EVENT / 1e12 /
+                                                       (148 * 128 * peaks()["sm_max_mhz"] * 1e6 / 1e12)}
     ode = run_ode_path(args, eng_cls=AbcEngine, betas=betas, d=d, se=se, dev=dev, world=world, rank=rank, local=local,
                        barrier=barrier)
     if rank == 0:
@@ -301,6 +319,8 @@ def run_b200(args):
                                    "unit": "GB/s", "frac": sc_gbs / pk["hbm_gbs"], "traffic": None,
                                    "peak_src": pk["src"], "share_of_step": sc_s / t_dev if t_dev > 0 else None}}
         line["ode_path"] = ode
+        line["ssa_full_direct"] = full_direct
+        line["roofline"]["events_per_particle"] = events / max(1, 5 * B * args.steps)
         if world == 1 and not args.no_cpu:
             cores = os.cpu_count() or 1
             v, dt, _ = cpu_reference_sample(args.ref_particles, cores)
@@ -400,7 +420,7 @@ def main():
     ap.add_argument("--steps", type=int, default=3)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--batch", type=int, default=1024, help="particles per model per step per GPU")
+    ap.add_argument("--batch", type=int, default=8192, help="particles per model per step per GPU")
     ap.add_argument("--n-cells", type=int, default=96)
     ap.add_argument("--n-pre", type=int, default=10)
     ap.add_argument("--ode-batch", type=int, default=8192, help="particles per model per step for the ODE-path line")

@@ -335,6 +335,55 @@ def test_ssa_hybrid_burnin_equals_full_direct_method(eng, betas, m, cond, age):
     assert abs(c_h - c_f) / np.sqrt(pr.var() / n + qr.var() / n + 1e-300) < 4.5
 
 
+CORNERS = [
+    (4, np.array([2.5, 2.2, 1.0, 1.5, 2.0, 2.5, 3.0, 1.5, -0.1]), 9, 0),      # config 5: high-rate corner, alpha steps
+    (5, np.array([2.0, 2.8, 2.6, 1.0, 1.3, 1.6, 1.9, 2.0, -0.3]), 4, 4),      # config 5: fast decay steps
+    (1, np.array([-2.7, -2.9, 2.9, -2.8, -0.5]), 6, 1),                       # slow switch, long-lived mRNA: Poisson(1e4)
+    (2, np.array([-1.0, 1.0, 2.0, -1.0, 0.0]), 8, 2),                         # bursty, no scaling, lambda = 1
+    (3, np.array([-3.0, 3.0, -3.0, 3.0, 0.0, 0.5, 2.0, -1.5, -0.7]), 10, 3),  # kon jumps by 6 decades between steps
+]
+
+
+@pytest.mark.parametrize("m,theta,cond,age", CORNERS)
+def test_ssa_hybrid_burnin_corner_cases(eng, m, theta, cond, age):
+    from scipy.stats import ks_2samp
+    n = 8192
+    with cells_per_readout(eng, n):
+        hyb = eng.ssa_cells(m, theta, particle_index=11, cond=cond, age=age, seed=5, exact_math=False).astype(np.float64)
+        eng.set_option("ssa_hybrid_burnin", 0)
+        try:
+            full = eng.ssa_cells(m, theta, particle_index=12, cond=cond, age=age, seed=5, exact_math=False).astype(np.float64)
+        finally:
+            eng.set_option("ssa_hybrid_burnin", 1)
+    for a, b in zip([hyb[0], hyb[1], hyb[2], hyb[3], hyb[0] + hyb[1]], [full[0], full[1], full[2], full[3], full[0] + full[1]]):
+        assert ks_2samp(a, b).pvalue > 1e-4, (ks_2samp(a, b), a.mean(), b.mean())
+        assert abs(a.mean() - b.mean()) / np.sqrt(a.var() / n + b.var() / n + 1e-300) < 4.5
+
+
+def test_ssa_hybrid_vs_full_over_prior_particles(eng):
+    """all 55 read-outs of 16 prior particles per model family: hybrid vs full direct method, z-scores of the
+    per-read-out means from the sample variances; calibrated (mean z^2 ~ 1) and without outliers"""
+    n = 2048
+    zs = []
+    with cells_per_readout(eng, n):
+        for m in (1, 4):
+            th = eng.fix_params(m, 16, particle_offset=900, seed=77)
+            mh, _ = eng.simulate_moments(m, th, particle_offset=900, seed=77)
+            eng.set_option("ssa_hybrid_burnin", 0)
+            try:
+                mf, _ = eng.simulate_moments(m, th, particle_offset=5000, seed=78)
+            finally:
+                eng.set_option("ssa_hybrid_burnin", 1)
+            for q, v in ((0, 2), (1, 4)):
+                se = np.sqrt((mh[..., v] + mf[..., v]) / n)
+                ok = se > 0
+                zs.append(((mh[..., q] - mf[..., q])[ok] / se[ok]).ravel())
+    zs = np.concatenate(zs)
+    assert len(zs) > 2000
+    assert np.abs(zs).max() < 5.5, np.abs(zs).max()
+    assert 0.8 < (zs ** 2).mean() < 1.25, (zs ** 2).mean()
+
+
 @pytest.mark.parametrize("m", [1, 3, 5])
 def test_ssa_moments_match_moment_odes(eng, betas, m):
     """z-tests of SSA sample moments against the reference's moment ODEs (oracle pinned on the goldens)"""
