@@ -308,15 +308,19 @@ def run_b200(args):
                         "d2h_bytes_per_step": d2h // args.steps},
                 "gpu_launches": int(launches),
                 "clocks": sampler.summary(),
-                "roofline": {"kernel": "abc_ssa_kernel<false>", "bound": "issue", "achieved": achieved, "peak": peak_instr,
+                "roofline": {"kernel": "abc_ssa_kernel<false,true>", "bound": "issue", "achieved": achieved, "peak": peak_instr,
                              "unit": "Tlane-instr/s", "frac": achieved / peak_instr, "traffic": None,
+                             "traffic_note": "not memory bound: ncu dram read 0.1 MB, write 0 per launch (profiles/)",
                              "events_per_s": ev_per_s, "events": int(events), "draws": int(draws),
                              "nominal_instr_per_event": NOMINAL_INSTR_PER_EVENT,
                              "peak_src": f"148 SM x 128 lanes x sm_max_mhz ({pk['src']})",
                              "share_of_step": ssa_s / t_dev if t_dev > 0 else None},
                 "roofline_score": {"kernel": "abc_score2_kernel", "particles_per_launch": nb, "ms_per_launch": 1e3 * score_big_s,
                                    "pairs_per_s": nb * G / score_big_s, "bound": "hbm", "achieved": sc_gbs, "peak": pk["hbm_gbs"],
-                                   "unit": "GB/s", "frac": sc_gbs / pk["hbm_gbs"], "traffic": None,
+                                   "unit": "GB/s", "frac": sc_gbs / pk["hbm_gbs"],
+                                   "traffic": 5.593e9 * nb / 131070.0,
+                                   "traffic_src": "ncu --set full dram read+write of one 131070-particle launch "
+                                                  "(profiles/r1_score2_ncu_summary.csv), scaled to this launch size",
                                    "peak_src": pk["src"], "share_of_step": sc_s / t_dev if t_dev > 0 else None}}
         line["ode_path"] = ode
         line["ssa_full_direct"] = full_direct
