@@ -260,20 +260,21 @@ __device__ __forceinline__ double exact_pair_error(const double* __restrict__ sp
     return (err > 10.0) ? 10.0 : err;
 }
 
+template <int LAYOUT>
 __device__ __forceinline__ void score2_store(const AbcScoreArgs& a, long long i, int g, double v) {
-    if (a.err == nullptr) return;
-    if (a.err_layout == ABC_ERR_GENE_MAJOR) a.err[(long long)g * a.n + i] = v;
-    else a.err[i * (long long)a.G + g] = v;
+    if (LAYOUT == ABC_ERR_GENE_MAJOR) a.err[(long long)g * a.n + i] = v;
+    else if (LAYOUT == ABC_ERR_PARTICLE_MAJOR) a.err[i * (long long)a.G + g] = v;
 }
 
 // stage 3 on one q2 entry: exact FP64; fused eps-acceptance
+template <int LAYOUT>
 __device__ __forceinline__ void score2_exact_round(const AbcScoreArgs& a, Score2Smem& sm, long long i0, int e) {
     const unsigned int id = sm.q2_id[e];
     const int g = (int)(id >> 16);
     const long long i = i0 + (long long)(id & 0xffffu);
     const double err = exact_pair_error(a.stats + i * ABC_NSTATS, a.d + (long long)g * ABC_NSTATS,
                                         a.den + (long long)g * ABC_NSTATS);
-    score2_store(a, i, g, err);
+    score2_store<LAYOUT>(a, i, g, err);
     if (err <= a.eps) {
         const unsigned long long slot = atomicAdd(a.acc_count, 1ull);
         atomicAdd(a.counts + g, 1ull);
@@ -286,11 +287,12 @@ __device__ __forceinline__ void score2_exact_round(const AbcScoreArgs& a, Score2
 }
 
 // drain q2: full rounds of SC2_THREADS entries; the remainder stays queued unless `final`
-__device__ void score2_drain_q2(const AbcScoreArgs& a, Score2Smem& sm, long long i0, bool final) {
+template <int LAYOUT>
+__device__ __noinline__ void score2_drain_q2(const AbcScoreArgs& a, Score2Smem& sm, long long i0, bool final) {
     __syncthreads();
     const int n2 = sm.q2n;
     const int full = final ? n2 : (n2 / SC2_THREADS) * SC2_THREADS;
-    for (int e = threadIdx.x; e < full; e += SC2_THREADS) score2_exact_round(a, sm, i0, e);
+    for (int e = threadIdx.x; e < full; e += SC2_THREADS) score2_exact_round<LAYOUT>(a, sm, i0, e);
     __syncthreads();
     const int rem = n2 - full;
     unsigned int keep = 0;
@@ -303,12 +305,13 @@ __device__ void score2_drain_q2(const AbcScoreArgs& a, Score2Smem& sm, long long
 
 // drain the warp-private stage-1 queues: stage 2 = FP32 lower bound over the remaining 38 terms, one queued
 // pair per thread.  Callers have published their fill counts in sm.q1cnt and reset their registers.
-__device__ void score2_drain_q1(const AbcScoreArgs& a, Score2Smem& sm, const float2* __restrict__ fbw,
+template <int LAYOUT>
+__device__ __noinline__ void score2_drain_q1(const AbcScoreArgs& a, Score2Smem& sm, const float2* __restrict__ fbw,
                                 const float2* __restrict__ fa, long long i0, bool final) {
     __syncthreads();
     int c0 = sm.q1cnt[0], c1 = c0 + sm.q1cnt[1], c2 = c1 + sm.q1cnt[2], total = c2 + sm.q1cnt[3];
     for (int base = 0; base < total; base += SC2_THREADS) {
-        if (sm.q2n > SC2_Q2 - SC2_THREADS) score2_drain_q2(a, sm, i0, false);      // block uniform
+        if (sm.q2n > SC2_Q2 - SC2_THREADS) score2_drain_q2<LAYOUT>(a, sm, i0, false);      // block uniform
         const int e = base + threadIdx.x;
         if (e < total) {
             const int w = (e >= c2) ? 3 : (e >= c1) ? 2 : (e >= c0) ? 1 : 0;
@@ -326,16 +329,17 @@ __device__ void score2_drain_q1(const AbcScoreArgs& a, Score2Smem& sm, const flo
                 p = __fmaf_rn(-c.x, sv, p);
                 p = __fmaf_rn(c.y, __fmul_rn(sv, sv), p);
             }
-            if (p > SC2_SURE) score2_store(a, i, g, 10.0);
+            if (p > SC2_SURE) score2_store<LAYOUT>(a, i, g, 10.0);
             else sm.q2_id[atomicAdd(&sm.q2n, 1)] = id;
         }
         __syncthreads();
     }
     if (threadIdx.x < SC2_WARPS) sm.q1cnt[threadIdx.x] = 0;
     __syncthreads();
-    if (final) score2_drain_q2(a, sm, i0, true);
+    if (final) score2_drain_q2<LAYOUT>(a, sm, i0, true);
 }
 
+template <int LAYOUT>
 __global__ void __launch_bounds__(SC2_THREADS, 4)
 abc_score2_kernel(const AbcScoreArgs a, const float2* __restrict__ fbw, const float2* __restrict__ fa) {
     __shared__ Score2Smem sm;
@@ -347,8 +351,8 @@ abc_score2_kernel(const AbcScoreArgs a, const float2* __restrict__ fbw, const fl
     const int g_lo = min(a.G, (int)blockIdx.y * gt_per * SC2_GT);
     const int g_hi = min(a.G, g_lo + gt_per * SC2_GT);
     const double qnan = __longlong_as_double(0x7ff8000000000000ll);
-    const bool pmajor = (a.err != nullptr) && (a.err_layout == ABC_ERR_PARTICLE_MAJOR);
-    const bool gmajor = (a.err != nullptr) && (a.err_layout == ABC_ERR_GENE_MAJOR);
+    constexpr bool pmajor = (LAYOUT == ABC_ERR_PARTICLE_MAJOR);
+    constexpr bool gmajor = (LAYOUT == ABC_ERR_GENE_MAJOR);
     if (tid < SC2_WARPS) sm.q1cnt[tid] = 0;
     if (tid == 0) { sm.q2n = 0; sm.any_nan = 0; }
     int q1w = 0;                                      // fill of this warp's queue (warp uniform)
@@ -421,7 +425,7 @@ abc_score2_kernel(const AbcScoreArgs a, const float2* __restrict__ fbw, const fl
                 if (want_drain) {
                     if (lane == 0) sm.q1cnt[warp] = q1w;
                     q1w = 0;
-                    score2_drain_q1(a, sm, fbw, fa, i0, false);
+                    score2_drain_q1<LAYOUT>(a, sm, fbw, fa, i0, false);
                 }
             }
             // particle-major: the "surely 10.0" values of this gene tile as contiguous row segments
@@ -447,7 +451,7 @@ abc_score2_kernel(const AbcScoreArgs a, const float2* __restrict__ fbw, const fl
         }
         if (lane == 0) sm.q1cnt[warp] = q1w;
         q1w = 0;
-        score2_drain_q1(a, sm, fbw, fa, i0, true);      // end of the particle tile: empty both queues
+        score2_drain_q1<LAYOUT>(a, sm, fbw, fa, i0, true);      // end of the particle tile: empty both queues
     }
 }
 
@@ -463,7 +467,8 @@ int abc_launch_score(const AbcScoreArgs& a, int sm_count, cudaStream_t st) {
     if (a.fbw != nullptr && a.fa != nullptr && a.fstats != nullptr && a.eps < 10.0 && a.G < 65536 && !a.force_reference_kernel) {
         const long long nt = (a.n + SC2_TILE - 1) / SC2_TILE;
         int per = 0;
-        ABC_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per, abc_score2_kernel, SC2_THREADS, 0));
+        const int lay = (a.err == nullptr) ? ABC_ERR_NONE : a.err_layout;
+        ABC_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per, abc_score2_kernel<ABC_ERR_PARTICLE_MAJOR>, SC2_THREADS, 0));
         if (per < 1) per = 1;
         long long gx2 = (long long)sm_count * per;
         if (gx2 > nt) gx2 = nt;
@@ -472,7 +477,10 @@ int abc_launch_score(const AbcScoreArgs& a, int sm_count, cudaStream_t st) {
         if (gy2 > ngt) gy2 = ngt;
         if (gy2 > 65535) gy2 = 65535;
         if (gy2 < 1) gy2 = 1;
-        abc_score2_kernel<<<dim3((unsigned)gx2, (unsigned)gy2), SC2_THREADS, 0, st>>>(a, a.fbw, a.fa);
+        const dim3 grid2((unsigned)gx2, (unsigned)gy2);
+        if (lay == ABC_ERR_NONE) abc_score2_kernel<ABC_ERR_NONE><<<grid2, SC2_THREADS, 0, st>>>(a, a.fbw, a.fa);
+        else if (lay == ABC_ERR_GENE_MAJOR) abc_score2_kernel<ABC_ERR_GENE_MAJOR><<<grid2, SC2_THREADS, 0, st>>>(a, a.fbw, a.fa);
+        else abc_score2_kernel<ABC_ERR_PARTICLE_MAJOR><<<grid2, SC2_THREADS, 0, st>>>(a, a.fbw, a.fa);
         ABC_CUDA_CHECK(cudaGetLastError());
         return ABC_OK;
     }

@@ -433,3 +433,31 @@ def test_simulate_statistics_equal_oracle_ssa_pipeline(eng, betas):
     _, st, _ = eng.simulate(m, theta=th, particle_offset=77, seed=1)
     want = oracle.summary_stats(mom, eng.design.age_dist)
     assert oracle.same_bits(st, want)
+
+
+def test_device_exports_for_multi_gpu_gather(eng, data_stats):
+    """abc_counts_dev / abc_accept_tuples_dev (what dist.gather_acceptance feeds to NCCL) == host fetch"""
+    import torch
+    from abc_inference_transcription_b200.dist import csr_from_tuples, gather_acceptance
+    d, se = data_stats
+    rng = np.random.default_rng(31)
+    s = synth_stats(rng, d, 900)
+    eng.accept_reset()
+    _, counts, _ = eng.score(s, eps=4.8, particle_offset=10_000, err_layout=ERR_NONE)
+    off, idx, errs = eng.accept_fetch()
+    dev = torch.device("cuda", 0)
+    c = torch.zeros(d.shape[0], dtype=torch.int64, device=dev)
+    eng.counts_dev(c.data_ptr())
+    torch.cuda.synchronize()
+    assert np.array_equal(c.cpu().numpy(), counts)
+    tot = eng.accept_total()
+    g = torch.zeros(tot, dtype=torch.int32, device=dev)
+    p = torch.zeros(tot, dtype=torch.int64, device=dev)
+    e = torch.zeros(tot, dtype=torch.float64, device=dev)
+    eng.accept_tuples_dev(g.data_ptr(), p.data_ptr(), e.data_ptr(), tot)
+    torch.cuda.synchronize()
+    o2, i2, e2 = csr_from_tuples(g.cpu().numpy(), p.cpu().numpy(), e.cpu().numpy(), d.shape[0])
+    assert np.array_equal(o2, off) and np.array_equal(i2, idx) and oracle.same_bits(e2, errs)
+    assert idx.min() > 10_000                      # global, 1-based particle indices
+    res = gather_acceptance(eng, 1)
+    assert np.array_equal(res["offsets"], off) and np.array_equal(res["idx"], idx) and np.array_equal(res["counts"], counts)
