@@ -80,6 +80,7 @@ struct abc_ctx {
     DevBuf<float> d_fstats;
     DevBuf<unsigned char> d_rnan;
     int force_reference_score = 0;
+    int stats_guards = -1;       // -1: sample guards iff sim_kind == SSA; 0 / 1 force
     int ssa_hybrid = 1;          // exact telegraph/Poisson burn-in before the label window
     // simulate work buffers
     DevBuf<double> d_theta, d_stats, d_moments, d_ss_iv;
@@ -323,7 +324,7 @@ static int simulate_device(abc_ctx* c, int m, int64_t n, int64_t offset, uint64_
         c->launches += 2;
         ABC_CUDA_CHECK(cudaEventRecord(c->ev[1], st));
         if (d_stats) {
-            if ((rc = abc_launch_summary_stats(d_mom_ode, c->d_age_dist.p, n, d_stats, st)) != ABC_OK) return rc;
+            if ((rc = abc_launch_summary_stats(d_mom_ode, c->d_age_dist.p, n, d_stats, c->stats_guards == 1, st)) != ABC_OK) return rc;
             c->launches++;
         }
         ABC_CUDA_CHECK(cudaEventRecord(c->ev[2], st));
@@ -363,7 +364,7 @@ static int simulate_device(abc_ctx* c, int m, int64_t n, int64_t offset, uint64_
     if ((rc = abc_launch_moments_from_sums(c->d_sums.p, n, c->design.n_cells, d_mom, st)) != ABC_OK) return rc;
     c->launches++;
     if (d_stats) {
-        if ((rc = abc_launch_summary_stats(d_mom, c->d_age_dist.p, n, d_stats, st)) != ABC_OK) return rc;
+        if ((rc = abc_launch_summary_stats(d_mom, c->d_age_dist.p, n, d_stats, c->stats_guards != 0, st)) != ABC_OK) return rc;
         c->launches++;
     }
     ABC_CUDA_CHECK(cudaEventRecord(c->ev[2], st));
@@ -479,7 +480,8 @@ extern "C" int abc_summary_stats(abc_ctx_t* c, const double* moments, int64_t n,
     if ((rc = c->d_moments.ensure((size_t)n * ABC_NREAD * 5)) != ABC_OK) return rc;
     if ((rc = c->d_stats.ensure((size_t)n * ABC_NSTATS)) != ABC_OK) return rc;
     ABC_CUDA_CHECK(cudaMemcpyAsync(c->d_moments.p, moments, (size_t)n * ABC_NREAD * 5 * sizeof(double), cudaMemcpyHostToDevice, c->stream));
-    if ((rc = abc_launch_summary_stats(c->d_moments.p, c->d_age_dist.p, n, c->d_stats.p, c->stream)) != ABC_OK) return rc;
+    const int guards = (c->stats_guards < 0) ? (c->design.sim_kind == ABC_SIM_SSA) : c->stats_guards;
+    if ((rc = abc_launch_summary_stats(c->d_moments.p, c->d_age_dist.p, n, c->d_stats.p, guards, c->stream)) != ABC_OK) return rc;
     c->launches++;
     ABC_CUDA_CHECK(cudaMemcpyAsync(stats, c->d_stats.p, (size_t)n * ABC_NSTATS * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
     ABC_CUDA_CHECK(cudaStreamSynchronize(c->stream));
@@ -706,6 +708,7 @@ extern "C" int abc_set_option(abc_ctx_t* c, const char* name, int64_t value) {
     CTX_GUARD(c);
     if (!name) { abc_set_error("abc_set_option: name is NULL"); return ABC_ERR_ARG; }
     if (strcmp(name, "score_reference_kernel") == 0) { c->force_reference_score = value ? 1 : 0; return ABC_OK; }
+    if (strcmp(name, "stats_sample_guards") == 0) { c->stats_guards = value < 0 ? -1 : (value ? 1 : 0); return ABC_OK; }
     if (strcmp(name, "ssa_hybrid_burnin") == 0) { c->ssa_hybrid = value ? 1 : 0; return ABC_OK; }
     abc_set_error("abc_set_option: unknown option '%s'", name);
     return ABC_ERR_ARG;

@@ -47,7 +47,7 @@ int abc_launch_order(const AbcRates* d_rates, int n, unsigned int* d_keys_in, un
 int abc_launch_moments_from_sums(const unsigned long long* d_sums, int64_t n, int n_cells, double* d_moments,
                                  cudaStream_t st);
 int abc_launch_summary_stats(const double* d_moments, const double* d_age_dist, int64_t n, double* d_stats,
-                             cudaStream_t st);
+                             int sample_guards, cudaStream_t st);
 
 // moment-ODE simulator (abc_ode.cu); counters[4] accumulates accepted integrator steps
 int abc_launch_ode(const double* d_theta, const abc_design_t& des, int m, int64_t n, const double* d_beta_mom,

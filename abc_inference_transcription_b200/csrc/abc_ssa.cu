@@ -674,8 +674,12 @@ __device__ __forceinline__ double wcov5(const double* x, const double* y, const 
     return s;
 }
 
+// sample_guards: the moments come from a finite sample of cells (SSA).  Degenerate samples are then treated as
+// the reference treats the real cells (scripts/data_summary_statistics.jl:64-71, 138-147): ratio = 0 when no
+// molecule was counted, both correlations = 0 when a total variance vanishes (and mean_corr = 0 when all
+// covariances vanish); the moment-ODE path never meets these cases and follows abc_simulation.jl:23-46 verbatim.
 __global__ void abc_stats_kernel(const double* __restrict__ mom, const double* __restrict__ age_dist, long long n,
-                                 double* __restrict__ stats) {
+                                 double* __restrict__ stats, int sample_guards) {
     long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     const double* mp = mom + i * (ABC_NREAD * 5);
@@ -689,12 +693,23 @@ __global__ void abc_stats_kernel(const double* __restrict__ mom, const double* _
             for (int q = 0; q < 5; ++q) c[q][a] = mp[(j * 5 + a) * 5 + q];
         }
         const double s1 = wsum5(w, c[0]), s2 = wsum5(w, c[1]);
-        st[20 + j] = __ddiv_rn(s2, d_add(s1, s2));
         const double v1 = d_add(wsum5(w, c[2]), wcov5(c[0], c[0], w));
         const double v2 = d_add(wsum5(w, c[4]), wcov5(c[1], c[1], w));
         const double stds = __dsqrt_rn(fabs(d_mul(v1, v2)));
-        st[31 + j] = __ddiv_rn(wsum5(w, c[3]), stds);
-        st[42 + j] = __ddiv_rn(wcov5(c[0], c[1], w), stds);
+        double ratio = __ddiv_rn(s2, d_add(s1, s2));
+        double mcorr = __ddiv_rn(wsum5(w, c[3]), stds);
+        double cmean = __ddiv_rn(wcov5(c[0], c[1], w), stds);
+        if (sample_guards) {
+            bool cov_all_zero = true;
+#pragma unroll
+            for (int a = 0; a < 5; ++a) cov_all_zero = cov_all_zero && (c[3][a] == 0.0);
+            if (!(d_add(s1, s2) > 0.0)) ratio = 0.0;
+            if (v1 == 0.0 || v2 == 0.0) { mcorr = 0.0; cmean = 0.0; }
+            if (cov_all_zero) mcorr = 0.0;
+        }
+        st[20 + j] = ratio;
+        st[31 + j] = mcorr;
+        st[42 + j] = cmean;
         if (j == 5 || j == 6) {
             double* mo = st + (j == 5 ? 0 : 10);
             double* ff = st + (j == 5 ? 5 : 15);
@@ -710,11 +725,11 @@ __global__ void abc_stats_kernel(const double* __restrict__ mom, const double* _
 }
 
 int abc_launch_summary_stats(const double* d_moments, const double* d_age_dist, int64_t n, double* d_stats,
-                             cudaStream_t st) {
+                             int sample_guards, cudaStream_t st) {
     if (n <= 0) return ABC_OK;
     int threads = 64;
     long long blocks = (n + threads - 1) / threads;
-    abc_stats_kernel<<<(unsigned)blocks, threads, 0, st>>>(d_moments, d_age_dist, (long long)n, d_stats);
+    abc_stats_kernel<<<(unsigned)blocks, threads, 0, st>>>(d_moments, d_age_dist, (long long)n, d_stats, sample_guards);
     ABC_CUDA_CHECK(cudaGetLastError());
     return ABC_OK;
 }

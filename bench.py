@@ -256,8 +256,19 @@ def run_b200(args):
 
     # ---- scoring kernel alone on a large resident batch (its own roofline; inputs = simulated prior statistics) ----
     nb = args.score_particles
-    reps = (nb + B - 1) // B
-    big_stats = st_dev.repeat(reps, 1)[:nb].contiguous()
+    # distinct prior particles: their statistics come from the device moment-ODE path (fast), shuffled
+    from abc_inference_transcription_b200 import SIM_ODE
+    eng_o = AbcEngine(local)
+    eng_o.set_design(synthetic_design(betas, sim_kind=SIM_ODE))
+    per = (nb + 4) // 5
+    big_stats = torch.empty((5 * per, 53), dtype=torch.float64, device=dev)
+    for m in range(1, 6):
+        th_tmp = torch.empty((per, 9), dtype=torch.float64, device=dev)
+        eng_o.simulate_dev(m, per, th_tmp.data_ptr(), big_stats[(m - 1) * per:].data_ptr(), particle_offset=10**7, seed=SEED,
+                           stream=stream)
+    torch.cuda.synchronize()
+    eng_o.close()
+    big_stats = big_stats[torch.randperm(5 * per, device=dev)][:nb].contiguous()
     big_err = torch.empty((nb, G), dtype=torch.float64, device=dev)
     score_big_ms = []
     for it in range(4):

@@ -162,6 +162,9 @@ int  abc_accept_tuples_dev(abc_ctx_t* ctx, int32_t* d_gene, int64_t* d_particle,
                            void* stream);
 /* tuning / diagnostics switches.  "score_reference_kernel" = 1: score with the plain FP64 kernel (every pair
  * evaluated in full) instead of the three-stage kernel; results are bit-identical either way.
+ * "stats_sample_guards" = -1 (default): when the moments come from SSA cells, degenerate samples follow the
+ * reference's data-side conventions (ratio = 0 without counts, correlations = 0 when a total variance is 0,
+ * scripts/data_summary_statistics.jl:64-71,138-147); the ODE path follows abc_simulation.jl:23-46 verbatim.  0 / 1 force.
  * "ssa_hybrid_burnin" = 0: run the full six-channel direct method from the first simulated cycle; 1 (default):
  * before the label window opens simulate only the gene switch and draw U ~ Poisson(Lam | gene path) at the
  * window start (exact); the exact_math variant of abc_ssa_cells always uses 0. */

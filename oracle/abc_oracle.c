@@ -355,8 +355,20 @@ static double wsum(const double* w, const double* x, int n) {
     return s;
 }
 
+static void summary_stats_impl(const double* mom, const double* age_dist, double* st, int sample_guards);
+
 /* abc_simulation.jl:23-46 */
 void orc_summary_stats(const double mom[ORC_NCOND * ORC_NAGE * 5], const double* age_dist, double st[ORC_NSTATS]) {
+    summary_stats_impl(mom, age_dist, st, 0);
+}
+
+/* the same statistics for moments estimated from a finite sample of cells: degenerate samples are handled as
+ * the reference handles the real cells, data_summary_statistics.jl:64-71 (ratio) and :138-147 (correlations) */
+void orc_summary_stats_sample(const double mom[ORC_NCOND * ORC_NAGE * 5], const double* age_dist, double st[ORC_NSTATS]) {
+    summary_stats_impl(mom, age_dist, st, 1);
+}
+
+static void summary_stats_impl(const double* mom, const double* age_dist, double* st, int sample_guards) {
     double* pulse_mean = st, *pulse_ff = st + 5, *chase_mean = st + 10, *chase_ff = st + 15;
     double* ratio = st + 20, *mean_corr = st + 31, *corr_mean = st + 42;
     for (int j = 0; j < ORC_NCOND; ++j) {
@@ -364,10 +376,18 @@ void orc_summary_stats(const double mom[ORC_NCOND * ORC_NAGE * 5], const double*
         double c[5][ORC_NAGE];
         for (int a = 0; a < ORC_NAGE; ++a) for (int q = 0; q < 5; ++q) c[q][a] = mom[(j*ORC_NAGE + a)*5 + q];
         ratio[j] = wsum(w, c[1], 5) / (wsum(w, c[0], 5) + wsum(w, c[1], 5));
-        double stds = sqrt(fabs((wsum(w, c[2], 5) + orc_weighted_cov(c[0], c[0], w, 5)) *
-                                (wsum(w, c[4], 5) + orc_weighted_cov(c[1], c[1], w, 5))));
+        double tv1 = wsum(w, c[2], 5) + orc_weighted_cov(c[0], c[0], w, 5);
+        double tv2 = wsum(w, c[4], 5) + orc_weighted_cov(c[1], c[1], w, 5);
+        double stds = sqrt(fabs(tv1 * tv2));
         mean_corr[j] = wsum(w, c[3], 5) / stds;
         corr_mean[j] = orc_weighted_cov(c[0], c[1], w, 5) / stds;
+        if (sample_guards) {
+            int cov_all_zero = 1;
+            for (int a = 0; a < ORC_NAGE; ++a) if (c[3][a] != 0.0) cov_all_zero = 0;
+            if (!(wsum(w, c[0], 5) + wsum(w, c[1], 5) > 0.0)) ratio[j] = 0.0;       /* :64-71 */
+            if (tv1 == 0.0 || tv2 == 0.0) { mean_corr[j] = 0.0; corr_mean[j] = 0.0; } /* :138-147 */
+            if (cov_all_zero) mean_corr[j] = 0.0;
+        }
         if (j == 5 || j == 6) {
             double* mo = (j == 5) ? pulse_mean : chase_mean;
             double* ff = (j == 5) ? pulse_ff : chase_ff;

@@ -72,6 +72,10 @@ double orc_weighted_cov(const double* x, const double* y, const double* w, int n
  * pulse_mean[5], pulse_ff[5], chase_mean[5], chase_ff[5], ratio[11], mean_corr[11], corr_mean[11] */
 void orc_summary_stats(const double moments[ORC_NCOND * ORC_NAGE * 5], const double* age_dist,
                        double stats[ORC_NSTATS]);
+/* same, for moments estimated from a finite sample of cells (SSA): degenerate samples as on the data side,
+ * data_summary_statistics.jl:64-71, 138-147 */
+void orc_summary_stats_sample(const double moments[ORC_NCOND * ORC_NAGE * 5], const double* age_dist,
+                              double stats[ORC_NSTATS]);
 /* full per-particle path: abc_sim / run_sim */
 int  orc_run_sim(const double* theta, int m, const orc_design_t* d, double stats[ORC_NSTATS],
                  double* moments_out /* nullable, [11][5][5] after optional downsampling */);

@@ -14,6 +14,7 @@ n = int(sys.argv[1]) if len(sys.argv) > 1 else 2048
 models = [int(c) for c in (sys.argv[2] if len(sys.argv) > 2 else "12345")]
 n_cells = int(sys.argv[3]) if len(sys.argv) > 3 else 96
 n_pre = int(sys.argv[4]) if len(sys.argv) > 4 else 10
+corner = len(sys.argv) > 5 and sys.argv[5] == "corner"   # BASELINE configs[4]: kon,koff,alpha ~ U(2,3), gamma ~ U(1,2)
 betas = np.load(os.path.join(ROOT, "tests", "golden", "ref_betas.npy"))
 eng = AbcEngine(0)
 eng.set_design(synthetic_design(betas, n_cells=n_cells, n_pre_cycles=n_pre))
@@ -23,7 +24,16 @@ tot_ev = tot_ms = 0.0
 for rep in range(2):
     for m in models:
         th = torch.empty((n, n_params(m)), dtype=torch.float64, device=dev)
-        eng.simulate_dev(m, n, th.data_ptr(), st.data_ptr(), particle_offset=rep * n, seed=20240229)
+        if corner:
+            P = n_params(m)
+            g = torch.Generator(device=dev).manual_seed(1 + rep)
+            u = torch.rand((n, P), dtype=torch.float64, device=dev, generator=g)
+            lo = torch.full((P,), 2.0, dtype=torch.float64, device=dev)
+            ngam = 5 if m == 5 else 1
+            lo[P - 1 - ngam:P - 1] = 1.0
+            th.copy_(lo + u)
+            th[:, P - 1] = -0.7 + 0.7 * u[:, P - 1]
+        eng.simulate_dev(m, n, th.data_ptr(), st.data_ptr(), particle_offset=rep * n, seed=20240229, prior_supplied=corner)
         c = eng.counters()
         if rep == 1:
             tot_ev += c["n_events"]; tot_ms += c["ms_simulate"]

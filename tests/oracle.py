@@ -141,12 +141,14 @@ def run_sim(theta, m, design):
     return stats, mom.reshape(11, 5, 5)
 
 
-def summary_stats(moments, age_dist):
+def summary_stats(moments, age_dist, sample_guards=False):
+    """S1; sample_guards=True: finite-sample conventions of the data side (what the SSA path uses)"""
     mom = np.ascontiguousarray(moments, dtype=np.float64).reshape(-1, 275)
     ad = np.ascontiguousarray(np.asarray(age_dist, dtype=np.float64).T.reshape(-1))
     out = np.zeros((mom.shape[0], 53))
+    fn = lib().orc_summary_stats_sample if sample_guards else lib().orc_summary_stats
     for i in range(mom.shape[0]):
-        lib().orc_summary_stats(_p(mom[i]), _p(ad), _p(out[i]))
+        fn(_p(mom[i]), _p(ad), _p(out[i]))
     return out
 
 

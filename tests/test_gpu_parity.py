@@ -249,13 +249,22 @@ def test_summary_stats_bit_exact(eng):
     d2 = copy.copy(des)
     d2.age_dist = ad
     eng.set_design(d2)
+    mom[1, 3, :, 1] = 0.0                          # condition 4: no labelled molecule in any age group
+    mom[1, 3, :, 3:] = 0.0
     try:
+        eng.set_option("stats_sample_guards", 0)
         got = eng.summary_stats(mom)
+        eng.set_option("stats_sample_guards", 1)
+        got_s = eng.summary_stats(mom)
     finally:
+        eng.set_option("stats_sample_guards", -1)
         eng.set_design(des)
-    want = oracle.summary_stats(mom, ad)
+    want = oracle.summary_stats(mom, ad)           # abc_simulation.jl:23-46 verbatim (moment-ODE inputs)
     assert oracle.same_bits(got, want)
     assert np.isnan(want[0, 20:]).all()
+    want_s = oracle.summary_stats(mom, ad, sample_guards=True)   # finite-sample conventions (SSA inputs)
+    assert oracle.same_bits(got_s, want_s)
+    assert (want_s[0, 20:] == 0).all() and want_s[1, 20 + 3] == 0.0 and want_s[1, 31 + 3] == 0.0 and np.isfinite(want_s).all()
 
 
 @pytest.mark.parametrize("m", [1, 2, 3, 4, 5])
@@ -431,7 +440,7 @@ def test_simulate_statistics_equal_oracle_ssa_pipeline(eng, betas):
     th = eng.fix_params(m, 3, particle_offset=77, seed=1)
     mom, _ = eng.simulate_moments(m, th, particle_offset=77, seed=1)
     _, st, _ = eng.simulate(m, theta=th, particle_offset=77, seed=1)
-    want = oracle.summary_stats(mom, eng.design.age_dist)
+    want = oracle.summary_stats(mom, eng.design.age_dist, sample_guards=True)
     assert oracle.same_bits(st, want)
 
 
