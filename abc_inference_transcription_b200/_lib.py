@@ -60,6 +60,8 @@ SYMBOLS = {
     "abc_device_count": (ctypes.c_int, []),
     "abc_n_params": (ctypes.c_int, [ctypes.c_int]),
     "abc_model_name": (ctypes.c_char_p, [ctypes.c_int]),
+    "abc_host_alloc": (ctypes.c_int, [ctypes.c_size_t, ctypes.POINTER(_vp)]),
+    "abc_host_free": (ctypes.c_int, [_vp]),
     "abc_set_design": (ctypes.c_int, [_vp, ctypes.POINTER(AbcDesign)]),
     "abc_set_data": (ctypes.c_int, [_vp, _vp, _vp, ctypes.c_int32]),
     "abc_fix_params": (ctypes.c_int, [_vp, ctypes.c_int, ctypes.c_int64, ctypes.c_int64, ctypes.c_uint64, _vp]),

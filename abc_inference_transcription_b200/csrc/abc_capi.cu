@@ -154,6 +154,26 @@ extern "C" int abc_destroy(abc_ctx_t* c) {
     return ABC_OK;
 }
 
+extern "C" int abc_host_alloc(size_t bytes, void** ptr) {
+    if (!ptr) { abc_set_error("abc_host_alloc: ptr is NULL"); return ABC_ERR_ARG; }
+    *ptr = nullptr;
+    if (bytes == 0) return ABC_OK;
+    cudaError_t e = cudaHostAlloc(ptr, bytes, cudaHostAllocPortable);
+    if (e != cudaSuccess) {
+        abc_set_error("cudaHostAlloc(%zu bytes) failed: %s", bytes, cudaGetErrorString(e));
+        cudaGetLastError();
+        *ptr = nullptr;
+        return ABC_ERR_NOMEM;
+    }
+    return ABC_OK;
+}
+
+extern "C" int abc_host_free(void* ptr) {
+    if (!ptr) return ABC_OK;
+    ABC_CUDA_CHECK(cudaFreeHost(ptr));
+    return ABC_OK;
+}
+
 // ------------------------------------------------------------------------------------------------
 extern "C" int abc_set_design(abc_ctx_t* c, const abc_design_t* d) {
     CTX_GUARD(c);

@@ -14,6 +14,27 @@ from .design import Design
 from .model import _check_m, n_params
 
 
+class PinnedArray:
+    """numpy view of page-locked host memory from abc_host_alloc (freed with the object)"""
+
+    def __init__(self, shape, dtype=np.float64):
+        self._lib = _lib.load()
+        self._ptr = ctypes.c_void_p()
+        nbytes = int(np.prod(shape)) * np.dtype(dtype).itemsize
+        _lib.check(self._lib.abc_host_alloc(max(nbytes, 1), ctypes.byref(self._ptr)))
+        buf = (ctypes.c_char * max(nbytes, 1)).from_address(self._ptr.value)
+        self.array = np.frombuffer(buf, dtype=dtype, count=int(np.prod(shape))).reshape(shape)
+
+    def __del__(self):
+        try:
+            if self._ptr:
+                self.array = None
+                self._lib.abc_host_free(self._ptr)
+                self._ptr = None
+        except Exception:
+            pass
+
+
 class AbcEngine:
     def __init__(self, device=0):
         self._lib = _lib.load()
@@ -112,16 +133,20 @@ class AbcEngine:
     def accept_reset(self):
         _lib.check(self._lib.abc_accept_reset(self._ctx))
 
-    def score(self, stats, eps=4.8, particle_offset=0, err_layout=_lib.ERR_PARTICLE_MAJOR, want_counts=True):
+    def score(self, stats, eps=4.8, particle_offset=0, err_layout=_lib.ERR_PARTICLE_MAJOR, want_counts=True, out=None):
         """compute_trunc_errors + eps-acceptance.  Returns (err or None, counts or None, counters).
-        err is (n, G) for ERR_PARTICLE_MAJOR (rows of error_<model>.txt) or (G, n) for ERR_GENE_MAJOR."""
+        err is (n, G) for ERR_PARTICLE_MAJOR (rows of error_<model>.txt) or (G, n) for ERR_GENE_MAJOR.
+        out: optional preallocated C-contiguous float64 array of that shape (e.g. PinnedArray(...).array)."""
         stats = np.ascontiguousarray(stats, dtype=np.float64).reshape(-1, _lib.NSTATS)
         n, G = stats.shape[0], self.n_genes
         err = None
-        if err_layout == _lib.ERR_PARTICLE_MAJOR:
-            err = np.empty((n, G), dtype=np.float64)
-        elif err_layout == _lib.ERR_GENE_MAJOR:
-            err = np.empty((G, n), dtype=np.float64)
+        shape = (n, G) if err_layout == _lib.ERR_PARTICLE_MAJOR else (G, n) if err_layout == _lib.ERR_GENE_MAJOR else None
+        if shape is not None:
+            if out is not None:
+                assert out.shape == shape and out.dtype == np.float64 and out.flags["C_CONTIGUOUS"]
+                err = out
+            else:
+                err = np.empty(shape, dtype=np.float64)
         counts = np.zeros(G, dtype=np.int64) if want_counts else None
         cnt = _lib.AbcCounters()
         _lib.check(self._lib.abc_score(self._ctx, _lib.ptr(stats), n, int(particle_offset), float(eps), int(err_layout),

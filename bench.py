@@ -234,6 +234,8 @@ def run_b200(args):
 
     # ---- end to end through the host-buffer C ABI ----------------------------------------------
     h2d = d2h = 0
+    from abc_inference_transcription_b200 import PinnedArray
+    err_host = PinnedArray((B, G))            # page-locked host buffer for the error matrix (abc_host_alloc)
     barrier()
     t0 = time.perf_counter()
     for k in range(args.steps):
@@ -241,7 +243,7 @@ def run_b200(args):
         for m in range(1, 6):
             off = offset_of(args.warmup + k, m)
             theta, stats, _ = eng.simulate(m, n_trials=B, particle_offset=off, seed=SEED)
-            err, counts, _ = eng.score(stats, eps=EPS, particle_offset=off, err_layout=ERR_PARTICLE_MAJOR)
+            err, counts, _ = eng.score(stats, eps=EPS, particle_offset=off, err_layout=ERR_PARTICLE_MAJOR, out=err_host.array)
             h2d += stats.nbytes
             d2h += theta.nbytes + stats.nbytes + err.nbytes + counts.nbytes
         res = gather_acceptance(eng, world, dev)     # NCCL: all-reduce counts, gather accepted tuples
@@ -364,6 +366,8 @@ def run_ode_path(args, eng_cls, betas, d, se, dev, world, rank, local, barrier):
     st_dev = torch.empty((B, 53), dtype=torch.float64, device=dev)
     err_dev = torch.empty((B, G), dtype=torch.float64, device=dev)
     steps = max(1, args.steps)
+    from abc_inference_transcription_b200 import PinnedArray
+    err_host = PinnedArray((B, G))
 
     def dev_step(k):
         eng.accept_reset()
@@ -389,7 +393,7 @@ def run_ode_path(args, eng_cls, betas, d, se, dev, world, rank, local, barrier):
         for m in range(1, 6):
             off = ((1 + k) * world + rank) * B
             theta, stats, _ = eng.simulate(m, n_trials=B, particle_offset=off, seed=SEED)
-            err, counts, _ = eng.score(stats, eps=EPS, particle_offset=off, err_layout=ERR_PARTICLE_MAJOR)
+            err, counts, _ = eng.score(stats, eps=EPS, particle_offset=off, err_layout=ERR_PARTICLE_MAJOR, out=err_host.array)
         eng.accept_fetch()
     barrier()
     t_e2e = time.perf_counter() - t0

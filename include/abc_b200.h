@@ -18,6 +18,7 @@
  */
 #ifndef ABC_B200_H
 #define ABC_B200_H
+#include <stddef.h>
 #include <stdint.h>
 
 #ifdef __cplusplus
@@ -93,6 +94,12 @@ int  abc_device_count(void);
 int  abc_n_params(int m);
 /* the reference's model_name table, abc_simulation.jl:82 */
 const char* abc_model_name(int m);
+
+/* page-locked host memory for the large outputs (error matrix, statistics): copies from the device into such
+ * buffers run at full PCIe rate and asynchronously.  A Julia host wraps the pointer with unsafe_wrap(Array, ...).
+ * Any ordinary (pageable) host array is accepted by every entry point as well. */
+int  abc_host_alloc(size_t bytes, void** ptr);
+int  abc_host_free(void* ptr);
 
 /* ---- configuration ----------------------------------------------------------------------- */
 /* replaces the globals consumed by abc_sim(), abc_simulation.jl:13-14, 65-79 */

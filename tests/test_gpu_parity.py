@@ -470,3 +470,17 @@ def test_device_exports_for_multi_gpu_gather(eng, data_stats):
     assert idx.min() > 10_000                      # global, 1-based particle indices
     res = gather_acceptance(eng, 1)
     assert np.array_equal(res["offsets"], off) and np.array_equal(res["idx"], idx) and np.array_equal(res["counts"], counts)
+
+
+def test_pinned_output_buffer(eng, data_stats):
+    """abc_host_alloc'ed (page-locked) output buffers give the same bits as pageable ones"""
+    from abc_inference_transcription_b200 import PinnedArray
+    d, se = data_stats
+    s = synth_stats(np.random.default_rng(41), d, 300)
+    pin = PinnedArray((300, d.shape[0]))
+    eng.accept_reset()
+    err_p, _, _ = eng.score(s, err_layout=ERR_PARTICLE_MAJOR, out=pin.array)
+    assert err_p is pin.array
+    eng.accept_reset()
+    err, _, _ = eng.score(s, err_layout=ERR_PARTICLE_MAJOR)
+    assert oracle.same_bits(err, err_p)
