@@ -97,7 +97,7 @@ struct abc_ctx {
     DevBuf<int32_t> d_acc_gene;
     DevBuf<long long> d_acc_particle;
     DevBuf<double> d_acc_err;
-    int64_t acc_capacity = 0;
+    int64_t acc_capacity = 0, acc_budget = 0, acc_min_capacity = 0;
     int64_t launches = 0;
     abc_counters_t last;
 };
@@ -276,6 +276,7 @@ extern "C" int abc_set_data(abc_ctx_t* c, const double* d, const double* se, int
     ABC_CUDA_CHECK(cudaMemset(c->d_acc_count.p, 0, sizeof(unsigned long long)));
     c->G = G;
     c->has_data = true;
+    c->acc_budget = 0;
     return ABC_OK;
 }
 
@@ -509,28 +510,36 @@ extern "C" int abc_summary_stats(abc_ctx_t* c, const double* moments, int64_t n,
 }
 
 // ------------------------------------------------------------------------------------------------
-static int ensure_accept(abc_ctx* c, int64_t want) {
+// make room for `want` accepted tuples in total, keeping the ones already stored (device-to-device copy)
+static int ensure_accept(abc_ctx* c, int64_t want, cudaStream_t st) {
     if (c->acc_capacity >= want) return ABC_OK;
+    unsigned long long cnt = 0;
     if (c->acc_capacity > 0) {
-        // growing would drop tuples already stored: only allowed while empty
-        unsigned long long cnt = 0;
+        ABC_CUDA_CHECK(cudaStreamSynchronize(st));
         ABC_CUDA_CHECK(cudaMemcpy(&cnt, c->d_acc_count.p, sizeof(cnt), cudaMemcpyDeviceToHost));
-        if (cnt != 0) return ABC_OK;
+        if ((int64_t)cnt > c->acc_capacity) { abc_set_error("accepted-tuple buffer overflowed"); return ABC_ERR_NOMEM; }
     }
+    DevBuf<int32_t> ng; DevBuf<long long> np_; DevBuf<double> ne;
     int rc;
-    if ((rc = c->d_acc_gene.ensure((size_t)want)) != ABC_OK) return rc;
-    if ((rc = c->d_acc_particle.ensure((size_t)want)) != ABC_OK) return rc;
-    if ((rc = c->d_acc_err.ensure((size_t)want)) != ABC_OK) return rc;
+    if ((rc = ng.ensure((size_t)want)) != ABC_OK) return rc;
+    if ((rc = np_.ensure((size_t)want)) != ABC_OK) { ng.release(); return rc; }
+    if ((rc = ne.ensure((size_t)want)) != ABC_OK) { ng.release(); np_.release(); return rc; }
+    if (cnt) {
+        ABC_CUDA_CHECK(cudaMemcpy(ng.p, c->d_acc_gene.p, cnt * sizeof(int32_t), cudaMemcpyDeviceToDevice));
+        ABC_CUDA_CHECK(cudaMemcpy(np_.p, c->d_acc_particle.p, cnt * sizeof(long long), cudaMemcpyDeviceToDevice));
+        ABC_CUDA_CHECK(cudaMemcpy(ne.p, c->d_acc_err.p, cnt * sizeof(double), cudaMemcpyDeviceToDevice));
+    }
+    c->d_acc_gene.release(); c->d_acc_particle.release(); c->d_acc_err.release();
+    c->d_acc_gene = ng; c->d_acc_particle = np_; c->d_acc_err = ne;
     c->acc_capacity = want;
     return ABC_OK;
 }
 
 static int64_t default_accept_capacity(int64_t n, int G) {
-    // generous: 2 % of the pairs of this call, at least 1 Mi tuples, at most 256 Mi
+    // generous: 2 % of the pairs of this call (measured: 0.16 % for prior draws at eps = 4.8), at least 1 Mi tuples
     double w = 0.02 * (double)n * (double)G;
     int64_t cap = (int64_t)w;
     if (cap < (1 << 20)) cap = 1 << 20;
-    if (cap > (1ll << 28)) cap = 1ll << 28;
     return cap;
 }
 
@@ -541,7 +550,10 @@ static int score_device(abc_ctx* c, const double* d_stats, int64_t n, int64_t of
         abc_set_error("unknown err_layout %d", layout);
         return ABC_ERR_ARG;
     }
-    int rc = ensure_accept(c, default_accept_capacity(n, c->G));
+    // room for this call: up to 2 % of its pairs on top of the budget already promised to earlier calls since
+    // the last reset (a conservative host-side running bound; the exact count is only read when growing)
+    c->acc_budget += default_accept_capacity(n, c->G);
+    int rc = ensure_accept(c, std::max<int64_t>(c->acc_budget, c->acc_min_capacity), st);
     if (rc != ABC_OK) return rc;
     AbcScoreArgs a;
     a.stats = d_stats; a.d = c->d_d.p; a.den = c->d_den.p; a.fbw = c->d_fbw.p; a.fa = c->d_fa.p;
@@ -624,6 +636,7 @@ extern "C" int abc_accept_reset(abc_ctx_t* c) {
     ABC_CUDA_CHECK(cudaStreamSynchronize(c->stream));
     ABC_CUDA_CHECK(cudaMemset(c->d_acc_count.p, 0, sizeof(unsigned long long)));
     if (c->G > 0) ABC_CUDA_CHECK(cudaMemset(c->d_counts.p, 0, (size_t)c->G * sizeof(unsigned long long)));
+    c->acc_budget = 0;
     return ABC_OK;
 }
 
@@ -728,6 +741,7 @@ extern "C" int abc_set_option(abc_ctx_t* c, const char* name, int64_t value) {
     CTX_GUARD(c);
     if (!name) { abc_set_error("abc_set_option: name is NULL"); return ABC_ERR_ARG; }
     if (strcmp(name, "score_reference_kernel") == 0) { c->force_reference_score = value ? 1 : 0; return ABC_OK; }
+    if (strcmp(name, "accept_capacity") == 0) { c->acc_min_capacity = value > 0 ? value : 0; return ABC_OK; }
     if (strcmp(name, "stats_sample_guards") == 0) { c->stats_guards = value < 0 ? -1 : (value ? 1 : 0); return ABC_OK; }
     if (strcmp(name, "ssa_hybrid_burnin") == 0) { c->ssa_hybrid = value ? 1 : 0; return ABC_OK; }
     abc_set_error("abc_set_option: unknown option '%s'", name);

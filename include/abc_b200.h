@@ -169,6 +169,9 @@ int  abc_accept_tuples_dev(abc_ctx_t* ctx, int32_t* d_gene, int64_t* d_particle,
                            void* stream);
 /* tuning / diagnostics switches.  "score_reference_kernel" = 1: score with the plain FP64 kernel (every pair
  * evaluated in full) instead of the three-stage kernel; results are bit-identical either way.
+ * "accept_capacity" = N: reserve room for at least N accepted tuples (20 bytes each); by default the buffer grows by
+ * 2 % of the pairs of every abc_score call since the last abc_accept_reset (a call whose acceptance rate exceeds
+ * that fails with ABC_ERR_NOMEM instead of dropping tuples).
  * "stats_sample_guards" = -1 (default): when the moments come from SSA cells, degenerate samples follow the
  * reference's data-side conventions (ratio = 0 without counts, correlations = 0 when a total variance is 0,
  * scripts/data_summary_statistics.jl:64-71,138-147); the ODE path follows abc_simulation.jl:23-46 verbatim.  0 / 1 force.

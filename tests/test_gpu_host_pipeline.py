@@ -50,3 +50,38 @@ def test_wrapper_section_2_and_3(tmp_path):
         assert len(lines) == 300 and sum(len(v) for v in lines) > 0
         for g in range(300):
             assert np.array_equal(lines[g], oracle.accept_gene(ref[:, g], 4.8))
+
+
+def test_wrapper_cli_sections_2_and_3(tmp_path):
+    """python -m abc_inference_transcription_b200.wrapper --m 2 --n_trials 24 --submit 1: files of wrapper.jl sections 2-3"""
+    from abc_inference_transcription_b200 import wrapper
+    from abc_inference_transcription_b200.jlfmt import writedlm_rows
+    betas = np.load(os.path.join(GOLD, "ref_betas.npy"))
+    z = np.load(os.path.join(GOLD, "ref_summary_stats.npz"))
+    d, se = z["d"][:120], z["se"][:120]
+    ss = tmp_path / "summary_stats"
+    ss.mkdir()
+    cols = {"pulse_mean": (0, 5), "pulse_ff": (5, 10), "chase_mean": (10, 15), "chase_ff": (15, 20),
+            "ratio": (20, 31), "mean_corr": (31, 42), "corr_mean": (42, 53)}
+    for k, (a, b) in cols.items():
+        dn = k if k in ("pulse_mean", "pulse_ff", "chase_mean", "chase_ff") else k + "_data"
+        with open(ss / f"{dn}.txt", "w") as fh:
+            writedlm_rows(fh, d[:, a:b])
+        with open(ss / f"{k}_se.txt", "w") as fh:
+            writedlm_rows(fh, se[:, a:b])
+    np.savetxt(tmp_path / "betas.txt", betas, fmt="%.17g")
+    wrapper.main(["--m", "2", "--n_trials", "24", "--submit", "1", "--root", str(tmp_path), "--summary_stats", str(ss),
+                  "--betas", str(tmp_path / "betas.txt"), "--n_cells", "32", "--n_pre_cycles", "8", "--errors"])
+    sim = tmp_path / "data" / "simulations" / "const_const"
+    assert sorted(os.listdir(sim)) == ["progress_const_const_1.txt", "s_chase_const_const_1.txt", "s_corr_mean_const_const_1.txt",
+                                       "s_mean_corr_const_const_1.txt", "s_pulse_const_const_1.txt", "s_ratios_const_const_1.txt",
+                                       "sets_const_const_1.txt"]
+    err = readdlm(str(tmp_path / "data" / "errors" / "error_const_const.txt"))
+    assert err.shape == (24, 120)
+    stats = compute_errors.pack_stats(*compute_errors.load_s_data(str(tmp_path / "data" / "simulations"), "const_const", "_1.txt"))
+    assert oracle.same_bits(err, oracle.compute_trunc_errors(stats, d, se))
+    assert np.array_equal(compute_errors.load_error_column(str(tmp_path / "data" / "errors"), "const_const", 7), err[:, 6])
+    lines = accepted_particles.read_particles(str(tmp_path / "data" / "posteriors" / "particles_const_const.txt"))
+    assert len(lines) == 120
+    for g in range(120):
+        assert np.array_equal(lines[g], oracle.accept_gene(err[:, g], 4.8))
