@@ -366,38 +366,41 @@ abc_ssa_kernel(const AbcRates* __restrict__ rates, const AbcSsaParams prm, const
                 uint4 b = next_block(s);
                 s.g = (b.x < srates[warp].pon_thr) ? 1 : 0;
             }
-            const int c_star = HYBRID ? tab.c_star : 0, e_star = HYBRID ? tab.e_star : 0;
-            float lam = 0.0f;                           // Poisson mean of U given the gene path (phase A)
-            for (int c = 0; c <= prm.n_pre; ++c) {
-                const int n_ent = tab.n_ent[c];
-                n_cross += (uint32_t)n_ent;
-                int e = 0;
-                float x = 0.0f;
-                Seg sg = tab.seg[c][0];
-                if (HYBRID && c <= c_star) {
-                    // phase A: telegraph process + closed-form Lam, one random word per draw
-                    const int e_end = (c == c_star) ? e_star : n_ent;
-                    while (e < e_end) {
-                        const uint4 b = next_block(s);
-                        const uint32_t w4[4] = {b.x, b.y, b.z, b.w};
+            int c_first = 0, e_first = 0;               // where the six-channel direct method starts
+            if (HYBRID) {
+                // phase A: telegraph process + closed-form Lam, one random word per draw.  Divisions only halve
+                // Lam, so the lanes run through all phase-A cycles without waiting for each other.
+                const int c_star = tab.c_star, e_star = tab.e_star;
+                int c = 0, e = 0, n_ent = tab.n_ent[0];
+                float x = 0.0f, lam = 0.0f;             // Lam: Poisson mean of U given the gene path
+                Seg sg = tab.seg[0][0];
+                bool done = (c == c_star) && (e == e_star);
+                while (!done) {
+                    const uint4 b = next_block(s);
+                    const uint32_t w4[4] = {b.x, b.y, b.z, b.w};
 #pragma unroll
-                        for (int j = 0; j < 4; ++j) {
-                            if (e < e_end) {
-                                if (telegraph_step(s, x, lam, sg, w4[j])) {
-                                    e += 1; x = 0.0f;
-                                    if (e < n_ent) sg = tab.seg[c][e];
-                                }
+                    for (int j = 0; j < 4; ++j) {
+                        if (!done && telegraph_step(s, x, lam, sg, w4[j])) {
+                            e += 1; x = 0.0f; n_cross += 1u;
+                            if (c < c_star && e == n_ent) {       // cell division: a Poisson count thins to half its mean
+                                lam = f_mul(lam, 0.5f);
+                                c += 1; e = 0; n_ent = tab.n_ent[c];
                             }
+                            done = (c == c_star) && (e == e_star);
+                            if (!done) sg = tab.seg[c][e];
                         }
                     }
-                    if (c == c_star) {                  // hand over: U ~ Poisson(Lam), L = 0
-                        WordSrc ws; ws.avail = 0;
-                        s.U = poisson_draw(lam, ws, s);
-                    } else {
-                        lam = f_mul(lam, 0.5f);         // division thins a Poisson count to half its mean
-                        continue;
-                    }
                 }
+                WordSrc ws; ws.avail = 0;               // hand over: U ~ Poisson(Lam), L = 0
+                s.U = poisson_draw(lam, ws, s);
+                c_first = c_star; e_first = e_star;
+            }
+            for (int c = c_first; c <= prm.n_pre; ++c) {
+                const int n_ent = tab.n_ent[c];
+                int e = (c == c_first) ? e_first : 0;
+                n_cross += (uint32_t)(n_ent - e);
+                float x = 0.0f;
+                Seg sg = tab.seg[c][e < n_ent ? e : 0];
                 while (e < n_ent) {
                     const uint4 b = next_block(s);
                     if (ssa_step<EXACT>(s, x, sg, b.x, b.y)) {
@@ -527,14 +530,15 @@ __global__ void abc_rates_kernel(const double* __restrict__ theta, int m, long l
     double pon = kon / (kon + koff);
     double thr = pon * 4294967296.0;
     r.pon_thr = (thr >= 4294967295.0) ? 0xFFFFFFFFu : (thr > 0.0 ? (uint32_t)thr : 0u);
-    // predicted SSA events per simulated hour (switching + births + deaths), used only to schedule the
+    // predicted SSA draws per simulated hour (switching + the label-window share of births/deaths), used only to schedule the
     // heaviest particles first (longest-processing-time order); it never influences a result
     float cost = 0.0f;
     for (int j = 0; j < 5; ++j) {
         const float s2 = r.kon[j] + r.koff[j];
         const float sw = 2.0f * r.kon[j] * r.koff[j] / s2;
         const float br = r.alpha[j] * (m != 2 ? 1.5f : 1.0f) * r.kon[j] / s2;
-        cost += 0.2f * (sw + 2.0f * br);
+        // with the hybrid burn-in births/deaths are simulated only inside the label window (~12 h of ~210 h)
+        cost += 0.2f * (sw + 0.115f * br);
     }
     r.pad0 = (cost == cost && cost > 0.0f) ? cost : 0.0f;
     r.pad1 = 0.0f;
