@@ -119,7 +119,7 @@ def run_reference(args):
     n = args.ref_particles
     vals = []
     for _ in range(args.warmup):
-        cpu_reference_sample(max(cores, n // 4), cores)
+        cpu_reference_sample(max(cores, n // 8), cores)
     t_all = 0.0
     for _ in range(args.steps):
         v, dt, _ = cpu_reference_sample(n, cores)
@@ -414,7 +414,7 @@ def cpu_ssa_sample(cores, args):
     from abc_inference_transcription_b200 import n_params, split_betas
     betas, _, _ = load_inputs()
     sd, keep = oracle.make_ssa_design(args.n_cells, args.n_pre, True, split_betas(betas))
-    jobs = [(1 + (i % 5), i, (7 * i) % 11, (3 * i) % 5) for i in range(4 * cores)]
+    jobs = [(1 + (i % 5), i, (7 * i) % 11, (3 * i) % 5) for i in range(16 * cores)]
 
     def one(job):
         m, i, c, a = job
@@ -444,7 +444,7 @@ def main():
     ap.add_argument("--n-pre", type=int, default=10)
     ap.add_argument("--ode-batch", type=int, default=8192, help="particles per model per step for the ODE-path line")
     ap.add_argument("--score-particles", type=int, default=131072, help="particles per launch for the scoring-kernel roofline")
-    ap.add_argument("--ref-particles", type=int, default=1600)
+    ap.add_argument("--ref-particles", type=int, default=24000, help="particles per bounded CPU sample (~10 s on 16 threads)")
     ap.add_argument("--no-cpu", action="store_true")
     args = ap.parse_args()
     if args.impl == "reference":

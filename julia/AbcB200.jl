@@ -86,6 +86,19 @@ function simulate(ctx::Context, m, n_trials; particle_offset=0, seed=UInt64(2024
     return θ, stats, c[]
 end
 
+"""set_option(ctx, "ssa_hybrid_burnin" | "stats_sample_guards" | "score_reference_kernel" | "accept_capacity", value)"""
+set_option(ctx::Context, name::AbstractString, value::Integer) =
+    check(ccall((:abc_set_option, LIB), Cint, (Ptr{Cvoid}, Cstring, Int64), ctx.ptr, name, value))
+
+"""pinned_matrix(rows, cols) -> (A::Matrix{Float64}, ptr): page-locked host memory for the error matrix; release with
+host_free(ptr) once A is no longer used"""
+function pinned_matrix(rows::Integer, cols::Integer)
+    p = Ref{Ptr{Cvoid}}(C_NULL)
+    check(ccall((:abc_host_alloc, LIB), Cint, (Csize_t, Ref{Ptr{Cvoid}}), rows * cols * sizeof(Float64), p))
+    return unsafe_wrap(Array, Ptr{Float64}(p[]), (rows, cols)), p[]
+end
+host_free(ptr::Ptr{Cvoid}) = check(ccall((:abc_host_free, LIB), Cint, (Ptr{Cvoid},), ptr))
+
 accept_reset(ctx::Context) = check(ccall((:abc_accept_reset, LIB), Cint, (Ptr{Cvoid},), ctx.ptr))
 
 """score(ctx, stats; eps, layout) -> (err, counts).  ERR_PARTICLE_MAJOR: err is G x n (column i = row i of
