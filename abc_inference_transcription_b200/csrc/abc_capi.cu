@@ -416,6 +416,16 @@ static int read_counters(abc_ctx* c, int64_t n, abc_counters_t* out, bool accumu
 
 #define SIM_CHUNK (1 << 17)
 
+// particles per device launch: bounded by the work buffers and by the 32-bit work-item counter of the SSA kernel
+static int64_t sim_chunk(const abc_ctx* c) {
+    int64_t ch = SIM_CHUNK;
+    if (c->has_design && c->design.sim_kind == ABC_SIM_SSA) {
+        const int64_t items_per_particle = (int64_t)ABC_NREAD * ((c->design.n_cells + 31) / 32);
+        ch = std::min<int64_t>(ch, std::max<int64_t>(1, 0xE0000000ll / items_per_particle));
+    }
+    return ch;
+}
+
 extern "C" int abc_simulate(abc_ctx_t* c, int m, int64_t n, int64_t offset, uint64_t seed, int prior_supplied,
                             double* theta, double* stats, abc_counters_t* counters) {
     CTX_GUARD(c);
@@ -424,8 +434,9 @@ extern "C" int abc_simulate(abc_ctx_t* c, int m, int64_t n, int64_t offset, uint
     if (n < 0 || (n > 0 && (!theta || !stats))) { abc_set_error("abc_simulate: bad arguments"); return ABC_ERR_ARG; }
     const int P = abc_n_params(m);
     memset(&c->last, 0, sizeof(c->last));
-    for (int64_t b0 = 0; b0 < n; b0 += SIM_CHUNK) {
-        const int64_t nb = std::min<int64_t>(SIM_CHUNK, n - b0);
+    const int64_t chunk = sim_chunk(c);
+    for (int64_t b0 = 0; b0 < n; b0 += chunk) {
+        const int64_t nb = std::min<int64_t>(chunk, n - b0);
         if ((rc = c->d_theta.ensure((size_t)nb * P)) != ABC_OK) return rc;
         if ((rc = c->d_stats.ensure((size_t)nb * ABC_NSTATS)) != ABC_OK) return rc;
         if (prior_supplied)
@@ -450,8 +461,9 @@ extern "C" int abc_simulate_moments(abc_ctx_t* c, int m, int64_t n, int64_t offs
     if (n < 0 || (n > 0 && (!theta || !moments))) { abc_set_error("abc_simulate_moments: bad arguments"); return ABC_ERR_ARG; }
     const int P = abc_n_params(m);
     memset(&c->last, 0, sizeof(c->last));
-    for (int64_t b0 = 0; b0 < n; b0 += SIM_CHUNK) {
-        const int64_t nb = std::min<int64_t>(SIM_CHUNK, n - b0);
+    const int64_t chunk = sim_chunk(c);
+    for (int64_t b0 = 0; b0 < n; b0 += chunk) {
+        const int64_t nb = std::min<int64_t>(chunk, n - b0);
         if ((rc = c->d_theta.ensure((size_t)nb * P)) != ABC_OK) return rc;
         if ((rc = c->d_moments.ensure((size_t)nb * ABC_NREAD * 5)) != ABC_OK) return rc;
         ABC_CUDA_CHECK(cudaMemcpyAsync(c->d_theta.p, theta + b0 * P, (size_t)nb * P * sizeof(double), cudaMemcpyHostToDevice, c->stream));
