@@ -62,3 +62,40 @@ def test_device_ode_statistics_match_oracle_run_sim(betas, m):
             ok = np.isfinite(want)
             assert np.array_equal(np.isfinite(stats[i]), ok)
             assert np.allclose(stats[i][ok], want[ok], rtol=2e-3, atol=1e-6), (i, np.abs(stats[i][ok] - want[ok]).max())
+
+
+def test_accepted_posteriors_agree_between_ssa_and_moment_odes(betas):
+    """north-star part 2: on a fixed gene set the accepted posteriors of the SSA path and of the moment-ODE path
+    (what the reference computes) agree: same parameter sets, 96 cells per read-out, eps = 4.8.  Tolerances from
+    profiles/r1_equivalence_ssa_vs_ode.json (Spearman 0.99, shift 0.06 SD at 20 000 particles)."""
+    from abc_inference_transcription_b200 import ERR_NONE
+    from abc_inference_transcription_b200.posteriors import get_posterior_estimate
+    z = np.load(os.path.join(GOLD, "ref_summary_stats.npz"))
+    d, se = z["d"], z["se"]
+    n, m = 8000, 1
+    with AbcEngine(0) as ssa, AbcEngine(0) as ode:
+        ssa.set_design(synthetic_design(betas, n_cells=96, n_pre_cycles=10))
+        ode.set_design(synthetic_design(betas, sim_kind=SIM_ODE))
+        ssa.set_data(d, se)
+        ode.set_data(d, se)
+        theta, s_ssa, _ = ssa.simulate(m, n_trials=n, particle_offset=0, seed=4)
+        _, s_ode, _ = ode.simulate(m, theta=theta)
+        assert np.isfinite(s_ssa).all()
+        acc = {}
+        for key, eng, st in (("ssa", ssa, s_ssa), ("ode", ode, s_ode)):
+            eng.accept_reset()
+            _, counts, _ = eng.score(st, eps=4.8, err_layout=ERR_NONE)
+            off, idx, _ = eng.accept_fetch()
+            acc[key] = (counts.astype(float), off, idx)
+    c_s, c_o = acc["ssa"][0], acc["ode"][0]
+    both = (c_s > 0) | (c_o > 0)
+    rs, ro = np.argsort(np.argsort(c_s[both])), np.argsort(np.argsort(c_o[both]))
+    assert np.corrcoef(rs, ro)[0, 1] > 0.93
+    assert 0.4 < c_s.sum() / c_o.sum() < 1.1                      # MC noise of 96-cell samples lowers acceptance
+    rich = np.nonzero((c_s >= 20) & (c_o >= 20))[0] + 1
+    assert len(rich) > 300
+    pm_s = get_posterior_estimate(theta, acc["ssa"][1], acc["ssa"][2], rich, "mean")
+    pm_o = get_posterior_estimate(theta, acc["ode"][1], acc["ode"][2], rich, "mean")
+    sd = np.array([theta[acc["ode"][2][acc["ode"][1][g - 1]:acc["ode"][1][g]] - 1].std(0) for g in rich])
+    shift = np.abs(pm_s - pm_o) / np.maximum(sd, 1e-6)
+    assert np.median(shift) < 0.15 and np.quantile(shift, 0.9) < 0.45, (np.median(shift), np.quantile(shift, 0.9))

@@ -484,3 +484,22 @@ def test_pinned_output_buffer(eng, data_stats):
     eng.accept_reset()
     err, _, _ = eng.score(s, err_layout=ERR_PARTICLE_MAJOR)
     assert oracle.same_bits(err, err_p)
+
+
+@pytest.mark.parametrize("m,cond,age", [(1, 8, 2), (4, 5, 4), (3, 10, 1)])
+def test_ssa_hybrid_high_power(eng, m, cond, age):
+    """262 144 cells per arm: means and variances of U, L, U', L' of the hybrid burn-in vs the full direct method
+    agree within 4.5 standard errors (SE ~ 0.2 % of the CV), i.e. no bias above ~1 % survives"""
+    n = 262144
+    with cells_per_readout(eng, n):
+        hyb = eng.ssa_cells(m, DEMO[m], particle_index=21, cond=cond, age=age, seed=99, exact_math=False).astype(np.float64)
+        eng.set_option("ssa_hybrid_burnin", 0)
+        try:
+            full = eng.ssa_cells(m, DEMO[m], particle_index=22, cond=cond, age=age, seed=99, exact_math=False).astype(np.float64)
+        finally:
+            eng.set_option("ssa_hybrid_burnin", 1)
+    for a, b in zip(hyb, full):
+        z_mean = (a.mean() - b.mean()) / np.sqrt(a.var() / n + b.var() / n + 1e-300)
+        da, db = (a - a.mean()) ** 2, (b - b.mean()) ** 2
+        z_var = (da.mean() - db.mean()) / np.sqrt(da.var() / n + db.var() / n + 1e-300)
+        assert abs(z_mean) < 4.5 and abs(z_var) < 4.5, (z_mean, z_var, a.mean(), b.mean())
