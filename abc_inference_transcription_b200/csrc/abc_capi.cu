@@ -83,7 +83,7 @@ struct abc_ctx {
     int stats_guards = -1;       // -1: sample guards iff sim_kind == SSA; 0 / 1 force
     int ssa_hybrid = 1;          // exact telegraph/Poisson burn-in before the label window
     // simulate work buffers
-    DevBuf<double> d_theta, d_stats, d_moments, d_ss_iv;
+    DevBuf<double> d_theta, d_stats, d_moments, d_ss_iv, d_prefix;
     DevBuf<AbcRates> d_rates;
     DevBuf<unsigned long long> d_sums, d_counters;
     DevBuf<unsigned int> d_work;
@@ -143,7 +143,7 @@ extern "C" int abc_destroy(abc_ctx_t* c) {
     cudaSetDevice(c->device);
     cudaStreamSynchronize(c->stream);
     c->d_beta.release(); c->d_age_dist.release(); c->d_beta_mom.release(); c->d_d.release(); c->d_den.release(); c->d_fbw.release(); c->d_fa.release(); c->d_fstats.release(); c->d_rnan.release();
-    c->d_theta.release(); c->d_stats.release(); c->d_moments.release(); c->d_ss_iv.release(); c->d_rates.release();
+    c->d_theta.release(); c->d_stats.release(); c->d_moments.release(); c->d_ss_iv.release(); c->d_prefix.release(); c->d_rates.release();
     c->d_keys_in.release(); c->d_keys_out.release(); c->d_idx_in.release(); c->d_order.release(); c->d_sort_tmp.release();
     c->d_sums.release(); c->d_counters.release(); c->d_work.release(); c->d_cells.release();
     c->d_sstats.release(); c->d_err.release(); c->d_counts.release(); c->d_acc_count.release();
@@ -339,10 +339,11 @@ static int simulate_device(abc_ctx* c, int m, int64_t n, int64_t offset, uint64_
             d_mom_ode = c->d_moments.p;
         }
         if ((rc = c->d_ss_iv.ensure((size_t)n * 9)) != ABC_OK) return rc;
+        if ((rc = c->d_prefix.ensure((size_t)n * ABC_NREAD * 9)) != ABC_OK) return rc;
         ABC_CUDA_CHECK(cudaMemsetAsync(c->d_counters.p, 0, 8 * sizeof(unsigned long long), st));
         ABC_CUDA_CHECK(cudaEventRecord(c->ev[0], st));
-        if ((rc = abc_launch_ode(d_theta, c->design, m, n, c->d_beta_mom.p, c->d_ss_iv.p, d_mom_ode, c->d_counters.p, st)) != ABC_OK) return rc;
-        c->launches += 2;
+        if ((rc = abc_launch_ode(d_theta, c->design, m, n, c->d_beta_mom.p, c->d_ss_iv.p, c->d_prefix.p, d_mom_ode, c->d_counters.p, st)) != ABC_OK) return rc;
+        c->launches += 3;
         ABC_CUDA_CHECK(cudaEventRecord(c->ev[1], st));
         if (d_stats) {
             if ((rc = abc_launch_summary_stats(d_mom_ode, c->d_age_dist.p, n, d_stats, c->stats_guards == 1, st)) != ABC_OK) return rc;

@@ -51,7 +51,7 @@ int abc_launch_summary_stats(const double* d_moments, const double* d_age_dist, 
 
 // moment-ODE simulator (abc_ode.cu); counters[4] accumulates accepted integrator steps
 int abc_launch_ode(const double* d_theta, const abc_design_t& des, int m, int64_t n, const double* d_beta_mom,
-                   double* d_ss_iv, double* d_moments, unsigned long long* d_counters, cudaStream_t st);
+                   double* d_ss_iv, double* d_prefix, double* d_moments, unsigned long long* d_counters, cudaStream_t st);
 
 // scoring
 int abc_launch_prepare_data(const double* d_d, const double* d_se, int G, double* d_den, float2* d_fbw, float2* d_fa,

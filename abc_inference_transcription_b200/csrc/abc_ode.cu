@@ -12,7 +12,8 @@
 // a piece, so the implicit stage equations reduce to nine 3x3 solves by forward substitution.
 //
 // Kernel 1: one thread per particle  -> cyclo-stationary post-division state ss_iv (transient_phase).
-// Kernel 2: one thread per (particle, condition, age) -> the 5 moments of that read-out (+ downsample).
+// Kernel 2: one thread per particle -> the unlabelled path shared by all read-outs, recorded at the 55 window starts.
+// Kernel 3: one thread per (particle, condition, age) -> label window + chase from the recorded state (+ downsample).
 #include "abc_common.cuh"
 #include "abc_internal.h"
 
@@ -193,6 +194,7 @@ struct AbcOdeParams {
     int m, scaling, downsampling;
     double cycle, t0, rtol, atol;
     double agevec[5], pulse[11], chase[11], iv[9];
+    int order[ABC_NREAD];     // read-outs sorted by their label-window start
 };
 
 // transient_phase (model.jl:114-142): one thread per particle
@@ -234,8 +236,47 @@ __global__ void abc_ode_transient_kernel(const double* __restrict__ theta, const
     atomicAdd(counters + 4, (unsigned long long)steps);
 }
 
-// trajectories + syntheticdata + downsample (model.jl:146-187, 221-239): one thread per (particle, read-out)
-__global__ void abc_ode_readout_kernel(const double* __restrict__ theta, const double* __restrict__ ss_iv,
+// trajectories (model.jl:146-174), shared prefix.  Until its label window opens, every (condition, age) read-out
+// of a particle follows the same unlabelled path (lambda = 0: the labelled moments stay 0) through the solves
+// [t0,t0+cycle], ..., [-cycle,0], [0,age]; the state at time t < age does not depend on age.  One thread per
+// particle integrates that path once and records the state at each of the 55 window starts texp = age-pulse-chase
+// (visited in increasing order, prm.order).
+__global__ void abc_ode_prefix_kernel(const double* __restrict__ theta, const double* __restrict__ ss_iv,
+                                      const AbcOdeParams prm, double* __restrict__ prefix,
+                                      unsigned long long* __restrict__ counters) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= prm.n) return;
+    const int P = (prm.m <= 2) ? 5 : 9;
+    OdeRates r;
+    ode_make_rates(theta + i * P, prm.m, r);
+    double y[9];
+#pragma unroll
+    for (int k = 0; k < 9; ++k) y[k] = ss_iv[i * 9 + k];
+    unsigned int steps = 0;
+    double pos = prm.t0;
+    int next = 0;                                           // next read-out (in texp order) to record
+    while (next < ABC_NREAD) {
+        const int ro = prm.order[next];
+        const double texp = prm.agevec[ro % ABC_NAGE] - prm.pulse[ro / ABC_NAGE] - prm.chase[ro / ABC_NAGE];
+        // advance to texp, applying periodic_boundary at every multiple of the cycle that is crossed
+        while (pos < texp) {
+            const double nb = prm.cycle * (floor(pos / prm.cycle + 1e-12) + 1.0);
+            const double stop = fmin(nb, texp);
+            steps += ode_model(r, prm.scaling, y, pos, stop, prm.cycle, -1e30, 0.0, prm.rtol, prm.atol);
+            pos = stop;
+            if (pos == nb && pos <= texp) ode_divide(y);   // the next solve starts from the divided state
+        }
+        double* o = prefix + (i * ABC_NREAD + ro) * 9;
+#pragma unroll
+        for (int k = 0; k < 9; ++k) o[k] = y[k];
+        next += 1;
+    }
+    atomicAdd(counters + 4, (unsigned long long)steps);
+}
+
+// label window + chase: one thread per (particle, read-out), from the recorded prefix state at texp to the read-out
+// age; then downsample (model.jl:221-239)
+__global__ void abc_ode_readout_kernel(const double* __restrict__ theta, const double* __restrict__ prefix,
                                        const AbcOdeParams prm, const double* __restrict__ beta_mom,
                                        double* __restrict__ mom, unsigned long long* __restrict__ counters) {
     const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
@@ -248,17 +289,15 @@ __global__ void abc_ode_readout_kernel(const double* __restrict__ theta, const d
     const double age = prm.agevec[a], pulse = prm.pulse[cond], texp = age - pulse - prm.chase[cond];
     double y[9];
 #pragma unroll
-    for (int k = 0; k < 9; ++k) y[k] = ss_iv[i * 9 + k];
-    // nsols solves: [t0,t0+cycle], ..., [-cycle,0], [0,age] with periodic_boundary in between (model.jl:153-172)
+    for (int k = 0; k < 9; ++k) y[k] = prefix[idx * 9 + k];
     unsigned int steps = 0;
-    double tau = prm.t0;
-    bool first = true;
-    while (tau < age) {
-        const double tf = (tau < 0.0) ? tau + prm.cycle : age;
-        if (!first) ode_divide(y);
-        steps += ode_model(r, prm.scaling, y, tau, tf, prm.cycle, texp, pulse, prm.rtol, prm.atol);
-        tau = tf;
-        first = false;
+    double pos = texp;
+    while (pos < age) {
+        const double nb = prm.cycle * (floor(pos / prm.cycle + 1e-12) + 1.0);
+        const double stop = fmin(nb, age);
+        steps += ode_model(r, prm.scaling, y, pos, stop, prm.cycle, texp, pulse, prm.rtol, prm.atol);
+        pos = stop;
+        if (pos == nb && pos < age) ode_divide(y);
     }
     double mu = y[1], ml = y[2], vu = y[6], cv = y[7], vl = y[8];
     if (prm.downsampling) {
@@ -276,7 +315,7 @@ __global__ void abc_ode_readout_kernel(const double* __restrict__ theta, const d
 }
 
 int abc_launch_ode(const double* d_theta, const abc_design_t& des, int m, int64_t n, const double* d_beta_mom,
-                   double* d_ss_iv, double* d_moments, unsigned long long* d_counters, cudaStream_t st) {
+                   double* d_ss_iv, double* d_prefix, double* d_moments, unsigned long long* d_counters, cudaStream_t st) {
     if (n <= 0) return ABC_OK;
     AbcOdeParams prm;
     prm.n = n; prm.m = m; prm.scaling = (m != 2) ? 1 : 0; prm.downsampling = des.downsampling;
@@ -284,11 +323,24 @@ int abc_launch_ode(const double* d_theta, const abc_design_t& des, int m, int64_
     for (int a = 0; a < 5; ++a) prm.agevec[a] = des.agevec[a];
     for (int j = 0; j < 11; ++j) { prm.pulse[j] = des.pulse[j]; prm.chase[j] = des.chase[j]; }
     for (int k = 0; k < 9; ++k) prm.iv[k] = des.iv[k];
+    // read-outs by increasing window start
+    double texp[ABC_NREAD];
+    for (int ro = 0; ro < ABC_NREAD; ++ro) {
+        prm.order[ro] = ro;
+        texp[ro] = des.agevec[ro % ABC_NAGE] - des.pulse[ro / ABC_NAGE] - des.chase[ro / ABC_NAGE];
+        if (texp[ro] < des.t0) { abc_set_error("label window of condition %d starts before t0", ro / ABC_NAGE + 1); return ABC_ERR_ARG; }
+    }
+    for (int x = 1; x < ABC_NREAD; ++x)
+        for (int yy = x; yy > 0 && texp[prm.order[yy]] < texp[prm.order[yy - 1]]; --yy) {
+            const int t = prm.order[yy]; prm.order[yy] = prm.order[yy - 1]; prm.order[yy - 1] = t;
+        }
     const int threads = 64;
     abc_ode_transient_kernel<<<(unsigned)((n + threads - 1) / threads), threads, 0, st>>>(d_theta, prm, d_ss_iv, d_counters);
     ABC_CUDA_CHECK(cudaGetLastError());
+    abc_ode_prefix_kernel<<<(unsigned)((n + threads - 1) / threads), threads, 0, st>>>(d_theta, d_ss_iv, prm, d_prefix, d_counters);
+    ABC_CUDA_CHECK(cudaGetLastError());
     const long long items = (long long)n * ABC_NREAD;
-    abc_ode_readout_kernel<<<(unsigned)((items + threads - 1) / threads), threads, 0, st>>>(d_theta, d_ss_iv, prm, d_beta_mom,
+    abc_ode_readout_kernel<<<(unsigned)((items + threads - 1) / threads), threads, 0, st>>>(d_theta, d_prefix, prm, d_beta_mom,
                                                                                           d_moments, d_counters);
     ABC_CUDA_CHECK(cudaGetLastError());
     return ABC_OK;
