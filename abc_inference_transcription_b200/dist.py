@@ -23,9 +23,12 @@ def csr_from_tuples(gene, particle, err, n_genes):
     return np.cumsum(offsets), particle.astype(np.int64), err
 
 
-def gather_acceptance(eng, world, device=None, backend_group=None):
-    """Returns {"counts": (G,) int64 summed over ranks, "offsets"/"idx"/"errs": merged CSR (every rank),
-    "bytes_d2h": bytes this rank copied to the host}.  world == 1 needs no torch."""
+def gather_acceptance(eng, world, device=None, backend_group=None, all_ranks=False):
+    """Returns {"counts": (G,) int64 summed over ranks, "offsets"/"idx"/"errs": merged CSR (rank 0; every rank if
+    all_ranks), "bytes_d2h": bytes this rank copied to the host}.  world == 1 needs no torch.
+
+    NCCL traffic: one all-reduce of G int64 and three padded all-gathers of the accepted tuples (acceptance rates are
+    << 1 %, so this is latency bound).  The merge -- stable sort by (gene, error, particle) -- runs on rank 0's GPU."""
     G = eng.n_genes
     if world <= 1:
         gene, part, err = eng.accept_tuples()
@@ -35,6 +38,7 @@ def gather_acceptance(eng, world, device=None, backend_group=None):
                 "bytes_d2h": gene.nbytes + part.nbytes + err.nbytes}
     import torch
     import torch.distributed as dist
+    rank = dist.get_rank(backend_group)
     stream = torch.cuda.current_stream().cuda_stream
     counts = torch.zeros(G, dtype=torch.int64, device=device)
     eng.counts_dev(counts.data_ptr(), stream=stream)
@@ -54,9 +58,18 @@ def gather_acceptance(eng, world, device=None, backend_group=None):
     dist.all_gather(gl, g, group=backend_group)                        # (ii) gather-v as padded all-gathers
     dist.all_gather(pl, p, group=backend_group)
     dist.all_gather(el, e, group=backend_group)
-    gene = torch.cat([t[:s] for t, s in zip(gl, sizes)]).cpu().numpy()
-    part = torch.cat([t[:s] for t, s in zip(pl, sizes)]).cpu().numpy()
-    err = torch.cat([t[:s] for t, s in zip(el, sizes)]).cpu().numpy()
-    offsets, idx, errs = csr_from_tuples(gene, part, err, G)
-    return {"counts": counts.cpu().numpy(), "offsets": offsets, "idx": idx, "errs": errs,
-            "bytes_d2h": gene.nbytes + part.nbytes + err.nbytes + G * 8}
+    out = {"counts": counts.cpu().numpy(), "offsets": None, "idx": None, "errs": None, "bytes_d2h": G * 8}
+    if rank == 0 or all_ranks:
+        gene = torch.cat([t[:s] for t, s in zip(gl, sizes)])
+        part = torch.cat([t[:s] for t, s in zip(pl, sizes)])
+        err = torch.cat([t[:s] for t, s in zip(el, sizes)])
+        # per gene: ascending error, ties by ascending particle index (accepted_particles.jl:20-24)
+        o = torch.sort(part, stable=True).indices
+        o = o[torch.sort(err[o], stable=True).indices]
+        o = o[torch.sort(gene[o], stable=True).indices]
+        gene, part, err = gene[o], part[o], err[o]
+        offsets = torch.zeros(G + 1, dtype=torch.int64, device=device)
+        offsets[1:] = torch.cumsum(torch.bincount(gene.to(torch.int64), minlength=G), 0)
+        out.update({"offsets": offsets.cpu().numpy(), "idx": part.cpu().numpy(), "errs": err.cpu().numpy()})
+        out["bytes_d2h"] += part.numel() * 16 + (G + 1) * 8
+    return out
