@@ -7,7 +7,6 @@ missing or no CUDA device is present every compute call raises.
 import ctypes
 import os
 
-import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libabcb200.so")

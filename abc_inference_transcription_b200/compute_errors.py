@@ -16,7 +16,6 @@ from . import _lib
 from .jlfmt import readdlm, writedlm_rows
 
 STAT_ORDER = ["pulse_mean", "pulse_ff", "chase_mean", "chase_ff", "ratio", "mean_corr", "corr_mean"]
-_DATA_FILE = {"ratio": "ratio_data", "mean_corr": "mean_corr_data", "corr_mean": "corr_mean_data"}
 
 
 def get_mean_subset(data):
@@ -45,10 +44,9 @@ def load_s_data(path, model_name, ext):
 
 def load_summary_stats(path, ext=".txt"):
     """the 14 data matrices in the order wrapper.jl:42 unpacks them"""
-    out = []
-    for k in STAT_ORDER[:4]:
-        pass
-    g = lambda name: readdlm(os.path.join(path, name + ext))
+    def g(name):
+        return readdlm(os.path.join(path, name + ext))
+
     return (g("pulse_mean"), g("pulse_ff"), g("pulse_mean_se"), g("pulse_ff_se"), g("chase_mean"), g("chase_ff"),
             g("chase_mean_se"), g("chase_ff_se"), g("ratio_data"), g("ratio_se"), g("mean_corr_data"), g("mean_corr_se"),
             g("corr_mean_data"), g("corr_mean_se"))

@@ -16,11 +16,7 @@
 #define ABC_DOM_PRIOR 1u
 
 // ---------------------------------------------------------------- Philox4x32-10 (Salmon et al. 2011)
-struct Philox {
-    uint32_t c0, c1, c2, c3;  // counter: c0 = block index, (c1,c2) = particle, c3 = tag
-    uint32_t k0, k1;          // key = seed
-};
-
+// counter = (block index, particle lo, particle hi, tag), key = seed
 __device__ __forceinline__ uint4 philox4x32_10(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3,
                                                uint32_t k0, uint32_t k1) {
     const uint32_t M0 = 0xD2511F53u, M1 = 0xCD9E8D57u, W0 = 0x9E3779B9u, W1 = 0xBB67AE85u;

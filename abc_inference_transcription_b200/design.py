@@ -6,7 +6,6 @@ age_id_distribution) from raw data that is not shipped.  ``syntheti
 the SURVEY section 8d stand-ins: uniform age weights, the shipped capture efficiencies split into
 chase rows 1-2364 / pulse rows 2365-5422 with round-robin age clusters.
 """
-import ctypes
 from dataclasses import dataclass, field
 
 import numpy as np

@@ -54,34 +54,42 @@ def peaks():
 
 
 class ClockSampler(threading.Thread):
-    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)"""
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe).  One sampler (rank 0)
+    watches all GPUs of the job so that the ranks do not compete with N nvidia-smi processes for the host cores."""
 
-    def __init__(self, index):
+    def __init__(self, indices):
         super().__init__(daemon=True)
-        self.index, self.rows, self.stop_flag = index, [], False
+        self.indices, self.rows, self.stop_flag = list(indices), [], False
 
     def run(self):
-        q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+        q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
              "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
              "clocks_event_reasons.sw_power_cap")
+        ids = ",".join(str(i) for i in self.indices)
         while not self.stop_flag:
             try:
-                out = subprocess.run(["nvidia-smi", f"--id={self.index}", f"--query-gpu={q}", "--format=csv,noheader,nounits"],
+                out = subprocess.run(["nvidia-smi", f"--id={ids}", f"--query-gpu={q}", "--format=csv,noheader,nounits"],
                                      capture_output=True, text=True, timeout=5).stdout.strip()
-                if out:
-                    self.rows.append([x.strip() for x in out.split(",")])
+                for line in out.splitlines():
+                    self.rows.append([x.strip() for x in line.split(",")])
             except Exception:
                 pass
-            time.sleep(0.2)
+            time.sleep(0.25)
 
     def summary(self):
         if not self.rows:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["unavailable"]}
-        sm = sorted(float(r[0]) for r in self.rows if r[0].replace(".", "").isdigit())
+        per_gpu = {}
+        for r in self.rows:
+            try:
+                per_gpu.setdefault(r[0], []).append(float(r[1]))
+            except (ValueError, IndexError):
+                pass
+        med = {k: sorted(v)[len(v) // 2] for k, v in per_gpu.items()}
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        reasons = [n for k, n in enumerate(names) if any(len(r) > 3 + k and r[3 + k] == "Active" for r in self.rows)]
-        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": float(self.rows[0][1]), "reasons": reasons,
-                "samples": len(self.rows)}
+        reasons = [n for k, n in enumerate(names) if any(len(r) > 4 + k and r[4 + k] == "Active" for r in self.rows)]
+        return {"sm_mhz": min(med.values()) if med else None, "sm_max_mhz": float(self.rows[0][2]), "reasons": reasons,
+                "samples": len(self.rows), "gpus": len(med)}
 
 
 # ------------------------------------------------------------------------------------------------
@@ -210,8 +218,9 @@ def run_b200(args):
         flush.fill_(w & 0xFF)
     barrier()
     launches0 = eng.launch_count()
-    sampler = ClockSampler(local)
-    sampler.start()
+    sampler = ClockSampler(range(world)) if rank == 0 else None
+    if sampler:
+        sampler.start()
     step_ms = []
     for k in range(args.steps):
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -222,7 +231,8 @@ def run_b200(args):
         barrier()
         step_ms.append(e0.elapsed_time(e1))
         flush.fill_(k & 0xFF)           # L2 flush between timed iterations (outside the timed region)
-    sampler.stop_flag = True
+    if sampler:
+        sampler.stop_flag = True
     launches = eng.launch_count() - launches0
     t_dev = sum(step_ms) / 1e3
     t = torch.tensor([t_dev], dtype=torch.float64, device=dev)
