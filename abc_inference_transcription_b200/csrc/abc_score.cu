@@ -310,6 +310,7 @@ __device__ __noinline__ void score2_drain_q1(const AbcScoreArgs& a, Score2Smem& 
                                 const float2* __restrict__ fa, long long i0, bool final) {
     __syncthreads();
     int c0 = sm.q1cnt[0], c1 = c0 + sm.q1cnt[1], c2 = c1 + sm.q1cnt[2], total = c2 + sm.q1cnt[3];
+    __syncthreads();                       // every thread has read the counts before they are reset below
     for (int base = 0; base < total; base += SC2_THREADS) {
         if (sm.q2n > SC2_Q2 - SC2_THREADS) score2_drain_q2<LAYOUT>(a, sm, i0, false);      // block uniform
         const int e = base + threadIdx.x;
