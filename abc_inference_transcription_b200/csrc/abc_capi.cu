@@ -80,6 +80,13 @@ struct abc_ctx {
     DevBuf<float> d_fstats;
     DevBuf<unsigned char> d_rnan;
     int force_reference_score = 0;
+    int score_tile_kernel = 1;   // 1: tile-pruned scoring (abc_score3.cu); 0: three-stage kernel of abc_score.cu
+    // tile-pruned scoring tables (per data set) and work buffers
+    int32_t s3_ntiles = 0;
+    DevBuf<float4> d_s3_tb, d_s3_ab;
+    DevBuf<double> d_s3_dT, d_s3_denT, d_s3_rcpT;
+    DevBuf<int32_t> d_s3_gidx;
+    DevBuf<uint32_t> d_s3_ok, d_s3_live, d_s3_nanw, d_s3_done;
     int stats_guards = -1;       // -1: sample guards iff sim_kind == SSA; 0 / 1 force
     int ssa_hybrid = 1;          // exact telegraph/Poisson burn-in before the label window
     // simulate work buffers
@@ -143,6 +150,8 @@ extern "C" int abc_destroy(abc_ctx_t* c) {
     cudaSetDevice(c->device);
     cudaStreamSynchronize(c->stream);
     c->d_beta.release(); c->d_age_dist.release(); c->d_beta_mom.release(); c->d_d.release(); c->d_den.release(); c->d_fbw.release(); c->d_fa.release(); c->d_fstats.release(); c->d_rnan.release();
+    c->d_s3_tb.release(); c->d_s3_ab.release(); c->d_s3_dT.release(); c->d_s3_denT.release(); c->d_s3_rcpT.release();
+    c->d_s3_gidx.release(); c->d_s3_ok.release(); c->d_s3_live.release(); c->d_s3_nanw.release(); c->d_s3_done.release();
     c->d_theta.release(); c->d_stats.release(); c->d_moments.release(); c->d_ss_iv.release(); c->d_prefix.release(); c->d_rates.release();
     c->d_keys_in.release(); c->d_keys_out.release(); c->d_idx_in.release(); c->d_order.release(); c->d_sort_tmp.release();
     c->d_sums.release(); c->d_counters.release(); c->d_work.release(); c->d_cells.release();
@@ -272,6 +281,28 @@ extern "C" int abc_set_data(abc_ctx_t* c, const double* d, const double* se, int
     }
     d_se.release();
     if (rc != ABC_OK) return rc;
+    {
+        // tables of the tile-pruned scoring path, built from the denominators exactly as the device computed them
+        std::vector<double> h_den(n);
+        ABC_CUDA_CHECK(cudaMemcpy(h_den.data(), c->d_den.p, n * sizeof(double), cudaMemcpyDeviceToHost));
+        AbcScore3Host h;
+        abc_score3_build(d, h_den.data(), G, h);
+        if ((rc = c->d_s3_tb.ensure(h.tb.size() / 4)) != ABC_OK) return rc;
+        if ((rc = c->d_s3_ab.ensure(h.ab.size() / 4)) != ABC_OK) return rc;
+        if ((rc = c->d_s3_dT.ensure(h.dT.size())) != ABC_OK) return rc;
+        if ((rc = c->d_s3_denT.ensure(h.denT.size())) != ABC_OK) return rc;
+        if ((rc = c->d_s3_rcpT.ensure(h.rcpT.size())) != ABC_OK) return rc;
+        if ((rc = c->d_s3_gidx.ensure(h.gidx.size())) != ABC_OK) return rc;
+        if ((rc = c->d_s3_ok.ensure(h.okmask.size())) != ABC_OK) return rc;
+        ABC_CUDA_CHECK(cudaMemcpy(c->d_s3_tb.p, h.tb.data(), h.tb.size() * sizeof(float), cudaMemcpyHostToDevice));
+        ABC_CUDA_CHECK(cudaMemcpy(c->d_s3_ab.p, h.ab.data(), h.ab.size() * sizeof(float), cudaMemcpyHostToDevice));
+        ABC_CUDA_CHECK(cudaMemcpy(c->d_s3_dT.p, h.dT.data(), h.dT.size() * sizeof(double), cudaMemcpyHostToDevice));
+        ABC_CUDA_CHECK(cudaMemcpy(c->d_s3_denT.p, h.denT.data(), h.denT.size() * sizeof(double), cudaMemcpyHostToDevice));
+        ABC_CUDA_CHECK(cudaMemcpy(c->d_s3_rcpT.p, h.rcpT.data(), h.rcpT.size() * sizeof(double), cudaMemcpyHostToDevice));
+        ABC_CUDA_CHECK(cudaMemcpy(c->d_s3_gidx.p, h.gidx.data(), h.gidx.size() * sizeof(int32_t), cudaMemcpyHostToDevice));
+        ABC_CUDA_CHECK(cudaMemcpy(c->d_s3_ok.p, h.okmask.data(), h.okmask.size() * sizeof(uint32_t), cudaMemcpyHostToDevice));
+        c->s3_ntiles = h.ntiles;
+    }
     ABC_CUDA_CHECK(cudaMemset(c->d_counts.p, 0, (size_t)G * sizeof(unsigned long long)));
     ABC_CUDA_CHECK(cudaMemset(c->d_acc_count.p, 0, sizeof(unsigned long long)));
     c->G = G;
@@ -577,6 +608,25 @@ static int score_device(abc_ctx* c, const double* d_stats, int64_t n, int64_t of
     a.acc_gene = c->d_acc_gene.p; a.acc_particle = c->d_acc_particle.p; a.acc_err = c->d_acc_err.p;
     a.fstats = nullptr; a.rnan = nullptr;
     ABC_CUDA_CHECK(cudaEventRecord(c->ev[3], st));
+    if (!c->force_reference_score && c->score_tile_kernel && eps < 10.0 && n > 0) {
+        // tile-pruned path: classification + one CTA per (gene tile, particle block)
+        AbcScore3Tables x;
+        x.ntiles = c->s3_ntiles;
+        x.W = (n + 31) / 32;
+        const size_t nblocks = abc_score3_blocks(n);
+        if ((rc = c->d_fstats.ensure((size_t)n * ABC_NSTATS)) != ABC_OK) return rc;
+        if ((rc = c->d_s3_live.ensure((size_t)x.ntiles * (size_t)x.W)) != ABC_OK) return rc;
+        if ((rc = c->d_s3_nanw.ensure((size_t)x.W)) != ABC_OK) return rc;
+        if ((rc = c->d_s3_done.ensure(nblocks)) != ABC_OK) return rc;
+        x.tb = c->d_s3_tb.p; x.ab = c->d_s3_ab.p; x.dT = c->d_s3_dT.p; x.denT = c->d_s3_denT.p; x.rcpT = c->d_s3_rcpT.p;
+        x.gidx = c->d_s3_gidx.p; x.okmask = c->d_s3_ok.p;
+        x.live = c->d_s3_live.p; x.nanw = c->d_s3_nanw.p; x.done = c->d_s3_done.p;
+        a.fstats = c->d_fstats.p;
+        rc = abc_launch_score3(a, x, st);
+        c->launches += 2;
+        ABC_CUDA_CHECK(cudaEventRecord(c->ev[4], st));
+        return rc;
+    }
     if (!c->force_reference_score && eps < 10.0) {
         if ((rc = c->d_fstats.ensure((size_t)n * ABC_NSTATS)) != ABC_OK) return rc;
         if ((rc = c->d_rnan.ensure((size_t)n)) != ABC_OK) return rc;
@@ -754,6 +804,7 @@ extern "C" int abc_set_option(abc_ctx_t* c, const char* name, int64_t value) {
     CTX_GUARD(c);
     if (!name) { abc_set_error("abc_set_option: name is NULL"); return ABC_ERR_ARG; }
     if (strcmp(name, "score_reference_kernel") == 0) { c->force_reference_score = value ? 1 : 0; return ABC_OK; }
+    if (strcmp(name, "score_tile_kernel") == 0) { c->score_tile_kernel = value ? 1 : 0; return ABC_OK; }
     if (strcmp(name, "accept_capacity") == 0) { c->acc_min_capacity = value > 0 ? value : 0; return ABC_OK; }
     if (strcmp(name, "stats_sample_guards") == 0) { c->stats_guards = value < 0 ? -1 : (value ? 1 : 0); return ABC_OK; }
     if (strcmp(name, "ssa_hybrid_burnin") == 0) { c->ssa_hybrid = value ? 1 : 0; return ABC_OK; }

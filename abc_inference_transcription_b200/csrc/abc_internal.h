@@ -77,4 +77,33 @@ struct AbcScoreArgs {
     int32_t* acc_gene; long long* acc_particle; double* acc_err;
 };
 int abc_launch_score(const AbcScoreArgs& a, int sm_count, cudaStream_t st);
+
+// tile-pruned scoring (abc_score3.cu): per-data-set tables built on the host by abc_score3_build
+struct AbcScore3Tables {
+    int32_t ntiles;
+    const float4* tb;        // [ntiles][31]: (amin, -bmax, bmin, -amax) of a = sqrt(w) d, b = sqrt(w), w = 1/(53 den)
+    const float4* ab;        // [ntiles][53][32]: (-b, -b, a, a) per (term, gene slot)
+    const double* dT;        // [ntiles][53][32] data statistics, denominators and their reciprocals in tile order
+    const double* denT;
+    const double* rcpT;
+    const int32_t* gidx;     // [ntiles][32] original gene index of a slot, -1 = padding
+    const uint32_t* okmask;  // [ntiles] bit l: slot l may divide through the stored reciprocal
+    uint32_t* live;          // [ntiles][W] work: bit = (tile, particle) needs stages 1-3
+    uint32_t* nanw;          // [W] work: bit = particle has a NaN statistic
+    uint32_t* done;          // [blocks] work: filled slices per particle block (particle-major layout)
+    int64_t W;               // ceil(n / 32)
+};
+#ifdef __cplusplus
+#include <vector>
+struct AbcScore3Host {
+    int ntiles = 0;
+    std::vector<float> tb, ab;
+    std::vector<double> dT, denT, rcpT;
+    std::vector<int32_t> gidx;
+    std::vector<uint32_t> okmask;
+};
+void abc_score3_build(const double* d, const double* den, int G, AbcScore3Host& out);
+#endif
+size_t abc_score3_blocks(int64_t n);
+int abc_launch_score3(const AbcScoreArgs& a, const AbcScore3Tables& x, cudaStream_t st);
 int abc_launch_score_prep(const double* d_stats, int64_t n, float* d_fstats, unsigned char* d_rnan, cudaStream_t st);

@@ -1,0 +1,625 @@
+// abc_score3.cu -- tile-pruned error scoring (compute_errors.jl:30-70 + accepted_particles.jl:20).  sm_100a.
+//
+// Same results, bit for bit, as abc_score_kernel (abc_score.cu); the work is organised so that the error
+// matrix is written at memory speed and arithmetic is spent only where a pair can be below 10.0:
+//
+//   * once per data set (host, abc_score3_build): genes are clustered into tiles of 32 by recursive bisection on
+//     log sqrt(w_t), w_t = 1/(53 den_t); per tile and statistic t < 31 the box [amin, amax] x [bmin, bmax] of
+//     a = sqrt(w) d, b = sqrt(w) is stored, so that for every gene of the tile and every s >= 0
+//         sqrt(w_t) |d_t - s_t|  >=  max(0, amin - bmax s, bmin s - amax);
+//   * abc_score3_classify_kernel: one thread per particle evaluates that bound against every tile (FP32) and
+//     emits one "live" bit per (tile, particle): bound <= 10.01.  A cleared bit proves err > 10 for the 32 pairs,
+//     which compute_errors.jl:62-64 clips to exactly 10.0;
+//   * abc_score3_tile_kernel: one CTA per (tile, block of 2048 particles) first writes its share of the matrix
+//     with 10.0 (NaN rows for particles with a NaN statistic) using 16-byte stores, then visits only the live
+//     particles of its tile: lane = gene, four particles per pass, packed FP32 FMAs (FFMA2):
+//         stage 1: lower bound over the first 15 terms; items without a lane <= 10.01 are finished;
+//         stage 2: the remaining 38 terms; pairs still <= 10.01 are queued;
+//         stage 3: queued pairs, 32 per round: the reference's FP64 arithmetic in the reference's order;
+//     values below 10.0 overwrite the fill, and eps-acceptance is fused into stage 3.
+//
+// Soundness of the FP32 bounds: every term is >= 0, so partial sums and box bounds bound the total from below.
+// With a = fl32(sqrt(w) d), b = fl32(sqrt(w)), s32 = fl32(s) and t = fma(-b, s32, a):
+// |t - sqrt(w)(d - s)| <= 2^-24 (3 sqrt(w)|d| + 3 |T|) with sqrt(w)|d| <= sqrt(100/53), hence for an exact total
+// P <= 10 the computed sum is below 10.0002 < 10.01.  NaN never compares "> 10.01" and falls through to stage 3.
+//
+// Stage 3 divides by the per-gene constant den with its precomputed correctly rounded reciprocal y = RN(1/den):
+// q0 = RN(x y), two Markstein corrections q <- fma(fma(-den, q, x), y, q); the second one starts from a faithful
+// quotient and therefore returns RN(x/den) (Markstein 1990).  Operands outside [1e-250, 1e200], NaN, and genes with
+// non-finite or extreme data use div.rn.f64.
+//
+// Particle-major output: the 32 genes of a tile are scattered over a row, so the fill is done on contiguous
+// slices of the block's rows instead and a per-block counter (release/acquire) orders "all slices filled" before
+// the first stage-3 store of the block.  CTAs of one block are adjacent in launch order and fill before they wait.
+#include "abc_common.cuh"
+#include "abc_internal.h"
+
+#include <algorithm>
+#include <cmath>
+#include <vector>
+
+#define S3_TG 32
+#define S3_NN 31          // statistics used by the tile bound: means, Fano factors, ratios (non-negative)
+#define S3_T1 15
+#define S3_WARPS 8                       // compute warps
+#define S3_THREADS (S3_WARPS * 32 + 32)  // + one service warp: table loads and the fill, both through the TMA engine
+#define S3_FILL_DOUBLES 512              // 4 KB of 10.0 in shared memory: the source of the bulk stores
+#define S3_AHEAD 2                       // particle-major: a CTA of block k fills its slice of block k + S3_AHEAD
+#define S3_PB 2048        // particles per CTA
+#define S3_NP 4           // particles per warp pass
+#define S3_SURE 10.01f
+#define S3C_THREADS 128
+#define S3C_TCH 24
+
+// ------------------------------------------------------------------------------------------------ host tables
+static float f32_down(double x) {
+    float f = (float)x;
+    if ((double)f > x) f = nextafterf(f, -INFINITY);
+    return f;
+}
+static float f32_up(double x) {
+    float f = (float)x;
+    if ((double)f < x) f = nextafterf(f, INFINITY);
+    return f;
+}
+
+void abc_score3_build(const double* d, const double* den, int G, AbcScore3Host& out) {
+    const int ntiles = (G + S3_TG - 1) / S3_TG;
+    std::vector<unsigned char> ok((size_t)G, 1);
+    std::vector<double> feat((size_t)G * S3_NN, 0.0);
+    for (int g = 0; g < G; ++g) {
+        for (int t = 0; t < ABC_NSTATS; ++t) {
+            const double dv = d[(size_t)g * ABC_NSTATS + t], nv = den[(size_t)g * ABC_NSTATS + t];
+            if (!(nv >= 1e-30 && nv <= 1e30) || !(std::fabs(dv) <= 1e15)) ok[g] = 0;
+        }
+        if (ok[g])
+            for (int t = 0; t < S3_NN; ++t) feat[(size_t)g * S3_NN + t] = -0.5 * std::log(53.0 * den[(size_t)g * ABC_NSTATS + t]);
+    }
+    // recursive bisection: split the widest feature at a multiple of the tile size nearest the median
+    std::vector<int> idx((size_t)G);
+    for (int g = 0; g < G; ++g) idx[g] = g;
+    std::vector<std::pair<int, int>> stack, leaves;
+    stack.push_back({0, G});
+    while (!stack.empty()) {
+        const auto r = stack.back();
+        stack.pop_back();
+        const int len = r.second - r.first;
+        if (len <= S3_TG) { leaves.push_back(r); continue; }
+        int best = 0;
+        double spread = -1.0;
+        for (int t = 0; t < S3_NN; ++t) {
+            double lo = INFINITY, hi = -INFINITY;
+            for (int k = r.first; k < r.second; ++k) {
+                const double v = feat[(size_t)idx[k] * S3_NN + t];
+                lo = std::min(lo, v); hi = std::max(hi, v);
+            }
+            if (hi - lo > spread) { spread = hi - lo; best = t; }
+        }
+        std::stable_sort(idx.begin() + r.first, idx.begin() + r.second, [&](int x, int y) {
+            return feat[(size_t)x * S3_NN + best] < feat[(size_t)y * S3_NN + best];
+        });
+        int h = std::max(S3_TG, ((len / 2 + S3_TG - 1) / S3_TG) * S3_TG);
+        if (h >= len) h = len / 2;
+        stack.push_back({r.first + h, r.second});
+        stack.push_back({r.first, r.first + h});
+    }
+    std::sort(leaves.begin(), leaves.end());
+    out.ntiles = ntiles;
+    out.tb.assign((size_t)ntiles * S3_NN * 4, 0.f);
+    out.ab.assign((size_t)ntiles * ABC_NSTATS * S3_TG * 4, 0.f);
+    out.dT.assign((size_t)ntiles * ABC_NSTATS * S3_TG, 0.0);
+    out.denT.assign((size_t)ntiles * ABC_NSTATS * S3_TG, 1.0);
+    out.rcpT.assign((size_t)ntiles * ABC_NSTATS * S3_TG, 1.0);
+    out.gidx.assign((size_t)ntiles * S3_TG, -1);
+    out.okmask.assign((size_t)ntiles, 0u);
+    const float qn = std::nanf("");
+    for (int T = 0; T < ntiles && T < (int)leaves.size(); ++T) {
+        const int lo = leaves[T].first, cnt = leaves[T].second - leaves[T].first;
+        bool tile_ok = true;
+        for (int l = 0; l < cnt; ++l) {
+            const int g = idx[lo + l];
+            out.gidx[(size_t)T * S3_TG + l] = g;
+            if (ok[g]) out.okmask[T] |= 1u << l; else tile_ok = false;
+            for (int t = 0; t < ABC_NSTATS; ++t) {
+                const double dv = d[(size_t)g * ABC_NSTATS + t], nv = den[(size_t)g * ABC_NSTATS + t];
+                const size_t o = ((size_t)T * ABC_NSTATS + t) * S3_TG + l;
+                out.dT[o] = dv; out.denT[o] = nv; out.rcpT[o] = 1.0 / nv;
+                float a = qn, b = qn;
+                if (ok[g]) { const double sw = std::sqrt(1.0 / (53.0 * nv)); a = (float)(sw * dv); b = (float)sw; }
+                out.ab[o * 4 + 0] = -b; out.ab[o * 4 + 1] = -b; out.ab[o * 4 + 2] = a; out.ab[o * 4 + 3] = a;
+            }
+        }
+        for (int t = 0; t < S3_NN; ++t) {
+            double amin = INFINITY, amax = -INFINITY, bmin = INFINITY, bmax = -INFINITY;
+            bool use = tile_ok && cnt > 0;
+            for (int l = 0; l < cnt && use; ++l) {
+                const int g = idx[lo + l];
+                const double dv = d[(size_t)g * ABC_NSTATS + t], nv = den[(size_t)g * ABC_NSTATS + t];
+                if (!(dv >= 0.0)) { use = false; break; }
+                const double sw = std::sqrt(1.0 / (53.0 * nv)), av = sw * dv;
+                amin = std::min(amin, av); amax = std::max(amax, av);
+                bmin = std::min(bmin, sw); bmax = std::max(bmax, sw);
+            }
+            float* o = &out.tb[((size_t)T * S3_NN + t) * 4];
+            if (use) {
+                // (amin, -bmax, bmin, -amax), each rounded so that the bound can only shrink
+                o[0] = f32_down(amin * (1.0 - 1e-12)); o[1] = -f32_up(bmax * (1.0 + 1e-12));
+                o[2] = f32_down(bmin * (1.0 - 1e-12)); o[3] = -f32_up(amax * (1.0 + 1e-12));
+            } else {
+                o[0] = -INFINITY; o[1] = 0.f; o[2] = 0.f; o[3] = -INFINITY;      // contributes 0
+            }
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------ classification
+// One thread = two particles (tile constants are read once for both).  Also writes the FP32 copy of the
+// statistics used by stages 1-2 and the per-particle NaN bits.
+__global__ void __launch_bounds__(S3C_THREADS)
+abc_score3_classify_kernel(const double* __restrict__ stats, long long n, int ntiles, const float4* __restrict__ tb,
+                           float* __restrict__ fstats, unsigned int* __restrict__ live, unsigned int* __restrict__ nanw,
+                           long long W) {
+    __shared__ float4 sh[S3C_TCH][S3_NN];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const long long base = (long long)blockIdx.x * (2 * S3C_THREADS);
+    float sx[2][S3_NN];
+    bool alive[2];
+    long long word[2];
+#pragma unroll
+    for (int pp = 0; pp < 2; ++pp) {
+        const long long i = base + pp * S3C_THREADS + tid;
+        const bool in = i < n;
+        const double* sp = stats + (in ? i : (n - 1)) * ABC_NSTATS;
+        bool nn = false;
+#pragma unroll
+        for (int t = 0; t < ABC_NSTATS; ++t) {
+            const double v = sp[t];
+            nn = nn || (v != v);
+            const float f = (float)v;
+            if (in) fstats[i * ABC_NSTATS + t] = f;
+            if (t < S3_NN) sx[pp][t] = fmaxf(f, 0.f);
+        }
+        word[pp] = (base + pp * S3C_THREADS) / 32 + warp;
+        const unsigned int nb = __ballot_sync(0xffffffffu, in && nn);
+        if (lane == 0 && word[pp] < W) nanw[word[pp]] = nb;
+        alive[pp] = in && !nn;
+    }
+    for (int t0 = 0; t0 < ntiles; t0 += S3C_TCH) {
+        const int nt = min(S3C_TCH, ntiles - t0);
+        __syncthreads();
+        for (int k = tid; k < nt * S3_NN; k += S3C_THREADS) (&sh[0][0])[k] = tb[(long long)t0 * S3_NN + k];
+        __syncthreads();
+        for (int tt = 0; tt < nt; ++tt) {
+            float lb0 = 0.f, lb1 = 0.f;
+#pragma unroll
+            for (int t = 0; t < S3_NN; ++t) {
+                const float4 c = sh[tt][t];
+                const float u0 = fmaxf(fmaxf(__fmaf_rn(c.y, sx[0][t], c.x), __fmaf_rn(c.z, sx[0][t], c.w)), 0.f);
+                const float u1 = fmaxf(fmaxf(__fmaf_rn(c.y, sx[1][t], c.x), __fmaf_rn(c.z, sx[1][t], c.w)), 0.f);
+                lb0 = __fmaf_rn(u0, u0, lb0);
+                lb1 = __fmaf_rn(u1, u1, lb1);
+            }
+            const unsigned int b0 = __ballot_sync(0xffffffffu, alive[0] && !(lb0 > S3_SURE));
+            const unsigned int b1 = __ballot_sync(0xffffffffu, alive[1] && !(lb1 > S3_SURE));
+            if (lane == 0) {
+                if (word[0] < W) live[(long long)(t0 + tt) * W + word[0]] = b0;
+                if (word[1] < W) live[(long long)(t0 + tt) * W + word[1]] = b1;
+            }
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------ tile kernel
+struct S3Smem {
+    float4 ab[ABC_NSTATS][S3_TG];              // (-b, -b, a, a) per (term, gene slot)
+    double d[ABC_NSTATS][S3_TG], den[ABC_NSTATS][S3_TG], rcp[ABC_NSTATS][S3_TG];   // stage-3 constants
+    float4 st[S3_WARPS][ABC_NSTATS];           // statistics of the four particles of a stage-1 pass, per warp
+    float4 qs[S3_WARPS][2][ABC_NSTATS];        // ring of two groups of four items waiting for stage 2 (statistics)
+    float part[S3_WARPS][2 * S3_NP][S3_TG];    // their stage-1 partial sums
+    unsigned short list[S3_PB + 2 * S3_WARPS * S3_NP];   // live particles of this (tile, block), padded
+    unsigned short q1[S3_WARPS][2 * S3_NP];    // their particle indices
+    unsigned short q2[S3_WARPS][S3_NP * 32 + 32];        // pairs waiting for stage 3: particle << 5 | gene slot
+    alignas(16) double tens[S3_FILL_DOUBLES];  // 10.0: source of the fill's bulk stores
+    unsigned long long mbar;                   // completion of the table loads
+    int gidx[S3_TG];
+    unsigned int livew[S3_PB / 32];
+    int cnt[S3_PB / 32];
+    int nlist;
+    int fill_flag;                             // gene-major: this CTA's fill has completed
+    unsigned int okmask;
+};
+
+// ---- TMA / mbarrier helpers (PTX ISA: cp.async.bulk, mbarrier)
+__device__ __forceinline__ unsigned int s3_saddr(const void* p) { return (unsigned int)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void s3_mbar_init(unsigned long long* mbar, unsigned int count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(s3_saddr(mbar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void s3_fence_proxy_async() { asm volatile("fence.proxy.async;" ::: "memory"); }
+__device__ __forceinline__ void s3_mbar_expect_tx(unsigned long long* mbar, unsigned int bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(s3_saddr(mbar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void s3_bulk_g2s(void* dst, const void* src, unsigned int bytes, unsigned long long* mbar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(s3_saddr(dst)), "l"(src), "r"(bytes), "r"(s3_saddr(mbar)) : "memory");
+}
+__device__ __forceinline__ void s3_mbar_wait(unsigned long long* mbar, unsigned int phase) {
+    unsigned int ok;
+    do {
+        asm volatile("{ .reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2; selp.u32 %0, 1, 0, p; }"
+                     : "=r"(ok) : "r"(s3_saddr(mbar)), "r"(phase) : "memory");
+    } while (!ok);
+}
+__device__ __forceinline__ void s3_bulk_s2g(void* dst, const void* src, unsigned int bytes) {
+    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst), "r"(s3_saddr(src)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void s3_bulk_commit_wait() {
+    asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+    asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+}
+__device__ __forceinline__ unsigned int s3_ld_relaxed(const unsigned int* p) {
+    unsigned int v;
+    asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+
+// fill p[0 .. len) with 10.0 by one warp: bulk stores (shared -> global) of up to 8 KB from sm.tens, at most one
+// plain store at either end for 16-byte alignment.  Returns after the lane has ISSUED its stores.
+__device__ __forceinline__ void s3_fill_tma(double* __restrict__ p, long long len, const double* tens, int lane) {
+    if (len <= 0) return;
+    const long long head = (long long)((reinterpret_cast<unsigned long long>(p) >> 3) & 1ull);
+    if (head && lane == 0) p[0] = 10.0;
+    const long long mid = (len - head) & ~1ll;
+    for (long long c = (long long)lane * S3_FILL_DOUBLES; c < mid; c += 32ll * S3_FILL_DOUBLES) {
+        const long long m = min((long long)S3_FILL_DOUBLES, mid - c);
+        s3_bulk_s2g(p + head + c, tens, (unsigned int)(m * 8));
+    }
+    if (head + mid < len && lane == 0) p[len - 1] = 10.0;
+}
+
+__device__ __forceinline__ bool s3_fast_range(double x) {
+    // hi words of ~1.4e-250 and ~1.5e200: also false for NaN/Inf (x is never negative)
+    return ((unsigned int)__double2hiint(x) - 0x0C100000u) <= (0x69800000u - 0x0C100000u);
+}
+
+// x / den through the stored reciprocal (two Markstein corrections, see the header); operands must be in range
+__device__ __forceinline__ double s3_div_fast(double x, double den, double rcp) {
+    const double q0 = __dmul_rn(x, rcp);
+    const double q1 = __fma_rn(__fma_rn(-den, q0, x), rcp, q0);
+    return __fma_rn(__fma_rn(-den, q1, x), rcp, q1);
+}
+
+__device__ __noinline__ double s3_div_slow(double x, double den) { return __ddiv_rn(x, den); }
+
+// compute_errors.jl:30-43: N consecutive terms of one group, e <- e + (d-s)^2/den in the reference's order.
+// The N quotients are independent (loads and Markstein chains overlap); only the final additions are ordered.
+template <int N>
+__device__ __forceinline__ double s3_chunk(double e, const double* __restrict__ sp, const S3Smem& sm, int gl, int t0, bool ok) {
+    double xx[N], q[N];
+    bool fast = ok;
+#pragma unroll
+    for (int j = 0; j < N; ++j) {
+        const double diff = __dadd_rn(sm.d[t0 + j][gl], -sp[t0 + j]);
+        xx[j] = __dmul_rn(diff, diff);
+        fast = fast && s3_fast_range(xx[j]);
+        q[j] = s3_div_fast(xx[j], sm.den[t0 + j][gl], sm.rcp[t0 + j][gl]);
+    }
+    if (!fast) {
+#pragma unroll
+        for (int j = 0; j < N; ++j)
+            if (!(ok && s3_fast_range(xx[j]))) q[j] = s3_div_slow(xx[j], sm.den[t0 + j][gl]);
+    }
+#pragma unroll
+    for (int j = 0; j < N; ++j) e = __dadd_rn(e, q[j]);
+    return e;
+}
+
+__device__ __forceinline__ double s3_div53(double e) {
+    if (s3_fast_range(e)) return s3_div_fast(e, 53.0, 1.0 / 53.0);
+    return s3_div_slow(e, 53.0);
+}
+
+// compute_errors.jl:55-64 for one (particle, gene slot); loops stay rolled (instruction cache)
+__device__ __forceinline__ double s3_exact(const double* __restrict__ sp, const S3Smem& sm, int gl, bool ok) {
+    double err = 0.0;
+#pragma unroll 1
+    for (int l = 0; l < 4; ++l)                       // pulse_mean, pulse_ff, chase_mean, chase_ff
+        err = __dadd_rn(err, s3_div53(s3_chunk<5>(0.0, sp, sm, gl, 5 * l, ok)));
+#pragma unroll 1
+    for (int l = 0; l < 3; ++l) {                     // ratio, mean_corr, corr_mean
+        double e = 0.0;
+#pragma unroll 1
+        for (int c = 0; c < 2; ++c) e = s3_chunk<4>(e, sp, sm, gl, 20 + 11 * l + 4 * c, ok);
+        e = s3_chunk<3>(e, sp, sm, gl, 28 + 11 * l, ok);
+        err = __dadd_rn(err, s3_div53(e));
+    }
+    return (err > 10.0) ? 10.0 : err;
+}
+
+// the FP32 statistics of four particles, two values per lane and particle (53 = 32 + 21)
+struct S3Regs { float v[2 * S3_NP]; };
+
+__device__ __forceinline__ void s3_load4(S3Regs& r, const float* __restrict__ fstats, long long i0, const unsigned short* ids,
+                                         int lane) {
+#pragma unroll
+    for (int p = 0; p < S3_NP; ++p) {
+        const float* sp = fstats + (i0 + ids[p]) * ABC_NSTATS;
+        r.v[2 * p] = sp[lane];
+        r.v[2 * p + 1] = (lane < ABC_NSTATS - 32) ? sp[32 + lane] : 0.f;
+    }
+}
+
+template <int LO, int HI, int UNROLL>
+__device__ __forceinline__ void s3_terms(const float4 (&ab)[ABC_NSTATS][S3_TG], const float4* __restrict__ st, int lane,
+                                         float2& p01, float2& p23) {
+#pragma unroll UNROLL
+    for (int t = LO; t < HI; ++t) {
+        const float4 c = ab[t][lane];
+        const float4 s = st[t];
+        const float2 t01 = __ffma2_rn(make_float2(c.x, c.y), make_float2(s.x, s.y), make_float2(c.z, c.w));
+        const float2 t23 = __ffma2_rn(make_float2(c.x, c.y), make_float2(s.z, s.w), make_float2(c.z, c.w));
+        p01 = __ffma2_rn(t01, t01, p01);
+        p23 = __ffma2_rn(t23, t23, p23);
+    }
+}
+
+template <int LAYOUT>
+__global__ void __launch_bounds__(S3_THREADS, 2)
+abc_score3_tile_kernel(const AbcScoreArgs a, const AbcScore3Tables x) {
+    extern __shared__ __align__(128) unsigned char s3_raw[];
+    S3Smem& sm = *reinterpret_cast<S3Smem*>(s3_raw);
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int T = (int)(blockIdx.x % (unsigned int)x.ntiles);
+    const long long k = blockIdx.x / (unsigned int)x.ntiles;
+    const long long i0 = k * S3_PB;
+    const long long nblocks = (a.n + S3_PB - 1) / S3_PB;
+    const double qnan = __longlong_as_double(0x7ff8000000000000ll);
+
+    if (tid < S3_PB / 32) {
+        const long long wi = k * (S3_PB / 32) + tid;
+        const unsigned int lw = (wi < x.W) ? x.live[(long long)T * x.W + wi] : 0u;
+        sm.livew[tid] = lw;
+        sm.cnt[tid] = __popc(lw);
+    }
+    if (tid < S3_TG) sm.gidx[tid] = x.gidx[T * S3_TG + tid];
+    if (tid == 0) { sm.okmask = x.okmask[T]; sm.fill_flag = 0; }
+    if (warp == S3_WARPS) {
+        for (int j = lane; j < S3_FILL_DOUBLES; j += 32) sm.tens[j] = 10.0;
+        if (lane == 0) s3_mbar_init(&sm.mbar, 1);
+        s3_fence_proxy_async();                // sm.tens and the barrier become visible to the async proxy
+    }
+    __syncthreads();
+
+    if (warp == S3_WARPS) {
+        // ================= service warp: tile constants in, fill out, both as bulk copies; then it retires
+        if (lane == 0) {
+            const unsigned int b_ab = (unsigned int)sizeof(sm.ab), b_d = (unsigned int)sizeof(sm.d);
+            s3_mbar_expect_tx(&sm.mbar, b_ab + 3u * b_d);
+            s3_bulk_g2s(&sm.ab[0][0], x.ab + (long long)T * ABC_NSTATS * S3_TG, b_ab, &sm.mbar);
+            s3_bulk_g2s(&sm.d[0][0], x.dT + (long long)T * ABC_NSTATS * S3_TG, b_d, &sm.mbar);
+            s3_bulk_g2s(&sm.den[0][0], x.denT + (long long)T * ABC_NSTATS * S3_TG, b_d, &sm.mbar);
+            s3_bulk_g2s(&sm.rcp[0][0], x.rcpT + (long long)T * ABC_NSTATS * S3_TG, b_d, &sm.mbar);
+        }
+        if (LAYOUT == ABC_ERR_GENE_MAJOR) {
+            // this CTA's own 32 gene rows x 2048 particles; a NaN-statistic particle makes its whole column NaN
+            const int rows = (int)min((long long)S3_PB, a.n - i0);
+            bool nn = false;
+            for (int j = lane; j < S3_PB / 32; j += 32) {
+                const long long wi = k * (S3_PB / 32) + j;
+                nn = nn || (wi < x.W && x.nanw[wi] != 0u);
+            }
+            const bool any_nan = __any_sync(0xffffffffu, nn);
+            for (int sl = 0; sl < S3_TG; ++sl) {
+                const int g = sm.gidx[sl];
+                if (g < 0) continue;
+                double* p = a.err + (long long)g * a.n + i0;
+                if (!any_nan) {
+                    s3_fill_tma(p, rows, sm.tens, lane);
+                } else {
+                    for (int r = lane; r < rows; r += 32)
+                        p[r] = ((x.nanw[k * (S3_PB / 32) + (r >> 5)] >> (r & 31)) & 1u) ? qnan : 10.0;
+                }
+            }
+            s3_bulk_commit_wait();
+            s3_fence_proxy_async();
+            __syncwarp();
+            if (lane == 0) { __threadfence_block(); *(volatile int*)&sm.fill_flag = 1; }
+        } else if (LAYOUT == ABC_ERR_PARTICLE_MAJOR) {
+            // slices of later blocks (contiguous rows): block k + S3_AHEAD, and blocks 0 .. S3_AHEAD-1 by the CTAs of block 0
+            for (int w = 0; w <= S3_AHEAD; ++w) {
+                const long long kf = (w == 0) ? k + S3_AHEAD : (long long)(w - 1);
+                if ((w > 0 && k != 0) || kf >= nblocks) continue;
+                const long long f0 = kf * S3_PB;
+                const int rows = (int)min((long long)S3_PB, a.n - f0);
+                bool nn = false;
+                for (int j = lane; j < S3_PB / 32; j += 32) {
+                    const long long wi = kf * (S3_PB / 32) + j;
+                    nn = nn || (wi < x.W && x.nanw[wi] != 0u);
+                }
+                const bool any_nan = __any_sync(0xffffffffu, nn);
+                const long long L = (long long)rows * a.G;
+                long long chunk = (L + x.ntiles - 1) / x.ntiles;
+                chunk += chunk & 1;
+                const long long lo = min(L, (long long)T * chunk), hi = min(L, lo + chunk);
+                double* base = a.err + f0 * (long long)a.G;
+                if (!any_nan) {
+                    s3_fill_tma(base + lo, hi - lo, sm.tens, lane);
+                } else {
+                    for (long long j = lo + lane; j < hi; j += 32) {
+                        const int r = (int)(j / a.G);
+                        base[j] = ((x.nanw[kf * (S3_PB / 32) + (r >> 5)] >> (r & 31)) & 1u) ? qnan : 10.0;
+                    }
+                }
+                s3_bulk_commit_wait();
+                s3_fence_proxy_async();
+                __syncwarp();
+                if (lane == 0) {
+                    __threadfence();           // release: the slice (all lanes, ordered by the warp barrier) before the count
+                    atomicAdd(x.done + kf, 1u);
+                }
+            }
+        }
+        return;
+    }
+
+    // ================= compute warps
+    // ---- list of live particles
+    if (tid < S3_PB / 32) {
+        int off = 0;
+        for (int q = 0; q < tid; ++q) off += sm.cnt[q];
+        unsigned int w = sm.livew[tid];
+        while (w) {
+            const int b = __ffs(w) - 1;
+            w &= w - 1u;
+            sm.list[off++] = (unsigned short)(tid * 32 + b);
+        }
+        if (tid == S3_PB / 32 - 1) sm.nlist = off;
+    }
+    asm volatile("bar.sync 1, %0;" ::"n"(S3_WARPS * 32) : "memory");
+    const int nl = sm.nlist;
+    // pad the list with its last entry so that passes can always read four entries and prefetch one pass ahead
+    if (nl > 0 && tid < 2 * S3_WARPS * S3_NP) sm.list[nl + tid] = sm.list[nl - 1];
+    asm volatile("bar.sync 1, %0;" ::"n"(S3_WARPS * 32) : "memory");
+    s3_mbar_wait(&sm.mbar, 0);                 // tile constants have landed (also: no bulk copy in flight at exit)
+    if (nl == 0) return;
+
+    // ---- per-warp pipeline.  One call site per stage (the unrolled stage bodies must stay in the instruction cache).
+    const bool lane_valid = sm.gidx[lane] >= 0;
+    const unsigned int lt_mask = (1u << lane) - 1u;
+    int q1head = 0, q1cnt = 0, nq2 = 0;        // ring of items waiting for stage 2 (slots 0..7), pairs waiting for stage 3
+    bool fill_ok = false;
+    float* stf = reinterpret_cast<float*>(&sm.st[warp][0]);
+    S3Regs nxt;
+    int base = warp * S3_NP;
+    bool more = base < nl;
+    if (more) s3_load4(nxt, a.fstats, i0, &sm.list[base], lane);
+    while (more || q1cnt > 0 || nq2 > 0) {
+        if (more) {
+            // ---- stage 1: four live particles, first 15 terms
+            const int nv = min(S3_NP, nl - base);
+            __syncwarp();
+#pragma unroll
+            for (int p = 0; p < S3_NP; ++p) {
+                stf[lane * 4 + p] = nxt.v[2 * p];
+                if (lane < ABC_NSTATS - 32) stf[(32 + lane) * 4 + p] = nxt.v[2 * p + 1];
+            }
+            __syncwarp();
+            const int nbase = base + S3_WARPS * S3_NP;
+            if (nbase < nl) s3_load4(nxt, a.fstats, i0, &sm.list[nbase], lane);    // in flight during this pass
+            float2 p01 = make_float2(0.f, 0.f), p23 = make_float2(0.f, 0.f);
+            s3_terms<0, S3_T1, S3_T1>(sm.ab, sm.st[warp], lane, p01, p23);
+            const float pp[S3_NP] = {p01.x, p01.y, p23.x, p23.y};
+#pragma unroll
+            for (int p = 0; p < S3_NP; ++p) {
+                const bool unsure = lane_valid && p < nv && !(pp[p] > S3_SURE);
+                if (__any_sync(0xffffffffu, unsure)) {
+                    // queue the item for stage 2: its statistics go into component (slot & 3) of ring group (slot >> 2)
+                    const int slot = (q1head + q1cnt) & (2 * S3_NP - 1);
+                    float* qf = reinterpret_cast<float*>(&sm.qs[warp][slot >> 2][0]) + (slot & 3);
+                    qf[lane * 4] = stf[lane * 4 + p];
+                    if (lane < ABC_NSTATS - 32) qf[(32 + lane) * 4] = stf[(32 + lane) * 4 + p];
+                    sm.part[warp][slot][lane] = pp[p];
+                    if (lane == 0) sm.q1[warp][slot] = sm.list[base + p];
+                    q1cnt++;
+                }
+            }
+            base = nbase;
+            more = base < nl;
+        }
+        if (q1cnt >= S3_NP || (!more && q1cnt > 0)) {
+            // ---- stage 2: head group of the ring, terms 15..52 on top of the stored stage-1 sums
+            const int nv = min(q1cnt, S3_NP);
+            __syncwarp();
+            float2 p01, p23;
+            p01.x = sm.part[warp][q1head][lane];
+            p01.y = sm.part[warp][q1head + 1][lane];
+            p23.x = sm.part[warp][q1head + 2][lane];
+            p23.y = sm.part[warp][q1head + 3][lane];
+            s3_terms<S3_T1, ABC_NSTATS, 19>(sm.ab, sm.qs[warp][q1head >> 2], lane, p01, p23);
+            const float pp[S3_NP] = {p01.x, p01.y, p23.x, p23.y};
+#pragma unroll
+            for (int p = 0; p < S3_NP; ++p) {
+                const bool unsure = lane_valid && p < nv && !(pp[p] > S3_SURE);
+                const unsigned int bal = __ballot_sync(0xffffffffu, unsure);
+                if (unsure) sm.q2[warp][nq2 + __popc(bal & lt_mask)] = (unsigned short)((sm.q1[warp][q1head + p] << 5) | lane);
+                nq2 += __popc(bal);
+            }
+            q1head = (q1head + S3_NP) & (2 * S3_NP - 1);
+            q1cnt -= nv;
+        }
+        while (nq2 >= 32 || (!more && q1cnt == 0 && nq2 > 0)) {
+            // ---- stage 3: one queued pair per lane, the reference's FP64 arithmetic; fused eps-acceptance
+            const int cnt = min(nq2, 32), e0 = nq2 - cnt;
+            __syncwarp();
+            if (LAYOUT != ABC_ERR_NONE && !fill_ok) {
+                // the fill of these rows must be complete before values overwrite it
+                if (lane == 0) {
+                    if (LAYOUT == ABC_ERR_PARTICLE_MAJOR) {
+                        while (s3_ld_relaxed(x.done + k) < (unsigned int)x.ntiles) __nanosleep(256);
+                        __threadfence();       // acquire
+                    } else {
+                        while (*(volatile int*)&sm.fill_flag == 0) __nanosleep(64);
+                        __threadfence_block();
+                    }
+                }
+                __syncwarp();
+                fill_ok = true;
+            }
+            bool acc = false;
+            double err = 0.0;
+            long long i = 0;
+            int g = 0;
+            if (lane < cnt) {
+                const unsigned int ent = sm.q2[warp][e0 + lane];
+                const int gl = (int)(ent & 31u);
+                i = i0 + (long long)(ent >> 5);
+                g = sm.gidx[gl];
+                err = s3_exact(a.stats + i * ABC_NSTATS, sm, gl, ((sm.okmask >> gl) & 1u) != 0u);
+                if (LAYOUT == ABC_ERR_GENE_MAJOR) a.err[(long long)g * a.n + i] = err;
+                else if (LAYOUT == ABC_ERR_PARTICLE_MAJOR) a.err[i * (long long)a.G + g] = err;
+                acc = err <= a.eps;                       // accepted_particles.jl:20; NaN is never accepted
+            }
+            const unsigned int mask = __ballot_sync(0xffffffffu, acc);
+            if (mask != 0u) {
+                const int leader = __ffs(mask) - 1;
+                unsigned long long slot = 0;
+                if (lane == leader) slot = atomicAdd(a.acc_count, (unsigned long long)__popc(mask));
+                slot = __shfl_sync(0xffffffffu, slot, leader) + (unsigned long long)__popc(mask & lt_mask);
+                if (acc) {
+                    atomicAdd(a.counts + g, 1ull);
+                    if ((long long)slot < a.acc_capacity) {
+                        a.acc_gene[slot] = g;
+                        a.acc_particle[slot] = a.particle_offset + i + 1;     // 1-based like Julia
+                        a.acc_err[slot] = err;
+                    }
+                }
+            }
+            nq2 = e0;
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------ launcher
+size_t abc_score3_blocks(int64_t n) { return (size_t)((n + S3_PB - 1) / S3_PB); }
+
+int abc_launch_score3(const AbcScoreArgs& a, const AbcScore3Tables& x, cudaStream_t st) {
+    if (a.n <= 0 || a.G <= 0) return ABC_OK;
+    const long long nblocks = (a.n + S3_PB - 1) / S3_PB;
+    if (nblocks * x.ntiles > 0x7fffffffll) { abc_set_error("abc_score: batch too large for one launch"); return ABC_ERR_ARG; }
+    const int lay = (a.err == nullptr) ? ABC_ERR_NONE : a.err_layout;
+    const int smem = (int)sizeof(S3Smem);
+    // per device and cheap: set on every launch
+    ABC_CUDA_CHECK(cudaFuncSetAttribute(abc_score3_tile_kernel<ABC_ERR_NONE>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    ABC_CUDA_CHECK(cudaFuncSetAttribute(abc_score3_tile_kernel<ABC_ERR_GENE_MAJOR>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    ABC_CUDA_CHECK(cudaFuncSetAttribute(abc_score3_tile_kernel<ABC_ERR_PARTICLE_MAJOR>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    if (lay == ABC_ERR_PARTICLE_MAJOR) ABC_CUDA_CHECK(cudaMemsetAsync(x.done, 0, (size_t)nblocks * sizeof(unsigned int), st));
+    const unsigned int cgrid = (unsigned int)((a.n + 2 * S3C_THREADS - 1) / (2 * S3C_THREADS));
+    abc_score3_classify_kernel<<<cgrid, S3C_THREADS, 0, st>>>(a.stats, (long long)a.n, x.ntiles, x.tb, const_cast<float*>(a.fstats),
+                                                              x.live, x.nanw, (long long)x.W);
+    ABC_CUDA_CHECK(cudaGetLastError());
+    const unsigned int grid = (unsigned int)(nblocks * x.ntiles);
+    if (lay == ABC_ERR_NONE) abc_score3_tile_kernel<ABC_ERR_NONE><<<grid, S3_THREADS, smem, st>>>(a, x);
+    else if (lay == ABC_ERR_GENE_MAJOR) abc_score3_tile_kernel<ABC_ERR_GENE_MAJOR><<<grid, S3_THREADS, smem, st>>>(a, x);
+    else abc_score3_tile_kernel<ABC_ERR_PARTICLE_MAJOR><<<grid, S3_THREADS, smem, st>>>(a, x);
+    ABC_CUDA_CHECK(cudaGetLastError());
+    return ABC_OK;
+}

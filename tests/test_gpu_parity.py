@@ -160,22 +160,29 @@ def test_accept_lists_match_reference_order(eng, data_stats):
 
 
 def test_score_kernels_agree_and_eps_above_clip(eng, data_stats):
-    """three-stage kernel == plain FP64 kernel == oracle; eps >= 10 (accepts the clipped pairs) takes the plain path"""
+    """tile-pruned kernel == three-stage kernel == plain FP64 kernel == oracle; eps >= 10 (accepts the clipped
+    pairs) takes the plain path"""
     d, se = data_stats
     rng = np.random.default_rng(8)
     s = synth_stats(rng, d, 600)
     s[5, 3] = np.nan
     ref = oracle.compute_trunc_errors(s, d, se)
     got = {}
-    for flag in (0, 1):
-        eng.set_option("score_reference_kernel", flag)
-        eng.accept_reset()
-        err, counts, _ = eng.score(s, eps=4.8, err_layout=ERR_GENE_MAJOR)
-        off, idx, errs = eng.accept_fetch()
-        got[flag] = (err, counts, off, idx)
-        assert oracle.same_bits(err, ref.T)
-    eng.set_option("score_reference_kernel", 0)
-    assert all(np.array_equal(a, b) for a, b in zip(got[0][1:], got[1][1:]))
+    for key, (tile, plain) in {"tile": (1, 0), "three_stage": (0, 0), "plain": (0, 1)}.items():
+        eng.set_option("score_tile_kernel", tile)
+        eng.set_option("score_reference_kernel", plain)
+        try:
+            for layout, want in ((ERR_GENE_MAJOR, ref.T), (ERR_PARTICLE_MAJOR, ref)):
+                eng.accept_reset()
+                err, counts, _ = eng.score(s, eps=4.8, err_layout=layout)
+                off, idx, errs = eng.accept_fetch()
+                assert oracle.same_bits(err, want), (key, layout)
+            got[key] = (counts, off, idx)
+        finally:
+            eng.set_option("score_tile_kernel", 1)
+            eng.set_option("score_reference_kernel", 0)
+    for key in ("three_stage", "plain"):
+        assert all(np.array_equal(a, b) for a, b in zip(got["tile"], got[key])), key
     eng.accept_reset()
     err, counts, _ = eng.score(s[:40], eps=10.0, err_layout=ERR_PARTICLE_MAJOR)
     assert oracle.same_bits(err, ref[:40])
@@ -183,6 +190,66 @@ def test_score_kernels_agree_and_eps_above_clip(eng, data_stats):
     off, idx, _ = eng.accept_fetch()
     for g in (0, 1711, 3418):
         assert np.array_equal(idx[off[g]:off[g + 1]], oracle.accept_gene(ref[:40, g], 10.0))
+
+
+def test_score_tile_pruning_wide_particles(eng, data_stats):
+    """particles spread over twelve decades, negative values in statistics that are non-negative for simulated
+    particles, several particle blocks, a ragged tail: the tile bounds must never drop a pair below 10"""
+    d, se = data_stats
+    rng = np.random.default_rng(31)
+    n = 2 * 2048 + 333
+    s = 10.0 ** rng.uniform(-6, 6, size=(n, 53)) * np.where(rng.random((n, 53)) < 0.1, -1.0, 1.0)
+    near = rng.random(n) < 0.4                       # particles near one gene, rescaled as a whole
+    g = rng.integers(0, d.shape[0], size=n)
+    s[near] = d[g[near]] * np.exp(rng.normal(0.0, 0.15, size=(near.sum(), 53))) * 10.0 ** rng.choice([0, 0, 0.5, -0.5, 1], size=(near.sum(), 1))
+    s[11, 20] = np.nan
+    s[2050, 52] = np.nan
+    s[4100, 0] = np.inf
+    ref = oracle.compute_trunc_errors(s, d, se)
+    assert 0.0005 < (ref < 10.0).mean() < 0.2 and np.isnan(ref[11]).all() and np.isnan(ref[2050]).all()
+    for layout, want in ((ERR_PARTICLE_MAJOR, ref), (ERR_GENE_MAJOR, ref.T)):
+        eng.accept_reset()
+        err, counts, _ = eng.score(s, eps=4.8, err_layout=layout)
+        assert oracle.same_bits(err, want), layout
+        assert np.array_equal(counts, (ref <= 4.8).sum(0))
+    eng.accept_reset()
+    _, counts, _ = eng.score(s, eps=4.8, err_layout=ERR_NONE)
+    assert np.array_equal(counts, (ref <= 4.8).sum(0))
+    off, idx, errs = eng.accept_fetch()
+    for gg in range(0, d.shape[0], 53):
+        want = oracle.accept_gene(ref[:, gg], 4.8)
+        assert np.array_equal(idx[off[gg]:off[gg + 1]], want)
+        assert oracle.same_bits(errs[off[gg]:off[gg + 1]], ref[want - 1, gg])
+
+
+def test_score_tile_pruning_signed_and_degenerate_data(eng, data_stats):
+    """data with negative entries in the 'non-negative' statistics, zero rows, tiny and huge magnitudes and a
+    gene count that is not a multiple of the tile size"""
+    d, se = data_stats
+    rng = np.random.default_rng(32)
+    G = 200 + 7
+    d2 = d[rng.choice(d.shape[0], G, replace=False)].copy()
+    se2 = se[rng.choice(se.shape[0], G, replace=False)].copy()
+    d2[3, :10] *= -1.0
+    d2[40] = 0.0
+    se2[40] = 0.0
+    d2[77] *= 1e-12
+    se2[77] *= 1e-12
+    d2[120] *= 1e9
+    d2[150, 12] = -np.inf
+    s = np.concatenate([d2[rng.integers(0, G, 900)] * np.exp(rng.normal(0, 0.2, (900, 53))),
+                        10.0 ** rng.uniform(-14, 10, size=(600, 53)), np.zeros((3, 53))])
+    eng.set_data(d2, se2)
+    try:
+        ref = oracle.compute_trunc_errors(s, d2, se2)
+        assert (ref < 10.0).mean() > 0.001
+        for layout, want in ((ERR_PARTICLE_MAJOR, ref), (ERR_GENE_MAJOR, ref.T)):
+            eng.accept_reset()
+            err, counts, _ = eng.score(s, eps=4.8, err_layout=layout)
+            assert oracle.same_bits(err, want), layout
+            assert np.array_equal(counts, (ref <= 4.8).sum(0))
+    finally:
+        eng.set_data(d, se)
 
 
 def test_score_near_matches_fill_the_queues(eng, data_stats):
