@@ -84,7 +84,7 @@ struct abc_ctx {
     // tile-pruned scoring tables (per data set) and work buffers
     int32_t s3_ntiles = 0;
     DevBuf<float4> d_s3_tb, d_s3_ab;
-    DevBuf<double> d_s3_dT, d_s3_denT, d_s3_rcpT;
+    DevBuf<uint32_t> d_s3_wt;
     DevBuf<int32_t> d_s3_gidx;
     DevBuf<uint32_t> d_s3_ok, d_s3_live, d_s3_nanw, d_s3_done;
     int stats_guards = -1;       // -1: sample guards iff sim_kind == SSA; 0 / 1 force
@@ -150,7 +150,7 @@ extern "C" int abc_destroy(abc_ctx_t* c) {
     cudaSetDevice(c->device);
     cudaStreamSynchronize(c->stream);
     c->d_beta.release(); c->d_age_dist.release(); c->d_beta_mom.release(); c->d_d.release(); c->d_den.release(); c->d_fbw.release(); c->d_fa.release(); c->d_fstats.release(); c->d_rnan.release();
-    c->d_s3_tb.release(); c->d_s3_ab.release(); c->d_s3_dT.release(); c->d_s3_denT.release(); c->d_s3_rcpT.release();
+    c->d_s3_tb.release(); c->d_s3_ab.release(); c->d_s3_wt.release();
     c->d_s3_gidx.release(); c->d_s3_ok.release(); c->d_s3_live.release(); c->d_s3_nanw.release(); c->d_s3_done.release();
     c->d_theta.release(); c->d_stats.release(); c->d_moments.release(); c->d_ss_iv.release(); c->d_prefix.release(); c->d_rates.release();
     c->d_keys_in.release(); c->d_keys_out.release(); c->d_idx_in.release(); c->d_order.release(); c->d_sort_tmp.release();
@@ -289,16 +289,12 @@ extern "C" int abc_set_data(abc_ctx_t* c, const double* d, const double* se, int
         abc_score3_build(d, h_den.data(), G, h);
         if ((rc = c->d_s3_tb.ensure(h.tb.size() / 4)) != ABC_OK) return rc;
         if ((rc = c->d_s3_ab.ensure(h.ab.size() / 4)) != ABC_OK) return rc;
-        if ((rc = c->d_s3_dT.ensure(h.dT.size())) != ABC_OK) return rc;
-        if ((rc = c->d_s3_denT.ensure(h.denT.size())) != ABC_OK) return rc;
-        if ((rc = c->d_s3_rcpT.ensure(h.rcpT.size())) != ABC_OK) return rc;
+        if ((rc = c->d_s3_wt.ensure(h.wt.size())) != ABC_OK) return rc;
         if ((rc = c->d_s3_gidx.ensure(h.gidx.size())) != ABC_OK) return rc;
         if ((rc = c->d_s3_ok.ensure(h.okmask.size())) != ABC_OK) return rc;
         ABC_CUDA_CHECK(cudaMemcpy(c->d_s3_tb.p, h.tb.data(), h.tb.size() * sizeof(float), cudaMemcpyHostToDevice));
         ABC_CUDA_CHECK(cudaMemcpy(c->d_s3_ab.p, h.ab.data(), h.ab.size() * sizeof(float), cudaMemcpyHostToDevice));
-        ABC_CUDA_CHECK(cudaMemcpy(c->d_s3_dT.p, h.dT.data(), h.dT.size() * sizeof(double), cudaMemcpyHostToDevice));
-        ABC_CUDA_CHECK(cudaMemcpy(c->d_s3_denT.p, h.denT.data(), h.denT.size() * sizeof(double), cudaMemcpyHostToDevice));
-        ABC_CUDA_CHECK(cudaMemcpy(c->d_s3_rcpT.p, h.rcpT.data(), h.rcpT.size() * sizeof(double), cudaMemcpyHostToDevice));
+        ABC_CUDA_CHECK(cudaMemcpy(c->d_s3_wt.p, h.wt.data(), h.wt.size() * sizeof(uint32_t), cudaMemcpyHostToDevice));
         ABC_CUDA_CHECK(cudaMemcpy(c->d_s3_gidx.p, h.gidx.data(), h.gidx.size() * sizeof(int32_t), cudaMemcpyHostToDevice));
         ABC_CUDA_CHECK(cudaMemcpy(c->d_s3_ok.p, h.okmask.data(), h.okmask.size() * sizeof(uint32_t), cudaMemcpyHostToDevice));
         c->s3_ntiles = h.ntiles;
@@ -618,7 +614,7 @@ static int score_device(abc_ctx* c, const double* d_stats, int64_t n, int64_t of
         if ((rc = c->d_s3_live.ensure((size_t)x.ntiles * (size_t)x.W)) != ABC_OK) return rc;
         if ((rc = c->d_s3_nanw.ensure((size_t)x.W)) != ABC_OK) return rc;
         if ((rc = c->d_s3_done.ensure(nblocks)) != ABC_OK) return rc;
-        x.tb = c->d_s3_tb.p; x.ab = c->d_s3_ab.p; x.dT = c->d_s3_dT.p; x.denT = c->d_s3_denT.p; x.rcpT = c->d_s3_rcpT.p;
+        x.tb = c->d_s3_tb.p; x.ab = c->d_s3_ab.p; x.wt = c->d_s3_wt.p;
         x.gidx = c->d_s3_gidx.p; x.okmask = c->d_s3_ok.p;
         x.live = c->d_s3_live.p; x.nanw = c->d_s3_nanw.p; x.done = c->d_s3_done.p;
         a.fstats = c->d_fstats.p;

@@ -82,10 +82,8 @@ int abc_launch_score(const AbcScoreArgs& a, int sm_count, cudaStream_t st);
 struct AbcScore3Tables {
     int32_t ntiles;
     const float4* tb;        // [ntiles][31]: (amin, -bmax, bmin, -amax) of a = sqrt(w) d, b = sqrt(w), w = 1/(53 den)
-    const float4* ab;        // [ntiles][53][32]: (-b, -b, a, a) per (term, gene slot)
-    const double* dT;        // [ntiles][53][32] data statistics, denominators and their reciprocals in tile order
-    const double* denT;
-    const double* rcpT;
+    const float4* ab;        // [ntiles][27][32]: (a_2j, a_2j+1, -b_2j, -b_2j+1) per (term pair, gene slot)
+    const uint32_t* wt;      // [ntiles][6][53][32]: d, den, RN(1/den) as (high, low) words in tile order
     const int32_t* gidx;     // [ntiles][32] original gene index of a slot, -1 = padding
     const uint32_t* okmask;  // [ntiles] bit l: slot l may divide through the stored reciprocal
     uint32_t* live;          // [ntiles][W] work: bit = (tile, particle) needs stages 1-3
@@ -98,7 +96,7 @@ struct AbcScore3Tables {
 struct AbcScore3Host {
     int ntiles = 0;
     std::vector<float> tb, ab;
-    std::vector<double> dT, denT, rcpT;
+    std::vector<uint32_t> wt;
     std::vector<int32_t> gidx;
     std::vector<uint32_t> okmask;
 };

@@ -36,17 +36,21 @@
 
 #include <algorithm>
 #include <cmath>
+#include <cstring>
 #include <vector>
 
 #define S3_TG 32
 #define S3_NN 31          // statistics used by the tile bound: means, Fano factors, ratios (non-negative)
-#define S3_T1 15
-#define S3_WARPS 8                       // compute warps
+#define S3_WARPS 11                      // compute warps
 #define S3_THREADS (S3_WARPS * 32 + 32)  // + one service warp: table loads and the fill, both through the TMA engine
 #define S3_FILL_DOUBLES 512              // 4 KB of 10.0 in shared memory: the source of the bulk stores
 #define S3_AHEAD 2                       // particle-major: a CTA of block k fills its slice of block k + S3_AHEAD
 #define S3_PB 2048        // particles per CTA
 #define S3_NP 4           // particles per warp pass
+#define S3_NPAIR 27       // term pairs (53 terms + one zero term)
+#define S3_SROW 56        // floats per staged particle (53 statistics, padded to whole float4)
+#define S3_Q2 512         // pairs a warp may queue for stage 3
+#define S3_Q2_DRAIN 352   // ... and the fill at which it leaves the filter loop (a pass adds up to 128)
 #define S3_SURE 10.01f
 #define S3C_THREADS 128
 #define S3C_TCH 24
@@ -106,10 +110,8 @@ void abc_score3_build(const double* d, const double* den, int G, AbcScore3Host& 
     std::sort(leaves.begin(), leaves.end());
     out.ntiles = ntiles;
     out.tb.assign((size_t)ntiles * S3_NN * 4, 0.f);
-    out.ab.assign((size_t)ntiles * ABC_NSTATS * S3_TG * 4, 0.f);
-    out.dT.assign((size_t)ntiles * ABC_NSTATS * S3_TG, 0.0);
-    out.denT.assign((size_t)ntiles * ABC_NSTATS * S3_TG, 1.0);
-    out.rcpT.assign((size_t)ntiles * ABC_NSTATS * S3_TG, 1.0);
+    out.ab.assign((size_t)ntiles * S3_NPAIR * S3_TG * 4, 0.f);
+    out.wt.assign((size_t)ntiles * 6 * ABC_NSTATS * S3_TG, 0u);
     out.gidx.assign((size_t)ntiles * S3_TG, -1);
     out.okmask.assign((size_t)ntiles, 0u);
     const float qn = std::nanf("");
@@ -122,11 +124,20 @@ void abc_score3_build(const double* d, const double* den, int G, AbcScore3Host& 
             if (ok[g]) out.okmask[T] |= 1u << l; else tile_ok = false;
             for (int t = 0; t < ABC_NSTATS; ++t) {
                 const double dv = d[(size_t)g * ABC_NSTATS + t], nv = den[(size_t)g * ABC_NSTATS + t];
-                const size_t o = ((size_t)T * ABC_NSTATS + t) * S3_TG + l;
-                out.dT[o] = dv; out.denT[o] = nv; out.rcpT[o] = 1.0 / nv;
+                // stage-3 constants d, den, RN(1/den) as separate high and low words: a 32-bit table row is one
+                // conflict-free shared-memory wavefront for any set of gene slots
+                const double w3[3] = {dv, nv, 1.0 / nv};
+                for (int q = 0; q < 3; ++q) {
+                    uint64_t bits;
+                    memcpy(&bits, &w3[q], 8);
+                    out.wt[(((size_t)T * 6 + 2 * q) * ABC_NSTATS + t) * S3_TG + l] = (uint32_t)(bits >> 32);
+                    out.wt[(((size_t)T * 6 + 2 * q + 1) * ABC_NSTATS + t) * S3_TG + l] = (uint32_t)bits;
+                }
                 float a = qn, b = qn;
                 if (ok[g]) { const double sw = std::sqrt(1.0 / (53.0 * nv)); a = (float)(sw * dv); b = (float)sw; }
-                out.ab[o * 4 + 0] = -b; out.ab[o * 4 + 1] = -b; out.ab[o * 4 + 2] = a; out.ab[o * 4 + 3] = a;
+                // terms (2j, 2j+1) packed for FFMA2: (a_2j, a_2j+1, -b_2j, -b_2j+1); term 52 is paired with zeros
+                float* pk = &out.ab[(((size_t)T * S3_NPAIR + t / 2) * S3_TG + l) * 4];
+                pk[t & 1] = a; pk[2 + (t & 1)] = -b;
             }
         }
         for (int t = 0; t < S3_NN; ++t) {
@@ -211,14 +222,11 @@ abc_score3_classify_kernel(const double* __restrict__ stats, long long n, int nt
 
 // ------------------------------------------------------------------------------------------------ tile kernel
 struct S3Smem {
-    float4 ab[ABC_NSTATS][S3_TG];              // (-b, -b, a, a) per (term, gene slot)
-    double d[ABC_NSTATS][S3_TG], den[ABC_NSTATS][S3_TG], rcp[ABC_NSTATS][S3_TG];   // stage-3 constants
-    float4 st[S3_WARPS][ABC_NSTATS];           // statistics of the four particles of a stage-1 pass, per warp
-    float4 qs[S3_WARPS][2][ABC_NSTATS];        // ring of two groups of four items waiting for stage 2 (statistics)
-    float part[S3_WARPS][2 * S3_NP][S3_TG];    // their stage-1 partial sums
+    float4 ab[S3_NPAIR][S3_TG];                // (a_2j, a_2j+1, -b_2j, -b_2j+1) per (term pair, gene slot): held in registers
+    unsigned int wt[6][ABC_NSTATS][S3_TG];     // stage-3 constants: d, den, 1/den as (high, low) words
+    float st[S3_WARPS][S3_NP][S3_SROW];        // statistics of the four particles of a pass, per warp
     unsigned short list[S3_PB + 2 * S3_WARPS * S3_NP];   // live particles of this (tile, block), padded
-    unsigned short q1[S3_WARPS][2 * S3_NP];    // their particle indices
-    unsigned short q2[S3_WARPS][S3_NP * 32 + 32];        // pairs waiting for stage 3: particle << 5 | gene slot
+    unsigned short q2[S3_WARPS][S3_Q2];        // pairs waiting for stage 3: particle << 5 | gene slot
     alignas(16) double tens[S3_FILL_DOUBLES];  // 10.0: source of the fill's bulk stores
     unsigned long long mbar;                   // completion of the table loads
     int gidx[S3_TG];
@@ -290,6 +298,10 @@ __device__ __forceinline__ double s3_div_fast(double x, double den, double rcp) 
 
 __device__ __noinline__ double s3_div_slow(double x, double den) { return __ddiv_rn(x, den); }
 
+__device__ __forceinline__ double s3_word(const S3Smem& sm, int q, int t, int gl) {
+    return __hiloint2double((int)sm.wt[2 * q][t][gl], (int)sm.wt[2 * q + 1][t][gl]);
+}
+
 // compute_errors.jl:30-43: N consecutive terms of one group, e <- e + (d-s)^2/den in the reference's order.
 // The N quotients are independent (loads and Markstein chains overlap); only the final additions are ordered.
 template <int N>
@@ -298,15 +310,15 @@ __device__ __forceinline__ double s3_chunk(double e, const double* __restrict__ 
     bool fast = ok;
 #pragma unroll
     for (int j = 0; j < N; ++j) {
-        const double diff = __dadd_rn(sm.d[t0 + j][gl], -sp[t0 + j]);
+        const double diff = __dadd_rn(s3_word(sm, 0, t0 + j, gl), -sp[t0 + j]);
         xx[j] = __dmul_rn(diff, diff);
         fast = fast && s3_fast_range(xx[j]);
-        q[j] = s3_div_fast(xx[j], sm.den[t0 + j][gl], sm.rcp[t0 + j][gl]);
+        q[j] = s3_div_fast(xx[j], s3_word(sm, 1, t0 + j, gl), s3_word(sm, 2, t0 + j, gl));
     }
     if (!fast) {
 #pragma unroll
         for (int j = 0; j < N; ++j)
-            if (!(ok && s3_fast_range(xx[j]))) q[j] = s3_div_slow(xx[j], sm.den[t0 + j][gl]);
+            if (!(ok && s3_fast_range(xx[j]))) q[j] = s3_div_slow(xx[j], s3_word(sm, 1, t0 + j, gl));
     }
 #pragma unroll
     for (int j = 0; j < N; ++j) e = __dadd_rn(e, q[j]);
@@ -348,22 +360,8 @@ __device__ __forceinline__ void s3_load4(S3Regs& r, const float* __restrict__ fs
     }
 }
 
-template <int LO, int HI, int UNROLL>
-__device__ __forceinline__ void s3_terms(const float4 (&ab)[ABC_NSTATS][S3_TG], const float4* __restrict__ st, int lane,
-                                         float2& p01, float2& p23) {
-#pragma unroll UNROLL
-    for (int t = LO; t < HI; ++t) {
-        const float4 c = ab[t][lane];
-        const float4 s = st[t];
-        const float2 t01 = __ffma2_rn(make_float2(c.x, c.y), make_float2(s.x, s.y), make_float2(c.z, c.w));
-        const float2 t23 = __ffma2_rn(make_float2(c.x, c.y), make_float2(s.z, s.w), make_float2(c.z, c.w));
-        p01 = __ffma2_rn(t01, t01, p01);
-        p23 = __ffma2_rn(t23, t23, p23);
-    }
-}
-
 template <int LAYOUT>
-__global__ void __launch_bounds__(S3_THREADS, 2)
+__global__ void __launch_bounds__(S3_THREADS, 1)
 abc_score3_tile_kernel(const AbcScoreArgs a, const AbcScore3Tables x) {
     extern __shared__ __align__(128) unsigned char s3_raw[];
     S3Smem& sm = *reinterpret_cast<S3Smem*>(s3_raw);
@@ -392,12 +390,10 @@ abc_score3_tile_kernel(const AbcScoreArgs a, const AbcScore3Tables x) {
     if (warp == S3_WARPS) {
         // ================= service warp: tile constants in, fill out, both as bulk copies; then it retires
         if (lane == 0) {
-            const unsigned int b_ab = (unsigned int)sizeof(sm.ab), b_d = (unsigned int)sizeof(sm.d);
-            s3_mbar_expect_tx(&sm.mbar, b_ab + 3u * b_d);
-            s3_bulk_g2s(&sm.ab[0][0], x.ab + (long long)T * ABC_NSTATS * S3_TG, b_ab, &sm.mbar);
-            s3_bulk_g2s(&sm.d[0][0], x.dT + (long long)T * ABC_NSTATS * S3_TG, b_d, &sm.mbar);
-            s3_bulk_g2s(&sm.den[0][0], x.denT + (long long)T * ABC_NSTATS * S3_TG, b_d, &sm.mbar);
-            s3_bulk_g2s(&sm.rcp[0][0], x.rcpT + (long long)T * ABC_NSTATS * S3_TG, b_d, &sm.mbar);
+            const unsigned int b_ab = (unsigned int)sizeof(sm.ab), b_wt = (unsigned int)sizeof(sm.wt);
+            s3_mbar_expect_tx(&sm.mbar, b_ab + b_wt);
+            s3_bulk_g2s(&sm.ab[0][0], x.ab + (long long)T * S3_NPAIR * S3_TG, b_ab, &sm.mbar);
+            s3_bulk_g2s(&sm.wt[0][0][0], x.wt + (long long)T * 6 * ABC_NSTATS * S3_TG, b_wt, &sm.mbar);
         }
         if (LAYOUT == ABC_ERR_GENE_MAJOR) {
             // this CTA's own 32 gene rows x 2048 particles; a NaN-statistic particle makes its whole column NaN
@@ -482,71 +478,68 @@ abc_score3_tile_kernel(const AbcScoreArgs a, const AbcScore3Tables x) {
     s3_mbar_wait(&sm.mbar, 0);                 // tile constants have landed (also: no bulk copy in flight at exit)
     if (nl == 0) return;
 
-    // ---- per-warp pipeline.  One call site per stage (the unrolled stage bodies must stay in the instruction cache).
+    // ---- per-warp pipeline: filter passes with the gene constants in registers, then stage-3 rounds; the constants
+    //      are reloaded after every drain so that they are not live across the FP64 code
     const bool lane_valid = sm.gidx[lane] >= 0;
     const unsigned int lt_mask = (1u << lane) - 1u;
-    int q1head = 0, q1cnt = 0, nq2 = 0;        // ring of items waiting for stage 2 (slots 0..7), pairs waiting for stage 3
+    int nq2 = 0;
     bool fill_ok = false;
-    float* stf = reinterpret_cast<float*>(&sm.st[warp][0]);
+    float* stw = &sm.st[warp][0][0];
     S3Regs nxt;
     int base = warp * S3_NP;
     bool more = base < nl;
     if (more) s3_load4(nxt, a.fstats, i0, &sm.list[base], lane);
-    while (more || q1cnt > 0 || nq2 > 0) {
+    for (int j = lane; j < S3_NP * (S3_SROW - ABC_NSTATS); j += 32)       // the padding stays 0
+        stw[(j / (S3_SROW - ABC_NSTATS)) * S3_SROW + ABC_NSTATS + j % (S3_SROW - ABC_NSTATS)] = 0.f;
+    while (more || nq2 > 0) {
         if (more) {
-            // ---- stage 1: four live particles, first 15 terms
-            const int nv = min(S3_NP, nl - base);
-            __syncwarp();
+            // gene constants of this lane: terms (2j, 2j+1) packed for FFMA2
+            float4 c[S3_NPAIR];
 #pragma unroll
-            for (int p = 0; p < S3_NP; ++p) {
-                stf[lane * 4 + p] = nxt.v[2 * p];
-                if (lane < ABC_NSTATS - 32) stf[(32 + lane) * 4 + p] = nxt.v[2 * p + 1];
-            }
-            __syncwarp();
-            const int nbase = base + S3_WARPS * S3_NP;
-            if (nbase < nl) s3_load4(nxt, a.fstats, i0, &sm.list[nbase], lane);    // in flight during this pass
-            float2 p01 = make_float2(0.f, 0.f), p23 = make_float2(0.f, 0.f);
-            s3_terms<0, S3_T1, S3_T1>(sm.ab, sm.st[warp], lane, p01, p23);
-            const float pp[S3_NP] = {p01.x, p01.y, p23.x, p23.y};
+            for (int j = 0; j < S3_NPAIR; ++j) c[j] = sm.ab[j][lane];
+            while (more && nq2 < S3_Q2_DRAIN) {
+                // ---- stages 1-2 in one pass: four live particles x 53 terms (FP32 lower bound, see the header)
+                const int nv = min(S3_NP, nl - base);
+                __syncwarp();
 #pragma unroll
-            for (int p = 0; p < S3_NP; ++p) {
-                const bool unsure = lane_valid && p < nv && !(pp[p] > S3_SURE);
-                if (__any_sync(0xffffffffu, unsure)) {
-                    // queue the item for stage 2: its statistics go into component (slot & 3) of ring group (slot >> 2)
-                    const int slot = (q1head + q1cnt) & (2 * S3_NP - 1);
-                    float* qf = reinterpret_cast<float*>(&sm.qs[warp][slot >> 2][0]) + (slot & 3);
-                    qf[lane * 4] = stf[lane * 4 + p];
-                    if (lane < ABC_NSTATS - 32) qf[(32 + lane) * 4] = stf[(32 + lane) * 4 + p];
-                    sm.part[warp][slot][lane] = pp[p];
-                    if (lane == 0) sm.q1[warp][slot] = sm.list[base + p];
-                    q1cnt++;
+                for (int p = 0; p < S3_NP; ++p) {
+                    stw[p * S3_SROW + lane] = nxt.v[2 * p];
+                    if (lane < ABC_NSTATS - 32) stw[p * S3_SROW + 32 + lane] = nxt.v[2 * p + 1];
                 }
-            }
-            base = nbase;
-            more = base < nl;
-        }
-        if (q1cnt >= S3_NP || (!more && q1cnt > 0)) {
-            // ---- stage 2: head group of the ring, terms 15..52 on top of the stored stage-1 sums
-            const int nv = min(q1cnt, S3_NP);
-            __syncwarp();
-            float2 p01, p23;
-            p01.x = sm.part[warp][q1head][lane];
-            p01.y = sm.part[warp][q1head + 1][lane];
-            p23.x = sm.part[warp][q1head + 2][lane];
-            p23.y = sm.part[warp][q1head + 3][lane];
-            s3_terms<S3_T1, ABC_NSTATS, 19>(sm.ab, sm.qs[warp][q1head >> 2], lane, p01, p23);
-            const float pp[S3_NP] = {p01.x, p01.y, p23.x, p23.y};
+                __syncwarp();
+                const int nbase = base + S3_WARPS * S3_NP;
+                if (nbase < nl) s3_load4(nxt, a.fstats, i0, &sm.list[nbase], lane);    // in flight during this pass
+                float2 acc[S3_NP];
 #pragma unroll
-            for (int p = 0; p < S3_NP; ++p) {
-                const bool unsure = lane_valid && p < nv && !(pp[p] > S3_SURE);
-                const unsigned int bal = __ballot_sync(0xffffffffu, unsure);
-                if (unsure) sm.q2[warp][nq2 + __popc(bal & lt_mask)] = (unsigned short)((sm.q1[warp][q1head + p] << 5) | lane);
-                nq2 += __popc(bal);
+                for (int p = 0; p < S3_NP; ++p) acc[p] = make_float2(0.f, 0.f);
+#pragma unroll
+                for (int q = 0; q < S3_SROW / 4; ++q) {
+#pragma unroll
+                    for (int p = 0; p < S3_NP; ++p) {
+                        const float4 sv = *reinterpret_cast<const float4*>(stw + p * S3_SROW + 4 * q);    // broadcast
+                        const float2 t0 = __ffma2_rn(make_float2(c[2 * q].z, c[2 * q].w), make_float2(sv.x, sv.y),
+                                                     make_float2(c[2 * q].x, c[2 * q].y));
+                        acc[p] = __ffma2_rn(t0, t0, acc[p]);
+                        if (2 * q + 1 < S3_NPAIR) {
+                            const float2 t1 = __ffma2_rn(make_float2(c[2 * q + 1].z, c[2 * q + 1].w), make_float2(sv.z, sv.w),
+                                                         make_float2(c[2 * q + 1].x, c[2 * q + 1].y));
+                            acc[p] = __ffma2_rn(t1, t1, acc[p]);
+                        }
+                    }
+                }
+#pragma unroll
+                for (int p = 0; p < S3_NP; ++p) {
+                    const float pp = __fadd_rn(acc[p].x, acc[p].y);
+                    const bool unsure = lane_valid && p < nv && !(pp > S3_SURE);
+                    const unsigned int bal = __ballot_sync(0xffffffffu, unsure);
+                    if (unsure) sm.q2[warp][nq2 + __popc(bal & lt_mask)] = (unsigned short)((sm.list[base + p] << 5) | lane);
+                    nq2 += __popc(bal);
+                }
+                base = nbase;
+                more = base < nl;
             }
-            q1head = (q1head + S3_NP) & (2 * S3_NP - 1);
-            q1cnt -= nv;
         }
-        while (nq2 >= 32 || (!more && q1cnt == 0 && nq2 > 0)) {
+        while (nq2 >= 32 || (!more && nq2 > 0)) {
             // ---- stage 3: one queued pair per lane, the reference's FP64 arithmetic; fused eps-acceptance
             const int cnt = min(nq2, 32), e0 = nq2 - cnt;
             __syncwarp();
