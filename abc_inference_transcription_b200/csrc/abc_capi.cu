@@ -86,7 +86,8 @@ struct abc_ctx {
     DevBuf<float4> d_s3_tb, d_s3_ab;
     DevBuf<uint32_t> d_s3_wt;
     DevBuf<int32_t> d_s3_gidx;
-    DevBuf<uint32_t> d_s3_ok, d_s3_live, d_s3_nanw, d_s3_done;
+    DevBuf<uint32_t> d_s3_ok, d_s3_live, d_s3_nanw, d_s3_qcnt;
+    DevBuf<uint16_t> d_s3_q2;
     int stats_guards = -1;       // -1: sample guards iff sim_kind == SSA; 0 / 1 force
     int ssa_hybrid = 1;          // exact telegraph/Poisson burn-in before the label window
     // simulate work buffers
@@ -151,7 +152,7 @@ extern "C" int abc_destroy(abc_ctx_t* c) {
     cudaStreamSynchronize(c->stream);
     c->d_beta.release(); c->d_age_dist.release(); c->d_beta_mom.release(); c->d_d.release(); c->d_den.release(); c->d_fbw.release(); c->d_fa.release(); c->d_fstats.release(); c->d_rnan.release();
     c->d_s3_tb.release(); c->d_s3_ab.release(); c->d_s3_wt.release();
-    c->d_s3_gidx.release(); c->d_s3_ok.release(); c->d_s3_live.release(); c->d_s3_nanw.release(); c->d_s3_done.release();
+    c->d_s3_gidx.release(); c->d_s3_ok.release(); c->d_s3_live.release(); c->d_s3_nanw.release(); c->d_s3_qcnt.release(); c->d_s3_q2.release();
     c->d_theta.release(); c->d_stats.release(); c->d_moments.release(); c->d_ss_iv.release(); c->d_prefix.release(); c->d_rates.release();
     c->d_keys_in.release(); c->d_keys_out.release(); c->d_idx_in.release(); c->d_order.release(); c->d_sort_tmp.release();
     c->d_sums.release(); c->d_counters.release(); c->d_work.release(); c->d_cells.release();
@@ -604,22 +605,36 @@ static int score_device(abc_ctx* c, const double* d_stats, int64_t n, int64_t of
     a.acc_gene = c->d_acc_gene.p; a.acc_particle = c->d_acc_particle.p; a.acc_err = c->d_acc_err.p;
     a.fstats = nullptr; a.rnan = nullptr;
     ABC_CUDA_CHECK(cudaEventRecord(c->ev[3], st));
+    a.gm_stride = n;
     if (!c->force_reference_score && c->score_tile_kernel && eps < 10.0 && n > 0) {
-        // tile-pruned path: classification + one CTA per (gene tile, particle block)
+        // tile-pruned path: classification, filter (one CTA per gene tile x particle block; also fills the matrix),
+        // stage 3 on the queued pairs.  The stage-3 queue has room for every pair of a sub-batch (2 bytes each),
+        // so a sub-batch is at most ~2 GB of queue.
         AbcScore3Tables x;
         x.ntiles = c->s3_ntiles;
-        x.W = (n + 31) / 32;
-        const size_t nblocks = abc_score3_blocks(n);
-        if ((rc = c->d_fstats.ensure((size_t)n * ABC_NSTATS)) != ABC_OK) return rc;
-        if ((rc = c->d_s3_live.ensure((size_t)x.ntiles * (size_t)x.W)) != ABC_OK) return rc;
-        if ((rc = c->d_s3_nanw.ensure((size_t)x.W)) != ABC_OK) return rc;
-        if ((rc = c->d_s3_done.ensure(nblocks)) != ABC_OK) return rc;
         x.tb = c->d_s3_tb.p; x.ab = c->d_s3_ab.p; x.wt = c->d_s3_wt.p;
         x.gidx = c->d_s3_gidx.p; x.okmask = c->d_s3_ok.p;
-        x.live = c->d_s3_live.p; x.nanw = c->d_s3_nanw.p; x.done = c->d_s3_done.p;
+        const int64_t per_particle = (int64_t)x.ntiles * 32 * 2;
+        int64_t sub = std::max<int64_t>(2048, ((int64_t)2000000000 / per_particle) / 2048 * 2048);
+        sub = std::min<int64_t>(sub, (n + 2047) / 2048 * 2048);
+        const size_t nblocks = abc_score3_blocks(sub);
+        if ((rc = c->d_fstats.ensure((size_t)sub * ABC_NSTATS)) != ABC_OK) return rc;
+        if ((rc = c->d_s3_live.ensure((size_t)x.ntiles * (size_t)((sub + 31) / 32))) != ABC_OK) return rc;
+        if ((rc = c->d_s3_nanw.ensure((size_t)((sub + 31) / 32))) != ABC_OK) return rc;
+        if ((rc = c->d_s3_qcnt.ensure(nblocks * (size_t)x.ntiles)) != ABC_OK) return rc;
+        if ((rc = c->d_s3_q2.ensure(abc_score3_queue_entries(sub, x.ntiles))) != ABC_OK) return rc;
+        x.live = c->d_s3_live.p; x.nanw = c->d_s3_nanw.p; x.q2 = c->d_s3_q2.p; x.qcnt = c->d_s3_qcnt.p;
         a.fstats = c->d_fstats.p;
-        rc = abc_launch_score3(a, x, st);
-        c->launches += 2;
+        for (int64_t s0 = 0; s0 < n && rc == ABC_OK; s0 += sub) {
+            AbcScoreArgs b = a;
+            b.n = std::min<int64_t>(sub, n - s0);
+            b.stats = d_stats + s0 * ABC_NSTATS;
+            b.particle_offset = offset + s0;
+            if (b.err != nullptr) b.err = (layout == ABC_ERR_GENE_MAJOR) ? d_err + s0 : d_err + s0 * (int64_t)c->G;
+            x.W = (b.n + 31) / 32;
+            rc = abc_launch_score3(b, x, st);
+            c->launches += 3;
+        }
         ABC_CUDA_CHECK(cudaEventRecord(c->ev[4], st));
         return rc;
     }

@@ -70,6 +70,7 @@ struct AbcScoreArgs {
     int64_t particle_offset;
     double  eps;
     int32_t err_layout;
+    int64_t gm_stride;     // gene-major layout: doubles between consecutive gene rows (the whole batch's n)
     double* err;           // nullable
     unsigned long long* counts;       // [G]
     unsigned long long* acc_count;    // [1] running number of accepted tuples
@@ -88,7 +89,8 @@ struct AbcScore3Tables {
     const uint32_t* okmask;  // [ntiles] bit l: slot l may divide through the stored reciprocal
     uint32_t* live;          // [ntiles][W] work: bit = (tile, particle) needs stages 1-3
     uint32_t* nanw;          // [W] work: bit = particle has a NaN statistic
-    uint32_t* done;          // [blocks] work: filled slices per particle block (particle-major layout)
+    uint16_t* q2;            // [blocks*ntiles][2048*32] work: pairs queued for stage 3 (particle << 5 | gene slot)
+    uint32_t* qcnt;          // [blocks*ntiles] work: fill of each segment
     int64_t W;               // ceil(n / 32)
 };
 #ifdef __cplusplus
@@ -103,5 +105,6 @@ struct AbcScore3Host {
 void abc_score3_build(const double* d, const double* den, int G, AbcScore3Host& out);
 #endif
 size_t abc_score3_blocks(int64_t n);
+size_t abc_score3_queue_entries(int64_t n, int ntiles);
 int abc_launch_score3(const AbcScoreArgs& a, const AbcScore3Tables& x, cudaStream_t st);
 int abc_launch_score_prep(const double* d_stats, int64_t n, float* d_fstats, unsigned char* d_rnan, cudaStream_t st);

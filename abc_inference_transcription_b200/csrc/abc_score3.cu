@@ -44,13 +44,10 @@
 #define S3_WARPS 11                      // compute warps
 #define S3_THREADS (S3_WARPS * 32 + 32)  // + one service warp: table loads and the fill, both through the TMA engine
 #define S3_FILL_DOUBLES 512              // 4 KB of 10.0 in shared memory: the source of the bulk stores
-#define S3_AHEAD 2                       // particle-major: a CTA of block k fills its slice of block k + S3_AHEAD
 #define S3_PB 2048        // particles per CTA
 #define S3_NP 4           // particles per warp pass
 #define S3_NPAIR 27       // term pairs (53 terms + one zero term)
 #define S3_SROW 56        // floats per staged particle (53 statistics, padded to whole float4)
-#define S3_Q2 512         // pairs a warp may queue for stage 3
-#define S3_Q2_DRAIN 352   // ... and the fill at which it leaves the filter loop (a pass adds up to 128)
 #define S3_SURE 10.01f
 #define S3C_THREADS 128
 #define S3C_TCH 24
@@ -223,18 +220,22 @@ abc_score3_classify_kernel(const double* __restrict__ stats, long long n, int nt
 // ------------------------------------------------------------------------------------------------ tile kernel
 struct S3Smem {
     float4 ab[S3_NPAIR][S3_TG];                // (a_2j, a_2j+1, -b_2j, -b_2j+1) per (term pair, gene slot): held in registers
-    unsigned int wt[6][ABC_NSTATS][S3_TG];     // stage-3 constants: d, den, 1/den as (high, low) words
     float st[S3_WARPS][S3_NP][S3_SROW];        // statistics of the four particles of a pass, per warp
     unsigned short list[S3_PB + 2 * S3_WARPS * S3_NP];   // live particles of this (tile, block), padded
-    unsigned short q2[S3_WARPS][S3_Q2];        // pairs waiting for stage 3: particle << 5 | gene slot
     alignas(16) double tens[S3_FILL_DOUBLES];  // 10.0: source of the fill's bulk stores
-    unsigned long long mbar;                   // completion of the table loads
+    unsigned long long mbar;                   // completion of the table load
     int gidx[S3_TG];
     unsigned int livew[S3_PB / 32];
     int cnt[S3_PB / 32];
     int nlist;
-    int fill_flag;                             // gene-major: this CTA's fill has completed
-    unsigned int okmask;
+    unsigned int qcount;                       // pairs queued for stage 3 by this CTA
+};
+
+// shared memory of the stage-3 kernel
+struct S3ExactSmem {
+    unsigned int wt[6][ABC_NSTATS][S3_TG];     // d, den, 1/den as (high, low) words
+    unsigned long long mbar;
+    int gidx[S3_TG];
 };
 
 // ---- TMA / mbarrier helpers (PTX ISA: cp.async.bulk, mbarrier)
@@ -298,14 +299,14 @@ __device__ __forceinline__ double s3_div_fast(double x, double den, double rcp) 
 
 __device__ __noinline__ double s3_div_slow(double x, double den) { return __ddiv_rn(x, den); }
 
-__device__ __forceinline__ double s3_word(const S3Smem& sm, int q, int t, int gl) {
+__device__ __forceinline__ double s3_word(const S3ExactSmem& sm, int q, int t, int gl) {
     return __hiloint2double((int)sm.wt[2 * q][t][gl], (int)sm.wt[2 * q + 1][t][gl]);
 }
 
 // compute_errors.jl:30-43: N consecutive terms of one group, e <- e + (d-s)^2/den in the reference's order.
 // The N quotients are independent (loads and Markstein chains overlap); only the final additions are ordered.
 template <int N>
-__device__ __forceinline__ double s3_chunk(double e, const double* __restrict__ sp, const S3Smem& sm, int gl, int t0, bool ok) {
+__device__ __forceinline__ double s3_chunk(double e, const double* __restrict__ sp, const S3ExactSmem& sm, int gl, int t0, bool ok) {
     double xx[N], q[N];
     bool fast = ok;
 #pragma unroll
@@ -331,7 +332,7 @@ __device__ __forceinline__ double s3_div53(double e) {
 }
 
 // compute_errors.jl:55-64 for one (particle, gene slot); loops stay rolled (instruction cache)
-__device__ __forceinline__ double s3_exact(const double* __restrict__ sp, const S3Smem& sm, int gl, bool ok) {
+__device__ __forceinline__ double s3_exact(const double* __restrict__ sp, const S3ExactSmem& sm, int gl, bool ok) {
     double err = 0.0;
 #pragma unroll 1
     for (int l = 0; l < 4; ++l)                       // pulse_mean, pulse_ff, chase_mean, chase_ff
@@ -369,7 +370,6 @@ abc_score3_tile_kernel(const AbcScoreArgs a, const AbcScore3Tables x) {
     const int T = (int)(blockIdx.x % (unsigned int)x.ntiles);
     const long long k = blockIdx.x / (unsigned int)x.ntiles;
     const long long i0 = k * S3_PB;
-    const long long nblocks = (a.n + S3_PB - 1) / S3_PB;
     const double qnan = __longlong_as_double(0x7ff8000000000000ll);
 
     if (tid < S3_PB / 32) {
@@ -379,7 +379,7 @@ abc_score3_tile_kernel(const AbcScoreArgs a, const AbcScore3Tables x) {
         sm.cnt[tid] = __popc(lw);
     }
     if (tid < S3_TG) sm.gidx[tid] = x.gidx[T * S3_TG + tid];
-    if (tid == 0) { sm.okmask = x.okmask[T]; sm.fill_flag = 0; }
+    if (tid == 0) sm.qcount = 0u;
     if (warp == S3_WARPS) {
         for (int j = lane; j < S3_FILL_DOUBLES; j += 32) sm.tens[j] = 10.0;
         if (lane == 0) s3_mbar_init(&sm.mbar, 1);
@@ -388,71 +388,51 @@ abc_score3_tile_kernel(const AbcScoreArgs a, const AbcScore3Tables x) {
     __syncthreads();
 
     if (warp == S3_WARPS) {
-        // ================= service warp: tile constants in, fill out, both as bulk copies; then it retires
+        // ================= service warp: gene constants in, fill out, both as bulk copies; then it retires.
+        // Nothing else writes the matrix in this kernel; stage 3 runs as the next kernel on the stream.
         if (lane == 0) {
-            const unsigned int b_ab = (unsigned int)sizeof(sm.ab), b_wt = (unsigned int)sizeof(sm.wt);
-            s3_mbar_expect_tx(&sm.mbar, b_ab + b_wt);
-            s3_bulk_g2s(&sm.ab[0][0], x.ab + (long long)T * S3_NPAIR * S3_TG, b_ab, &sm.mbar);
-            s3_bulk_g2s(&sm.wt[0][0][0], x.wt + (long long)T * 6 * ABC_NSTATS * S3_TG, b_wt, &sm.mbar);
+            s3_mbar_expect_tx(&sm.mbar, (unsigned int)sizeof(sm.ab));
+            s3_bulk_g2s(&sm.ab[0][0], x.ab + (long long)T * S3_NPAIR * S3_TG, (unsigned int)sizeof(sm.ab), &sm.mbar);
         }
-        if (LAYOUT == ABC_ERR_GENE_MAJOR) {
-            // this CTA's own 32 gene rows x 2048 particles; a NaN-statistic particle makes its whole column NaN
+        if (LAYOUT != ABC_ERR_NONE) {
             const int rows = (int)min((long long)S3_PB, a.n - i0);
             bool nn = false;
             for (int j = lane; j < S3_PB / 32; j += 32) {
                 const long long wi = k * (S3_PB / 32) + j;
                 nn = nn || (wi < x.W && x.nanw[wi] != 0u);
             }
+            // a particle with a NaN statistic has NaN errors for every gene (all 53 statistics enter every error)
             const bool any_nan = __any_sync(0xffffffffu, nn);
-            for (int sl = 0; sl < S3_TG; ++sl) {
-                const int g = sm.gidx[sl];
-                if (g < 0) continue;
-                double* p = a.err + (long long)g * a.n + i0;
-                if (!any_nan) {
-                    s3_fill_tma(p, rows, sm.tens, lane);
-                } else {
-                    for (int r = lane; r < rows; r += 32)
-                        p[r] = ((x.nanw[k * (S3_PB / 32) + (r >> 5)] >> (r & 31)) & 1u) ? qnan : 10.0;
+            if (LAYOUT == ABC_ERR_GENE_MAJOR) {
+                // this CTA's own 32 gene rows x 2048 particles
+                for (int sl = 0; sl < S3_TG; ++sl) {
+                    const int g = sm.gidx[sl];
+                    if (g < 0) continue;
+                    double* p = a.err + (long long)g * a.gm_stride + i0;
+                    if (!any_nan) {
+                        s3_fill_tma(p, rows, sm.tens, lane);
+                    } else {
+                        for (int r = lane; r < rows; r += 32)
+                            p[r] = ((x.nanw[k * (S3_PB / 32) + (r >> 5)] >> (r & 31)) & 1u) ? qnan : 10.0;
+                    }
                 }
-            }
-            s3_bulk_commit_wait();
-            s3_fence_proxy_async();
-            __syncwarp();
-            if (lane == 0) { __threadfence_block(); *(volatile int*)&sm.fill_flag = 1; }
-        } else if (LAYOUT == ABC_ERR_PARTICLE_MAJOR) {
-            // slices of later blocks (contiguous rows): block k + S3_AHEAD, and blocks 0 .. S3_AHEAD-1 by the CTAs of block 0
-            for (int w = 0; w <= S3_AHEAD; ++w) {
-                const long long kf = (w == 0) ? k + S3_AHEAD : (long long)(w - 1);
-                if ((w > 0 && k != 0) || kf >= nblocks) continue;
-                const long long f0 = kf * S3_PB;
-                const int rows = (int)min((long long)S3_PB, a.n - f0);
-                bool nn = false;
-                for (int j = lane; j < S3_PB / 32; j += 32) {
-                    const long long wi = kf * (S3_PB / 32) + j;
-                    nn = nn || (wi < x.W && x.nanw[wi] != 0u);
-                }
-                const bool any_nan = __any_sync(0xffffffffu, nn);
+            } else {
+                // the block's rows are contiguous: slice T of ntiles
                 const long long L = (long long)rows * a.G;
                 long long chunk = (L + x.ntiles - 1) / x.ntiles;
                 chunk += chunk & 1;
                 const long long lo = min(L, (long long)T * chunk), hi = min(L, lo + chunk);
-                double* base = a.err + f0 * (long long)a.G;
+                double* base = a.err + i0 * (long long)a.G;
                 if (!any_nan) {
                     s3_fill_tma(base + lo, hi - lo, sm.tens, lane);
                 } else {
                     for (long long j = lo + lane; j < hi; j += 32) {
                         const int r = (int)(j / a.G);
-                        base[j] = ((x.nanw[kf * (S3_PB / 32) + (r >> 5)] >> (r & 31)) & 1u) ? qnan : 10.0;
+                        base[j] = ((x.nanw[k * (S3_PB / 32) + (r >> 5)] >> (r & 31)) & 1u) ? qnan : 10.0;
                     }
                 }
-                s3_bulk_commit_wait();
-                s3_fence_proxy_async();
-                __syncwarp();
-                if (lane == 0) {
-                    __threadfence();           // release: the slice (all lanes, ordered by the warp barrier) before the count
-                    atomicAdd(x.done + kf, 1u);
-                }
             }
+            s3_bulk_commit_wait();             // the source buffer must outlive the reads; the kernel boundary orders the rest
         }
         return;
     }
@@ -475,124 +455,133 @@ abc_score3_tile_kernel(const AbcScoreArgs a, const AbcScore3Tables x) {
     // pad the list with its last entry so that passes can always read four entries and prefetch one pass ahead
     if (nl > 0 && tid < 2 * S3_WARPS * S3_NP) sm.list[nl + tid] = sm.list[nl - 1];
     asm volatile("bar.sync 1, %0;" ::"n"(S3_WARPS * 32) : "memory");
-    s3_mbar_wait(&sm.mbar, 0);                 // tile constants have landed (also: no bulk copy in flight at exit)
-    if (nl == 0) return;
+    s3_mbar_wait(&sm.mbar, 0);                 // gene constants have landed (also: no bulk copy in flight at exit)
 
-    // ---- per-warp pipeline: filter passes with the gene constants in registers, then stage-3 rounds; the constants
-    //      are reloaded after every drain so that they are not live across the FP64 code
+    // ---- filter passes: four live particles x 53 terms per pass, the gene constants of the lane in registers
     const bool lane_valid = sm.gidx[lane] >= 0;
     const unsigned int lt_mask = (1u << lane) - 1u;
-    int nq2 = 0;
-    bool fill_ok = false;
+    unsigned short* seg = x.q2 + (size_t)blockIdx.x * (S3_PB * S3_TG);
     float* stw = &sm.st[warp][0][0];
-    S3Regs nxt;
     int base = warp * S3_NP;
-    bool more = base < nl;
-    if (more) s3_load4(nxt, a.fstats, i0, &sm.list[base], lane);
-    for (int j = lane; j < S3_NP * (S3_SROW - ABC_NSTATS); j += 32)       // the padding stays 0
-        stw[(j / (S3_SROW - ABC_NSTATS)) * S3_SROW + ABC_NSTATS + j % (S3_SROW - ABC_NSTATS)] = 0.f;
-    while (more || nq2 > 0) {
-        if (more) {
-            // gene constants of this lane: terms (2j, 2j+1) packed for FFMA2
-            float4 c[S3_NPAIR];
+    if (base < nl) {
+        S3Regs nxt;
+        s3_load4(nxt, a.fstats, i0, &sm.list[base], lane);
+        for (int j = lane; j < S3_NP * (S3_SROW - ABC_NSTATS); j += 32)       // the padding stays 0
+            stw[(j / (S3_SROW - ABC_NSTATS)) * S3_SROW + ABC_NSTATS + j % (S3_SROW - ABC_NSTATS)] = 0.f;
+        float4 c[S3_NPAIR];
 #pragma unroll
-            for (int j = 0; j < S3_NPAIR; ++j) c[j] = sm.ab[j][lane];
-            while (more && nq2 < S3_Q2_DRAIN) {
-                // ---- stages 1-2 in one pass: four live particles x 53 terms (FP32 lower bound, see the header)
-                const int nv = min(S3_NP, nl - base);
-                __syncwarp();
+        for (int j = 0; j < S3_NPAIR; ++j) c[j] = sm.ab[j][lane];
+        for (; base < nl; base += S3_WARPS * S3_NP) {
+            const int nv = min(S3_NP, nl - base);
+            __syncwarp();
+#pragma unroll
+            for (int p = 0; p < S3_NP; ++p) {
+                stw[p * S3_SROW + lane] = nxt.v[2 * p];
+                if (lane < ABC_NSTATS - 32) stw[p * S3_SROW + 32 + lane] = nxt.v[2 * p + 1];
+            }
+            __syncwarp();
+            const int nbase = base + S3_WARPS * S3_NP;
+            if (nbase < nl) s3_load4(nxt, a.fstats, i0, &sm.list[nbase], lane);    // in flight during this pass
+            float2 acc[S3_NP];
+#pragma unroll
+            for (int p = 0; p < S3_NP; ++p) acc[p] = make_float2(0.f, 0.f);
+#pragma unroll
+            for (int q = 0; q < S3_SROW / 4; ++q) {
 #pragma unroll
                 for (int p = 0; p < S3_NP; ++p) {
-                    stw[p * S3_SROW + lane] = nxt.v[2 * p];
-                    if (lane < ABC_NSTATS - 32) stw[p * S3_SROW + 32 + lane] = nxt.v[2 * p + 1];
-                }
-                __syncwarp();
-                const int nbase = base + S3_WARPS * S3_NP;
-                if (nbase < nl) s3_load4(nxt, a.fstats, i0, &sm.list[nbase], lane);    // in flight during this pass
-                float2 acc[S3_NP];
-#pragma unroll
-                for (int p = 0; p < S3_NP; ++p) acc[p] = make_float2(0.f, 0.f);
-#pragma unroll
-                for (int q = 0; q < S3_SROW / 4; ++q) {
-#pragma unroll
-                    for (int p = 0; p < S3_NP; ++p) {
-                        const float4 sv = *reinterpret_cast<const float4*>(stw + p * S3_SROW + 4 * q);    // broadcast
-                        const float2 t0 = __ffma2_rn(make_float2(c[2 * q].z, c[2 * q].w), make_float2(sv.x, sv.y),
-                                                     make_float2(c[2 * q].x, c[2 * q].y));
-                        acc[p] = __ffma2_rn(t0, t0, acc[p]);
-                        if (2 * q + 1 < S3_NPAIR) {
-                            const float2 t1 = __ffma2_rn(make_float2(c[2 * q + 1].z, c[2 * q + 1].w), make_float2(sv.z, sv.w),
-                                                         make_float2(c[2 * q + 1].x, c[2 * q + 1].y));
-                            acc[p] = __ffma2_rn(t1, t1, acc[p]);
-                        }
+                    const float4 sv = *reinterpret_cast<const float4*>(stw + p * S3_SROW + 4 * q);    // broadcast
+                    const float2 t0 = __ffma2_rn(make_float2(c[2 * q].z, c[2 * q].w), make_float2(sv.x, sv.y),
+                                                 make_float2(c[2 * q].x, c[2 * q].y));
+                    acc[p] = __ffma2_rn(t0, t0, acc[p]);
+                    if (2 * q + 1 < S3_NPAIR) {
+                        const float2 t1 = __ffma2_rn(make_float2(c[2 * q + 1].z, c[2 * q + 1].w), make_float2(sv.z, sv.w),
+                                                     make_float2(c[2 * q + 1].x, c[2 * q + 1].y));
+                        acc[p] = __ffma2_rn(t1, t1, acc[p]);
                     }
                 }
+            }
 #pragma unroll
-                for (int p = 0; p < S3_NP; ++p) {
-                    const float pp = __fadd_rn(acc[p].x, acc[p].y);
-                    const bool unsure = lane_valid && p < nv && !(pp > S3_SURE);
-                    const unsigned int bal = __ballot_sync(0xffffffffu, unsure);
-                    if (unsure) sm.q2[warp][nq2 + __popc(bal & lt_mask)] = (unsigned short)((sm.list[base + p] << 5) | lane);
-                    nq2 += __popc(bal);
+            for (int p = 0; p < S3_NP; ++p) {
+                const float pp = __fadd_rn(acc[p].x, acc[p].y);
+                const bool unsure = lane_valid && p < nv && !(pp > S3_SURE);
+                const unsigned int bal = __ballot_sync(0xffffffffu, unsure);
+                if (bal != 0u) {
+                    // queue the pairs for stage 3 in this CTA's segment: particle << 5 | gene slot
+                    unsigned int pos = 0;
+                    if (lane == 0) pos = atomicAdd(&sm.qcount, (unsigned int)__popc(bal));
+                    pos = __shfl_sync(0xffffffffu, pos, 0);
+                    if (unsure) seg[pos + __popc(bal & lt_mask)] = (unsigned short)((sm.list[base + p] << 5) | lane);
                 }
-                base = nbase;
-                more = base < nl;
             }
         }
-        while (nq2 >= 32 || (!more && nq2 > 0)) {
-            // ---- stage 3: one queued pair per lane, the reference's FP64 arithmetic; fused eps-acceptance
-            const int cnt = min(nq2, 32), e0 = nq2 - cnt;
-            __syncwarp();
-            if (LAYOUT != ABC_ERR_NONE && !fill_ok) {
-                // the fill of these rows must be complete before values overwrite it
-                if (lane == 0) {
-                    if (LAYOUT == ABC_ERR_PARTICLE_MAJOR) {
-                        while (s3_ld_relaxed(x.done + k) < (unsigned int)x.ntiles) __nanosleep(256);
-                        __threadfence();       // acquire
-                    } else {
-                        while (*(volatile int*)&sm.fill_flag == 0) __nanosleep(64);
-                        __threadfence_block();
-                    }
+    }
+    asm volatile("bar.sync 1, %0;" ::"n"(S3_WARPS * 32) : "memory");
+    if (tid == 0) x.qcnt[blockIdx.x] = sm.qcount;
+}
+
+// Stage 3: one CTA per (tile, particle block) segment, one queued pair per thread: the reference's FP64 arithmetic
+// (compute_errors.jl:30-43, 55-64), the value stored over the fill, fused eps-acceptance (accepted_particles.jl:20).
+#define S3E_THREADS 256
+template <int LAYOUT>
+__global__ void __launch_bounds__(S3E_THREADS, 4)
+abc_score3_exact_kernel(const AbcScoreArgs a, const AbcScore3Tables x) {
+    __shared__ __align__(128) S3ExactSmem sm;
+    const unsigned int cnt = x.qcnt[blockIdx.x];
+    if (cnt == 0u) return;
+    const int tid = threadIdx.x, lane = tid & 31;
+    const int T = (int)(blockIdx.x % (unsigned int)x.ntiles);
+    const long long i0 = (long long)(blockIdx.x / (unsigned int)x.ntiles) * S3_PB;
+    if (tid < S3_TG) sm.gidx[tid] = x.gidx[T * S3_TG + tid];
+    if (tid == 0) {
+        s3_mbar_init(&sm.mbar, 1);
+        s3_fence_proxy_async();
+    }
+    __syncthreads();
+    if (tid == 0) {
+        s3_mbar_expect_tx(&sm.mbar, (unsigned int)sizeof(sm.wt));
+        s3_bulk_g2s(&sm.wt[0][0][0], x.wt + (long long)T * 6 * ABC_NSTATS * S3_TG, (unsigned int)sizeof(sm.wt), &sm.mbar);
+    }
+    const unsigned int okmask = x.okmask[T];
+    const unsigned short* seg = x.q2 + (size_t)blockIdx.x * (S3_PB * S3_TG);
+    const unsigned int lt_mask = (1u << lane) - 1u;
+    s3_mbar_wait(&sm.mbar, 0);
+    for (unsigned int e0 = 0; e0 < cnt; e0 += S3E_THREADS) {
+        const unsigned int e = e0 + tid;
+        bool acc = false;
+        double err = 0.0;
+        long long i = 0;
+        int g = 0;
+        if (e < cnt) {
+            const unsigned int ent = seg[e];
+            const int gl = (int)(ent & 31u);
+            i = i0 + (long long)(ent >> 5);
+            g = sm.gidx[gl];
+            err = s3_exact(a.stats + i * ABC_NSTATS, sm, gl, ((okmask >> gl) & 1u) != 0u);
+            if (LAYOUT == ABC_ERR_GENE_MAJOR) a.err[(long long)g * a.gm_stride + i] = err;
+            else if (LAYOUT == ABC_ERR_PARTICLE_MAJOR) a.err[i * (long long)a.G + g] = err;
+            acc = err <= a.eps;                       // NaN is never accepted
+        }
+        const unsigned int mask = __ballot_sync(0xffffffffu, acc);
+        if (mask != 0u) {
+            const int leader = __ffs(mask) - 1;
+            unsigned long long slot = 0;
+            if (lane == leader) slot = atomicAdd(a.acc_count, (unsigned long long)__popc(mask));
+            slot = __shfl_sync(0xffffffffu, slot, leader) + (unsigned long long)__popc(mask & lt_mask);
+            if (acc) {
+                atomicAdd(a.counts + g, 1ull);
+                if ((long long)slot < a.acc_capacity) {
+                    a.acc_gene[slot] = g;
+                    a.acc_particle[slot] = a.particle_offset + i + 1;     // 1-based like Julia
+                    a.acc_err[slot] = err;
                 }
-                __syncwarp();
-                fill_ok = true;
             }
-            bool acc = false;
-            double err = 0.0;
-            long long i = 0;
-            int g = 0;
-            if (lane < cnt) {
-                const unsigned int ent = sm.q2[warp][e0 + lane];
-                const int gl = (int)(ent & 31u);
-                i = i0 + (long long)(ent >> 5);
-                g = sm.gidx[gl];
-                err = s3_exact(a.stats + i * ABC_NSTATS, sm, gl, ((sm.okmask >> gl) & 1u) != 0u);
-                if (LAYOUT == ABC_ERR_GENE_MAJOR) a.err[(long long)g * a.n + i] = err;
-                else if (LAYOUT == ABC_ERR_PARTICLE_MAJOR) a.err[i * (long long)a.G + g] = err;
-                acc = err <= a.eps;                       // accepted_particles.jl:20; NaN is never accepted
-            }
-            const unsigned int mask = __ballot_sync(0xffffffffu, acc);
-            if (mask != 0u) {
-                const int leader = __ffs(mask) - 1;
-                unsigned long long slot = 0;
-                if (lane == leader) slot = atomicAdd(a.acc_count, (unsigned long long)__popc(mask));
-                slot = __shfl_sync(0xffffffffu, slot, leader) + (unsigned long long)__popc(mask & lt_mask);
-                if (acc) {
-                    atomicAdd(a.counts + g, 1ull);
-                    if ((long long)slot < a.acc_capacity) {
-                        a.acc_gene[slot] = g;
-                        a.acc_particle[slot] = a.particle_offset + i + 1;     // 1-based like Julia
-                        a.acc_err[slot] = err;
-                    }
-                }
-            }
-            nq2 = e0;
         }
     }
 }
 
 // ------------------------------------------------------------------------------------------------ launcher
 size_t abc_score3_blocks(int64_t n) { return (size_t)((n + S3_PB - 1) / S3_PB); }
+size_t abc_score3_queue_entries(int64_t n, int ntiles) { return abc_score3_blocks(n) * (size_t)ntiles * (size_t)(S3_PB * S3_TG); }
 
 int abc_launch_score3(const AbcScoreArgs& a, const AbcScore3Tables& x, cudaStream_t st) {
     if (a.n <= 0 || a.G <= 0) return ABC_OK;
@@ -604,15 +593,21 @@ int abc_launch_score3(const AbcScoreArgs& a, const AbcScore3Tables& x, cudaStrea
     ABC_CUDA_CHECK(cudaFuncSetAttribute(abc_score3_tile_kernel<ABC_ERR_NONE>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     ABC_CUDA_CHECK(cudaFuncSetAttribute(abc_score3_tile_kernel<ABC_ERR_GENE_MAJOR>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     ABC_CUDA_CHECK(cudaFuncSetAttribute(abc_score3_tile_kernel<ABC_ERR_PARTICLE_MAJOR>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-    if (lay == ABC_ERR_PARTICLE_MAJOR) ABC_CUDA_CHECK(cudaMemsetAsync(x.done, 0, (size_t)nblocks * sizeof(unsigned int), st));
     const unsigned int cgrid = (unsigned int)((a.n + 2 * S3C_THREADS - 1) / (2 * S3C_THREADS));
     abc_score3_classify_kernel<<<cgrid, S3C_THREADS, 0, st>>>(a.stats, (long long)a.n, x.ntiles, x.tb, const_cast<float*>(a.fstats),
                                                               x.live, x.nanw, (long long)x.W);
     ABC_CUDA_CHECK(cudaGetLastError());
     const unsigned int grid = (unsigned int)(nblocks * x.ntiles);
-    if (lay == ABC_ERR_NONE) abc_score3_tile_kernel<ABC_ERR_NONE><<<grid, S3_THREADS, smem, st>>>(a, x);
-    else if (lay == ABC_ERR_GENE_MAJOR) abc_score3_tile_kernel<ABC_ERR_GENE_MAJOR><<<grid, S3_THREADS, smem, st>>>(a, x);
-    else abc_score3_tile_kernel<ABC_ERR_PARTICLE_MAJOR><<<grid, S3_THREADS, smem, st>>>(a, x);
+    if (lay == ABC_ERR_NONE) {
+        abc_score3_tile_kernel<ABC_ERR_NONE><<<grid, S3_THREADS, smem, st>>>(a, x);
+        abc_score3_exact_kernel<ABC_ERR_NONE><<<grid, S3E_THREADS, 0, st>>>(a, x);
+    } else if (lay == ABC_ERR_GENE_MAJOR) {
+        abc_score3_tile_kernel<ABC_ERR_GENE_MAJOR><<<grid, S3_THREADS, smem, st>>>(a, x);
+        abc_score3_exact_kernel<ABC_ERR_GENE_MAJOR><<<grid, S3E_THREADS, 0, st>>>(a, x);
+    } else {
+        abc_score3_tile_kernel<ABC_ERR_PARTICLE_MAJOR><<<grid, S3_THREADS, smem, st>>>(a, x);
+        abc_score3_exact_kernel<ABC_ERR_PARTICLE_MAJOR><<<grid, S3E_THREADS, 0, st>>>(a, x);
+    }
     ABC_CUDA_CHECK(cudaGetLastError());
     return ABC_OK;
 }
