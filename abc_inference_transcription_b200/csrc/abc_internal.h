@@ -92,6 +92,7 @@ struct AbcScore3Tables {
     uint16_t* q2;            // [blocks*ntiles][2048*32] work: pairs queued for stage 3 (particle << 5 | gene slot)
     uint32_t* qcnt;          // [blocks*ntiles] work: fill of each segment
     int64_t W;               // ceil(n / 32)
+    float sure;              // FP32 bounds above this prove that a pair is not needed (set by the launcher)
 };
 #ifdef __cplusplus
 #include <vector>

@@ -41,12 +41,13 @@
 
 #define S3_TG 32
 #define S3_NN 31          // statistics used by the tile bound: means, Fano factors, ratios (non-negative)
-#define S3_WARPS 11                      // compute warps
+#define S3_WARPS 5                       // compute warps
 #define S3_THREADS (S3_WARPS * 32 + 32)  // + one service warp: table loads and the fill, both through the TMA engine
 #define S3_FILL_DOUBLES 512              // 4 KB of 10.0 in shared memory: the source of the bulk stores
 #define S3_PB 2048        // particles per CTA
 #define S3_NP 4           // particles per warp pass
 #define S3_NPAIR 27       // term pairs (53 terms + one zero term)
+#define S3_DEPTH 3        // staging ring: the statistics of a pass are requested two passes ahead
 #define S3_SROW 56        // floats per staged particle (53 statistics, padded to whole float4)
 #define S3_SURE 10.01f
 #define S3C_THREADS 128
@@ -166,7 +167,7 @@ void abc_score3_build(const double* d, const double* den, int G, AbcScore3Host& 
 __global__ void __launch_bounds__(S3C_THREADS)
 abc_score3_classify_kernel(const double* __restrict__ stats, long long n, int ntiles, const float4* __restrict__ tb,
                            float* __restrict__ fstats, unsigned int* __restrict__ live, unsigned int* __restrict__ nanw,
-                           long long W) {
+                           long long W, float sure) {
     __shared__ float4 sh[S3C_TCH][S3_NN];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const long long base = (long long)blockIdx.x * (2 * S3C_THREADS);
@@ -207,8 +208,8 @@ abc_score3_classify_kernel(const double* __restrict__ stats, long long n, int nt
                 lb0 = __fmaf_rn(u0, u0, lb0);
                 lb1 = __fmaf_rn(u1, u1, lb1);
             }
-            const unsigned int b0 = __ballot_sync(0xffffffffu, alive[0] && !(lb0 > S3_SURE));
-            const unsigned int b1 = __ballot_sync(0xffffffffu, alive[1] && !(lb1 > S3_SURE));
+            const unsigned int b0 = __ballot_sync(0xffffffffu, alive[0] && !(lb0 > sure));
+            const unsigned int b1 = __ballot_sync(0xffffffffu, alive[1] && !(lb1 > sure));
             if (lane == 0) {
                 if (word[0] < W) live[(long long)(t0 + tt) * W + word[0]] = b0;
                 if (word[1] < W) live[(long long)(t0 + tt) * W + word[1]] = b1;
@@ -220,7 +221,7 @@ abc_score3_classify_kernel(const double* __restrict__ stats, long long n, int nt
 // ------------------------------------------------------------------------------------------------ tile kernel
 struct S3Smem {
     float4 ab[S3_NPAIR][S3_TG];                // (a_2j, a_2j+1, -b_2j, -b_2j+1) per (term pair, gene slot): held in registers
-    float st[S3_WARPS][S3_NP][S3_SROW];        // statistics of the four particles of a pass, per warp
+    float st[S3_WARPS][S3_DEPTH][S3_NP][S3_SROW];   // statistics of the four particles of a pass: cp.async ring per warp
     unsigned short list[S3_PB + 2 * S3_WARPS * S3_NP];   // live particles of this (tile, block), padded
     alignas(16) double tens[S3_FILL_DOUBLES];  // 10.0: source of the fill's bulk stores
     unsigned long long mbar;                   // completion of the table load
@@ -229,6 +230,8 @@ struct S3Smem {
     int cnt[S3_PB / 32];
     int nlist;
     unsigned int qcount;                       // pairs queued for stage 3 by this CTA
+    int next;                                  // next unassigned entry of the list (passes are handed out dynamically)
+    int warps_done;
 };
 
 // shared memory of the stage-3 kernel
@@ -348,21 +351,8 @@ __device__ __forceinline__ double s3_exact(const double* __restrict__ sp, const 
     return (err > 10.0) ? 10.0 : err;
 }
 
-// the FP32 statistics of four particles, two values per lane and particle (53 = 32 + 21)
-struct S3Regs { float v[2 * S3_NP]; };
-
-__device__ __forceinline__ void s3_load4(S3Regs& r, const float* __restrict__ fstats, long long i0, const unsigned short* ids,
-                                         int lane) {
-#pragma unroll
-    for (int p = 0; p < S3_NP; ++p) {
-        const float* sp = fstats + (i0 + ids[p]) * ABC_NSTATS;
-        r.v[2 * p] = sp[lane];
-        r.v[2 * p + 1] = (lane < ABC_NSTATS - 32) ? sp[32 + lane] : 0.f;
-    }
-}
-
 template <int LAYOUT>
-__global__ void __launch_bounds__(S3_THREADS, 1)
+__global__ void __launch_bounds__(S3_THREADS, 2)
 abc_score3_tile_kernel(const AbcScoreArgs a, const AbcScore3Tables x) {
     extern __shared__ __align__(128) unsigned char s3_raw[];
     S3Smem& sm = *reinterpret_cast<S3Smem*>(s3_raw);
@@ -379,7 +369,7 @@ abc_score3_tile_kernel(const AbcScoreArgs a, const AbcScore3Tables x) {
         sm.cnt[tid] = __popc(lw);
     }
     if (tid < S3_TG) sm.gidx[tid] = x.gidx[T * S3_TG + tid];
-    if (tid == 0) sm.qcount = 0u;
+    if (tid == 0) { sm.qcount = 0u; sm.next = 0; sm.warps_done = 0; }
     if (warp == S3_WARPS) {
         for (int j = lane; j < S3_FILL_DOUBLES; j += 32) sm.tens[j] = 10.0;
         if (lane == 0) s3_mbar_init(&sm.mbar, 1);
@@ -457,31 +447,48 @@ abc_score3_tile_kernel(const AbcScoreArgs a, const AbcScore3Tables x) {
     asm volatile("bar.sync 1, %0;" ::"n"(S3_WARPS * 32) : "memory");
     s3_mbar_wait(&sm.mbar, 0);                 // gene constants have landed (also: no bulk copy in flight at exit)
 
-    // ---- filter passes: four live particles x 53 terms per pass, the gene constants of the lane in registers
+    // ---- filter passes: four live particles x 53 terms per pass, the gene constants of the lane in registers.
+    //      Passes are handed out by a shared counter; the statistics of a pass arrive through cp.async two passes ahead.
     const bool lane_valid = sm.gidx[lane] >= 0;
     const unsigned int lt_mask = (1u << lane) - 1u;
     unsigned short* seg = x.q2 + (size_t)blockIdx.x * (S3_PB * S3_TG);
-    float* stw = &sm.st[warp][0][0];
-    int base = warp * S3_NP;
-    if (base < nl) {
-        S3Regs nxt;
-        s3_load4(nxt, a.fstats, i0, &sm.list[base], lane);
-        for (int j = lane; j < S3_NP * (S3_SROW - ABC_NSTATS); j += 32)       // the padding stays 0
-            stw[(j / (S3_SROW - ABC_NSTATS)) * S3_SROW + ABC_NSTATS + j % (S3_SROW - ABC_NSTATS)] = 0.f;
+    if (nl > 0) {
+        for (int j = lane; j < S3_DEPTH * S3_NP * (S3_SROW - ABC_NSTATS); j += 32)       // the padding stays 0
+            (&sm.st[warp][0][0][0])[(j / (S3_SROW - ABC_NSTATS)) * S3_SROW + ABC_NSTATS + j % (S3_SROW - ABC_NSTATS)] = 0.f;
         float4 c[S3_NPAIR];
 #pragma unroll
         for (int j = 0; j < S3_NPAIR; ++j) c[j] = sm.ab[j][lane];
-        for (; base < nl; base += S3_WARPS * S3_NP) {
-            const int nv = min(S3_NP, nl - base);
-            __syncwarp();
+        int bq[S3_DEPTH];                      // list positions of the passes in flight (slot = pass number mod depth)
+        auto request = [&](int slot) {
+            int b = 0;
+            if (lane == 0) b = atomicAdd(&sm.next, S3_NP);
+            b = __shfl_sync(0xffffffffu, b, 0);
+            if (b < nl) {
 #pragma unroll
-            for (int p = 0; p < S3_NP; ++p) {
-                stw[p * S3_SROW + lane] = nxt.v[2 * p];
-                if (lane < ABC_NSTATS - 32) stw[p * S3_SROW + 32 + lane] = nxt.v[2 * p + 1];
+                for (int p = 0; p < S3_NP; ++p) {
+                    const float* sp = a.fstats + (i0 + sm.list[b + p]) * ABC_NSTATS;
+                    float* dst = &sm.st[warp][slot][p][0];
+                    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(s3_saddr(dst + lane)), "l"(sp + lane) : "memory");
+                    if (lane < ABC_NSTATS - 32)
+                        asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(s3_saddr(dst + 32 + lane)), "l"(sp + 32 + lane) : "memory");
+                }
             }
+            asm volatile("cp.async.commit_group;" ::: "memory");
+            return b;
+        };
+        __syncwarp();
+#pragma unroll
+        for (int j = 0; j < S3_DEPTH; ++j) bq[j] = request(j);
+        int slot = 0;
+        while (true) {
+            int base = bq[0];
+#pragma unroll
+            for (int j = 1; j < S3_DEPTH; ++j) base = (slot == j) ? bq[j] : base;
+            if (base >= nl) break;
+            const int nv = min(S3_NP, nl - base);
+            asm volatile("cp.async.wait_group %0;" ::"n"(S3_DEPTH - 1) : "memory");
             __syncwarp();
-            const int nbase = base + S3_WARPS * S3_NP;
-            if (nbase < nl) s3_load4(nxt, a.fstats, i0, &sm.list[nbase], lane);    // in flight during this pass
+            const float* stw = &sm.st[warp][slot][0][0];
             float2 acc[S3_NP];
 #pragma unroll
             for (int p = 0; p < S3_NP; ++p) acc[p] = make_float2(0.f, 0.f);
@@ -500,23 +507,41 @@ abc_score3_tile_kernel(const AbcScoreArgs a, const AbcScore3Tables x) {
                     }
                 }
             }
+            // queue the pairs that may be below the threshold for stage 3 in this CTA's segment: particle << 5 | gene slot
+            unsigned int bal[S3_NP];
+            bool unsure[S3_NP];
+            int total = 0;
 #pragma unroll
             for (int p = 0; p < S3_NP; ++p) {
                 const float pp = __fadd_rn(acc[p].x, acc[p].y);
-                const bool unsure = lane_valid && p < nv && !(pp > S3_SURE);
-                const unsigned int bal = __ballot_sync(0xffffffffu, unsure);
-                if (bal != 0u) {
-                    // queue the pairs for stage 3 in this CTA's segment: particle << 5 | gene slot
-                    unsigned int pos = 0;
-                    if (lane == 0) pos = atomicAdd(&sm.qcount, (unsigned int)__popc(bal));
-                    pos = __shfl_sync(0xffffffffu, pos, 0);
-                    if (unsure) seg[pos + __popc(bal & lt_mask)] = (unsigned short)((sm.list[base + p] << 5) | lane);
+                unsure[p] = lane_valid && p < nv && !(pp > x.sure);
+                bal[p] = __ballot_sync(0xffffffffu, unsure[p]);
+                total += __popc(bal[p]);
+            }
+            if (total > 0) {
+                unsigned int pos = 0;
+                if (lane == 0) pos = atomicAdd(&sm.qcount, (unsigned int)total);
+                pos = __shfl_sync(0xffffffffu, pos, 0);
+#pragma unroll
+                for (int p = 0; p < S3_NP; ++p) {
+                    if (unsure[p]) seg[pos + __popc(bal[p] & lt_mask)] = (unsigned short)((sm.list[base + p] << 5) | lane);
+                    pos += __popc(bal[p]);
                 }
             }
+            __syncwarp();                      // every lane is done with this slot before it is refilled
+            const int nb = request(slot);
+#pragma unroll
+            for (int j = 0; j < S3_DEPTH; ++j) bq[j] = (slot == j) ? nb : bq[j];
+            slot = (slot + 1 == S3_DEPTH) ? 0 : slot + 1;
         }
+        asm volatile("cp.async.wait_group 0;" ::: "memory");
     }
-    asm volatile("bar.sync 1, %0;" ::"n"(S3_WARPS * 32) : "memory");
-    if (tid == 0) x.qcnt[blockIdx.x] = sm.qcount;
+    // the last warp to finish publishes the fill of the segment
+    __syncwarp();
+    if (lane == 0) {
+        __threadfence_block();
+        if (atomicAdd(&sm.warps_done, 1) == S3_WARPS - 1) x.qcnt[blockIdx.x] = *(volatile unsigned int*)&sm.qcount;
+    }
 }
 
 // Stage 3: one CTA per (tile, particle block) segment, one queued pair per thread: the reference's FP64 arithmetic
@@ -583,19 +608,24 @@ abc_score3_exact_kernel(const AbcScoreArgs a, const AbcScore3Tables x) {
 size_t abc_score3_blocks(int64_t n) { return (size_t)((n + S3_PB - 1) / S3_PB); }
 size_t abc_score3_queue_entries(int64_t n, int ntiles) { return abc_score3_blocks(n) * (size_t)ntiles * (size_t)(S3_PB * S3_TG); }
 
-int abc_launch_score3(const AbcScoreArgs& a, const AbcScore3Tables& x, cudaStream_t st) {
+int abc_launch_score3(const AbcScoreArgs& a, const AbcScore3Tables& x_in, cudaStream_t st) {
     if (a.n <= 0 || a.G <= 0) return ABC_OK;
     const long long nblocks = (a.n + S3_PB - 1) / S3_PB;
-    if (nblocks * x.ntiles > 0x7fffffffll) { abc_set_error("abc_score: batch too large for one launch"); return ABC_ERR_ARG; }
+    if (nblocks * x_in.ntiles > 0x7fffffffll) { abc_set_error("abc_score: batch too large for one launch"); return ABC_ERR_ARG; }
     const int lay = (a.err == nullptr) ? ABC_ERR_NONE : a.err_layout;
     const int smem = (int)sizeof(S3Smem);
+    // "surely above" threshold of the FP32 bounds: 10.01 when the matrix is wanted (every value below 10 is needed);
+    // without a matrix only pairs that can be accepted matter, i.e. err <= eps (eps < 10 on this path)
+    AbcScore3Tables x = x_in;
+    x.sure = S3_SURE;
+    if (lay == ABC_ERR_NONE && a.eps == a.eps) x.sure = fminf(S3_SURE, f32_up(a.eps + 0.01));
     // per device and cheap: set on every launch
     ABC_CUDA_CHECK(cudaFuncSetAttribute(abc_score3_tile_kernel<ABC_ERR_NONE>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     ABC_CUDA_CHECK(cudaFuncSetAttribute(abc_score3_tile_kernel<ABC_ERR_GENE_MAJOR>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     ABC_CUDA_CHECK(cudaFuncSetAttribute(abc_score3_tile_kernel<ABC_ERR_PARTICLE_MAJOR>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     const unsigned int cgrid = (unsigned int)((a.n + 2 * S3C_THREADS - 1) / (2 * S3C_THREADS));
     abc_score3_classify_kernel<<<cgrid, S3C_THREADS, 0, st>>>(a.stats, (long long)a.n, x.ntiles, x.tb, const_cast<float*>(a.fstats),
-                                                              x.live, x.nanw, (long long)x.W);
+                                                              x.live, x.nanw, (long long)x.W, x.sure);
     ABC_CUDA_CHECK(cudaGetLastError());
     const unsigned int grid = (unsigned int)(nblocks * x.ntiles);
     if (lay == ABC_ERR_NONE) {
