@@ -86,8 +86,16 @@ struct abc_ctx {
     DevBuf<float4> d_s3_tb, d_s3_ab;
     DevBuf<uint32_t> d_s3_wt;
     DevBuf<int32_t> d_s3_gidx;
-    DevBuf<uint32_t> d_s3_ok, d_s3_live, d_s3_nanw, d_s3_qcnt;
-    DevBuf<uint16_t> d_s3_q2;
+    DevBuf<uint32_t> d_s3_ok;
+    // two lanes of work buffers: sub-batches alternate between two internal streams so that the filter kernel of one
+    // (FP32 pipe + bulk stores) overlaps the stage-3 kernel of the other (FP64 pipe + shared memory)
+    DevBuf<uint32_t> d_s3_live[2], d_s3_nanw[2], d_s3_qcnt[2];
+    DevBuf<uint16_t> d_s3_q2[2];
+    DevBuf<float> d_s3_fstats[2];
+    cudaStream_t s3_stream[2] = {nullptr, nullptr};
+    cudaEvent_t s3_ev_begin = nullptr, s3_ev_end[2] = {nullptr, nullptr};
+    int score_overlap = 1;
+    int score_sub_batches = 0;   // sub-batches per call when overlapping; 0 = 2 below 256k particles, else 4
     int stats_guards = -1;       // -1: sample guards iff sim_kind == SSA; 0 / 1 force
     int ssa_hybrid = 1;          // exact telegraph/Poisson burn-in before the label window
     // simulate work buffers
@@ -135,6 +143,11 @@ extern "C" int abc_create(int device, abc_ctx_t** out) {
     c->sm_count = prop.multiProcessorCount;
     ABC_CUDA_CHECK(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
     for (int i = 0; i < 5; ++i) ABC_CUDA_CHECK(cudaEventCreate(&c->ev[i]));
+    for (int l = 0; l < 2; ++l) {
+        ABC_CUDA_CHECK(cudaStreamCreateWithFlags(&c->s3_stream[l], cudaStreamNonBlocking));
+        ABC_CUDA_CHECK(cudaEventCreateWithFlags(&c->s3_ev_end[l], cudaEventDisableTiming));
+    }
+    ABC_CUDA_CHECK(cudaEventCreateWithFlags(&c->s3_ev_begin, cudaEventDisableTiming));
     memset(&c->last, 0, sizeof(c->last));
     memset(&c->design, 0, sizeof(c->design));
     int rc = c->d_counters.ensure(8);
@@ -152,7 +165,7 @@ extern "C" int abc_destroy(abc_ctx_t* c) {
     cudaStreamSynchronize(c->stream);
     c->d_beta.release(); c->d_age_dist.release(); c->d_beta_mom.release(); c->d_d.release(); c->d_den.release(); c->d_fbw.release(); c->d_fa.release(); c->d_fstats.release(); c->d_rnan.release();
     c->d_s3_tb.release(); c->d_s3_ab.release(); c->d_s3_wt.release();
-    c->d_s3_gidx.release(); c->d_s3_ok.release(); c->d_s3_live.release(); c->d_s3_nanw.release(); c->d_s3_qcnt.release(); c->d_s3_q2.release();
+    c->d_s3_gidx.release(); c->d_s3_ok.release(); for (int l = 0; l < 2; ++l) { c->d_s3_live[l].release(); c->d_s3_nanw[l].release(); c->d_s3_qcnt[l].release(); c->d_s3_q2[l].release(); c->d_s3_fstats[l].release(); }
     c->d_theta.release(); c->d_stats.release(); c->d_moments.release(); c->d_ss_iv.release(); c->d_prefix.release(); c->d_rates.release();
     c->d_keys_in.release(); c->d_keys_out.release(); c->d_idx_in.release(); c->d_order.release(); c->d_sort_tmp.release();
     c->d_sums.release(); c->d_counters.release(); c->d_work.release(); c->d_cells.release();
@@ -160,6 +173,11 @@ extern "C" int abc_destroy(abc_ctx_t* c) {
     c->d_acc_gene.release(); c->d_acc_particle.release(); c->d_acc_err.release();
     for (int i = 0; i < 5; ++i) if (c->ev[i]) cudaEventDestroy(c->ev[i]);
     if (c->stream) cudaStreamDestroy(c->stream);
+    for (int l = 0; l < 2; ++l) {
+        if (c->s3_stream[l]) cudaStreamDestroy(c->s3_stream[l]);
+        if (c->s3_ev_end[l]) cudaEventDestroy(c->s3_ev_end[l]);
+    }
+    if (c->s3_ev_begin) cudaEventDestroy(c->s3_ev_begin);
     delete c;
     return ABC_OK;
 }
@@ -616,24 +634,43 @@ static int score_device(abc_ctx* c, const double* d_stats, int64_t n, int64_t of
         x.gidx = c->d_s3_gidx.p; x.okmask = c->d_s3_ok.p;
         const int64_t per_particle = (int64_t)x.ntiles * 32 * 2;
         int64_t sub = std::max<int64_t>(2048, ((int64_t)2000000000 / per_particle) / 2048 * 2048);
+        // at least four sub-batches of >= 16 particle blocks when the batch is large enough to pipeline
+        const int nsb = c->score_sub_batches >= 2 ? c->score_sub_batches : (n < 262144 ? 2 : 4);
+        const bool overlap = c->score_overlap && n >= (int64_t)nsb * 4 * 2048;
+        if (overlap) sub = std::min<int64_t>(sub, ((n + nsb - 1) / nsb + 2047) / 2048 * 2048);
         sub = std::min<int64_t>(sub, (n + 2047) / 2048 * 2048);
         const size_t nblocks = abc_score3_blocks(sub);
-        if ((rc = c->d_fstats.ensure((size_t)sub * ABC_NSTATS)) != ABC_OK) return rc;
-        if ((rc = c->d_s3_live.ensure((size_t)x.ntiles * (size_t)((sub + 31) / 32))) != ABC_OK) return rc;
-        if ((rc = c->d_s3_nanw.ensure((size_t)((sub + 31) / 32))) != ABC_OK) return rc;
-        if ((rc = c->d_s3_qcnt.ensure(nblocks * (size_t)x.ntiles)) != ABC_OK) return rc;
-        if ((rc = c->d_s3_q2.ensure(abc_score3_queue_entries(sub, x.ntiles))) != ABC_OK) return rc;
-        x.live = c->d_s3_live.p; x.nanw = c->d_s3_nanw.p; x.q2 = c->d_s3_q2.p; x.qcnt = c->d_s3_qcnt.p;
-        a.fstats = c->d_fstats.p;
-        for (int64_t s0 = 0; s0 < n && rc == ABC_OK; s0 += sub) {
+        const int lanes = overlap ? 2 : 1;
+        for (int l = 0; l < lanes; ++l) {
+            if ((rc = c->d_s3_fstats[l].ensure((size_t)sub * ABC_NSTATS)) != ABC_OK) return rc;
+            if ((rc = c->d_s3_live[l].ensure((size_t)x.ntiles * (size_t)((sub + 31) / 32))) != ABC_OK) return rc;
+            if ((rc = c->d_s3_nanw[l].ensure((size_t)((sub + 31) / 32))) != ABC_OK) return rc;
+            if ((rc = c->d_s3_qcnt[l].ensure(nblocks * (size_t)x.ntiles)) != ABC_OK) return rc;
+            if ((rc = c->d_s3_q2[l].ensure(abc_score3_queue_entries(sub, x.ntiles))) != ABC_OK) return rc;
+        }
+        if (overlap) {
+            ABC_CUDA_CHECK(cudaEventRecord(c->s3_ev_begin, st));
+            for (int l = 0; l < 2; ++l) ABC_CUDA_CHECK(cudaStreamWaitEvent(c->s3_stream[l], c->s3_ev_begin, 0));
+        }
+        int j = 0;
+        for (int64_t s0 = 0; s0 < n && rc == ABC_OK; s0 += sub, ++j) {
+            const int l = overlap ? (j & 1) : 0;
             AbcScoreArgs b = a;
             b.n = std::min<int64_t>(sub, n - s0);
             b.stats = d_stats + s0 * ABC_NSTATS;
             b.particle_offset = offset + s0;
+            b.fstats = c->d_s3_fstats[l].p;
             if (b.err != nullptr) b.err = (layout == ABC_ERR_GENE_MAJOR) ? d_err + s0 : d_err + s0 * (int64_t)c->G;
+            x.live = c->d_s3_live[l].p; x.nanw = c->d_s3_nanw[l].p; x.q2 = c->d_s3_q2[l].p; x.qcnt = c->d_s3_qcnt[l].p;
             x.W = (b.n + 31) / 32;
-            rc = abc_launch_score3(b, x, st);
+            rc = abc_launch_score3(b, x, overlap ? c->s3_stream[l] : st);
             c->launches += 3;
+        }
+        if (overlap) {
+            for (int l = 0; l < 2; ++l) {
+                ABC_CUDA_CHECK(cudaEventRecord(c->s3_ev_end[l], c->s3_stream[l]));
+                ABC_CUDA_CHECK(cudaStreamWaitEvent(st, c->s3_ev_end[l], 0));
+            }
         }
         ABC_CUDA_CHECK(cudaEventRecord(c->ev[4], st));
         return rc;
@@ -816,6 +853,8 @@ extern "C" int abc_set_option(abc_ctx_t* c, const char* name, int64_t value) {
     if (!name) { abc_set_error("abc_set_option: name is NULL"); return ABC_ERR_ARG; }
     if (strcmp(name, "score_reference_kernel") == 0) { c->force_reference_score = value ? 1 : 0; return ABC_OK; }
     if (strcmp(name, "score_tile_kernel") == 0) { c->score_tile_kernel = value ? 1 : 0; return ABC_OK; }
+    if (strcmp(name, "score_overlap") == 0) { c->score_overlap = value ? 1 : 0; return ABC_OK; }
+    if (strcmp(name, "score_sub_batches") == 0) { c->score_sub_batches = (int)std::min<int64_t>(std::max<int64_t>(value, 0), 64); return ABC_OK; }
     if (strcmp(name, "accept_capacity") == 0) { c->acc_min_capacity = value > 0 ? value : 0; return ABC_OK; }
     if (strcmp(name, "stats_sample_guards") == 0) { c->stats_guards = value < 0 ? -1 : (value ? 1 : 0); return ABC_OK; }
     if (strcmp(name, "ssa_hybrid_burnin") == 0) { c->ssa_hybrid = value ? 1 : 0; return ABC_OK; }

@@ -36,6 +36,7 @@ SEED = 20240229
 EPS = 4.8
 NOMINAL_INSTR_PER_EVENT = 64.0       # algorithmic lane-instructions per SSA event
 ALG_BYTES_PER_PARTICLE_SCORE = 27776  # 424 B read + G*8 B written, G = 3419
+SCORE_TRAFFIC_131070 = 4.04e9         # measured dram bytes (read + write) of one 131070-particle scoring call, see profiles/
 
 
 def load_inputs():
@@ -295,6 +296,20 @@ def run_b200(args):
         if it > 0:
             score_big_ms.append(e0.elapsed_time(e1))
     score_big_s = sum(score_big_ms) / len(score_big_ms) / 1e3
+    # acceptance only (no matrix: what a full prior sweep uses, the matrix of 5e6 x 3419 doubles is 137 GB per model)
+    from abc_inference_transcription_b200 import ERR_NONE
+    score_acc_ms = []
+    for it in range(4):
+        eng.accept_reset()
+        flush.fill_(it)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        eng.score_dev(big_stats.data_ptr(), nb, eps=EPS, particle_offset=0, err_layout=ERR_NONE, d_err_ptr=0, stream=stream)
+        e1.record()
+        torch.cuda.synchronize()
+        if it > 0:
+            score_acc_ms.append(e0.elapsed_time(e1))
+    score_acc_s = sum(score_acc_ms) / len(score_acc_ms) / 1e3
     del big_err, big_stats
     # ---- the same SSA without the hybrid burn-in (all six channels from the first cycle), small batch ----
     eng.set_option("ssa_hybrid_burnin", 0)
@@ -338,13 +353,17 @@ def run_b200(args):
                              "nominal_instr_per_event": NOMINAL_INSTR_PER_EVENT,
                              "peak_src": f"148 SM x 128 lanes x sm_max_mhz ({pk['src']})",
                              "share_of_step": ssa_s / t_dev if t_dev > 0 else None},
-                "roofline_score": {"kernel": "abc_score2_kernel", "particles_per_launch": nb, "ms_per_launch": 1e3 * score_big_s,
+                "roofline_score": {"kernel": "abc_score3_classify_kernel + abc_score3_tile_kernel<2> + abc_score3_exact_kernel<2>",
+                                   "particles_per_launch": nb, "ms_per_launch": 1e3 * score_big_s,
                                    "pairs_per_s": nb * G / score_big_s, "bound": "hbm", "achieved": sc_gbs, "peak": pk["hbm_gbs"],
                                    "unit": "GB/s", "frac": sc_gbs / pk["hbm_gbs"],
-                                   "traffic": 5.593e9 * nb / 131070.0,
-                                   "traffic_src": "ncu --set full dram read+write of one 131070-particle launch "
-                                                  "(profiles/r1_score2_ncu_summary.csv), scaled to this launch size",
-                                   "peak_src": pk["src"], "share_of_step": sc_s / t_dev if t_dev > 0 else None}}
+                                   "traffic": SCORE_TRAFFIC_131070 * nb / 131070.0,
+                                   "traffic_src": "ncu --set full dram read+write of the three kernels of one 131070-particle "
+                                                  "call (profiles/r1_score3_*_ncu_summary.csv), scaled to this launch size",
+                                   "peak_src": pk["src"], "share_of_step": sc_s / t_dev if t_dev > 0 else None,
+                                   "accept_only": {"ms_per_launch": 1e3 * score_acc_s, "particles_per_s": nb / score_acc_s,
+                                                   "pairs_per_s": nb * G / score_acc_s,
+                                                   "note": "err_layout = ABC_ERR_NONE: fused eps-acceptance, no matrix"}}}
         line["ode_path"] = ode
         line["ssa_full_direct"] = full_direct
         line["roofline"]["events_per_particle"] = events / max(1, 5 * B * args.steps)
