@@ -222,6 +222,42 @@ def test_score_tile_pruning_wide_particles(eng, data_stats):
         assert oracle.same_bits(errs[off[gg]:off[gg + 1]], ref[want - 1, gg])
 
 
+def test_score_sub_batches_on_two_streams(eng, data_stats):
+    """large calls are split into sub-batches that alternate between two internal streams (and, above the queue
+    limit, into several launches): the result must equal the one-stream result and the oracle"""
+    d, se = data_stats
+    rng = np.random.default_rng(33)
+    n = 70000                                        # > 2 x 4 x 2048: the overlapped path
+    s = synth_stats(rng, d, n)
+    s[12345, 7] = np.nan
+    eng.accept_reset()
+    err, counts, _ = eng.score(s, eps=4.8, err_layout=ERR_PARTICLE_MAJOR)
+    off, idx, errs = eng.accept_fetch()
+    sub = rng.choice(n, 150, replace=False)
+    ref = oracle.compute_trunc_errors(s[sub], d, se)
+    assert oracle.same_bits(err[sub], ref)
+    assert np.isnan(err[12345]).all() and np.nanmax(err) <= 10.0
+    for sb in (1, 5):                                # one stream; five sub-batches
+        eng.set_option("score_overlap", 1 if sb > 1 else 0)
+        eng.set_option("score_sub_batches", sb if sb > 1 else 0)
+        try:
+            eng.accept_reset()
+            err2, counts2, _ = eng.score(s, eps=4.8, err_layout=ERR_PARTICLE_MAJOR)
+            off2, idx2, errs2 = eng.accept_fetch()
+        finally:
+            eng.set_option("score_overlap", 1)
+            eng.set_option("score_sub_batches", 0)
+        assert oracle.same_bits(err2, err) and np.array_equal(counts2, counts)
+        assert np.array_equal(off2, off) and np.array_equal(idx2, idx) and oracle.same_bits(errs2, errs)
+    eng.accept_reset()
+    _, counts3, _ = eng.score(s, eps=4.8, err_layout=ERR_NONE)      # acceptance only prunes at eps, same lists
+    off3, idx3, errs3 = eng.accept_fetch()
+    assert np.array_equal(counts3, counts) and np.array_equal(idx3, idx) and oracle.same_bits(errs3, errs)
+    eng.accept_reset()
+    errg, countsg, _ = eng.score(s[:40000], eps=4.8, err_layout=ERR_GENE_MAJOR)
+    assert oracle.same_bits(errg, err[:40000].T)
+
+
 def test_score_tile_pruning_signed_and_degenerate_data(eng, data_stats):
     """data with negative entries in the 'non-negative' statistics, zero rows, tiny and huge magnitudes and a
     gene count that is not a multiple of the tile size"""
