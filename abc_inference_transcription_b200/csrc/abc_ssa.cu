@@ -80,8 +80,23 @@ struct Seg {
 #define SSA_SEG_PER_CYCLE 7
 #define SSA_WARPS 8
 
+// the same sub-interval as the telegraph phase of the hybrid burn-in sees it (48 B): waiting-time factors and the
+// antiderivative F of alpha(w) exp(-gam (len - w)), so that the Poisson mean advances by F(x2) - F(x1) over an "on"
+// stretch [x1, x2].
+//   k1 != 0: F(x) = 2^(k1 (x - len)) (p0 + p1 x),  p0 = A0/gam - A1/gam^2, p1 = A1/gam, p2 = F(0)
+//   k1 == 0 (gam * step < 1/4): F(x) = x (p0 + p1 x + ... + p5 x^5), the series of the same integral from 0
+struct TSeg {
+    float len, qon, qoff, dec;     // q = -ln2 / rate (waiting time = lg2(u) * q), dec = exp(-gam len)
+    float Flen, k1, p0, p1;
+    float p2, p3, p4, p5;
+};
+union Slot {
+    Seg s;
+    TSeg t;
+};
+
 struct WarpTable {
-    Seg seg[SSA_MAX_CYCLES][SSA_SEG_PER_CYCLE];
+    Slot slot[SSA_MAX_CYCLES][SSA_SEG_PER_CYCLE];
     int n_ent[SSA_MAX_CYCLES];
     int c_star, e_star;     // cycle / entry at which the label window opens (hybrid burn-in hands over here)
 };
@@ -187,45 +202,61 @@ __device__ __forceinline__ bool ssa_step(Lineage& s, float& x, const Seg& sg, ui
 // every constant-g stretch (alpha is linear in time there); at t* it draws U ~ Poisson(Lam), L = 0, and the
 // full direct-method SSA of all six channels takes over.  The law of (g, U) at t* is exactly the one the
 // full SSA would have produced from the same start (U = 0 at the first simulated cycle).
-__device__ __forceinline__ float exp_neg(float z) {      // e^-z, z >= 0
-    float r;
-    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(f_mul(z, -1.4426950408889634f)));
-    return r;
+//
+// Lam over one sub-interval: Lam_end = Lam_start exp(-gam len) + sum over "on" stretches [x1, x2] of F(x2) - F(x1),
+// F' = alpha(w) exp(-gam (len - w)).  A switch at x therefore only adds +F(x) (the gene goes off) or -F(x) (it goes on) to
+// an accumulator: one MUFU and four FP32 operations per draw; the boundary terms F(0), F(len) are per-segment constants.
+__device__ __forceinline__ float tseg_F(const TSeg* tp, float len, float k1, float p0, float p1, float x) {
+    if (k1 != 0.0f) {
+        float D;
+        asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(D) : "f"(f_mul(k1, f_add(x, -len))));
+        return f_mul(D, f_fma(p1, x, p0));
+    }
+    float h = f_fma(tp->p5, x, tp->p4);
+    h = f_fma(h, x, tp->p3);
+    h = f_fma(h, x, tp->p2);
+    h = f_fma(h, x, p1);
+    h = f_fma(h, x, p0);
+    return f_mul(h, x);
 }
 
-// Lam <- Lam e^{-gam d} + g * int_0^d (a + A1 w) e^{-gam (d - w)} dw
-__device__ __forceinline__ float lam_advance(float lam, int g, float a, float A1, float gam, float d) {
-    const float z = f_mul(gam, d);
-    const float ez = exp_neg(z);
-    // phi1 = (1 - e^-z)/z, psi = (z - 1 + e^-z)/z^2 = (1 - phi1)/z; series below z = 0.25 (cancellation)
-    float p1s = f_fma(z, f_fma(z, f_fma(z, f_fma(z, 1.0f / 120.0f, -1.0f / 24.0f), 1.0f / 6.0f), -0.5f), 1.0f);
-    float pss = f_fma(z, f_fma(z, f_fma(z, f_fma(z, 1.0f / 720.0f, -1.0f / 120.0f), 1.0f / 24.0f), -1.0f / 6.0f), 0.5f);
-    float rz;
-    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(rz) : "f"(z));
-    const float p1d = f_mul(f_add(1.0f, -ez), rz);
-    const float psd = f_mul(f_add(1.0f, -p1d), rz);
-    const bool small = z < 0.25f;
-    const float phi1 = small ? p1s : p1d, psi = small ? pss : psd;
-    const float inc = f_mul(d, f_fma(f_mul(A1, d), psi, f_mul(a, phi1)));
-    return f_fma(lam, ez, gate(g, inc));
-}
-
-// one telegraph draw in sub-interval sg at position x; returns true when the boundary is crossed
-__device__ __forceinline__ bool telegraph_step(Lineage& s, float& x, float& lam, const Seg& sg, uint32_t w) {
-    const int g = s.g;
-    const float asw = pick(g, sg.kon, sg.koff);
-    const float E = exp_variate<false>(w);
-    float q;
-    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(q) : "f"(asw));
-    const float xn = f_fma(E, q, x);
-    const bool crossed = !(xn < sg.len);
-    const float x1 = crossed ? sg.len : xn;
-    lam = lam_advance(lam, g, f_fma(sg.A1, x, sg.A0), sg.A1, sg.gam, f_add(x1, -x));
-    if (crossed) return true;
-    x = xn;
-    s.g = g ^ 1;
-    s.n_events += 1u;
-    return false;
+// Seg -> TSeg, once per sub-interval and read-out.  step_len = cycle / 5 bounds len.
+__device__ __forceinline__ TSeg make_tseg(const Seg& sg, float step_len) {
+    const float len = sg.len, gam = sg.gam, A0 = sg.A0, A1 = sg.A1;
+    float dec;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(dec) : "f"(f_mul(f_mul(gam, len), -1.4426950408889634f)));
+    TSeg t;
+    t.len = len;
+    t.qon = __fdiv_rn(-0.693147182464599609375f, sg.kon);
+    t.qoff = __fdiv_rn(-0.693147182464599609375f, sg.koff);
+    t.dec = dec;
+    if (f_mul(gam, step_len) < 0.25f) {
+        // F(x) = dec * sum_j x^j [A0 gam^(j-1)/j! + A1 gam^(j-2)/((j-2)! j)]: six terms in the kernel (the next one is
+        // below 5e-8 relative), nine for the boundary value F(len)
+        const float rj[9] = {1.0f, 1.0f / 2, 1.0f / 6, 1.0f / 24, 1.0f / 120, 1.0f / 720, 1.0f / 5040, 1.0f / 40320, 1.0f / 362880};
+        const float sj[9] = {0.0f, 1.0f / 2, 1.0f / 3, 1.0f / 8, 1.0f / 30, 1.0f / 144, 1.0f / 840, 1.0f / 5760, 1.0f / 45360};
+        float cj[9], gp = dec, gq = 0.0f;       // gp = dec gam^(j-1), gq = dec gam^(j-2)
+#pragma unroll
+        for (int j = 0; j < 9; ++j) {
+            cj[j] = f_fma(f_mul(A0, gp), rj[j], f_mul(f_mul(A1, gq), sj[j]));
+            gq = gp;
+            gp = f_mul(gp, gam);
+        }
+        float h = cj[8];
+#pragma unroll
+        for (int j = 7; j >= 0; --j) h = f_fma(h, len, cj[j]);
+        t.Flen = f_mul(h, len);
+        t.k1 = 0.0f;
+        t.p0 = cj[0]; t.p1 = cj[1]; t.p2 = cj[2]; t.p3 = cj[3]; t.p4 = cj[4]; t.p5 = cj[5];
+    } else {
+        const float e = __fdiv_rn(A1, gam), c = __fdiv_rn(f_add(A0, -e), gam);
+        t.k1 = f_mul(gam, 1.4426950408889634f);
+        t.p0 = c; t.p1 = e;
+        t.p2 = f_mul(dec, c);               // F(0)
+        t.p3 = 0.0f; t.p4 = 0.0f; t.p5 = 0.0f;
+        t.Flen = f_fma(e, len, c);
+    }
+    return t;
 }
 
 // Poisson(lam): inversion by sequential search below 12, Hoermann's PTRS (1993) above; the rarely taken
@@ -297,7 +328,7 @@ __device__ __forceinline__ void build_table(WarpTable& tab, const AbcRates& r, c
             sg.lamf = lab ? r.lam : 0.0f;
             sg.pad = 0.0f;
             if (lab && pos == l0) { tab.c_star = c; tab.e_star = n; }
-            tab.seg[c][n] = sg;
+            tab.slot[c][n].s = sg;
             n += 1;
             pos = nxt;
             if (!(pos < step_end)) k += 1;
@@ -350,6 +381,18 @@ abc_ssa_kernel(const AbcRates* __restrict__ rates, const AbcSsaParams prm, const
         __syncwarp();
         if (lane == 0 && tab.c_star < 0) { tab.c_star = prm.n_pre; tab.e_star = tab.n_ent[prm.n_pre]; }   // empty window
         __syncwarp();
+        if (HYBRID) {      // sub-intervals before the label window: telegraph-phase form, one slot per lane and round
+            const int n_conv = tab.c_star * SSA_SEG_PER_CYCLE + tab.e_star;
+            const float step_len = (float)(prm.cycle / 5.0);
+            for (int k = lane; k < n_conv; k += 32) {
+                const int cc = k / SSA_SEG_PER_CYCLE, ee = k % SSA_SEG_PER_CYCLE;
+                if (ee < tab.n_ent[cc]) {
+                    const Seg sg = tab.slot[cc][ee].s;
+                    tab.slot[cc][ee].t = make_tseg(sg, step_len);
+                }
+            }
+        }
+        __syncwarp();
 
         const int cell = chunk * 32 + lane;
         const bool live = cell < prm.n_cells;
@@ -373,24 +416,58 @@ abc_ssa_kernel(const AbcRates* __restrict__ rates, const AbcSsaParams prm, const
                 const int c_star = tab.c_star, e_star = tab.e_star;
                 int c = 0, e = 0, n_ent = tab.n_ent[0];
                 float x = 0.0f, lam = 0.0f;             // Lam: Poisson mean of U given the gene path
-                Seg sg = tab.seg[0][0];
+                const TSeg* tp = &tab.slot[0][0].t;
                 bool done = (c == c_star) && (e == e_star);
+                float len = 0.0f, k1 = 0.0f, p0 = 0.0f, p1 = 0.0f, acc = 0.0f;
+                float sgn = s.g ? 1.0f : -1.0f;         // +1 while the gene is on
+                uint32_t qsum = 0u, qb = 0u;            // bit patterns: q of the current state, qon + qoff
+                if (!done) {
+                    len = tp->len; k1 = tp->k1; p0 = tp->p0; p1 = tp->p1;
+                    qsum = __float_as_uint(tp->qon) + __float_as_uint(tp->qoff);
+                    qb = __float_as_uint(s.g ? tp->qoff : tp->qon);
+                    acc = (s.g && k1 != 0.0f) ? -tp->p2 : 0.0f;
+                }
+                const uint32_t ctr0 = s.ctr;
+                uint32_t unused = 0u;                   // words of the last block that were not drawn
                 while (!done) {
                     const uint4 b = next_block(s);
                     const uint32_t w4[4] = {b.x, b.y, b.z, b.w};
 #pragma unroll
                     for (int j = 0; j < 4; ++j) {
-                        if (!done && telegraph_step(s, x, lam, sg, w4[j])) {
+                        const float u = f_fma((float)w4[j], 2.3283064365386963e-10f, 1.1641532182693481e-10f);
+                        float l;
+                        asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(l) : "f"(u));
+                        const float xn = f_fma(l, __uint_as_float(qb), x);
+                        if (xn < len) {                 // the gene switches at xn
+                            acc = f_fma(sgn, tseg_F(tp, len, k1, p0, p1, xn), acc);
+                            sgn = -sgn;
+                            qb = qsum - qb;
+                            x = xn;
+                        } else if (!done) {             // sub-interval boundary (memoryless: the draw is discarded)
+                            const float gs = f_fma(sgn, 0.5f, 0.5f);
+                            lam = f_fma(lam, tp->dec, f_fma(gs, tp->Flen, acc));
                             e += 1; x = 0.0f; n_cross += 1u;
                             if (c < c_star && e == n_ent) {       // cell division: a Poisson count thins to half its mean
                                 lam = f_mul(lam, 0.5f);
                                 c += 1; e = 0; n_ent = tab.n_ent[c];
                             }
                             done = (c == c_star) && (e == e_star);
-                            if (!done) sg = tab.seg[c][e];
+                            if (!done) {
+                                tp = &tab.slot[c][e].t;
+                                len = tp->len; k1 = tp->k1; p0 = tp->p0; p1 = tp->p1;
+                                qsum = __float_as_uint(tp->qon) + __float_as_uint(tp->qoff);
+                                qb = __float_as_uint(sgn > 0.0f ? tp->qoff : tp->qon);
+                                acc = (k1 != 0.0f) ? f_mul(-gs, tp->p2) : 0.0f;
+                            } else {
+                                len = -INFINITY;        // a finished lane draws no further event in this block
+                                unused = (uint32_t)(3 - j);
+                            }
                         }
                     }
                 }
+                // draws = words consumed; every draw is either a switch or a boundary crossing
+                s.n_events += 4u * (s.ctr - ctr0) - unused - n_cross;
+                s.g = (sgn > 0.0f) ? 1 : 0;
                 WordSrc ws; ws.avail = 0;               // hand over: U ~ Poisson(Lam), L = 0
                 s.U = poisson_draw(lam, ws, s);
                 c_first = c_star; e_first = e_star;
@@ -400,17 +477,17 @@ abc_ssa_kernel(const AbcRates* __restrict__ rates, const AbcSsaParams prm, const
                 int e = (c == c_first) ? e_first : 0;
                 n_cross += (uint32_t)(n_ent - e);
                 float x = 0.0f;
-                Seg sg = tab.seg[c][e < n_ent ? e : 0];
+                Seg sg = tab.slot[c][e < n_ent ? e : 0].s;
                 while (e < n_ent) {
                     const uint4 b = next_block(s);
                     if (ssa_step<EXACT>(s, x, sg, b.x, b.y)) {
                         e += 1; x = 0.0f;
-                        if (e < n_ent) sg = tab.seg[c][e];
+                        if (e < n_ent) sg = tab.slot[c][e].s;
                     }
                     if (e < n_ent) {
                         if (ssa_step<EXACT>(s, x, sg, b.z, b.w)) {
                             e += 1; x = 0.0f;
-                            if (e < n_ent) sg = tab.seg[c][e];
+                            if (e < n_ent) sg = tab.slot[c][e].s;
                         }
                     }
                 }
@@ -470,6 +547,11 @@ int abc_launch_ssa(const AbcRates* d_rates, const AbcSsaParams& prm, const uint3
         return ABC_ERR_ARG;
     }
     ABC_CUDA_CHECK(cudaMemsetAsync(d_work, 0, sizeof(unsigned int), st));
+    {   // 4 CTAs x 44 KB of schedule tables per SM; the kernel does not use L1 (per device: set at every launch)
+        ABC_CUDA_CHECK(cudaFuncSetAttribute(abc_ssa_kernel<true, false>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+        ABC_CUDA_CHECK(cudaFuncSetAttribute(abc_ssa_kernel<false, true>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+        ABC_CUDA_CHECK(cudaFuncSetAttribute(abc_ssa_kernel<false, false>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+    }
     const bool hybrid = (prm.hybrid != 0) && !exact_math;
     int per_sm = 0;
     if (exact_math) {
@@ -537,8 +619,9 @@ __global__ void abc_rates_kernel(const double* __restrict__ theta, int m, long l
         const float s2 = r.kon[j] + r.koff[j];
         const float sw = 2.0f * r.kon[j] * r.koff[j] / s2;
         const float br = r.alpha[j] * (m != 2 ? 1.5f : 1.0f) * r.kon[j] / s2;
-        // with the hybrid burn-in births/deaths are simulated only inside the label window (~12 h of ~210 h)
-        cost += 0.2f * (sw + 0.115f * br);
+        // with the hybrid burn-in births/deaths are simulated only inside the label window (~12 h of ~210 h), at about
+        // twice the instructions of a telegraph draw
+        cost += 0.2f * (sw + 0.2f * br);
     }
     r.pad0 = (cost == cost && cost > 0.0f) ? cost : 0.0f;
     r.pad1 = 0.0f;

@@ -453,6 +453,8 @@ CORNERS = [
     (1, np.array([-2.7, -2.9, 2.9, -2.8, -0.5]), 6, 1),                       # slow switch, long-lived mRNA: Poisson(1e4)
     (2, np.array([-1.0, 1.0, 2.0, -1.0, 0.0]), 8, 2),                         # bursty, no scaling, lambda = 1
     (3, np.array([-3.0, 3.0, -3.0, 3.0, 0.0, 0.5, 2.0, -1.5, -0.7]), 10, 3),  # kon jumps by 6 decades between steps
+    (5, np.array([1.0, 1.5, 2.0, -2.5, -1.6, -1.1, 0.0, 1.5, -0.2]), 7, 3),   # decay steps on both sides of the series/closed-form split
+    (1, np.array([-0.5, 2.9, 2.5, -3.0, -0.4]), 2, 4),                        # P_on = 4e-4, immortal mRNA: short on-stretches, slow decay
 ]
 
 
