@@ -71,25 +71,30 @@ __device__ __forceinline__ float wait_time(float c0, float c1, float E) {
 }
 
 // one sub-interval of the rate schedule: constant kon, koff, gamma, lam; alpha(x) = A0 + A1*x
-struct Seg {
+struct __align__(8) Seg {
     float len, kon, koff, A0;
     float A1, gam, lamf, pad;
 };
 
-#define SSA_MAX_CYCLES 16
+#define SSA_MAX_CYCLES 14
 #define SSA_SEG_PER_CYCLE 7
 #define SSA_WARPS 8
 
-// the same sub-interval as the telegraph phase of the hybrid burn-in sees it (48 B): waiting-time factors and the
+// the same sub-interval as the telegraph phase of the hybrid burn-in sees it (56 B): waiting-time factors and the
 // antiderivative F of alpha(w) exp(-gam (len - w)), so that the Poisson mean advances by F(x2) - F(x1) over an "on"
 // stretch [x1, x2].
 //   k1 != 0: F(x) = 2^(k1 (x - len)) (p0 + p1 x),  p0 = A0/gam - A1/gam^2, p1 = A1/gam, p2 = F(0)
 //   k1 == 0 (gam * step < 1/4): F(x) = x (p0 + p1 x + ... + p5 x^5), the series of the same integral from 0
-struct TSeg {
+struct __align__(8) TSeg {
     float len, qon, qoff, dec;     // q = -ln2 / rate (waiting time = lg2(u) * q), dec = exp(-gam len)
     float Flen, k1, p0, p1;
     float p2, p3, p4, p5;
+    float lamf;                    // labelled share of the births in this sub-interval
+    int meta;                      // bit 0: a cell division follows, bit 1: last sub-interval of the telegraph phase,
+                                   // bits 8..: byte offset to the next sub-interval's slot
 };
+#define TSEG_DIV 1
+#define TSEG_LAST 2
 union Slot {
     Seg s;
     TSeg t;
@@ -227,6 +232,7 @@ __device__ __forceinline__ TSeg make_tseg(const Seg& sg, float step_len) {
     asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(dec) : "f"(f_mul(f_mul(gam, len), -1.4426950408889634f)));
     TSeg t;
     t.len = len;
+    t.lamf = sg.lamf; t.meta = 0;
     t.qon = __fdiv_rn(-0.693147182464599609375f, sg.kon);
     t.qoff = __fdiv_rn(-0.693147182464599609375f, sg.koff);
     t.dec = dec;
@@ -296,8 +302,10 @@ __device__ __forceinline__ unsigned long long warp_sum_u64(unsigned long long v)
 }
 
 // build the schedule of one read-out: lane c builds cycle c
+// n_steps: rate steps per cycle (5 = scripts/model.jl:1-22; 1 when no rate varies and the caller does not need the
+// step boundaries, i.e. the telegraph-only mode of models 1 and 2)
 __device__ __forceinline__ void build_table(WarpTable& tab, const AbcRates& r, const AbcSsaParams& prm,
-                                            int cond, int age_i, int lane) {
+                                            int cond, int age_i, int lane, int n_steps) {
     const int c = lane;
     if (c <= prm.n_pre) {
         const double cycle = prm.cycle;
@@ -307,7 +315,7 @@ __device__ __forceinline__ void build_table(WarpTable& tab, const AbcRates& r, c
         const double Tc = (double)(c - prm.n_pre) * cycle;
         const double cyc_end = (c == prm.n_pre) ? age : cycle;
         const double l0 = tl0 - Tc, l1 = tl1 - Tc;
-        const double step_len = cycle / 5.0;
+        const double step_len = cycle / (double)n_steps;
         const double sc = prm.scaling ? 1.0 : 0.0;
         double pos = 0.0;
         int k = 0, n = 0;
@@ -332,13 +340,13 @@ __device__ __forceinline__ void build_table(WarpTable& tab, const AbcRates& r, c
             n += 1;
             pos = nxt;
             if (!(pos < step_end)) k += 1;
-            if (k > 4) k = 4;
+            if (k > n_steps - 1) k = n_steps - 1;
         }
         tab.n_ent[c] = n;
     }
 }
 
-template <bool EXACT, bool HYBRID>
+template <bool EXACT, int HYBRID>      // HYBRID: 0 = six-channel direct method throughout, 1 = telegraph burn-in, 2 = telegraph to the read-out
 __global__ void __launch_bounds__(SSA_WARPS * 32, 4)
 abc_ssa_kernel(const AbcRates* __restrict__ rates, const AbcSsaParams prm, const uint32_t* __restrict__ beta_q32,
                unsigned long long* __restrict__ sums, unsigned long long* __restrict__ counters,
@@ -377,18 +385,29 @@ abc_ssa_kernel(const AbcRates* __restrict__ rates, const AbcSsaParams prm, const
         __syncwarp();
         if (lane == 0) { tab.c_star = -1; tab.e_star = 0; }
         __syncwarp();
-        build_table(tab, srates[warp], prm, cond, age_i, lane);
+        const int n_steps = (HYBRID == 2 && prm.m <= 2) ? 1 : 5;
+        build_table(tab, srates[warp], prm, cond, age_i, lane, n_steps);
         __syncwarp();
-        if (lane == 0 && tab.c_star < 0) { tab.c_star = prm.n_pre; tab.e_star = tab.n_ent[prm.n_pre]; }   // empty window
+        if (lane == 0 && (tab.c_star < 0 || HYBRID == 2)) {
+            // empty window, or hybrid mode 2: the telegraph phase runs to the read-out
+            tab.c_star = prm.n_pre; tab.e_star = tab.n_ent[prm.n_pre];
+        }
         __syncwarp();
-        if (HYBRID) {      // sub-intervals before the label window: telegraph-phase form, one slot per lane and round
-            const int n_conv = tab.c_star * SSA_SEG_PER_CYCLE + tab.e_star;
-            const float step_len = (float)(prm.cycle / 5.0);
+        if (HYBRID) {      // sub-intervals before the hand-over: telegraph-phase form, one slot per lane and round
+            const int c_star = tab.c_star, e_star = tab.e_star;
+            const int n_conv = c_star * SSA_SEG_PER_CYCLE + e_star;
+            const float step_len = (float)(prm.cycle / (double)n_steps);
             for (int k = lane; k < n_conv; k += 32) {
                 const int cc = k / SSA_SEG_PER_CYCLE, ee = k % SSA_SEG_PER_CYCLE;
                 if (ee < tab.n_ent[cc]) {
                     const Seg sg = tab.slot[cc][ee].s;
-                    tab.slot[cc][ee].t = make_tseg(sg, step_len);
+                    TSeg t = make_tseg(sg, step_len);
+                    int c2 = cc, e2 = ee + 1, meta = 0;
+                    if (cc < c_star && e2 == tab.n_ent[cc]) { meta |= TSEG_DIV; c2 = cc + 1; e2 = 0; }
+                    if (c2 == c_star && e2 == e_star) meta |= TSEG_LAST;
+                    meta |= (((c2 - cc) * SSA_SEG_PER_CYCLE + (e2 - ee)) * (int)sizeof(Slot)) << 8;
+                    t.meta = meta;
+                    tab.slot[cc][ee].t = t;
                 }
             }
         }
@@ -413,12 +432,10 @@ abc_ssa_kernel(const AbcRates* __restrict__ rates, const AbcSsaParams prm, const
             if (HYBRID) {
                 // phase A: telegraph process + closed-form Lam, one random word per draw.  Divisions only halve
                 // Lam, so the lanes run through all phase-A cycles without waiting for each other.
-                const int c_star = tab.c_star, e_star = tab.e_star;
-                int c = 0, e = 0, n_ent = tab.n_ent[0];
-                float x = 0.0f, lam = 0.0f;             // Lam: Poisson mean of U given the gene path
+                float x = 0.0f, lam = 0.0f, lamL = 0.0f;   // Poisson means of U and L given the gene path
                 const TSeg* tp = &tab.slot[0][0].t;
-                bool done = (c == c_star) && (e == e_star);
-                float len = 0.0f, k1 = 0.0f, p0 = 0.0f, p1 = 0.0f, acc = 0.0f;
+                bool done = (tab.c_star == 0) && (tab.e_star == 0);
+                float len = -INFINITY, k1 = 0.0f, p0 = 0.0f, p1 = 0.0f, acc = 0.0f;
                 float sgn = s.g ? 1.0f : -1.0f;         // +1 while the gene is on
                 uint32_t qsum = 0u, qb = 0u;            // bit patterns: q of the current state, qon + qoff
                 if (!done) {
@@ -445,22 +462,25 @@ abc_ssa_kernel(const AbcRates* __restrict__ rates, const AbcSsaParams prm, const
                             x = xn;
                         } else if (!done) {             // sub-interval boundary (memoryless: the draw is discarded)
                             const float gs = f_fma(sgn, 0.5f, 0.5f);
-                            lam = f_fma(lam, tp->dec, f_fma(gs, tp->Flen, acc));
-                            e += 1; x = 0.0f; n_cross += 1u;
-                            if (c < c_star && e == n_ent) {       // cell division: a Poisson count thins to half its mean
+                            const float inc = f_fma(gs, tp->Flen, acc), incL = f_mul(tp->lamf, inc), dec = tp->dec;
+                            const int meta = tp->meta;
+                            lam = f_fma(lam, dec, f_add(inc, -incL));
+                            lamL = f_fma(lamL, dec, incL);
+                            x = 0.0f; n_cross += 1u;
+                            if (meta & TSEG_DIV) {      // cell division: a Poisson count thins to half its mean
                                 lam = f_mul(lam, 0.5f);
-                                c += 1; e = 0; n_ent = tab.n_ent[c];
+                                lamL = f_mul(lamL, 0.5f);
                             }
-                            done = (c == c_star) && (e == e_star);
-                            if (!done) {
-                                tp = &tab.slot[c][e].t;
+                            if (meta & TSEG_LAST) {
+                                done = true;
+                                len = -INFINITY;        // a finished lane draws no further event in this block
+                                unused = (uint32_t)(3 - j);
+                            } else {
+                                tp = (const TSeg*)((const char*)tp + (meta >> 8));
                                 len = tp->len; k1 = tp->k1; p0 = tp->p0; p1 = tp->p1;
                                 qsum = __float_as_uint(tp->qon) + __float_as_uint(tp->qoff);
                                 qb = __float_as_uint(sgn > 0.0f ? tp->qoff : tp->qon);
                                 acc = (k1 != 0.0f) ? f_mul(-gs, tp->p2) : 0.0f;
-                            } else {
-                                len = -INFINITY;        // a finished lane draws no further event in this block
-                                unused = (uint32_t)(3 - j);
                             }
                         }
                     }
@@ -468,10 +488,12 @@ abc_ssa_kernel(const AbcRates* __restrict__ rates, const AbcSsaParams prm, const
                 // draws = words consumed; every draw is either a switch or a boundary crossing
                 s.n_events += 4u * (s.ctr - ctr0) - unused - n_cross;
                 s.g = (sgn > 0.0f) ? 1 : 0;
-                WordSrc ws; ws.avail = 0;               // hand over: U ~ Poisson(Lam), L = 0
+                WordSrc ws; ws.avail = 0;               // hand over: U ~ Poisson(Lam); L = 0 unless the window was included
                 s.U = poisson_draw(lam, ws, s);
-                c_first = c_star; e_first = e_star;
+                s.L = poisson_draw(lamL, ws, s);
+                c_first = tab.c_star; e_first = tab.e_star;
             }
+            if (HYBRID != 2)
             for (int c = c_first; c <= prm.n_pre; ++c) {
                 const int n_ent = tab.n_ent[c];
                 int e = (c == c_first) ? e_first : 0;
@@ -547,20 +569,15 @@ int abc_launch_ssa(const AbcRates* d_rates, const AbcSsaParams& prm, const uint3
         return ABC_ERR_ARG;
     }
     ABC_CUDA_CHECK(cudaMemsetAsync(d_work, 0, sizeof(unsigned int), st));
-    {   // 4 CTAs x 44 KB of schedule tables per SM; the kernel does not use L1 (per device: set at every launch)
-        ABC_CUDA_CHECK(cudaFuncSetAttribute(abc_ssa_kernel<true, false>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
-        ABC_CUDA_CHECK(cudaFuncSetAttribute(abc_ssa_kernel<false, true>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
-        ABC_CUDA_CHECK(cudaFuncSetAttribute(abc_ssa_kernel<false, false>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
-    }
-    const bool hybrid = (prm.hybrid != 0) && !exact_math;
+    const int hybrid = exact_math ? 0 : (prm.hybrid <= 0 ? 0 : (prm.hybrid == 1 ? 1 : 2));
+    const void* fn = exact_math    ? (const void*)abc_ssa_kernel<true, 0>
+                     : hybrid == 2 ? (const void*)abc_ssa_kernel<false, 2>
+                     : hybrid == 1 ? (const void*)abc_ssa_kernel<false, 1>
+                                   : (const void*)abc_ssa_kernel<false, 0>;
+    // 4 CTAs x 45 KB of schedule tables per SM; the kernel does not use L1 (per device: set at every launch)
+    ABC_CUDA_CHECK(cudaFuncSetAttribute(fn, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
     int per_sm = 0;
-    if (exact_math) {
-        ABC_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, abc_ssa_kernel<true, false>, SSA_WARPS * 32, 0));
-    } else if (hybrid) {
-        ABC_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, abc_ssa_kernel<false, true>, SSA_WARPS * 32, 0));
-    } else {
-        ABC_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, abc_ssa_kernel<false, false>, SSA_WARPS * 32, 0));
-    }
+    ABC_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fn, SSA_WARPS * 32, 0));
     if (per_sm < 1) per_sm = 1;
     unsigned long long items = (prm.single_readout >= 0) ? (unsigned long long)prm.chunks
                                : (unsigned long long)prm.n_particles * ABC_NREAD * prm.chunks;
@@ -572,19 +589,17 @@ int abc_launch_ssa(const AbcRates* d_rates, const AbcSsaParams& prm, const uint3
     unsigned long long grid = (unsigned long long)sm_count * per_sm;
     if (grid > want) grid = want;
     if (grid < 1) grid = 1;
-    if (exact_math)
-        abc_ssa_kernel<true, false><<<(unsigned)grid, SSA_WARPS * 32, 0, st>>>(d_rates, prm, d_beta_q32, d_sums, d_counters, d_work, d_cells_out, d_order);
-    else if (hybrid)
-        abc_ssa_kernel<false, true><<<(unsigned)grid, SSA_WARPS * 32, 0, st>>>(d_rates, prm, d_beta_q32, d_sums, d_counters, d_work, d_cells_out, d_order);
-    else
-        abc_ssa_kernel<false, false><<<(unsigned)grid, SSA_WARPS * 32, 0, st>>>(d_rates, prm, d_beta_q32, d_sums, d_counters, d_work, d_cells_out, d_order);
+    void* args[] = {(void*)&d_rates, (void*)&prm, (void*)&d_beta_q32, (void*)&d_sums, (void*)&d_counters, (void*)&d_work,
+                    (void*)&d_cells_out, (void*)&d_order};
+    ABC_CUDA_CHECK(cudaLaunchKernel(fn, dim3((unsigned)grid), dim3(SSA_WARPS * 32), args, 0, st));
     ABC_CUDA_CHECK(cudaGetLastError());
     return ABC_OK;
 }
 
 // ------------------------------------------------------------------------------------------------
 // theta (log10, [n][P]) -> linear float rates.  vary_map of model.jl:30-43 / abc_simulation.jl:82-85.
-__global__ void abc_rates_kernel(const double* __restrict__ theta, int m, long long n, AbcRates* __restrict__ out) {
+__global__ void abc_rates_kernel(const double* __restrict__ theta, int m, long long n, AbcRates* __restrict__ out,
+                                 int ssa_hybrid) {
     long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     const int P = (m <= 2) ? 5 : 9;
@@ -612,16 +627,17 @@ __global__ void abc_rates_kernel(const double* __restrict__ theta, int m, long l
     double pon = kon / (kon + koff);
     double thr = pon * 4294967296.0;
     r.pon_thr = (thr >= 4294967295.0) ? 0xFFFFFFFFu : (thr > 0.0 ? (uint32_t)thr : 0u);
-    // predicted SSA draws per simulated hour (switching + the label-window share of births/deaths), used only to schedule the
-    // heaviest particles first (longest-processing-time order); it never influences a result
+    // predicted SSA work per simulated hour (in telegraph draws), used only to schedule the heaviest particles first
+    // (longest-processing-time order); it never influences a result.  Births and deaths are simulated over the whole
+    // lineage (mode 0), inside the label window only (mode 1: ~12 h of ~210 h, at about twice the instructions of a
+    // telegraph draw) or not at all (mode 2).
+    const float wb = (ssa_hybrid == 0) ? 2.0f : (ssa_hybrid == 1) ? 0.2f : 0.0f;
     float cost = 0.0f;
     for (int j = 0; j < 5; ++j) {
         const float s2 = r.kon[j] + r.koff[j];
         const float sw = 2.0f * r.kon[j] * r.koff[j] / s2;
         const float br = r.alpha[j] * (m != 2 ? 1.5f : 1.0f) * r.kon[j] / s2;
-        // with the hybrid burn-in births/deaths are simulated only inside the label window (~12 h of ~210 h), at about
-        // twice the instructions of a telegraph draw
-        cost += 0.2f * (sw + 0.2f * br);
+        cost += 0.2f * (sw + wb * br);
     }
     r.pad0 = (cost == cost && cost > 0.0f) ? cost : 0.0f;
     r.pad1 = 0.0f;
@@ -654,11 +670,11 @@ int abc_launch_order(const AbcRates* d_rates, int n, unsigned int* d_keys_in, un
     return ABC_OK;
 }
 
-int abc_launch_rates(const double* d_theta, int m, int64_t n, AbcRates* d_rates, cudaStream_t st) {
+int abc_launch_rates(const double* d_theta, int m, int64_t n, AbcRates* d_rates, int ssa_hybrid, cudaStream_t st) {
     if (n <= 0) return ABC_OK;
     int threads = 128;
     long long blocks = (n + threads - 1) / threads;
-    abc_rates_kernel<<<(unsigned)blocks, threads, 0, st>>>(d_theta, m, (long long)n, d_rates);
+    abc_rates_kernel<<<(unsigned)blocks, threads, 0, st>>>(d_theta, m, (long long)n, d_rates, ssa_hybrid);
     ABC_CUDA_CHECK(cudaGetLastError());
     return ABC_OK;
 }

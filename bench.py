@@ -34,7 +34,12 @@ METRIC = "abc_particles_simulated_and_scored_per_s"
 UNIT = "particles/s"
 SEED = 20240229
 EPS = 4.8
-NOMINAL_INSTR_PER_EVENT = 64.0       # algorithmic lane-instructions per SSA event
+# nominal lane-instructions per draw: a six-channel direct-method event and a
+# telegraph draw of the hybrid modes (1/4 Philox4x32-10 block 11, uniform -> exponential variate 3, time advance and
+# boundary test 2, antiderivative F 5, accumulate and flip the state 3)
+NOMINAL_INSTR_PER_EVENT = 64.0
+NOMINAL_INSTR_PER_TELEGRAPH_DRAW = 24.0
+SSA_MODE = 2                          # ssa_hybrid_burnin of the headline run (library default)
 ALG_BYTES_PER_PARTICLE_SCORE = 27776  # 424 B read + G*8 B written, G = 3419
 SCORE_TRAFFIC_131070 = 4.04e9         # measured dram bytes (read + write) of one 131070-particle scoring call, see profiles/
 
@@ -154,7 +159,8 @@ def workload_config(args):
             "models": 5, "particles_per_model_per_step_per_gpu": args.batch, "n_cells_per_readout": args.n_cells,
             "n_pre_cycles": args.n_pre, "readouts": 55, "genes": 3419, "eps": EPS, "seed": SEED,
             "l2": "flushed between steps (256 MiB write)", "lineages": "independent per (condition, age, cell)",
-            "ssa": "direct method; exact telegraph+Poisson burn-in before the label window (ssa_hybrid_burnin=1)"}
+            "ssa": "Gillespie SSA of the gene switch to the read-out, U and L ~ Poisson given the gene path (exact; "
+                   "ssa_hybrid_burnin=2), binomial division and capture-efficiency thinning sampled per cell"}
 
 
 # ------------------------------------------------------------------------------------------------
@@ -311,23 +317,26 @@ def run_b200(args):
             score_acc_ms.append(e0.elapsed_time(e1))
     score_acc_s = sum(score_acc_ms) / len(score_acc_ms) / 1e3
     del big_err, big_stats
-    # ---- the same SSA without the hybrid burn-in (all six channels from the first cycle), small batch ----
-    eng.set_option("ssa_hybrid_burnin", 0)
+    # ---- the same SSA with all six channels simulated explicitly: from the first cycle (mode 0) and inside the
+    # ---- label window only (mode 1), small batch ----
     nfd = min(B, 1024)
-    full_direct = {}
-    ev_fd = ms_fd = 0.0
-    for rep in range(2):
-        for m in range(1, 6):
-            eng.simulate_dev(m, nfd, th_dev[m - 1].data_ptr(), st_dev.data_ptr(), particle_offset=rep * nfd, seed=SEED,
-                             prior_supplied=False, stream=stream)
-            c = eng.counters()
-            if rep == 1:
-                ev_fd += c["n_events"]; ms_fd += c["ms_simulate"]
-    eng.set_option("ssa_hybrid_burnin", 1)
-    full_direct = {"particles_per_s": 5 * nfd / (ms_fd / 1e3), "events_per_s": ev_fd / (ms_fd / 1e3),
-                   "events_per_particle": ev_fd / (5 * nfd), "particles_per_model": nfd,
-                   "frac_of_issue_roofline_nominal64": ev_fd / (ms_fd / 1e3) * NOMINAL_INSTR_PER_EVENT / 1e12 /
-                                                       (148 * 128 * peaks()["sm_max_mhz"] * 1e6 / 1e12)}
+    cmp_modes = {}
+    for mode in (0, 1):
+        eng.set_option("ssa_hybrid_burnin", mode)
+        ev_fd = ms_fd = 0.0
+        for rep in range(2):
+            for m in range(1, 6):
+                eng.simulate_dev(m, nfd, th_dev[m - 1].data_ptr(), st_dev.data_ptr(), particle_offset=rep * nfd, seed=SEED,
+                                 prior_supplied=False, stream=stream)
+                c = eng.counters()
+                if rep == 1:
+                    ev_fd += c["n_events"]; ms_fd += c["ms_simulate"]
+        cmp_modes[mode] = {"particles_per_s": 5 * nfd / (ms_fd / 1e3), "events_per_s": ev_fd / (ms_fd / 1e3),
+                           "events_per_particle": ev_fd / (5 * nfd), "particles_per_model": nfd,
+                           "frac_of_issue_roofline_nominal64": ev_fd / (ms_fd / 1e3) * NOMINAL_INSTR_PER_EVENT / 1e12 /
+                                                               (148 * 128 * peaks()["sm_max_mhz"] * 1e6 / 1e12)}
+    eng.set_option("ssa_hybrid_burnin", SSA_MODE)
+    full_direct = cmp_modes[0]
     ode = run_ode_path(args, eng_cls=AbcEngine, betas=betas, d=d, se=se, dev=dev, world=world, rank=rank, local=local,
                        barrier=barrier)
     if rank == 0:
@@ -335,7 +344,8 @@ def run_b200(args):
         peak_instr = 148 * 128 * pk["sm_max_mhz"] * 1e6 / 1e12        # T lane-instr/s at max clock
         ssa_s = sum(sim_ms) / 1e3
         ev_per_s = events / ssa_s if ssa_s > 0 else 0.0
-        achieved = ev_per_s * NOMINAL_INSTR_PER_EVENT / 1e12
+        draws_per_s = draws / ssa_s if ssa_s > 0 else 0.0
+        achieved = draws_per_s * NOMINAL_INSTR_PER_TELEGRAPH_DRAW / 1e12
         sc_s = sum(score_ms) / 1e3
         sc_gbs = nb * ALG_BYTES_PER_PARTICLE_SCORE / score_big_s / 1e9
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
@@ -346,11 +356,13 @@ def run_b200(args):
                         "d2h_bytes_per_step": d2h // args.steps},
                 "gpu_launches": int(launches),
                 "clocks": sampler.summary(),
-                "roofline": {"kernel": "abc_ssa_kernel<false,true>", "bound": "issue", "achieved": achieved, "peak": peak_instr,
+                "roofline": {"kernel": "abc_ssa_kernel<false,2>", "bound": "issue", "achieved": achieved, "peak": peak_instr,
                              "unit": "Tlane-instr/s", "frac": achieved / peak_instr, "traffic": None,
                              "traffic_note": "not memory bound: ncu dram read 0.1 MB, write 0 per launch (profiles/)",
                              "events_per_s": ev_per_s, "events": int(events), "draws": int(draws),
-                             "nominal_instr_per_event": NOMINAL_INSTR_PER_EVENT,
+                             "draws_per_s": draws_per_s,
+                             "nominal_instr_per_draw": NOMINAL_INSTR_PER_TELEGRAPH_DRAW,
+                             "work_unit": "telegraph draw (switch event or sub-interval boundary)",
                              "peak_src": f"148 SM x 128 lanes x sm_max_mhz ({pk['src']})",
                              "share_of_step": ssa_s / t_dev if t_dev > 0 else None},
                 "roofline_score": {"kernel": "abc_score3_classify_kernel + abc_score3_tile_kernel<2> + abc_score3_exact_kernel<2>",
@@ -366,6 +378,7 @@ def run_b200(args):
                                                    "note": "err_layout = ABC_ERR_NONE: fused eps-acceptance, no matrix"}}}
         line["ode_path"] = ode
         line["ssa_full_direct"] = full_direct
+        line["ssa_six_channel_window"] = cmp_modes[1]
         line["roofline"]["events_per_particle"] = events / max(1, 5 * B * args.steps)
         if world == 1 and not args.no_cpu:
             cores = os.cpu_count() or 1

@@ -175,9 +175,12 @@ int  abc_accept_tuples_dev(abc_ctx_t* ctx, int32_t* d_gene, int64_t* d_particle,
  * "stats_sample_guards" = -1 (default): when the moments come from SSA cells, degenerate samples follow the
  * reference's data-side conventions (ratio = 0 without counts, correlations = 0 when a total variance is 0,
  * scripts/data_summary_statistics.jl:64-71,138-147); the ODE path follows abc_simulation.jl:23-46 verbatim.  0 / 1 force.
- * "ssa_hybrid_burnin" = 0: run the full six-channel direct method from the first simulated cycle; 1 (default):
- * before the label window opens simulate only the gene switch and draw U ~ Poisson(Lam | gene path) at the
- * window start (exact); the exact_math variant of abc_ssa_cells always uses 0. */
+ * "ssa_hybrid_burnin" = 0: run the full six-channel direct method from the first simulated cycle; 1: before the
+ * label window opens simulate only the gene switch (Gillespie on the telegraph process) and draw
+ * U ~ Poisson(Lam | gene path) at the window start, then run the six-channel direct method to the read-out;
+ * 2 (default): simulate the gene switch to the read-out and draw U ~ Poisson(Lam_U | gene path),
+ * L ~ Poisson(Lam_L | gene path) there.  All three sample the same law of (g, U, L) at the read-out;
+ * the exact_math variant of abc_ssa_cells always uses 0. */
 int  abc_set_option(abc_ctx_t* ctx, const char* name, int64_t value);
 /* device counters of the last *_dev launches (synchronises the stream) */
 int  abc_counters(abc_ctx_t* ctx, abc_counters_t* counters);
