@@ -449,12 +449,28 @@ abc_ssa_kernel(const AbcRates* __restrict__ rates, const AbcSsaParams prm, const
                 while (!done) {
                     const uint4 b = next_block(s);
                     const uint32_t w4[4] = {b.x, b.y, b.z, b.w};
+                    float l4[4];
 #pragma unroll
                     for (int j = 0; j < 4; ++j) {
                         const float u = f_fma((float)w4[j], 2.3283064365386963e-10f, 1.1641532182693481e-10f);
-                        float l;
-                        asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(l) : "f"(u));
-                        const float xn = f_fma(l, __uint_as_float(qb), x);
+                        asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(l4[j]) : "f"(u));
+                    }
+                    // fast path: all four draws of every lane of the warp are switches inside the current sub-interval
+                    // (the waiting-time factor alternates between the two gene states); same arithmetic as the
+                    // draw-by-draw path below for the event times, F enters as sgn ((F1 - F2) + (F3 - F4))
+                    const float qc = __uint_as_float(qb), qo = __uint_as_float(qsum - qb);
+                    const float x1 = f_fma(l4[0], qc, x), x2 = f_fma(l4[1], qo, x1);
+                    const float x3 = f_fma(l4[2], qc, x2), x4 = f_fma(l4[3], qo, x3);
+                    if (__all_sync(__activemask(), x4 < len)) {
+                        const float t = f_add(f_add(tseg_F(tp, len, k1, p0, p1, x1), -tseg_F(tp, len, k1, p0, p1, x2)),
+                                              f_add(tseg_F(tp, len, k1, p0, p1, x3), -tseg_F(tp, len, k1, p0, p1, x4)));
+                        acc = f_fma(sgn, t, acc);
+                        x = x4;
+                        continue;
+                    }
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                        const float xn = f_fma(l4[j], __uint_as_float(qb), x);
                         if (xn < len) {                 // the gene switches at xn
                             acc = f_fma(sgn, tseg_F(tp, len, k1, p0, p1, xn), acc);
                             sgn = -sgn;
