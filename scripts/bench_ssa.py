@@ -1,5 +1,5 @@
 """SSA-kernel micro-benchmark: one simulate_dev launch per model on a resident batch, events/s from the in-kernel
-counters and the library's CUDA-event timing.  Usage: python scripts/bench_ssa.py [n_particles] [models e.g. 12345] [n_cells] [n_pre]"""
+counters and the library's CUDA-event timing.  Usage: python scripts/bench_ssa.py [n_particles] [models e.g. 12345] [n_cells] [n_pre] [corner|prior] [mode]"""
 import os
 import sys
 
@@ -14,10 +14,12 @@ n = int(sys.argv[1]) if len(sys.argv) > 1 else 2048
 models = [int(c) for c in (sys.argv[2] if len(sys.argv) > 2 else "12345")]
 n_cells = int(sys.argv[3]) if len(sys.argv) > 3 else 96
 n_pre = int(sys.argv[4]) if len(sys.argv) > 4 else 10
-corner = len(sys.argv) > 5 and sys.argv[5] == "corner"   # BASELINE configs[4]: kon,koff,alpha ~ U(2,3), gamma ~ U(1,2)
+corner = len(sys.argv) > 5 and sys.argv[5] == "corner"
+mode = int(sys.argv[6]) if len(sys.argv) > 6 else 2        # ssa_hybrid_burnin   # BASELINE configs[4]: kon,koff,alpha ~ U(2,3), gamma ~ U(1,2)
 betas = np.load(os.path.join(ROOT, "tests", "golden", "ref_betas.npy"))
 eng = AbcEngine(0)
 eng.set_design(synthetic_design(betas, n_cells=n_cells, n_pre_cycles=n_pre))
+eng.set_option("ssa_hybrid_burnin", mode)
 dev = torch.device("cuda", 0)
 st = torch.empty((n, 53), dtype=torch.float64, device=dev)
 tot_ev = tot_ms = 0.0
@@ -39,4 +41,5 @@ for rep in range(2):
             tot_ev += c["n_events"]; tot_ms += c["ms_simulate"]
             print(f"m={m} n={n}: {c['ms_simulate']:.1f} ms  {c['n_events']/c['ms_simulate']/1e6:.1f} Gev/s  "
                   f"{n/c['ms_simulate']*1e3:.0f} particles/s  events/particle {c['n_events']/n:.3g}")
-print(f"total: {tot_ev/tot_ms/1e6:.1f} Gev/s  roofline frac (64 instr/event nominal) {tot_ev/tot_ms*1e3*64/37.225e12:.3f}")
+print(f"total: {tot_ev/tot_ms/1e6:.1f} Gev/s  issue-roofline frac: {tot_ev/tot_ms*1e3*24/37.225e12:.3f} at 24 lane-instr per telegraph draw "
+      f"(modes 1-2), {tot_ev/tot_ms*1e3*64/37.225e12:.3f} at 64 per six-channel event (mode 0)")
