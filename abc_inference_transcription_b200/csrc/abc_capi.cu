@@ -98,6 +98,7 @@ struct abc_ctx {
     int score_sub_batches = 0;   // sub-batches per call when overlapping; 0 = 2 below 256k particles, else 4
     int stats_guards = -1;       // -1: sample guards iff sim_kind == SSA; 0 / 1 force
     int ssa_hybrid = 2;          // exact telegraph + conditional-Poisson sampling: 1 = burn-in only, 2 = to the read-out
+    int ssa_adaptive = 1;        // burn-in cycles per particle from the decay of the discarded history (modes 1, 2)
     // simulate work buffers
     DevBuf<double> d_theta, d_stats, d_moments, d_ss_iv, d_prefix;
     DevBuf<AbcRates> d_rates;
@@ -361,6 +362,7 @@ static AbcSsaParams make_ssa_params(const abc_ctx* c, int m, int64_t n, int64_t 
     p.downsampling = c->design.downsampling;
     p.single_readout = -1;
     p.hybrid = c->ssa_hybrid;
+    p.adaptive = c->ssa_adaptive;
     p.cycle = c->design.cycle;
     for (int a = 0; a < 5; ++a) p.agevec[a] = c->design.agevec[a];
     for (int j = 0; j < 11; ++j) { p.pulse[j] = c->design.pulse[j]; p.chase[j] = c->design.chase[j]; p.beta_off[j] = c->beta_off[j]; }
@@ -405,7 +407,8 @@ static int simulate_device(abc_ctx* c, int m, int64_t n, int64_t offset, uint64_
         if ((rc = c->d_moments.ensure((size_t)n * ABC_NREAD * 5)) != ABC_OK) return rc;
         d_mom = c->d_moments.p;
     }
-    if ((rc = abc_launch_rates(d_theta, m, n, c->d_rates.p, c->ssa_hybrid, st)) != ABC_OK) return rc;
+    if ((rc = abc_launch_rates(d_theta, m, n, c->d_rates.p, c->ssa_hybrid, (c->ssa_adaptive && c->ssa_hybrid) ? c->design.n_pre_cycles : 0,
+                               c->design.cycle, st)) != ABC_OK) return rc;
     c->launches++;
     // longest-processing-time-first order of the particles (scheduling only, results are order independent)
     const int* d_order = nullptr;
@@ -538,7 +541,7 @@ extern "C" int abc_ssa_cells(abc_ctx_t* c, int m, const double* theta, int64_t p
     if ((rc = c->d_rates.ensure(1)) != ABC_OK) return rc;
     if ((rc = c->d_cells.ensure((size_t)4 * nc)) != ABC_OK) return rc;
     ABC_CUDA_CHECK(cudaMemcpyAsync(c->d_theta.p, theta, P * sizeof(double), cudaMemcpyHostToDevice, c->stream));
-    if ((rc = abc_launch_rates(c->d_theta.p, m, 1, c->d_rates.p, c->ssa_hybrid, c->stream)) != ABC_OK) return rc;
+    if ((rc = abc_launch_rates(c->d_theta.p, m, 1, c->d_rates.p, c->ssa_hybrid, 0, c->design.cycle, c->stream)) != ABC_OK) return rc;
     ABC_CUDA_CHECK(cudaMemsetAsync(c->d_counters.p, 0, 8 * sizeof(unsigned long long), c->stream));
     AbcSsaParams prm = make_ssa_params(c, m, 1, particle_index, seed);
     prm.single_readout = cond * ABC_NAGE + age;
@@ -857,6 +860,7 @@ extern "C" int abc_set_option(abc_ctx_t* c, const char* name, int64_t value) {
     if (strcmp(name, "score_sub_batches") == 0) { c->score_sub_batches = (int)std::min<int64_t>(std::max<int64_t>(value, 0), 64); return ABC_OK; }
     if (strcmp(name, "accept_capacity") == 0) { c->acc_min_capacity = value > 0 ? value : 0; return ABC_OK; }
     if (strcmp(name, "stats_sample_guards") == 0) { c->stats_guards = value < 0 ? -1 : (value ? 1 : 0); return ABC_OK; }
+    if (strcmp(name, "ssa_adaptive_burnin") == 0) { c->ssa_adaptive = value ? 1 : 0; return ABC_OK; }
     if (strcmp(name, "ssa_hybrid_burnin") == 0) { c->ssa_hybrid = value <= 0 ? 0 : (value == 1 ? 1 : 2); return ABC_OK; }
     abc_set_error("abc_set_option: unknown option '%s'", name);
     return ABC_ERR_ARG;

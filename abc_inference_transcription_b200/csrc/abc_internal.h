@@ -27,6 +27,8 @@ struct AbcSsaParams {
     int32_t  single_readout;   // >= 0: debug mode, simulate only this read-out of particle 0
     int32_t  hybrid;           // 1: exact telegraph + Poisson burn-in before the label window; 2: to the read-out
                                // (fast-math kernel only)
+    int32_t  adaptive;         // 1: per-particle burn-in length with the truncation bias bound of n_pre cycles (modes 1, 2)
+    int32_t  pad_;
     double   cycle;
     double   agevec[5];
     double   pulse[11];
@@ -37,7 +39,8 @@ struct AbcSsaParams {
 // device buffers produced by the simulate stage
 //   sums:     [particle][55][5] uint64  (sum u, sum l, sum u^2, sum u*l, sum l^2 over the cells)
 //   counters: [4] uint64 (lineages, events, draws, spare)
-int abc_launch_rates(const double* d_theta, int m, int64_t n, AbcRates* d_rates, int ssa_hybrid, cudaStream_t st);
+int abc_launch_rates(const double* d_theta, int m, int64_t n, AbcRates* d_rates, int ssa_hybrid, int n_pre_adaptive,
+                     double cycle, cudaStream_t st);
 int abc_launch_prior(double* d_theta, int m, int64_t n, int64_t offset, uint64_t seed, cudaStream_t st);
 int abc_launch_ssa(const AbcRates* d_rates, const AbcSsaParams& prm, const uint32_t* d_beta_q32,
                    unsigned long long* d_sums, unsigned long long* d_counters, unsigned int* d_work,

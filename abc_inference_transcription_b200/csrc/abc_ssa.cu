@@ -301,13 +301,36 @@ __device__ __forceinline__ unsigned long long warp_sum_u64(unsigned long long v)
     return v;
 }
 
-// build the schedule of one read-out: lane c builds cycle c
+// Adaptive burn-in (modes 1 and 2).  A lineage that starts k complete cycles before the read-out cycle with U = 0 misses
+// the transcripts born earlier; their share of Lam at the read-out is at most (1/2 exp(-sum_s gam_s cycle/5))^k (dilution
+// and decay per cycle), so the smallest k with k (1 + log2(e) gam cycle) >= n_pre has the truncation bias bound 2^-n_pre of
+// the configured n_pre cycles.  The gene starts in its stationary law, which is exact for constant kon, koff; for model 3
+// (kon varies over the cycle) the start law is only approximate and its memory, exp(-(kon + koff) t), must have
+// decayed as well.  The label window must lie inside the simulated range.  The reference's own burn-in is adaptive too
+// (transient_phase iterates until 1 % change, scripts/model.jl:114-142).
+__device__ __forceinline__ int burnin_cycles(const AbcRates& r, const AbcSsaParams& prm, int cond, int age_i) {
+    const float step = (float)(prm.cycle / 5.0);
+    float zg = 0.0f, zr = 0.0f;
+#pragma unroll
+    for (int j = 0; j < 5; ++j) { zg += r.gamma[j]; zr += r.kon[j] + r.koff[j]; }
+    float bits = 1.0f + 1.4426950f * zg * step;
+    float need = (float)prm.n_pre;
+    if (prm.m == 3) { bits = fminf(bits, 1.4426950f * zr * step); need += 6.0f; }
+    int k = prm.n_pre;
+    if (bits * (float)prm.n_pre >= need) k = (int)ceilf(need / bits);
+    const double tl0 = prm.agevec[age_i] - prm.pulse[cond] - prm.chase[cond];
+    const int k_win = (tl0 < 0.0) ? (int)ceil(-tl0 / prm.cycle) : 0;
+    k = max(k, max(k_win, 1));
+    return min(k, prm.n_pre);
+}
+
+// build the schedule of one read-out: lane c builds cycle c (c >= c0)
 // n_steps: rate steps per cycle (5 = scripts/model.jl:1-22; 1 when no rate varies and the caller does not need the
 // step boundaries, i.e. the telegraph-only mode of models 1 and 2)
 __device__ __forceinline__ void build_table(WarpTable& tab, const AbcRates& r, const AbcSsaParams& prm,
-                                            int cond, int age_i, int lane, int n_steps) {
+                                            int cond, int age_i, int lane, int n_steps, int c0) {
     const int c = lane;
-    if (c <= prm.n_pre) {
+    if (c >= c0 && c <= prm.n_pre) {
         const double cycle = prm.cycle;
         const double age = prm.agevec[age_i];
         const double tl0 = age - prm.pulse[cond] - prm.chase[cond];
@@ -386,7 +409,8 @@ abc_ssa_kernel(const AbcRates* __restrict__ rates, const AbcSsaParams prm, const
         if (lane == 0) { tab.c_star = -1; tab.e_star = 0; }
         __syncwarp();
         const int n_steps = (HYBRID == 2 && prm.m <= 2) ? 1 : 5;
-        build_table(tab, srates[warp], prm, cond, age_i, lane, n_steps);
+        const int c0 = (HYBRID && prm.adaptive) ? prm.n_pre - burnin_cycles(srates[warp], prm, cond, age_i) : 0;   // first simulated cycle
+        build_table(tab, srates[warp], prm, cond, age_i, lane, n_steps, c0);
         __syncwarp();
         if (lane == 0 && (tab.c_star < 0 || HYBRID == 2)) {
             // empty window, or hybrid mode 2: the telegraph phase runs to the read-out
@@ -397,7 +421,7 @@ abc_ssa_kernel(const AbcRates* __restrict__ rates, const AbcSsaParams prm, const
             const int c_star = tab.c_star, e_star = tab.e_star;
             const int n_conv = c_star * SSA_SEG_PER_CYCLE + e_star;
             const float step_len = (float)(prm.cycle / (double)n_steps);
-            for (int k = lane; k < n_conv; k += 32) {
+            for (int k = c0 * SSA_SEG_PER_CYCLE + lane; k < n_conv; k += 32) {
                 const int cc = k / SSA_SEG_PER_CYCLE, ee = k % SSA_SEG_PER_CYCLE;
                 if (ee < tab.n_ent[cc]) {
                     const Seg sg = tab.slot[cc][ee].s;
@@ -433,8 +457,8 @@ abc_ssa_kernel(const AbcRates* __restrict__ rates, const AbcSsaParams prm, const
                 // phase A: telegraph process + closed-form Lam, one random word per draw.  Divisions only halve
                 // Lam, so the lanes run through all phase-A cycles without waiting for each other.
                 float x = 0.0f, lam = 0.0f, lamL = 0.0f;   // Poisson means of U and L given the gene path
-                const TSeg* tp = &tab.slot[0][0].t;
-                bool done = (tab.c_star == 0) && (tab.e_star == 0);
+                const TSeg* tp = &tab.slot[c0][0].t;
+                bool done = (tab.c_star == c0) && (tab.e_star == 0);
                 float len = -INFINITY, k1 = 0.0f, p0 = 0.0f, p1 = 0.0f, acc = 0.0f;
                 float sgn = s.g ? 1.0f : -1.0f;         // +1 while the gene is on
                 uint32_t qsum = 0u, qb = 0u;            // bit patterns: q of the current state, qon + qoff
@@ -615,7 +639,7 @@ int abc_launch_ssa(const AbcRates* d_rates, const AbcSsaParams& prm, const uint3
 // ------------------------------------------------------------------------------------------------
 // theta (log10, [n][P]) -> linear float rates.  vary_map of model.jl:30-43 / abc_simulation.jl:82-85.
 __global__ void abc_rates_kernel(const double* __restrict__ theta, int m, long long n, AbcRates* __restrict__ out,
-                                 int ssa_hybrid) {
+                                 int ssa_hybrid, int n_pre_adaptive, float cycle) {
     long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     const int P = (m <= 2) ? 5 : 9;
@@ -655,6 +679,14 @@ __global__ void abc_rates_kernel(const double* __restrict__ theta, int m, long l
         const float br = r.alpha[j] * (m != 2 ? 1.5f : 1.0f) * r.kon[j] / s2;
         cost += 0.2f * (sw + wb * br);
     }
+    if (n_pre_adaptive > 0) {   // shorter burn-in for short-lived transcripts (burnin_cycles)
+        float zg = 0.0f, zr = 0.0f;
+        for (int j = 0; j < 5; ++j) { zg += r.gamma[j]; zr += r.kon[j] + r.koff[j]; }
+        float bits = 1.0f + 1.4426950f * zg * cycle * 0.2f;
+        if (m == 3) bits = fminf(bits, 1.4426950f * zr * cycle * 0.2f);
+        const float k = fminf((float)n_pre_adaptive, fmaxf(1.5f, (float)n_pre_adaptive / bits));
+        cost *= (k + 0.5f) / ((float)n_pre_adaptive + 0.5f);
+    }
     r.pad0 = (cost == cost && cost > 0.0f) ? cost : 0.0f;
     r.pad1 = 0.0f;
     out[i] = r;
@@ -686,11 +718,13 @@ int abc_launch_order(const AbcRates* d_rates, int n, unsigned int* d_keys_in, un
     return ABC_OK;
 }
 
-int abc_launch_rates(const double* d_theta, int m, int64_t n, AbcRates* d_rates, int ssa_hybrid, cudaStream_t st) {
+int abc_launch_rates(const double* d_theta, int m, int64_t n, AbcRates* d_rates, int ssa_hybrid, int n_pre_adaptive,
+                     double cycle, cudaStream_t st) {
     if (n <= 0) return ABC_OK;
     int threads = 128;
     long long blocks = (n + threads - 1) / threads;
-    abc_rates_kernel<<<(unsigned)blocks, threads, 0, st>>>(d_theta, m, (long long)n, d_rates, ssa_hybrid);
+    abc_rates_kernel<<<(unsigned)blocks, threads, 0, st>>>(d_theta, m, (long long)n, d_rates, ssa_hybrid, n_pre_adaptive,
+                                                          (float)cycle);
     ABC_CUDA_CHECK(cudaGetLastError());
     return ABC_OK;
 }

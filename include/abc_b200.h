@@ -180,7 +180,10 @@ int  abc_accept_tuples_dev(abc_ctx_t* ctx, int32_t* d_gene, int64_t* d_particle,
  * U ~ Poisson(Lam | gene path) at the window start, then run the six-channel direct method to the read-out;
  * 2 (default): simulate the gene switch to the read-out and draw U ~ Poisson(Lam_U | gene path),
  * L ~ Poisson(Lam_L | gene path) there.  All three sample the same law of (g, U, L) at the read-out;
- * the exact_math variant of abc_ssa_cells always uses 0. */
+ * the exact_math variant of abc_ssa_cells always uses 0.
+ * "ssa_adaptive_burnin" = 1 (default; modes 1 and 2): n_pre_cycles is the maximum; a particle whose transcripts decay
+ * fast starts k <= n_pre_cycles cycles before the read-out cycle, k the smallest number for which the discarded history
+ * contributes less than 2^-n_pre_cycles of the Poisson mean (the bias bound of the full burn-in); 0 = always n_pre_cycles. */
 int  abc_set_option(abc_ctx_t* ctx, const char* name, int64_t value);
 /* device counters of the last *_dev launches (synchronises the stream) */
 int  abc_counters(abc_ctx_t* ctx, abc_counters_t* counters);
