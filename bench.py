@@ -157,7 +157,7 @@ def workload_config(args):
     return {"workload": "BASELINE configs[1]: all 5 models, prior draws streamed in batches, SSA + 53 statistics + "
                         "error scoring vs 3419 genes + eps=4.8 acceptance",
             "models": 5, "particles_per_model_per_step_per_gpu": args.batch, "n_cells_per_readout": args.n_cells,
-            "n_pre_cycles": args.n_pre, "readouts": 55, "genes": 3419, "eps": EPS, "seed": SEED,
+            "n_pre_cycles": args.n_pre, "burn_in": "per particle k <= n_pre_cycles with (1/2 exp(-sum gamma_s cycle/5))^k <= 2^-n_pre_cycles (ssa_adaptive_burnin=1)", "readouts": 55, "genes": 3419, "eps": EPS, "seed": SEED,
             "l2": "flushed between steps (256 MiB write)", "lineages": "independent per (condition, age, cell)",
             "ssa": "Gillespie SSA of the gene switch to the read-out, U and L ~ Poisson given the gene path (exact; "
                    "ssa_hybrid_burnin=2), binomial division and capture-efficiency thinning sampled per cell"}
