@@ -110,10 +110,23 @@ struct abc_ctx {
     DevBuf<unsigned char> d_sort_tmp;
     // score work buffers
     DevBuf<double> d_sstats, d_err;
+    // abc_simulate_score: two sets of output buffers, the copy stream that drains them, per-set events and a page-locked
+    // landing zone for the per-sub-batch device counters
+    DevBuf<double> d_p_theta[2], d_p_stats[2], d_p_err[2];
+    cudaStream_t copy_stream = nullptr;
+    cudaEvent_t p_done[2] = {nullptr, nullptr}, p_copied[2] = {nullptr, nullptr}, p_t0[2] = {nullptr, nullptr},
+                p_t1[2] = {nullptr, nullptr}, p_t2[2] = {nullptr, nullptr};
+    unsigned long long* h_p_counters = nullptr;      // [2][8]
     DevBuf<unsigned long long> d_counts, d_acc_count;
     DevBuf<int32_t> d_acc_gene;
     DevBuf<long long> d_acc_particle;
     DevBuf<double> d_acc_err;
+    // abc_accept_fetch: work buffers of the device sort (abc_accept.cu)
+    DevBuf<unsigned long long> d_as_k64[2];
+    DevBuf<uint32_t> d_as_k32[2], d_as_perm[2];
+    DevBuf<long long> d_as_idx;
+    DevBuf<double> d_as_err;
+    DevBuf<unsigned char> d_as_tmp;
     int64_t acc_capacity = 0, acc_budget = 0, acc_min_capacity = 0;
     int64_t launches = 0;
     abc_counters_t last;
@@ -149,6 +162,15 @@ extern "C" int abc_create(int device, abc_ctx_t** out) {
         ABC_CUDA_CHECK(cudaEventCreateWithFlags(&c->s3_ev_end[l], cudaEventDisableTiming));
     }
     ABC_CUDA_CHECK(cudaEventCreateWithFlags(&c->s3_ev_begin, cudaEventDisableTiming));
+    ABC_CUDA_CHECK(cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking));
+    for (int l = 0; l < 2; ++l) {
+        ABC_CUDA_CHECK(cudaEventCreateWithFlags(&c->p_done[l], cudaEventDisableTiming));
+        ABC_CUDA_CHECK(cudaEventCreateWithFlags(&c->p_copied[l], cudaEventDisableTiming));
+        ABC_CUDA_CHECK(cudaEventCreate(&c->p_t0[l]));
+        ABC_CUDA_CHECK(cudaEventCreate(&c->p_t1[l]));
+        ABC_CUDA_CHECK(cudaEventCreate(&c->p_t2[l]));
+    }
+    ABC_CUDA_CHECK(cudaHostAlloc((void**)&c->h_p_counters, 16 * sizeof(unsigned long long), cudaHostAllocDefault));
     memset(&c->last, 0, sizeof(c->last));
     memset(&c->design, 0, sizeof(c->design));
     int rc = c->d_counters.ensure(8);
@@ -172,6 +194,8 @@ extern "C" int abc_destroy(abc_ctx_t* c) {
     c->d_sums.release(); c->d_counters.release(); c->d_work.release(); c->d_cells.release();
     c->d_sstats.release(); c->d_err.release(); c->d_counts.release(); c->d_acc_count.release();
     c->d_acc_gene.release(); c->d_acc_particle.release(); c->d_acc_err.release();
+    for (int l = 0; l < 2; ++l) { c->d_as_k64[l].release(); c->d_as_k32[l].release(); c->d_as_perm[l].release(); }
+    c->d_as_idx.release(); c->d_as_err.release(); c->d_as_tmp.release();
     for (int i = 0; i < 5; ++i) if (c->ev[i]) cudaEventDestroy(c->ev[i]);
     if (c->stream) cudaStreamDestroy(c->stream);
     for (int l = 0; l < 2; ++l) {
@@ -179,6 +203,16 @@ extern "C" int abc_destroy(abc_ctx_t* c) {
         if (c->s3_ev_end[l]) cudaEventDestroy(c->s3_ev_end[l]);
     }
     if (c->s3_ev_begin) cudaEventDestroy(c->s3_ev_begin);
+    if (c->copy_stream) cudaStreamDestroy(c->copy_stream);
+    for (int l = 0; l < 2; ++l) {
+        if (c->p_done[l]) cudaEventDestroy(c->p_done[l]);
+        if (c->p_copied[l]) cudaEventDestroy(c->p_copied[l]);
+        if (c->p_t0[l]) cudaEventDestroy(c->p_t0[l]);
+        if (c->p_t1[l]) cudaEventDestroy(c->p_t1[l]);
+        if (c->p_t2[l]) cudaEventDestroy(c->p_t2[l]);
+        c->d_p_theta[l].release(); c->d_p_stats[l].release(); c->d_p_err[l].release();
+    }
+    if (c->h_p_counters) cudaFreeHost(c->h_p_counters);
     delete c;
     return ABC_OK;
 }
@@ -736,6 +770,96 @@ extern "C" int abc_score(abc_ctx_t* c, const double* stats, int64_t n, int64_t o
     return ABC_OK;
 }
 
+// wrapper.jl sections 2 and 3 for one batch in one call: simulate -> statistics -> errors -> acceptance, pipelined over
+// sub-batches so that the device-to-host copy of one sub-batch's outputs (the error matrix is 27 KB per particle) runs
+// on a second stream under the simulation of the next one.  Results are identical to abc_simulate followed by abc_score.
+extern "C" int abc_simulate_score(abc_ctx_t* c, int m, int64_t n, int64_t offset, uint64_t seed, int prior_supplied,
+                                  double* theta, double* stats, double eps, int layout, double* err, int64_t* counts,
+                                  abc_counters_t* counters) {
+    CTX_GUARD(c);
+    int rc = check_model(m);
+    if (rc != ABC_OK) return rc;
+    if (!c->has_data) { abc_set_error("abc_set_data has not been called"); return ABC_ERR_STATE; }
+    if (n < 0 || (n > 0 && (!theta || !stats)) || (layout != ABC_ERR_NONE && n > 0 && !err)) {
+        abc_set_error("abc_simulate_score: bad arguments");
+        return ABC_ERR_ARG;
+    }
+    const int P = abc_n_params(m), G = c->G;
+    memset(&c->last, 0, sizeof(c->last));
+    // two sub-batches per call when that leaves >= 8192 particles each (the SSA's longest lineages take ~25 ms whatever the
+    // batch, so shallow launches waste their tail), bounded by the simulate chunk and by ~2 GB of device error matrix per set
+    int64_t sub = (n >= 16384) ? (n + 1) / 2 : std::max<int64_t>(n, 1);
+    sub = std::min<int64_t>(sub, sim_chunk(c));
+    if (layout != ABC_ERR_NONE) sub = std::min<int64_t>(sub, std::max<int64_t>(1024, (int64_t)(2.0e9 / (8.0 * G))));
+    double ms_sim = 0.0, ms_score = 0.0;       // simulate incl. prior draw and statistics; scoring
+    auto drain = [&](int l, int64_t nb) -> int {          // outputs of set l are on the host; account its counters
+        ABC_CUDA_CHECK(cudaEventSynchronize(c->p_copied[l]));
+        const unsigned long long* h = c->h_p_counters + 8 * l;
+        c->last.n_particles += (uint64_t)nb; c->last.n_lineages += h[0]; c->last.n_events += h[1];
+        c->last.n_draws += h[2]; c->last.n_ode_steps += h[4];
+        float a = 0.f, b = 0.f;
+        if (cudaEventElapsedTime(&a, c->p_t0[l], c->p_t1[l]) != cudaSuccess) cudaGetLastError();
+        if (cudaEventElapsedTime(&b, c->p_t1[l], c->p_t2[l]) != cudaSuccess) cudaGetLastError();
+        ms_sim += a; ms_score += b;
+        return ABC_OK;
+    };
+    int64_t nb_of[2] = {0, 0};
+    int j = 0;
+    for (int64_t b0 = 0; b0 < n; b0 += sub, ++j) {
+        const int l = j & 1;
+        const int64_t nb = std::min<int64_t>(sub, n - b0);
+        if (j >= 2 && (rc = drain(l, nb_of[l])) != ABC_OK) return rc;
+        nb_of[l] = nb;
+        if ((rc = c->d_p_theta[l].ensure((size_t)nb * P)) != ABC_OK) return rc;
+        if ((rc = c->d_p_stats[l].ensure((size_t)nb * ABC_NSTATS)) != ABC_OK) return rc;
+        if (layout != ABC_ERR_NONE && (rc = c->d_p_err[l].ensure((size_t)nb * G)) != ABC_OK) return rc;
+        if (prior_supplied)
+            ABC_CUDA_CHECK(cudaMemcpyAsync(c->d_p_theta[l].p, theta + b0 * P, (size_t)nb * P * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+        ABC_CUDA_CHECK(cudaEventRecord(c->p_t0[l], c->stream));
+        rc = simulate_device(c, m, nb, offset + b0, seed, prior_supplied, c->d_p_theta[l].p, c->d_p_stats[l].p, nullptr, c->stream);
+        if (rc != ABC_OK) return rc;
+        // the device counters are reset by the next sub-batch: park this one's in page-locked memory (stream ordered)
+        ABC_CUDA_CHECK(cudaMemcpyAsync(c->h_p_counters + 8 * l, c->d_counters.p, 8 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, c->stream));
+        ABC_CUDA_CHECK(cudaEventRecord(c->p_t1[l], c->stream));
+        rc = score_device(c, c->d_p_stats[l].p, nb, offset + b0, eps, layout, c->d_p_err[l].p, c->stream);
+        if (rc != ABC_OK) return rc;
+        ABC_CUDA_CHECK(cudaEventRecord(c->p_t2[l], c->stream));
+        ABC_CUDA_CHECK(cudaEventRecord(c->p_done[l], c->stream));
+        ABC_CUDA_CHECK(cudaStreamWaitEvent(c->copy_stream, c->p_done[l], 0));
+        if (!prior_supplied)
+            ABC_CUDA_CHECK(cudaMemcpyAsync(theta + b0 * P, c->d_p_theta[l].p, (size_t)nb * P * sizeof(double), cudaMemcpyDeviceToHost, c->copy_stream));
+        ABC_CUDA_CHECK(cudaMemcpyAsync(stats + b0 * ABC_NSTATS, c->d_p_stats[l].p, (size_t)nb * ABC_NSTATS * sizeof(double), cudaMemcpyDeviceToHost, c->copy_stream));
+        if (layout == ABC_ERR_PARTICLE_MAJOR) {
+            ABC_CUDA_CHECK(cudaMemcpyAsync(err + b0 * G, c->d_p_err[l].p, (size_t)nb * G * sizeof(double), cudaMemcpyDeviceToHost, c->copy_stream));
+        } else if (layout == ABC_ERR_GENE_MAJOR) {
+            ABC_CUDA_CHECK(cudaMemcpy2DAsync(err + b0, (size_t)n * sizeof(double), c->d_p_err[l].p, (size_t)nb * sizeof(double),
+                                             (size_t)nb * sizeof(double), (size_t)G, cudaMemcpyDeviceToHost, c->copy_stream));
+        }
+        ABC_CUDA_CHECK(cudaEventRecord(c->p_copied[l], c->copy_stream));
+        // the next sub-batch reuses the simulate work buffers in stream order; this set's output buffers are only
+        // rewritten after drain(l)
+    }
+    // the last (up to) two sets
+    for (int k = std::max(0, j - 2); k < j; ++k)
+        if ((rc = drain(k & 1, nb_of[k & 1])) != ABC_OK) return rc;
+    ABC_CUDA_CHECK(cudaStreamSynchronize(c->stream));
+    c->last.ms_simulate = ms_sim; c->last.ms_score = ms_score;
+    unsigned long long total = 0;
+    ABC_CUDA_CHECK(cudaMemcpy(&total, c->d_acc_count.p, sizeof(total), cudaMemcpyDeviceToHost));
+    if ((int64_t)total > c->acc_capacity) {
+        abc_set_error("accepted-tuple buffer overflow: %llu accepted pairs > capacity %lld; lower eps or score in smaller batches",
+                      total, (long long)c->acc_capacity);
+        return ABC_ERR_NOMEM;
+    }
+    if (counts) {
+        std::vector<unsigned long long> h((size_t)G);
+        ABC_CUDA_CHECK(cudaMemcpy(h.data(), c->d_counts.p, (size_t)G * sizeof(unsigned long long), cudaMemcpyDeviceToHost));
+        for (int g = 0; g < G; ++g) counts[g] = (int64_t)h[g];
+    }
+    if (counters) *counters = c->last;
+    return ABC_OK;
+}
+
 extern "C" int64_t abc_accept_total(abc_ctx_t* c) {
     if (!c) return -1;
     if (cudaSetDevice(c->device) != cudaSuccess) return -1;
@@ -784,25 +908,51 @@ extern "C" int abc_accept_tuples(abc_ctx_t* c, int32_t* gene, int64_t* particle,
 extern "C" int abc_accept_fetch(abc_ctx_t* c, int64_t* offsets, int64_t* idx, double* errs) {
     CTX_GUARD(c);
     if (!c->has_data || !offsets) { abc_set_error("abc_accept_fetch: bad state/arguments"); return ABC_ERR_ARG; }
-    std::vector<int32_t> g; std::vector<long long> p; std::vector<double> e;
-    int rc = fetch_tuples(c, g, p, e);
-    if (rc != ABC_OK) return rc;
-    const size_t total = g.size();
-    std::vector<size_t> ord(total);
-    std::iota(ord.begin(), ord.end(), (size_t)0);
-    // per gene: ascending error, ties by ascending particle index == v[sortperm(err[v])] (stable)
-    std::sort(ord.begin(), ord.end(), [&](size_t a, size_t b) {
-        if (g[a] != g[b]) return g[a] < g[b];
-        if (e[a] != e[b]) return e[a] < e[b];
-        return p[a] < p[b];
-    });
-    for (int k = 0; k <= c->G; ++k) offsets[k] = 0;
-    for (size_t k = 0; k < total; ++k) offsets[g[k] + 1] += 1;
-    for (int k = 0; k < c->G; ++k) offsets[k + 1] += offsets[k];
-    for (size_t k = 0; k < total; ++k) {
-        if (idx) idx[k] = (int64_t)p[ord[k]];
-        if (errs) errs[k] = e[ord[k]];
+    ABC_CUDA_CHECK(cudaStreamSynchronize(c->stream));
+    unsigned long long total = 0;
+    ABC_CUDA_CHECK(cudaMemcpy(&total, c->d_acc_count.p, sizeof(total), cudaMemcpyDeviceToHost));
+    if ((int64_t)total > c->acc_capacity) { abc_set_error("accepted-tuple buffer overflowed"); return ABC_ERR_NOMEM; }
+    // offsets from the per-gene counts the scoring kernels keep next to the tuples
+    std::vector<unsigned long long> h((size_t)c->G);
+    ABC_CUDA_CHECK(cudaMemcpy(h.data(), c->d_counts.p, (size_t)c->G * sizeof(unsigned long long), cudaMemcpyDeviceToHost));
+    offsets[0] = 0;
+    for (int g = 0; g < c->G; ++g) offsets[g + 1] = offsets[g] + (int64_t)h[g];
+    if ((unsigned long long)offsets[c->G] != total) {
+        abc_set_error("abc_accept_fetch: per-gene counts (%lld) and stored tuples (%llu) disagree", (long long)offsets[c->G], total);
+        return ABC_ERR_STATE;
     }
+    if (total == 0 || (!idx && !errs)) return ABC_OK;
+    // per gene: ascending error, ties by ascending particle index == v[sortperm(err[v])] (stable): three stable radix
+    // passes on the device (abc_accept.cu)
+    int rc = ABC_OK;
+    DevBuf<unsigned long long>* k64 = c->d_as_k64;
+    DevBuf<uint32_t>*k32 = c->d_as_k32, *perm = c->d_as_perm;
+    DevBuf<long long>& out_idx = c->d_as_idx;
+    DevBuf<double>& out_err = c->d_as_err;
+    DevBuf<unsigned char>& tmp = c->d_as_tmp;
+    const size_t tmp_bytes = abc_accept_sort_temp_bytes((size_t)total);
+    for (int l = 0; l < 2; ++l) {
+        if ((rc = k64[l].ensure((size_t)total)) != ABC_OK) return rc;
+        if ((rc = k32[l].ensure((size_t)total)) != ABC_OK) return rc;
+        if ((rc = perm[l].ensure((size_t)total)) != ABC_OK) return rc;
+    }
+    if ((rc = out_idx.ensure((size_t)total)) != ABC_OK) return rc;
+    if ((rc = out_err.ensure((size_t)total)) != ABC_OK) return rc;
+    if ((rc = tmp.ensure(tmp_bytes)) != ABC_OK) return rc;
+    unsigned long long* pk64[2] = {k64[0].p, k64[1].p};
+    uint32_t* pk32[2] = {k32[0].p, k32[1].p};
+    uint32_t* pperm[2] = {perm[0].p, perm[1].p};
+    int nl = 0;
+    rc = abc_launch_accept_sort(c->d_acc_gene.p, c->d_acc_particle.p, c->d_acc_err.p, (size_t)total, c->G, pk64, pk32, pperm,
+                                tmp.p, tmp_bytes, out_idx.p, out_err.p, &nl, c->stream);
+    c->launches += nl;
+    cudaError_t e = cudaSuccess;
+    if (rc == ABC_OK && idx) e = cudaMemcpyAsync(idx, out_idx.p, (size_t)total * sizeof(long long), cudaMemcpyDeviceToHost, c->stream);
+    if (rc == ABC_OK && e == cudaSuccess && errs)
+        e = cudaMemcpyAsync(errs, out_err.p, (size_t)total * sizeof(double), cudaMemcpyDeviceToHost, c->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(c->stream);
+    if (rc != ABC_OK) return rc;
+    if (e != cudaSuccess) { abc_set_error("CUDA error in abc_accept_fetch: %s", cudaGetErrorString(e)); return ABC_ERR_CUDA; }
     return ABC_OK;
 }
 

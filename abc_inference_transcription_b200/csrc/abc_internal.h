@@ -113,3 +113,9 @@ size_t abc_score3_blocks(int64_t n);
 size_t abc_score3_queue_entries(int64_t n, int ntiles);
 int abc_launch_score3(const AbcScoreArgs& a, const AbcScore3Tables& x, cudaStream_t st);
 int abc_launch_score_prep(const double* d_stats, int64_t n, float* d_fstats, unsigned char* d_rnan, cudaStream_t st);
+
+// A1 ordering on the device (abc_accept.cu)
+size_t abc_accept_sort_temp_bytes(size_t total);
+int abc_launch_accept_sort(const int32_t* d_gene, const long long* d_particle, const double* d_err, size_t total, int G,
+                           unsigned long long* d_key64[2], uint32_t* d_key32[2], uint32_t* d_perm[2], void* d_temp,
+                           size_t temp_bytes, long long* d_out_idx, double* d_out_err, int* n_launches, cudaStream_t st);

@@ -31,11 +31,10 @@ def gather_acceptance(eng, world, device=None, backend_group=None, all_ranks=Fal
     << 1 %, so this is latency bound).  The merge -- stable sort by (gene, error, particle) -- runs on rank 0's GPU."""
     G = eng.n_genes
     if world <= 1:
-        gene, part, err = eng.accept_tuples()
-        offsets, idx, errs = csr_from_tuples(gene, part, err, G)
+        offsets, idx, errs = eng.accept_fetch()           # per-gene order built on the device (csrc/abc_accept.cu)
         counts = np.diff(offsets)
         return {"counts": counts, "offsets": offsets, "idx": idx, "errs": errs,
-                "bytes_d2h": gene.nbytes + part.nbytes + err.nbytes}
+                "bytes_d2h": offsets.nbytes + idx.nbytes + errs.nbytes}
     import torch
     import torch.distributed as dist
     rank = dist.get_rank(backend_group)

@@ -153,6 +153,39 @@ class AbcEngine:
                                        _lib.ptr(err), _lib.ptr(counts), ctypes.byref(cnt)))
         return err, counts, cnt.as_dict()
 
+    def simulate_score(self, m, n_trials=None, theta=None, particle_offset=0, seed=20240229, eps=4.8,
+                       err_layout=_lib.ERR_PARTICLE_MAJOR, want_counts=True, out=None, theta_out=None, stats_out=None):
+        """wrapper.jl sections 2 + 3 for one batch in one pipelined call (abc_simulate_score): the same results as
+        simulate() followed by score().  Returns (theta, stats, err or None, counts or None, counters).
+        out / theta_out / stats_out: optional preallocated (ideally page-locked) output arrays."""
+        P = n_params(_check_m(m))
+        if theta is None:
+            n = int(n_trials)
+            theta = theta_out if theta_out is not None else np.empty((n, P), dtype=np.float64)
+            supplied = 0
+        else:
+            theta = np.ascontiguousarray(theta, dtype=np.float64).reshape(-1, P)
+            n = theta.shape[0]
+            supplied = 1
+        assert theta.shape == (n, P) and theta.dtype == np.float64 and theta.flags["C_CONTIGUOUS"]
+        stats = stats_out if stats_out is not None else np.empty((n, _lib.NSTATS), dtype=np.float64)
+        assert stats.shape == (n, _lib.NSTATS) and stats.dtype == np.float64 and stats.flags["C_CONTIGUOUS"]
+        G = self.n_genes
+        err = None
+        shape = (n, G) if err_layout == _lib.ERR_PARTICLE_MAJOR else (G, n) if err_layout == _lib.ERR_GENE_MAJOR else None
+        if shape is not None:
+            if out is not None:
+                assert out.shape == shape and out.dtype == np.float64 and out.flags["C_CONTIGUOUS"]
+                err = out
+            else:
+                err = np.empty(shape, dtype=np.float64)
+        counts = np.zeros(G, dtype=np.int64) if want_counts else None
+        cnt = _lib.AbcCounters()
+        _lib.check(self._lib.abc_simulate_score(self._ctx, m, n, int(particle_offset), int(seed), supplied, _lib.ptr(theta),
+                                                _lib.ptr(stats), float(eps), int(err_layout), _lib.ptr(err), _lib.ptr(counts),
+                                                ctypes.byref(cnt)))
+        return theta, stats, err, counts, cnt.as_dict()
+
     def accept_total(self):
         t = self._lib.abc_accept_total(self._ctx)
         if t < 0:

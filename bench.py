@@ -10,7 +10,7 @@ B particles are drawn (Philox, keyed by the global particle index), simulated wi
 and gathers the per-gene acceptance counts and accepted tuples with NCCL.
 
 `value`  : whole-job particles/s with inputs resident in HBM (abc_*_dev entry points, CUDA events).
-`e2e`    : the same through the host-buffer C ABI a Julia host calls (abc_simulate + abc_score with the
+`e2e`    : the same through the host-buffer C ABI a Julia host calls (abc_simulate_score = abc_simulate + abc_score with the
            error matrix and the accepted lists copied back), wall clock around synchronous calls.
 `--impl reference` times the reference's own CPU algorithm (moment ODEs -> 53 statistics -> errors ->
 acceptance; oracle port, the Julia/Sundials original cannot run here) on all host cores.
@@ -252,16 +252,23 @@ def run_b200(args):
     # ---- end to end through the host-buffer C ABI ----------------------------------------------
     h2d = d2h = 0
     from abc_inference_transcription_b200 import PinnedArray
-    err_host = PinnedArray((B, G))            # page-locked host buffer for the error matrix (abc_host_alloc)
+    err_host = PinnedArray((B, G))            # page-locked host buffers (abc_host_alloc) for the error matrix, statistics, theta
+    stats_host = PinnedArray((B, 53))
+    theta_host = [PinnedArray((B, n_params(m))) for m in range(1, 6)]
     barrier()
     t0 = time.perf_counter()
     for k in range(args.steps):
         eng.accept_reset()
         for m in range(1, 6):
             off = offset_of(args.warmup + k, m)
-            theta, stats, _ = eng.simulate(m, n_trials=B, particle_offset=off, seed=SEED)
-            err, counts, _ = eng.score(stats, eps=EPS, particle_offset=off, err_layout=ERR_PARTICLE_MAJOR, out=err_host.array)
-            h2d += stats.nbytes
+            if args.e2e_separate:      # the two reference seams as two blocking calls (wrapper.jl section 2, then 3)
+                theta, stats, _ = eng.simulate(m, n_trials=B, particle_offset=off, seed=SEED)
+                err, counts, _ = eng.score(stats, eps=EPS, particle_offset=off, err_layout=ERR_PARTICLE_MAJOR, out=err_host.array)
+                h2d += stats.nbytes
+            else:                      # one call per (model, batch): abc_simulate_score, copies pipelined under the SSA
+                theta, stats, err, counts, _ = eng.simulate_score(m, n_trials=B, particle_offset=off, seed=SEED, eps=EPS,
+                                                                  err_layout=ERR_PARTICLE_MAJOR, out=err_host.array,
+                                                                  theta_out=theta_host[m - 1].array, stats_out=stats_host.array)
             d2h += theta.nbytes + stats.nbytes + err.nbytes + counts.nbytes
         res = gather_acceptance(eng, world, dev)     # NCCL: all-reduce counts, gather accepted tuples
         d2h += res["bytes_d2h"]
@@ -488,6 +495,7 @@ def main():
     ap.add_argument("--score-particles", type=int, default=131072, help="particles per launch for the scoring-kernel roofline")
     ap.add_argument("--ref-particles", type=int, default=24000, help="particles per bounded CPU sample (~10 s on 16 threads)")
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--e2e-separate", action="store_true", help="e2e through abc_simulate + abc_score instead of abc_simulate_score")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

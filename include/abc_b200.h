@@ -144,6 +144,12 @@ int  abc_summary_stats(abc_ctx_t* ctx, const double* moments, int64_t n, double*
  * The accepted set is kept in the context for abc_accept_fetch. */
 int  abc_score(abc_ctx_t* ctx, const double* stats, int64_t n, int64_t particle_offset, double eps,
                int err_layout, double* err, int64_t* counts, abc_counters_t* counters);
+/* wrapper.jl:59-66 followed by wrapper.jl:72-78 for one batch: abc_simulate and abc_score in one call (same arguments,
+ * same results).  Batches of >= 16384 particles are pipelined in sub-batches: the device-to-host copy of theta, stats and
+ * the error matrix of one sub-batch runs under the simulation of the next one (page-locked outputs: abc_host_alloc). */
+int  abc_simulate_score(abc_ctx_t* ctx, int m, int64_t n_trials, int64_t particle_offset, uint64_t seed,
+                        int prior_supplied, double* theta, double* stats, double eps, int err_layout, double* err,
+                        int64_t* counts, abc_counters_t* counters);
 /* number of accepted (gene, particle) pairs of the last abc_score call(s) since abc_accept_reset */
 int64_t abc_accept_total(abc_ctx_t* ctx);
 int  abc_accept_reset(abc_ctx_t* ctx);

@@ -86,7 +86,8 @@ function simulate(ctx::Context, m, n_trials; particle_offset=0, seed=UInt64(2024
     return θ, stats, c[]
 end
 
-"""set_option(ctx, "ssa_hybrid_burnin" | "stats_sample_guards" | "score_reference_kernel" | "accept_capacity", value)"""
+"""set_option(ctx, "ssa_hybrid_burnin" | "ssa_adaptive_burnin" | "stats_sample_guards" | "score_reference_kernel" |
+"accept_capacity", value)"""
 set_option(ctx::Context, name::AbstractString, value::Integer) =
     check(ccall((:abc_set_option, LIB), Cint, (Ptr{Cvoid}, Cstring, Int64), ctx.ptr, name, value))
 
@@ -112,6 +113,26 @@ function score(ctx::Context, stats::Matrix{Float64}; eps=4.8, particle_offset=0,
                 (Ptr{Cvoid}, Ptr{Cdouble}, Int64, Int64, Cdouble, Cint, Ptr{Cdouble}, Ptr{Int64}, Ptr{Cvoid}),
                 ctx.ptr, stats, n, particle_offset, eps, layout, layout == ERR_NONE ? C_NULL : pointer(err), counts, C_NULL))
     return err, counts
+end
+
+"""simulate_score(ctx, m, n_trials; eps, layout, err) -> (θ, stats, err, counts, counters): wrapper.jl sections 2 and 3 for
+one batch in one ccall (abc_simulate_score); the device-to-host copies are pipelined under the simulation.  Pass a
+`pinned_matrix` as `err` (G x n for ERR_PARTICLE_MAJOR, n x G for ERR_GENE_MAJOR) to receive the error matrix at PCIe rate."""
+function simulate_score(ctx::Context, m, n_trials; particle_offset=0, seed=UInt64(20240229), theta=nothing, eps=4.8,
+                        layout=ERR_PARTICLE_MAJOR, err=nothing)
+    θ = theta === nothing ? Matrix{Float64}(undef, n_params(m), n_trials) : theta
+    n, G = size(θ, 2), ctx.n_genes
+    stats = Matrix{Float64}(undef, 53, n)
+    e = err !== nothing ? err : layout == ERR_NONE ? Matrix{Float64}(undef, 0, 0) :
+        layout == ERR_PARTICLE_MAJOR ? Matrix{Float64}(undef, G, n) : Matrix{Float64}(undef, n, G)
+    counts = Vector{Int64}(undef, G)
+    c = Ref{Counters}()
+    check(ccall((:abc_simulate_score, LIB), Cint,
+                (Ptr{Cvoid}, Cint, Int64, Int64, UInt64, Cint, Ptr{Cdouble}, Ptr{Cdouble}, Cdouble, Cint, Ptr{Cdouble},
+                 Ptr{Int64}, Ref{Counters}),
+                ctx.ptr, m, n, particle_offset, seed, theta === nothing ? 0 : 1, θ, stats, eps, layout,
+                layout == ERR_NONE ? C_NULL : pointer(e), counts, c))
+    return θ, stats, e, counts, c[]
 end
 
 """accept_fetch(ctx) -> (offsets G+1, idx): idx[offsets[g]+1 : offsets[g+1]] == v[sortperm(err[v])] of gene g"""

@@ -653,3 +653,25 @@ def test_ssa_adaptive_burnin_keeps_the_bias_bound(eng, m, theta, cond, age):
         pa = (ada[i] - ada[i].mean()) * (ada[j] - ada[j].mean())
         pb = (full[i] - full[i].mean()) * (full[j] - full[j].mean())
         assert abs(pa.mean() - pb.mean()) / np.sqrt(pa.var() / n + pb.var() / n + 1e-300) < 4.5
+
+
+@pytest.mark.parametrize("layout", [ERR_PARTICLE_MAJOR, ERR_GENE_MAJOR, ERR_NONE])
+def test_simulate_score_pipelined_equals_separate_calls(eng, data_stats, layout):
+    """abc_simulate_score (sub-batches pipelined over two streams) == abc_simulate followed by abc_score, bit for bit:
+    theta, statistics, error matrix, counts and the accepted lists; prior drawn and prior supplied; ragged sizes"""
+    for n, supplied in ((16400, False), (4097, True), (300, False)):
+        eng.accept_reset()
+        th0, st0, _ = eng.simulate(3, n_trials=n, particle_offset=777, seed=5)
+        err0, cnt0, _ = eng.score(st0, eps=4.8, particle_offset=777, err_layout=layout)
+        off0, idx0, e0 = eng.accept_fetch()
+        eng.accept_reset()
+        th1, st1, err1, cnt1, c = eng.simulate_score(3, n_trials=n, theta=th0 if supplied else None, particle_offset=777, seed=5,
+                                                     eps=4.8, err_layout=layout)
+        off1, idx1, e1 = eng.accept_fetch()
+        assert c["n_particles"] == n and c["n_events"] > 0
+        assert np.array_equal(th0, th1) and oracle.same_bits(st0, st1)
+        if layout == ERR_NONE:
+            assert err0 is None and err1 is None
+        else:
+            assert oracle.same_bits(err0, err1)
+        assert np.array_equal(cnt0, cnt1) and np.array_equal(off0, off1) and np.array_equal(idx0, idx1) and oracle.same_bits(e0, e1)
