@@ -365,7 +365,7 @@ def run_b200(args):
                 "clocks": sampler.summary(),
                 "roofline": {"kernel": "abc_ssa_kernel<false,2>", "bound": "issue", "achieved": achieved, "peak": peak_instr,
                              "unit": "Tlane-instr/s", "frac": achieved / peak_instr, "traffic": None,
-                             "traffic_note": "not memory bound: ncu dram read 0.1 MB, write 0 per launch (profiles/)",
+                             "traffic_note": "not memory bound: ncu dram read 6 MB, write 0.9 MB per launch (profiles/r1_ssa_mode2_ncu_summary.csv)",
                              "events_per_s": ev_per_s, "events": int(events), "draws": int(draws),
                              "draws_per_s": draws_per_s,
                              "nominal_instr_per_draw": NOMINAL_INSTR_PER_TELEGRAPH_DRAW,
