@@ -79,6 +79,8 @@ SYMBOLS = {
     "abc_accept_reset": (ctypes.c_int, [_vp]),
     "abc_accept_fetch": (ctypes.c_int, [_vp, _vp, _vp, _vp]),
     "abc_accept_tuples": (ctypes.c_int, [_vp, _vp, _vp, _vp]),
+    "abc_posterior_summary": (ctypes.c_int, [_vp, _vp, ctypes.c_int64, ctypes.c_int32, ctypes.c_int64, ctypes.c_double,
+                                             _vp, _vp, _vp, _vp, _vp]),
     "abc_simulate_dev": (ctypes.c_int, [_vp, ctypes.c_int, ctypes.c_int64, ctypes.c_int64, ctypes.c_uint64,
                                         ctypes.c_int, _vp, _vp, _vp]),
     "abc_score_dev": (ctypes.c_int, [_vp, _vp, ctypes.c_int64, ctypes.c_int64, ctypes.c_double, ctypes.c_int, _vp, _vp]),

@@ -74,3 +74,113 @@ int abc_launch_accept_sort(const int32_t* d_gene, const long long* d_particle, c
     if (n_launches) *n_launches = 4 + 3;      // own kernels + the three radix sorts (several CUB kernels each)
     return ABC_OK;
 }
+
+// ------------------------------------------------------------------------------------------------
+// posterior summaries over the ordered accepted lists (scripts/posterior_kinetics.jl:10-33).
+//   MAP  = parameters of the first accepted index = smallest error           (posterior_kinetics.jl:14)
+//   mean = mean over the accepted parameter rows, summed in list order        (posterior_kinetics.jl:18-22)
+//   lo / hi = quantile(1 - q), quantile(q) with Julia's default definition (julia_quantile below; posterior_kinetics.jl:26-33)
+#include <cub/device/device_segmented_sort.cuh>
+
+__global__ void posterior_map_mean_kernel(const long long* __restrict__ idx, const long long* __restrict__ offsets,
+                                          const double* __restrict__ theta, long long n, int P, long long particle_offset,
+                                          int G, double* __restrict__ map, double* __restrict__ mean, int* __restrict__ bad) {
+    const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= (long long)G * P) return;
+    const int g = (int)(t / P), p = (int)(t % P);
+    const long long b = offsets[g], e = offsets[g + 1];
+    const double nan = __longlong_as_double(0x7ff8000000000000ll);
+    if (e <= b) {
+        if (map) map[t] = nan;
+        if (mean) mean[t] = nan;
+        return;
+    }
+    double s = 0.0, first = nan;
+    for (long long k = b; k < e; ++k) {
+        const long long row = idx[k] - 1 - particle_offset;
+        if (row < 0 || row >= n) { atomicExch(bad, 1); return; }
+        const double v = theta[row * P + p];
+        if (k == b) first = v;
+        s = __dadd_rn(s, v);
+    }
+    if (map) map[t] = first;
+    if (mean) mean[t] = __ddiv_rn(s, (double)(e - b));
+}
+
+__global__ void posterior_gather_kernel(const long long* __restrict__ idx, size_t total, const double* __restrict__ theta,
+                                        long long n, int P, int p, long long particle_offset, double* __restrict__ vals) {
+    const size_t k = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= total) return;
+    const long long row = idx[k] - 1 - particle_offset;
+    vals[k] = (row >= 0 && row < n) ? theta[row * P + p] : __longlong_as_double(0x7ff8000000000000ll);
+}
+
+// Statistics.jl _quantile with alpha = beta = 1 (the default of quantile(v, p)):
+//   aleph = n p + (1 - p);  j = clamp(trunc(aleph), 1, n - 1);  gamma = clamp(aleph - j, 0, 1);  v[j] + gamma (v[j+1] - v[j])
+__device__ __forceinline__ double julia_quantile(const double* v, long long cnt, double pr) {
+    if (cnt == 1) return v[0];
+    const double aleph = __dadd_rn(__dmul_rn((double)cnt, pr), __dadd_rn(1.0, -pr));
+    long long j = (long long)trunc(aleph);
+    j = j < 1 ? 1 : (j > cnt - 1 ? cnt - 1 : j);
+    double gam = __dadd_rn(aleph, -(double)j);
+    gam = gam < 0.0 ? 0.0 : (gam > 1.0 ? 1.0 : gam);
+    const double a = v[j - 1], b = v[j];
+    return __dadd_rn(a, __dmul_rn(gam, __dadd_rn(b, -a)));
+}
+
+__global__ void posterior_quantile_kernel(const double* __restrict__ sorted, const long long* __restrict__ offsets, int G, int P,
+                                          int p, double q, double* __restrict__ lo, double* __restrict__ hi) {
+    const int g = blockIdx.x * blockDim.x + threadIdx.x;
+    if (g >= G) return;
+    const long long b = offsets[g], cnt = offsets[g + 1] - b;
+    const double nan = __longlong_as_double(0x7ff8000000000000ll);
+    double l = nan, u = nan;
+    if (cnt > 0) {
+        l = julia_quantile(sorted + b, cnt, __dadd_rn(1.0, -q));
+        u = julia_quantile(sorted + b, cnt, q);
+    }
+    if (lo) lo[(size_t)g * P + p] = l;
+    if (hi) hi[(size_t)g * P + p] = u;
+}
+
+size_t abc_posterior_temp_bytes(size_t total, int G) {
+    size_t bytes = 0;
+    cub::DoubleBuffer<double> keys(nullptr, nullptr);
+    cub::DeviceSegmentedSort::SortKeys(nullptr, bytes, keys, (int)total, G, (const long long*)nullptr, (const long long*)nullptr);
+    return bytes;
+}
+
+// d_idx: ordered accepted lists (abc_launch_accept_sort), d_offsets: [G+1] on the device, d_theta: [n][P] on the device.
+// d_vals: two buffers of `total` doubles.  Outputs [G][P] on the device, any of them may be NULL.
+int abc_launch_posterior(const long long* d_idx, const long long* d_offsets, size_t total, int G, const double* d_theta,
+                         long long n, int P, long long particle_offset, double q, double* d_vals[2], void* d_temp,
+                         size_t temp_bytes, int* d_bad, double* d_map, double* d_mean, double* d_lo, double* d_hi,
+                         int* n_launches, cudaStream_t st) {
+    if (total >= 0x7FFFFFFFull) { abc_set_error("too many accepted tuples for one summary (%zu)", total); return ABC_ERR_ARG; }
+    int launches = 0;
+    ABC_CUDA_CHECK(cudaMemsetAsync(d_bad, 0, sizeof(int), st));
+    {
+        const long long items = (long long)G * P;
+        posterior_map_mean_kernel<<<(unsigned)((items + 127) / 128), 128, 0, st>>>(d_idx, d_offsets, d_theta, n, P, particle_offset,
+                                                                                G, d_map, d_mean, d_bad);
+        launches++;
+    }
+    if ((d_lo || d_hi) && total > 0) {
+        const unsigned blocks = (unsigned)((total + 255) / 256);
+        for (int p = 0; p < P; ++p) {
+            cub::DoubleBuffer<double> keys(d_vals[0], d_vals[1]);
+            posterior_gather_kernel<<<blocks, 256, 0, st>>>(d_idx, total, d_theta, n, P, p, particle_offset, keys.Current());
+            ABC_CUDA_CHECK(cub::DeviceSegmentedSort::SortKeys(d_temp, temp_bytes, keys, (int)total, G, d_offsets, d_offsets + 1, st));
+            posterior_quantile_kernel<<<(G + 127) / 128, 128, 0, st>>>(keys.Current(), d_offsets, G, P, p, q, d_lo, d_hi);
+            launches += 3;
+        }
+    } else if (d_lo || d_hi) {
+        for (int p = 0; p < P; ++p) {
+            posterior_quantile_kernel<<<(G + 127) / 128, 128, 0, st>>>(nullptr, d_offsets, G, P, p, q, d_lo, d_hi);
+            launches++;
+        }
+    }
+    ABC_CUDA_CHECK(cudaGetLastError());
+    if (n_launches) *n_launches = launches;
+    return ABC_OK;
+}

@@ -905,54 +905,104 @@ extern "C" int abc_accept_tuples(abc_ctx_t* c, int32_t* gene, int64_t* particle,
     return ABC_OK;
 }
 
-extern "C" int abc_accept_fetch(abc_ctx_t* c, int64_t* offsets, int64_t* idx, double* errs) {
-    CTX_GUARD(c);
-    if (!c->has_data || !offsets) { abc_set_error("abc_accept_fetch: bad state/arguments"); return ABC_ERR_ARG; }
+// offsets[G+1] (host) from the per-gene counts, and -- if want_lists -- the per-gene ordered lists in c->d_as_idx / c->d_as_err:
+// ascending error, ties by ascending particle index == v[sortperm(err[v])] (stable), three stable radix passes on the device
+// (abc_accept.cu).  Work is enqueued on c->stream; the caller synchronises.
+static int build_accepted_lists(abc_ctx* c, int64_t* offsets, unsigned long long* total_out, bool want_lists) {
     ABC_CUDA_CHECK(cudaStreamSynchronize(c->stream));
     unsigned long long total = 0;
     ABC_CUDA_CHECK(cudaMemcpy(&total, c->d_acc_count.p, sizeof(total), cudaMemcpyDeviceToHost));
     if ((int64_t)total > c->acc_capacity) { abc_set_error("accepted-tuple buffer overflowed"); return ABC_ERR_NOMEM; }
-    // offsets from the per-gene counts the scoring kernels keep next to the tuples
     std::vector<unsigned long long> h((size_t)c->G);
     ABC_CUDA_CHECK(cudaMemcpy(h.data(), c->d_counts.p, (size_t)c->G * sizeof(unsigned long long), cudaMemcpyDeviceToHost));
     offsets[0] = 0;
     for (int g = 0; g < c->G; ++g) offsets[g + 1] = offsets[g] + (int64_t)h[g];
     if ((unsigned long long)offsets[c->G] != total) {
-        abc_set_error("abc_accept_fetch: per-gene counts (%lld) and stored tuples (%llu) disagree", (long long)offsets[c->G], total);
+        abc_set_error("per-gene counts (%lld) and stored tuples (%llu) disagree", (long long)offsets[c->G], total);
         return ABC_ERR_STATE;
     }
-    if (total == 0 || (!idx && !errs)) return ABC_OK;
-    // per gene: ascending error, ties by ascending particle index == v[sortperm(err[v])] (stable): three stable radix
-    // passes on the device (abc_accept.cu)
+    *total_out = total;
+    if (total == 0 || !want_lists) return ABC_OK;
     int rc = ABC_OK;
-    DevBuf<unsigned long long>* k64 = c->d_as_k64;
-    DevBuf<uint32_t>*k32 = c->d_as_k32, *perm = c->d_as_perm;
-    DevBuf<long long>& out_idx = c->d_as_idx;
-    DevBuf<double>& out_err = c->d_as_err;
-    DevBuf<unsigned char>& tmp = c->d_as_tmp;
     const size_t tmp_bytes = abc_accept_sort_temp_bytes((size_t)total);
     for (int l = 0; l < 2; ++l) {
-        if ((rc = k64[l].ensure((size_t)total)) != ABC_OK) return rc;
-        if ((rc = k32[l].ensure((size_t)total)) != ABC_OK) return rc;
-        if ((rc = perm[l].ensure((size_t)total)) != ABC_OK) return rc;
+        if ((rc = c->d_as_k64[l].ensure((size_t)total)) != ABC_OK) return rc;
+        if ((rc = c->d_as_k32[l].ensure((size_t)total)) != ABC_OK) return rc;
+        if ((rc = c->d_as_perm[l].ensure((size_t)total)) != ABC_OK) return rc;
     }
-    if ((rc = out_idx.ensure((size_t)total)) != ABC_OK) return rc;
-    if ((rc = out_err.ensure((size_t)total)) != ABC_OK) return rc;
-    if ((rc = tmp.ensure(tmp_bytes)) != ABC_OK) return rc;
-    unsigned long long* pk64[2] = {k64[0].p, k64[1].p};
-    uint32_t* pk32[2] = {k32[0].p, k32[1].p};
-    uint32_t* pperm[2] = {perm[0].p, perm[1].p};
+    if ((rc = c->d_as_idx.ensure((size_t)total)) != ABC_OK) return rc;
+    if ((rc = c->d_as_err.ensure((size_t)total)) != ABC_OK) return rc;
+    if ((rc = c->d_as_tmp.ensure(tmp_bytes)) != ABC_OK) return rc;
+    unsigned long long* pk64[2] = {c->d_as_k64[0].p, c->d_as_k64[1].p};
+    uint32_t* pk32[2] = {c->d_as_k32[0].p, c->d_as_k32[1].p};
+    uint32_t* pperm[2] = {c->d_as_perm[0].p, c->d_as_perm[1].p};
     int nl = 0;
     rc = abc_launch_accept_sort(c->d_acc_gene.p, c->d_acc_particle.p, c->d_acc_err.p, (size_t)total, c->G, pk64, pk32, pperm,
-                                tmp.p, tmp_bytes, out_idx.p, out_err.p, &nl, c->stream);
+                                c->d_as_tmp.p, tmp_bytes, c->d_as_idx.p, c->d_as_err.p, &nl, c->stream);
     c->launches += nl;
-    cudaError_t e = cudaSuccess;
-    if (rc == ABC_OK && idx) e = cudaMemcpyAsync(idx, out_idx.p, (size_t)total * sizeof(long long), cudaMemcpyDeviceToHost, c->stream);
-    if (rc == ABC_OK && e == cudaSuccess && errs)
-        e = cudaMemcpyAsync(errs, out_err.p, (size_t)total * sizeof(double), cudaMemcpyDeviceToHost, c->stream);
-    if (e == cudaSuccess) e = cudaStreamSynchronize(c->stream);
+    return rc;
+}
+
+extern "C" int abc_accept_fetch(abc_ctx_t* c, int64_t* offsets, int64_t* idx, double* errs) {
+    CTX_GUARD(c);
+    if (!c->has_data || !offsets) { abc_set_error("abc_accept_fetch: bad state/arguments"); return ABC_ERR_ARG; }
+    unsigned long long total = 0;
+    int rc = build_accepted_lists(c, offsets, &total, idx || errs);
     if (rc != ABC_OK) return rc;
-    if (e != cudaSuccess) { abc_set_error("CUDA error in abc_accept_fetch: %s", cudaGetErrorString(e)); return ABC_ERR_CUDA; }
+    if (total == 0 || (!idx && !errs)) return ABC_OK;
+    if (idx) ABC_CUDA_CHECK(cudaMemcpyAsync(idx, c->d_as_idx.p, (size_t)total * sizeof(long long), cudaMemcpyDeviceToHost, c->stream));
+    if (errs) ABC_CUDA_CHECK(cudaMemcpyAsync(errs, c->d_as_err.p, (size_t)total * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+    ABC_CUDA_CHECK(cudaStreamSynchronize(c->stream));
+    return ABC_OK;
+}
+
+// SURVEY 8f-3 (posterior_kinetics.jl:10-33): MAP, mean and the (1-q, q) quantiles of the accepted parameter rows per gene
+extern "C" int abc_posterior_summary(abc_ctx_t* c, const double* theta, int64_t n, int32_t P, int64_t particle_offset, double q,
+                                     double* map, double* mean, double* lo, double* hi, int64_t* n_acc) {
+    CTX_GUARD(c);
+    if (!c->has_data) { abc_set_error("abc_set_data has not been called"); return ABC_ERR_STATE; }
+    if (!theta || n <= 0 || P < 1 || P > ABC_MAXP || !(q >= 0.0 && q <= 1.0)) { abc_set_error("abc_posterior_summary: bad arguments"); return ABC_ERR_ARG; }
+    const int G = c->G;
+    std::vector<int64_t> offsets((size_t)G + 1);
+    unsigned long long total = 0;
+    int rc = build_accepted_lists(c, offsets.data(), &total, true);
+    if (rc != ABC_OK) return rc;
+    if (n_acc) for (int g = 0; g < G; ++g) n_acc[g] = offsets[g + 1] - offsets[g];
+    DevBuf<long long> d_off;
+    DevBuf<double> d_theta, d_vals[2], d_out[4];
+    DevBuf<unsigned char> d_tmp;
+    DevBuf<int> d_bad;
+    auto release = [&]() {
+        d_off.release(); d_theta.release(); d_vals[0].release(); d_vals[1].release(); d_tmp.release(); d_bad.release();
+        for (int k = 0; k < 4; ++k) d_out[k].release();
+    };
+    const size_t tmp_bytes = abc_posterior_temp_bytes((size_t)std::max<unsigned long long>(total, 1), G);
+    rc = d_off.ensure((size_t)G + 1);
+    if (rc == ABC_OK) rc = d_theta.ensure((size_t)n * P);
+    if (rc == ABC_OK) rc = d_vals[0].ensure((size_t)std::max<unsigned long long>(total, 1));
+    if (rc == ABC_OK) rc = d_vals[1].ensure((size_t)std::max<unsigned long long>(total, 1));
+    if (rc == ABC_OK) rc = d_tmp.ensure(std::max<size_t>(tmp_bytes, 16));
+    if (rc == ABC_OK) rc = d_bad.ensure(1);
+    double* host_out[4] = {map, mean, lo, hi};
+    for (int k = 0; k < 4 && rc == ABC_OK; ++k) if (host_out[k]) rc = d_out[k].ensure((size_t)G * P);
+    if (rc != ABC_OK) { release(); return rc; }
+    cudaError_t e = cudaMemcpyAsync(d_off.p, offsets.data(), ((size_t)G + 1) * sizeof(long long), cudaMemcpyHostToDevice, c->stream);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(d_theta.p, theta, (size_t)n * P * sizeof(double), cudaMemcpyHostToDevice, c->stream);
+    int nl = 0, bad = 0;
+    if (e == cudaSuccess) {
+        double* pv[2] = {d_vals[0].p, d_vals[1].p};
+        rc = abc_launch_posterior(c->d_as_idx.p, d_off.p, (size_t)total, G, d_theta.p, n, P, particle_offset, q, pv, d_tmp.p,
+                                  std::max<size_t>(tmp_bytes, 16), d_bad.p, d_out[0].p, d_out[1].p, d_out[2].p, d_out[3].p, &nl, c->stream);
+        c->launches += nl;
+    }
+    for (int k = 0; k < 4 && rc == ABC_OK && e == cudaSuccess; ++k)
+        if (host_out[k]) e = cudaMemcpyAsync(host_out[k], d_out[k].p, (size_t)G * P * sizeof(double), cudaMemcpyDeviceToHost, c->stream);
+    if (rc == ABC_OK && e == cudaSuccess) e = cudaMemcpyAsync(&bad, d_bad.p, sizeof(int), cudaMemcpyDeviceToHost, c->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(c->stream);
+    release();
+    if (rc != ABC_OK) return rc;
+    if (e != cudaSuccess) { abc_set_error("CUDA error in abc_posterior_summary: %s", cudaGetErrorString(e)); cudaGetLastError(); return ABC_ERR_CUDA; }
+    if (bad) { abc_set_error("abc_posterior_summary: an accepted particle index lies outside [particle_offset+1, particle_offset+n]"); return ABC_ERR_ARG; }
     return ABC_OK;
 }
 

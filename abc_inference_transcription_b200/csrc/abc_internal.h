@@ -119,3 +119,10 @@ size_t abc_accept_sort_temp_bytes(size_t total);
 int abc_launch_accept_sort(const int32_t* d_gene, const long long* d_particle, const double* d_err, size_t total, int G,
                            unsigned long long* d_key64[2], uint32_t* d_key32[2], uint32_t* d_perm[2], void* d_temp,
                            size_t temp_bytes, long long* d_out_idx, double* d_out_err, int* n_launches, cudaStream_t st);
+
+// SURVEY 8f-3 posterior summaries over the ordered lists (abc_accept.cu)
+size_t abc_posterior_temp_bytes(size_t total, int G);
+int abc_launch_posterior(const long long* d_idx, const long long* d_offsets, size_t total, int G, const double* d_theta,
+                         long long n, int P, long long particle_offset, double q, double* d_vals[2], void* d_temp,
+                         size_t temp_bytes, int* d_bad, double* d_map, double* d_mean, double* d_lo, double* d_hi,
+                         int* n_launches, cudaStream_t st);

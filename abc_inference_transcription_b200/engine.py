@@ -201,6 +201,20 @@ class AbcEngine:
         _lib.check(self._lib.abc_accept_fetch(self._ctx, _lib.ptr(offsets), _lib.ptr(idx), _lib.ptr(errs)))
         return offsets, idx, errs
 
+    def posterior_summary(self, theta, particle_offset=0, q=0.95):
+        """SURVEY 8f-3 on the device (posterior_kinetics.jl:10-33) over the lists accepted since the last accept_reset:
+        {"map", "mean", "lo", "hi": (G, P) arrays (NaN rows for genes without accepted particles), "n": (G,) counts}.
+        theta: (n, P) parameter sets of the particles particle_offset+1 .. particle_offset+n."""
+        theta = np.ascontiguousarray(theta, dtype=np.float64)
+        n, P = theta.shape
+        G = self.n_genes
+        out = {k: np.empty((G, P), dtype=np.float64) for k in ("map", "mean", "lo", "hi")}
+        out["n"] = np.zeros(G, dtype=np.int64)
+        _lib.check(self._lib.abc_posterior_summary(self._ctx, _lib.ptr(theta), n, P, int(particle_offset), float(q),
+                                                   _lib.ptr(out["map"]), _lib.ptr(out["mean"]), _lib.ptr(out["lo"]),
+                                                   _lib.ptr(out["hi"]), _lib.ptr(out["n"])))
+        return out
+
     def accept_tuples(self):
         total = self.accept_total()
         gene = np.empty(total, dtype=np.int32)

@@ -10,6 +10,8 @@ get_posterior_estimate "map"/"mean"          get_posterior_estimate(sets, offset
   (posterior_kinetics.jl:10-24)               MAP = the FIRST accepted index = smallest error (posterior_kinetics.jl:14)
 get_posterior_ci (posterior_kinetics.jl:26-33) get_posterior_ci(sets, offsets, idx, gene_vec, q); Julia quantile == numpy default
 Particle indices are 1-based like the files the reference reads (data/posteriors/particles_<model>.txt).
+The device version of the estimate / CI rows is AbcEngine.posterior_summary (abc_posterior_summary, csrc/abc_accept.cu);
+the functions below are the host-side mirror used for file-based workflows and as its cross-check.
 """
 import numpy as np
 

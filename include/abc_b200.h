@@ -158,6 +158,18 @@ int  abc_accept_reset(abc_ctx_t* ctx);
  * errs (nullable) the matching error values.  A gene with offsets[g+1]==offsets[g] is the
  * reference's "0" line (accepted_particles.jl:27-29). */
 int  abc_accept_fetch(abc_ctx_t* ctx, int64_t* offsets, int64_t* idx, double* errs);
+/* ---- next row: get_posterior_estimate / get_posterior_ci, posterior_kinetics.jl:10-33 -----------------
+ * Over the accepted lists of the abc_score calls since the last abc_accept_reset, for every gene g:
+ *   map[g][P]  = theta of the first accepted index = smallest error            (posterior_kinetics.jl:14)
+ *   mean[g][P] = mean of the accepted theta rows, summed in list order          (posterior_kinetics.jl:18-22)
+ *   lo[g][P], hi[g][P] = quantile(1-q), quantile(q) with Julia's default definition (Statistics.jl, alpha = beta = 1):
+ *                        aleph = n p + (1-p), j = clamp(trunc(aleph), 1, n-1), v[j] + clamp(aleph-j, 0, 1)(v[j+1] - v[j])
+ *                        on the sorted values  (posterior_kinetics.jl:26-33)
+ * theta: host, n x P row-major (Julia P x n): the parameter sets of the particles with global 1-based indices
+ * particle_offset+1 .. particle_offset+n (rows of sets_<model>.txt).  n_acc[g]: accepted particles; genes without any get NaN
+ * rows.  Any output may be NULL.  Lists are ordered, values gathered, sorted per gene and reduced on the device. */
+int  abc_posterior_summary(abc_ctx_t* ctx, const double* theta, int64_t n, int32_t P, int64_t particle_offset, double q,
+                           double* map, double* mean, double* lo, double* hi, int64_t* n_acc);
 /* unsorted accepted tuples (for multi-GPU gathers): gene int32, particle int64 (1-based global), err double */
 int  abc_accept_tuples(abc_ctx_t* ctx, int32_t* gene, int64_t* particle, double* err);
 

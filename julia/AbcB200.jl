@@ -143,4 +143,17 @@ function accept_fetch(ctx::Context)
     return offsets, idx, errs
 end
 
+"""posterior_summary(ctx, θ; particle_offset, q) -> (map, mean, lo, hi, n): get_posterior_estimate / get_posterior_ci of
+posterior_kinetics.jl:10-33 for every gene over the lists accepted since accept_reset (P x G matrices; NaN columns for genes
+without accepted particles).  θ is P x n: the parameter sets of particles particle_offset+1 .. particle_offset+n."""
+function posterior_summary(ctx::Context, θ::Matrix{Float64}; particle_offset=0, q=0.95)
+    P, n, G = size(θ, 1), size(θ, 2), ctx.n_genes
+    out = [Matrix{Float64}(undef, P, G) for _ in 1:4]
+    nacc = Vector{Int64}(undef, G)
+    check(ccall((:abc_posterior_summary, LIB), Cint,
+                (Ptr{Cvoid}, Ptr{Cdouble}, Int64, Int32, Int64, Cdouble, Ptr{Cdouble}, Ptr{Cdouble}, Ptr{Cdouble}, Ptr{Cdouble}, Ptr{Int64}),
+                ctx.ptr, θ, n, P, particle_offset, q, out[1], out[2], out[3], out[4], nacc))
+    return out[1], out[2], out[3], out[4], nacc
+end
+
 end # module

@@ -11,7 +11,7 @@ import numpy as np
 import pytest
 
 import oracle
-from abc_inference_transcription_b200 import (AbcEngine, ERR_GENE_MAJOR, ERR_NONE, ERR_PARTICLE_MAJOR, n_params,
+from abc_inference_transcription_b200 import (AbcEngine, AbcError, ERR_GENE_MAJOR, ERR_NONE, ERR_PARTICLE_MAJOR, n_params,
                                               split_betas, synthetic_design)
 
 pytestmark = pytest.mark.gpu
@@ -675,3 +675,52 @@ def test_simulate_score_pipelined_equals_separate_calls(eng, data_stats, layout)
         else:
             assert oracle.same_bits(err0, err1)
         assert np.array_equal(cnt0, cnt1) and np.array_equal(off0, off1) and np.array_equal(idx0, idx1) and oracle.same_bits(e0, e1)
+
+
+def _julia_quantile(v, p):
+    """Statistics.jl quantile(v, p) (alpha = beta = 1) on sorted v"""
+    n = len(v)
+    if n == 1:
+        return v[0]
+    aleph = n * p + (1.0 - p)
+    j = min(max(int(np.trunc(aleph)), 1), n - 1)
+    gam = min(max(aleph - j, 0.0), 1.0)
+    return v[j - 1] + gam * (v[j] - v[j - 1])
+
+
+@pytest.mark.parametrize("m,offset", [(1, 0), (4, 123456)])
+def test_posterior_summary_on_device(eng, data_stats, m, offset):
+    """SURVEY 8f-3 (posterior_kinetics.jl:10-33) on the device: MAP, mean, quantiles per gene over the device-ordered lists,
+    bit-exact against a numpy restatement of the same arithmetic and within 1e-12 of posteriors.py (numpy mean / quantile)"""
+    from abc_inference_transcription_b200 import posteriors
+    n = 3000
+    eng.accept_reset()
+    theta, stats, _ = eng.simulate(m, n_trials=n, particle_offset=offset, seed=9)
+    eng.score(stats, eps=4.8, particle_offset=offset, err_layout=ERR_NONE)
+    offsets, idx, _ = eng.accept_fetch()
+    got = eng.posterior_summary(theta, particle_offset=offset, q=0.95)
+    assert np.array_equal(got["n"], np.diff(offsets)) and got["n"].sum() > 1000
+    P = theta.shape[1]
+    genes = np.nonzero(got["n"] > 0)[0]
+    assert len(genes) > 100 and (got["n"] > 5).any()
+    for g in genes:
+        rows = theta[idx[offsets[g]:offsets[g + 1]] - 1 - offset]
+        assert oracle.same_bits(got["map"][g], rows[0])
+        assert oracle.same_bits(got["mean"][g], np.cumsum(rows, axis=0)[-1] / len(rows))      # summed in list order
+        srt = np.sort(rows, axis=0)
+        lo = np.array([_julia_quantile(srt[:, p], 1.0 - 0.95) for p in range(P)])
+        hi = np.array([_julia_quantile(srt[:, p], 0.95) for p in range(P)])
+        assert oracle.same_bits(got["lo"][g], lo) and oracle.same_bits(got["hi"][g], hi)
+    empty = np.nonzero(got["n"] == 0)[0]
+    assert all(np.isnan(got[k][empty]).all() for k in ("map", "mean", "lo", "hi"))
+    # the host-side mirror (numpy mean / numpy quantile) agrees to rounding
+    gv = genes[:200] + 1
+    ref_map = posteriors.get_posterior_estimate(theta, offsets, idx - offset, gv, "map")
+    ref_mean = posteriors.get_posterior_estimate(theta, offsets, idx - offset, gv, "mean")
+    ref_lo, ref_hi = posteriors.get_posterior_ci(theta, offsets, idx - offset, gv, 0.95)
+    assert np.array_equal(ref_map, got["map"][gv - 1])
+    assert np.allclose(ref_mean, got["mean"][gv - 1], rtol=1e-12, atol=1e-12)
+    assert np.allclose(ref_lo, got["lo"][gv - 1], rtol=1e-12, atol=1e-12) and np.allclose(ref_hi, got["hi"][gv - 1], rtol=1e-12, atol=1e-12)
+    # a theta window that does not cover the accepted indices is an error, not a silent gather
+    with pytest.raises(AbcError, match="outside"):
+        eng.posterior_summary(theta[:10], particle_offset=offset, q=0.95)
