@@ -99,6 +99,7 @@ struct abc_ctx {
     int stats_guards = -1;       // -1: sample guards iff sim_kind == SSA; 0 / 1 force
     int ssa_hybrid = 2;          // exact telegraph + conditional-Poisson sampling: 1 = burn-in only, 2 = to the read-out
     int ssa_adaptive = 1;        // burn-in cycles per particle from the decay of the discarded history (modes 1, 2)
+    int64_t simscore_sub_min = 8192;   // abc_simulate_score: smallest sub-batch worth pipelining
     // simulate work buffers
     DevBuf<double> d_theta, d_stats, d_moments, d_ss_iv, d_prefix;
     DevBuf<AbcRates> d_rates;
@@ -786,9 +787,11 @@ extern "C" int abc_simulate_score(abc_ctx_t* c, int m, int64_t n, int64_t offset
     }
     const int P = abc_n_params(m), G = c->G;
     memset(&c->last, 0, sizeof(c->last));
-    // two sub-batches per call when that leaves >= 8192 particles each (the SSA's longest lineages take ~25 ms whatever the
-    // batch, so shallow launches waste their tail), bounded by the simulate chunk and by ~2 GB of device error matrix per set
-    int64_t sub = (n >= 16384) ? (n + 1) / 2 : std::max<int64_t>(n, 1);
+    // up to four sub-batches per call, none below `simulate_score_sub_batch` particles (the SSA's longest lineages take ~25 ms
+    // whatever the batch, so shallow launches waste their tail), bounded by the simulate chunk and by ~2 GB of device error
+    // matrix per set
+    const int64_t sub_min = std::max<int64_t>(c->simscore_sub_min, 256);
+    int64_t sub = (n >= 2 * sub_min) ? std::max<int64_t>(sub_min, (n + 3) / 4) : std::max<int64_t>(n, 1);
     sub = std::min<int64_t>(sub, sim_chunk(c));
     if (layout != ABC_ERR_NONE) sub = std::min<int64_t>(sub, std::max<int64_t>(1024, (int64_t)(2.0e9 / (8.0 * G))));
     double ms_sim = 0.0, ms_score = 0.0;       // simulate incl. prior draw and statistics; scoring
@@ -1060,6 +1063,7 @@ extern "C" int abc_set_option(abc_ctx_t* c, const char* name, int64_t value) {
     if (strcmp(name, "score_sub_batches") == 0) { c->score_sub_batches = (int)std::min<int64_t>(std::max<int64_t>(value, 0), 64); return ABC_OK; }
     if (strcmp(name, "accept_capacity") == 0) { c->acc_min_capacity = value > 0 ? value : 0; return ABC_OK; }
     if (strcmp(name, "stats_sample_guards") == 0) { c->stats_guards = value < 0 ? -1 : (value ? 1 : 0); return ABC_OK; }
+    if (strcmp(name, "simulate_score_sub_batch") == 0) { c->simscore_sub_min = value > 0 ? value : 8192; return ABC_OK; }
     if (strcmp(name, "ssa_adaptive_burnin") == 0) { c->ssa_adaptive = value ? 1 : 0; return ABC_OK; }
     if (strcmp(name, "ssa_hybrid_burnin") == 0) { c->ssa_hybrid = value <= 0 ? 0 : (value == 1 ? 1 : 2); return ABC_OK; }
     abc_set_error("abc_set_option: unknown option '%s'", name);

@@ -306,7 +306,7 @@ __device__ __forceinline__ unsigned long long warp_sum_u64(unsigned long long v)
 // and decay per cycle), so the smallest k with k (1 + log2(e) gam cycle) >= n_pre has the truncation bias bound 2^-n_pre of
 // the configured n_pre cycles.  The gene starts in its stationary law, which is exact for constant kon, koff; for model 3
 // (kon varies over the cycle) the start law is only approximate and its memory, exp(-(kon + koff) t), must have
-// decayed as well.  The label window must lie inside the simulated range.  The reference's own burn-in is adaptive too
+// decayed as well.  The reference's own burn-in is adaptive too
 // (transient_phase iterates until 1 % change, scripts/model.jl:114-142).
 __device__ __forceinline__ int burnin_cycles(const AbcRates& r, const AbcSsaParams& prm, int cond, int age_i) {
     const float step = (float)(prm.cycle / 5.0);
@@ -318,9 +318,12 @@ __device__ __forceinline__ int burnin_cycles(const AbcRates& r, const AbcSsaPara
     if (prm.m == 3) { bits = fminf(bits, 1.4426950f * zr * step); need += 6.0f; }
     int k = prm.n_pre;
     if (bits * (float)prm.n_pre >= need) k = (int)ceilf(need / bits);
+    // The k cycles are counted back from the cycle in which the label window opens, not from the read-out cycle: the
+    // unlabelled transcripts seen after a long pulse are all older than the window, and correlations normalise their
+    // magnitude away, so the bound must hold relative to that history too.
     const double tl0 = prm.agevec[age_i] - prm.pulse[cond] - prm.chase[cond];
     const int k_win = (tl0 < 0.0) ? (int)ceil(-tl0 / prm.cycle) : 0;
-    k = max(k, max(k_win, 1));
+    k = max(k + k_win, 1);
     return min(k, prm.n_pre);
 }
 
@@ -684,7 +687,7 @@ __global__ void abc_rates_kernel(const double* __restrict__ theta, int m, long l
         for (int j = 0; j < 5; ++j) { zg += r.gamma[j]; zr += r.kon[j] + r.koff[j]; }
         float bits = 1.0f + 1.4426950f * zg * cycle * 0.2f;
         if (m == 3) bits = fminf(bits, 1.4426950f * zr * cycle * 0.2f);
-        const float k = fminf((float)n_pre_adaptive, fmaxf(1.5f, (float)n_pre_adaptive / bits));
+        const float k = fminf((float)n_pre_adaptive, fmaxf(1.0f, (float)n_pre_adaptive / bits) + 0.6f);   // + mean k_win
         cost *= (k + 0.5f) / ((float)n_pre_adaptive + 0.5f);
     }
     r.pad0 = (cost == cost && cost > 0.0f) ? cost : 0.0f;

@@ -101,8 +101,8 @@ def burnin_cycles(gam5, kon5, koff5, m, n_pre, cycle, tl0):
     k = n_pre
     if bits * n_pre >= need:
         k = math.ceil(need / bits)
-    k_win = math.ceil(-tl0 / cycle) if tl0 < 0 else 0
-    return min(max(k, k_win, 1), n_pre)
+    k_win = math.ceil(-tl0 / cycle) if tl0 < 0 else 0          # cycles back to the one in which the label window opens
+    return min(max(k + k_win, 1), n_pre)
 
 
 def test_adaptive_burnin_keeps_the_bias_bound_of_the_full_burnin():
@@ -116,9 +116,12 @@ def test_adaptive_burnin_keeps_the_bias_bound_of_the_full_burnin():
         k = burnin_cycles(gam5, kon5, koff5, m, 10, 20.0, tl0)
         assert 1 <= k <= 10 and k * 20.0 >= -tl0
         if k < 10:
-            # share of Lam_U born before the simulated range: (1/2 exp(-sum gam_s 4))^k <= 2^-10
-            assert (0.5 * math.exp(-sum(gam5) * 4.0)) ** k <= 2.0 ** -10 * (1 + 1e-6)
+            # complete cycles simulated before the cycle in which the label window opens
+            kb = k - (math.ceil(-tl0 / 20.0) if tl0 < 0 else 0)
+            assert kb >= 1
+            # share of the pre-window Lam_U born before the simulated range: (1/2 exp(-sum gam_s 4))^kb <= 2^-10
+            assert (0.5 * math.exp(-sum(gam5) * 4.0)) ** kb <= 2.0 ** -10 * (1 + 1e-6)
             if m == 3:      # the approximate start law of the gene has decayed as well
-                assert math.exp(-sum(a + b for a, b in zip(kon5, koff5)) * 4.0 * k) <= 2.0 ** -10
+                assert math.exp(-sum(a + b for a, b in zip(kon5, koff5)) * 4.0 * kb) <= 2.0 ** -10
     assert burnin_cycles([1.0] * 5, [1.0] * 5, [1.0] * 5, 1, 10, 20.0, 1.0) == 1
     assert burnin_cycles([1e-3] * 5, [1.0] * 5, [1.0] * 5, 1, 10, 20.0, 1.0) == 10
