@@ -791,7 +791,8 @@ extern "C" int abc_simulate_score(abc_ctx_t* c, int m, int64_t n, int64_t offset
     // whatever the batch, so shallow launches waste their tail), bounded by the simulate chunk and by ~2 GB of device error
     // matrix per set
     const int64_t sub_min = std::max<int64_t>(c->simscore_sub_min, 256);
-    int64_t sub = (n >= 2 * sub_min) ? std::max<int64_t>(sub_min, (n + 3) / 4) : std::max<int64_t>(n, 1);
+    const int64_t nsb = std::min<int64_t>(4, n / sub_min);           // equal sub-batches, no short tail
+    int64_t sub = (nsb >= 2) ? (n + nsb - 1) / nsb : std::max<int64_t>(n, 1);
     sub = std::min<int64_t>(sub, sim_chunk(c));
     if (layout != ABC_ERR_NONE) sub = std::min<int64_t>(sub, std::max<int64_t>(1024, (int64_t)(2.0e9 / (8.0 * G))));
     double ms_sim = 0.0, ms_score = 0.0;       // simulate incl. prior draw and statistics; scoring
