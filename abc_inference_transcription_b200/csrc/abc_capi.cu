@@ -253,7 +253,7 @@ extern "C" int abc_set_design(abc_ctx_t* c, const abc_design_t* d) {
     if (d->sim_kind != ABC_SIM_SSA && d->sim_kind != ABC_SIM_ODE) { abc_set_error("unknown sim_kind %d", d->sim_kind); return ABC_ERR_ARG; }
     if (d->sim_kind == ABC_SIM_SSA) {
         if (d->n_cells < 2 || d->n_cells > (1 << 20)) { abc_set_error("n_cells must be in [2, 2^20]"); return ABC_ERR_ARG; }
-        if (d->n_pre_cycles < 0 || d->n_pre_cycles > 15) { abc_set_error("n_pre_cycles must be in [0, 15]"); return ABC_ERR_ARG; }
+        if (d->n_pre_cycles < 0 || d->n_pre_cycles > 13) { abc_set_error("n_pre_cycles must be in [0, 13]"); return ABC_ERR_ARG; }
         // the label window must start inside the simulated time span
         for (int j = 0; j < ABC_NCOND; ++j)
             for (int a = 0; a < ABC_NAGE; ++a)

@@ -58,7 +58,8 @@ typedef struct {
     double  iv[9];                       /* ODE path initial moments            abc_simulation.jl:70-71 */
     int32_t downsampling;                /* 1: apply capture efficiencies       abc_simulation.jl:79 */
     int32_t n_cells;                     /* SSA: cells per (condition, age) read-out (>= 2) */
-    int32_t n_pre_cycles;                /* SSA: complete cell cycles simulated before the read-out cycle */
+    int32_t n_pre_cycles;                /* SSA: complete cell cycles simulated before the read-out cycle (<= 13; the maximum
+                                          * when ssa_adaptive_burnin = 1, see abc_set_option) */
     int32_t sim_kind;                    /* ABC_SIM_SSA or ABC_SIM_ODE */
     /* capture efficiencies betas[pulse_idx], age[pulse_idx] and betas[chase_idx], age[chase_idx]
      * (abc_simulation.jl:24,36); cluster ids are 1..5 */
