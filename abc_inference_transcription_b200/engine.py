@@ -77,10 +77,11 @@ class AbcEngine:
         self.n_genes = d.shape[0]
 
     # ---- P1 ----------------------------------------------------------------------------------
-    def fix_params(self, m, n, particle_offset=0, seed=20240229):
-        """fix_params(vary_map, N) (abc_simulation.jl:3-11) -> (n, P) log10 parameters"""
+    def fix_params(self, m, n, particle_offset=0, seed=20240229, out=None):
+        """fix_params(vary_map, N) (abc_simulation.jl:3-11) -> (n, P) log10 parameters (written into `out` if given)"""
         P = n_params(_check_m(m))
-        theta = np.empty((int(n), P), dtype=np.float64)
+        theta = out if out is not None else np.empty((int(n), P), dtype=np.float64)
+        assert theta.shape == (int(n), P) and theta.dtype == np.float64 and theta.flags["C_CONTIGUOUS"]
         _lib.check(self._lib.abc_fix_params(self._ctx, m, int(n), int(particle_offset), int(seed), _lib.ptr(theta)))
         return theta
 

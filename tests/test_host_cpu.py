@@ -115,3 +115,38 @@ def test_model_probs_and_posterior_summaries():
     assert np.allclose(ubs[0], np.quantile(sets[[6, 1, 8]], 0.95, axis=0)) and (lbs <= ubs).all()
     with pytest.raises(ValueError):
         posteriors.get_posterior_estimate(sets, offsets, idx, [2], "map")
+
+
+def test_engine_argument_plumbing_with_stub_library():
+    """the numpy side of fix_params(out=...) -> simulate_score(theta=...) (what bench.py's end-to-end loop calls) against a
+    stub of the C library: shapes, contiguity checks and that caller-provided (page-locked-like) buffers are passed through"""
+    import ctypes
+    from abc_inference_transcription_b200 import engine as eng_mod
+
+    calls = []
+
+    class Stub:
+        def __getattr__(self, name):
+            def f(*a):
+                calls.append((name, a))
+                return 0
+            return f
+
+    e = object.__new__(eng_mod.AbcEngine)
+    e._lib, e._ctx, e.n_genes, e.design, e.device = Stub(), ctypes.c_void_p(1), 7, None, 0
+    B, m, P = 16, 3, 9
+    buf = (ctypes.c_char * (B * P * 8))()
+    th_host = np.frombuffer(buf, dtype=np.float64, count=B * P).reshape(B, P)          # like PinnedArray.array
+    th = e.fix_params(m, B, particle_offset=5, seed=1, out=th_host)
+    assert th is th_host
+    err = np.empty((B, 7)); st = np.empty((B, 53))
+    theta, stats, err_o, counts, cnt = e.simulate_score(m, theta=th, particle_offset=5, seed=1, eps=4.8, err_layout=2, out=err,
+                                                        stats_out=st)
+    assert theta.ctypes.data == th_host.ctypes.data and stats is st and err_o is err and counts.shape == (7,)
+    name, a = calls[-1]
+    assert name == "abc_simulate_score" and a[1] == m and a[2] == B and a[3] == 5 and a[5] == 1        # prior supplied
+    theta2, *_ = e.simulate_score(m, n_trials=B, theta_out=th_host, stats_out=st, out=err, err_layout=2)
+    assert theta2 is th_host and calls[-1][1][5] == 0
+    with pytest.raises(AssertionError):
+        e.fix_params(m, B, out=np.empty((B, 5)))
+    e._ctx = None
