@@ -52,3 +52,52 @@ def test_design_struct_layout_matches_header():
     """field order/types of the ctypes mirror vs the C struct (sizes computed from the header text)"""
     assert ctypes.sizeof(_lib.AbcDesign) == 8 * (2 + 5 + 11 + 11 + 55 + 9) + 4 * 4 + (8 + 8 + 8) * 2 + 16
     assert ctypes.sizeof(_lib.AbcCounters) == 8 * 8
+
+
+def header_prototypes():
+    """{name: number of parameters} from include/abc_b200.h"""
+    src = open(os.path.join(ROOT, "include", "abc_b200.h")).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    protos = {}
+    for name, params in re.findall(r"\b(abc_[a-z0-9_]+)\s*\(([^()]*)\)\s*;", src):
+        params = params.strip()
+        protos[name] = 0 if params in ("", "void") else params.count(",") + 1
+    return protos
+
+
+def julia_ccalls():
+    """(symbol, number of argument types) of every ccall in julia/*.jl (the Julia host cannot be executed here)"""
+    out = []
+    jdir = os.path.join(ROOT, "julia")
+    for fn in sorted(os.listdir(jdir)):
+        if not fn.endswith(".jl"):
+            continue
+        src = open(os.path.join(jdir, fn)).read()
+        for mt in re.finditer(r"ccall\(\(:(abc_[a-z0-9_]+),\s*LIB\),\s*\w+,\s*\(", src):
+            i, depth = mt.end(), 1
+            start = i
+            while depth:                       # matching parenthesis of the argument-type tuple
+                depth += {"(": 1, ")": -1}.get(src[i], 0)
+                i += 1
+            types = src[start:i - 1].strip().rstrip(",")
+            n, d = (0 if types == "" else 1), 0
+            for ch in types:                   # top-level commas only (Ref{Ptr{Cvoid}} has none, but be safe)
+                d += {"{": 1, "}": -1, "(": 1, ")": -1}.get(ch, 0)
+                n += (ch == "," and d == 0)
+            out.append((fn, mt.group(1), n))
+    return out
+
+
+def test_julia_binding_matches_the_header():
+    """every ccall of the Julia host names a declared entry point and passes as many arguments as the prototype has"""
+    protos = header_prototypes()
+    calls = julia_ccalls()
+    assert len(calls) >= 15
+    for fn, name, nargs in calls:
+        assert name in protos, f"{fn}: ccall of undeclared symbol {name}"
+        assert nargs == protos[name], f"{fn}: {name} is called with {nargs} argument types, the header declares {protos[name]}"
+    # the hot-path entry points are all bound
+    bound = {name for _, name, _ in calls}
+    for need in ("abc_create", "abc_set_design", "abc_set_data", "abc_fix_params", "abc_simulate", "abc_score",
+                 "abc_simulate_score", "abc_accept_fetch", "abc_posterior_summary", "abc_set_option", "abc_host_alloc"):
+        assert need in bound, need
