@@ -1,0 +1,122 @@
+"""CPU check of the sampler the GPU runs by default (SSA mode 2), independent of the GPU:
+a numpy restatement -- Gillespie on the gene switch, Poisson means of the unlabelled / labelled transcripts carried through
+the +-F(x) accumulator, halving at divisions, the (1 - lambda) : lambda split inside the label window, U ~ Poisson(Lam_U),
+L ~ Poisson(Lam_L) at the read-out, burn-in length from the adaptive rule -- against the reference's moment equations
+(oracle/abc_oracle.c, pinned on the reference's golden vectors).  Chain of trust for the product path:
+golden vectors -> moment-ODE oracle -> (z-tests, here) -> telegraph + conditional-Poisson sampler -> (KS, GPU tests) -> kernel."""
+import math
+
+import numpy as np
+import pytest
+
+import oracle
+from test_tseg_math_cpu import burnin_cycles
+
+CYCLE, AGES = 20.0, [2.0, 6.0, 10.0, 14.0, 18.0]
+PULSE = [0.25, 0.5, 0.75, 1, 2, 3, 22, 22, 22, 22, 22]          # scripts/abc_simulation.jl:65
+CHASE = [0, 0, 0, 0, 0, 0, 0, 1, 2, 4, 6]
+
+
+def rates_of(theta, m):
+    """scripts/model.jl:1-22, 30-43: per-step linear rates (kon, koff, alpha, gamma)[5] and lambda"""
+    vary = {3: 0, 4: 2, 5: 3}.get(m, -1)
+    th, k, out = 10.0 ** np.asarray(theta, dtype=np.float64), 0, []
+    for q in range(4):
+        if q == vary:
+            out.append(th[k:k + 5].copy()); k += 5
+        else:
+            out.append(np.full(5, th[k])); k += 1
+    return out[0], out[1], out[2], out[3], min(th[k], 1.0)
+
+
+def segments(theta, m, cond, age, k_pre):
+    """[(len, kon, koff, A0, A1, gam, lam_eff, division_after)] from k_pre cycles before the read-out cycle to the read-out"""
+    kon, koff, alpha, gam, lam = rates_of(theta, m)
+    sc = 0.0 if m == 2 else 1.0
+    tl0, tl1 = age - PULSE[cond] - CHASE[cond], age - CHASE[cond]
+    segs = []
+    for c in range(-k_pre, 1):
+        end = age if c == 0 else CYCLE
+        cuts = sorted({0.0, end} | {s for s in (4.0, 8.0, 12.0, 16.0) if s < end}
+                      | {t - c * CYCLE for t in (tl0, tl1) if 0.0 < t - c * CYCLE < end})
+        for a, b in zip(cuts[:-1], cuts[1:]):
+            s = min(int(a // 4.0), 4)
+            mid = 0.5 * (a + b) + c * CYCLE
+            segs.append([b - a, kon[s], koff[s], alpha[s] * (1 + sc * a / CYCLE), alpha[s] * sc / CYCLE, gam[s],
+                         lam if tl0 <= mid <= tl1 else 0.0, False])
+        segs[-1][7] = c < 0
+    return segs
+
+
+def F(x, ln, A0, A1, g):
+    """antiderivative of (A0 + A1 w) exp(-g (ln - w)) (FP64: no series needed for g >= 1e-3)"""
+    return np.exp(-g * (ln - x)) * ((A0 + A1 * x) / g - A1 / g ** 2)
+
+
+def sample_readout(theta, m, cond, age, n_cells, k_pre, rng):
+    kon, koff, *_ = rates_of(theta, m)
+    g = (rng.random(n_cells) < kon[4] / (kon[4] + koff[4])).astype(np.int8)          # stationary start (last step's rates)
+    lam_u, lam_l = np.zeros(n_cells), np.zeros(n_cells)
+    for ln, kn, kf, A0, A1, gm, lf, div in segments(theta, m, cond, age, k_pre):
+        x = np.zeros(n_cells)
+        acc = -g * F(0.0, ln, A0, A1, gm)
+        live = np.ones(n_cells, dtype=bool)
+        while live.any():
+            idx = np.nonzero(live)[0]
+            xn = x[idx] + rng.exponential(1.0, len(idx)) / np.where(g[idx] == 1, kf, kn)
+            ev = xn < ln
+            e = idx[ev]
+            acc[e] += np.where(g[e] == 1, 1.0, -1.0) * F(xn[ev], ln, A0, A1, gm)
+            g[e] ^= 1
+            x[e] = xn[ev]
+            live[idx[~ev]] = False
+        inc = acc + g * F(ln, ln, A0, A1, gm)
+        dec = math.exp(-gm * ln)
+        lam_u = lam_u * dec + (1.0 - lf) * inc
+        lam_l = lam_l * dec + lf * inc
+        if div:
+            lam_u *= 0.5
+            lam_l *= 0.5
+    return rng.poisson(lam_u).astype(np.float64), rng.poisson(lam_l).astype(np.float64)
+
+
+CASES = [
+    (1, np.log10([0.5, 1.0, 20.0, 0.1, 0.7]), 5, 0),                     # demo theta of model 1, 3 h pulse, age 2 h
+    (1, np.log10([0.5, 1.0, 20.0, 0.1, 0.7]), 9, 3),                     # 22 h pulse + 4 h chase: window opens two cycles back
+    (2, np.log10([2.0, 0.5, 8.0, 0.6, 1.0]), 7, 1),                      # no scaling, lambda = 1, fast decay: one pre-cycle
+    (4, np.log10([1.0, 1.0, 1.0, 1.0, 40.0, 1.0, 1.0, 0.1, 0.7]), 2, 2), # alpha steps
+    (5, np.log10([2.0, 1.0, 8.5, 0.05, 0.3, 1.0, 0.1, 0.02, 0.7]), 6, 4),# decay steps around the series / closed-form split
+]
+
+
+@pytest.mark.parametrize("m,theta,cond,age_i", CASES)
+def test_telegraph_poisson_sampler_matches_the_moment_odes(m, theta, cond, age_i):
+    n = 40000
+    rng = np.random.default_rng(100 * m + cond)
+    kon, koff, _, gam, _ = rates_of(theta, m)
+    tl0 = AGES[age_i] - PULSE[cond] - CHASE[cond]
+    k_pre = burnin_cycles(list(gam), list(kon), list(koff), m, 10, CYCLE, tl0)
+    u, l = sample_readout(theta, m, cond, AGES[age_i], n, k_pre, rng)
+    od = oracle.make_design(iv_index=1, downsampling=False, rtol=1e-9)
+    mom, _ = oracle.run_part_sim(theta, m, od)
+    ref = mom[cond, age_i]                                                # mean_u, mean_l, var_u, cov_ul, var_l
+    zs = [(u.mean() - ref[0]) / (u.std(ddof=1) / math.sqrt(n) + 1e-12), (l.mean() - ref[1]) / (l.std(ddof=1) / math.sqrt(n) + 1e-12)]
+    for xs, ys, target in ((u, u, ref[2]), (u, l, ref[3]), (l, l, ref[4])):
+        p = (xs - xs.mean()) * (ys - ys.mean())
+        zs.append((p.sum() / (n - 1) - target) / (p.std(ddof=1) / math.sqrt(n) + 1e-12))
+    # burn-in bias bound 2^-10 and the oracle's tolerance are far below the Monte-Carlo error of 40 000 cells
+    assert np.abs(zs).max() < 4.5, (k_pre, zs, ref, u.mean(), l.mean())
+    assert k_pre <= 10 and ref[0] + ref[1] > 0
+
+
+def test_the_comparison_has_power_a_too_short_burnin_is_detected():
+    """negative control: gamma = 0.1/h needs four pre-cycles for the 2^-10 bound; with a single one the unlabelled mean is
+    ~3 % short and the z-test above rejects it"""
+    m, theta, cond, age_i = CASES[0]
+    kon, koff, _, gam, _ = rates_of(theta, m)
+    assert burnin_cycles(list(gam), list(kon), list(koff), m, 10, CYCLE, AGES[age_i] - PULSE[cond]) == 4
+    n = 40000
+    u, l = sample_readout(theta, m, cond, AGES[age_i], n, 1, np.random.default_rng(5))
+    mom, _ = oracle.run_part_sim(theta, m, oracle.make_design(iv_index=1, downsampling=False, rtol=1e-9))
+    z = (u.mean() - mom[cond, age_i][0]) / (u.std(ddof=1) / math.sqrt(n))
+    assert z < -4.5, z
