@@ -86,6 +86,8 @@ CASES = [
     (2, np.log10([2.0, 0.5, 8.0, 0.6, 1.0]), 7, 1),                      # no scaling, lambda = 1, fast decay: one pre-cycle
     (4, np.log10([1.0, 1.0, 1.0, 1.0, 40.0, 1.0, 1.0, 0.1, 0.7]), 2, 2), # alpha steps
     (5, np.log10([2.0, 1.0, 8.5, 0.05, 0.3, 1.0, 0.1, 0.02, 0.7]), 6, 4),# decay steps around the series / closed-form split
+    (3, np.log10([0.1, 0.1, 30.0, 0.1, 0.1, 1.0, 15.0, 0.1, 0.7]), 8, 2),# kon steps (model_realisation.jl:304): approximate start law of the gene
+    (3, np.log10([0.02, 0.05, 0.3, 0.05, 0.02, 0.03, 25.0, 1.0, 0.5]), 4, 1),  # slow gene, fast decay: the gene's memory sets the burn-in
 ]
 
 
