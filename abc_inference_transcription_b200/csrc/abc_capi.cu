@@ -7,6 +7,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <numeric>
+#include <utility>
 #include <vector>
 
 #include "abc_common.cuh"
@@ -39,10 +40,20 @@ extern "C" const char* abc_model_name(int m) {
     return (m >= 1 && m <= 5) ? names[m - 1] : nullptr;
 }
 
+// owning device buffer: freed with its owner (a context member or a local of an entry point, whatever the exit path)
 template <typename T>
 struct DevBuf {
     T* p = nullptr;
     size_t cap = 0;
+    DevBuf() = default;
+    DevBuf(const DevBuf&) = delete;
+    DevBuf& operator=(const DevBuf&) = delete;
+    DevBuf(DevBuf&& o) noexcept : p(o.p), cap(o.cap) { o.p = nullptr; o.cap = 0; }
+    DevBuf& operator=(DevBuf&& o) noexcept {
+        if (this != &o) { release(); p = o.p; cap = o.cap; o.p = nullptr; o.cap = 0; }
+        return *this;
+    }
+    ~DevBuf() { release(); }
     int ensure(size_t n) {
         if (n <= cap) return ABC_OK;
         if (p) cudaFree(p);
@@ -56,7 +67,7 @@ struct DevBuf {
         cap = n;
         return ABC_OK;
     }
-    void release() { if (p) cudaFree(p); p = nullptr; cap = 0; }
+    void release() { if (p) { cudaFree(p); p = nullptr; } cap = 0; }
 };
 
 struct abc_ctx {
@@ -131,7 +142,26 @@ struct abc_ctx {
     int64_t acc_capacity = 0, acc_budget = 0, acc_min_capacity = 0;
     int64_t launches = 0;
     abc_counters_t last;
+    // the *_dev entry points enqueue on the caller's stream: an event recorded there after every such call orders the
+    // accept_* / posterior entry points (which read d_acc_count / d_counts on the host) behind that work
+    cudaEvent_t ev_user = nullptr;
+    bool user_pending = false;
 };
+
+// all work this context has enqueued -- on its own stream and on caller streams of the *_dev entry points -- is complete
+static int sync_ctx(abc_ctx* c) {
+    ABC_CUDA_CHECK(cudaStreamSynchronize(c->stream));
+    if (c->user_pending) {
+        ABC_CUDA_CHECK(cudaEventSynchronize(c->ev_user));
+        c->user_pending = false;
+    }
+    return ABC_OK;
+}
+static int mark_user_stream(abc_ctx* c, cudaStream_t st) {
+    ABC_CUDA_CHECK(cudaEventRecord(c->ev_user, st));
+    c->user_pending = true;
+    return ABC_OK;
+}
 
 #define CTX_GUARD(ctx)                                                       \
     if (!(ctx)) { abc_set_error("null context"); return ABC_ERR_ARG; }       \
@@ -163,6 +193,7 @@ extern "C" int abc_create(int device, abc_ctx_t** out) {
         ABC_CUDA_CHECK(cudaEventCreateWithFlags(&c->s3_ev_end[l], cudaEventDisableTiming));
     }
     ABC_CUDA_CHECK(cudaEventCreateWithFlags(&c->s3_ev_begin, cudaEventDisableTiming));
+    ABC_CUDA_CHECK(cudaEventCreateWithFlags(&c->ev_user, cudaEventDisableTiming));
     ABC_CUDA_CHECK(cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking));
     for (int l = 0; l < 2; ++l) {
         ABC_CUDA_CHECK(cudaEventCreateWithFlags(&c->p_done[l], cudaEventDisableTiming));
@@ -187,6 +218,7 @@ extern "C" int abc_destroy(abc_ctx_t* c) {
     if (!c) return ABC_OK;
     cudaSetDevice(c->device);
     cudaStreamSynchronize(c->stream);
+    if (c->user_pending) cudaEventSynchronize(c->ev_user);
     c->d_beta.release(); c->d_age_dist.release(); c->d_beta_mom.release(); c->d_d.release(); c->d_den.release(); c->d_fbw.release(); c->d_fa.release(); c->d_fstats.release(); c->d_rnan.release();
     c->d_s3_tb.release(); c->d_s3_ab.release(); c->d_s3_wt.release();
     c->d_s3_gidx.release(); c->d_s3_ok.release(); for (int l = 0; l < 2; ++l) { c->d_s3_live[l].release(); c->d_s3_nanw[l].release(); c->d_s3_qcnt[l].release(); c->d_s3_q2[l].release(); c->d_s3_fstats[l].release(); }
@@ -204,6 +236,7 @@ extern "C" int abc_destroy(abc_ctx_t* c) {
         if (c->s3_ev_end[l]) cudaEventDestroy(c->s3_ev_end[l]);
     }
     if (c->s3_ev_begin) cudaEventDestroy(c->s3_ev_begin);
+    if (c->ev_user) cudaEventDestroy(c->ev_user);
     if (c->copy_stream) cudaStreamDestroy(c->copy_stream);
     for (int l = 0; l < 2; ++l) {
         if (c->p_done[l]) cudaEventDestroy(c->p_done[l]);
@@ -325,7 +358,7 @@ extern "C" int abc_set_data(abc_ctx_t* c, const double* d, const double* se, int
     DevBuf<double> d_se;
     if (rc == ABC_OK) rc = d_se.ensure(n);
     if (rc == ABC_OK) rc = c->d_counts.ensure((size_t)G);
-    if (rc != ABC_OK) { d_se.release(); return rc; }
+    if (rc != ABC_OK) return rc;
     ABC_CUDA_CHECK(cudaMemcpy(c->d_d.p, d, n * sizeof(double), cudaMemcpyHostToDevice));
     ABC_CUDA_CHECK(cudaMemcpy(d_se.p, se, n * sizeof(double), cudaMemcpyHostToDevice));
     rc = abc_launch_prepare_data(c->d_d.p, d_se.p, G, c->d_den.p, c->d_fbw.p, c->d_fa.p, c->stream);
@@ -619,17 +652,28 @@ static int ensure_accept(abc_ctx* c, int64_t want, cudaStream_t st) {
     DevBuf<int32_t> ng; DevBuf<long long> np_; DevBuf<double> ne;
     int rc;
     if ((rc = ng.ensure((size_t)want)) != ABC_OK) return rc;
-    if ((rc = np_.ensure((size_t)want)) != ABC_OK) { ng.release(); return rc; }
-    if ((rc = ne.ensure((size_t)want)) != ABC_OK) { ng.release(); np_.release(); return rc; }
+    if ((rc = np_.ensure((size_t)want)) != ABC_OK) return rc;
+    if ((rc = ne.ensure((size_t)want)) != ABC_OK) return rc;
     if (cnt) {
         ABC_CUDA_CHECK(cudaMemcpy(ng.p, c->d_acc_gene.p, cnt * sizeof(int32_t), cudaMemcpyDeviceToDevice));
         ABC_CUDA_CHECK(cudaMemcpy(np_.p, c->d_acc_particle.p, cnt * sizeof(long long), cudaMemcpyDeviceToDevice));
         ABC_CUDA_CHECK(cudaMemcpy(ne.p, c->d_acc_err.p, cnt * sizeof(double), cudaMemcpyDeviceToDevice));
     }
-    c->d_acc_gene.release(); c->d_acc_particle.release(); c->d_acc_err.release();
-    c->d_acc_gene = ng; c->d_acc_particle = np_; c->d_acc_err = ne;
+    c->d_acc_gene = std::move(ng); c->d_acc_particle = std::move(np_); c->d_acc_err = std::move(ne);
     c->acc_capacity = want;
     return ABC_OK;
+}
+
+// more pairs were accepted than the tuple buffer holds: the surplus tuples were dropped (counts[] still include them).  The
+// stored count is clamped back to the capacity so that the context stays usable; the caller must abc_accept_reset and
+// rescore with a larger "accept_capacity" (or a lower eps / smaller batches).
+static int accept_overflow(abc_ctx* c, unsigned long long total) {
+    const unsigned long long cap = (unsigned long long)c->acc_capacity;
+    cudaMemcpy(c->d_acc_count.p, &cap, sizeof(cap), cudaMemcpyHostToDevice);
+    abc_set_error("accepted-tuple buffer overflow: %llu accepted pairs > capacity %lld (surplus dropped; per-gene counts include "
+                  "them): call abc_accept_reset, then raise the option accept_capacity, lower eps or score in smaller batches",
+                  total, (long long)c->acc_capacity);
+    return ABC_ERR_NOMEM;
 }
 
 static int64_t default_accept_capacity(int64_t n, int G) {
@@ -649,7 +693,17 @@ static int score_device(abc_ctx* c, const double* d_stats, int64_t n, int64_t of
     }
     // room for this call: up to 2 % of its pairs on top of the budget already promised to earlier calls since
     // the last reset (a conservative host-side running bound; the exact count is only read when growing)
-    c->acc_budget += default_accept_capacity(n, c->G);
+    // eps >= 10 accepts every finite pair (errors are clipped at 10.0): room for all of them, or a clear refusal
+    if (eps >= 10.0) {
+        if ((double)n * (double)c->G > 1.0e9) {
+            abc_set_error("eps = %g >= 10 accepts every (particle, gene) pair: %lld x %d tuples do not fit; score in batches of "
+                          "<= %lld particles or use eps < 10", eps, (long long)n, c->G, (long long)(1000000000ll / c->G));
+            return ABC_ERR_ARG;
+        }
+        c->acc_budget += n * (int64_t)c->G;
+    } else {
+        c->acc_budget += default_accept_capacity(n, c->G);
+    }
     int rc = ensure_accept(c, std::max<int64_t>(c->acc_budget, c->acc_min_capacity), st);
     if (rc != ABC_OK) return rc;
     AbcScoreArgs a;
@@ -757,11 +811,7 @@ extern "C" int abc_score(abc_ctx_t* c, const double* stats, int64_t n, int64_t o
     c->last.ms_score = ms_total;
     unsigned long long total = 0;
     ABC_CUDA_CHECK(cudaMemcpy(&total, c->d_acc_count.p, sizeof(total), cudaMemcpyDeviceToHost));
-    if ((int64_t)total > c->acc_capacity) {
-        abc_set_error("accepted-tuple buffer overflow: %llu accepted pairs > capacity %lld; lower eps or score in smaller batches",
-                      total, (long long)c->acc_capacity);
-        return ABC_ERR_NOMEM;
-    }
+    if ((int64_t)total > c->acc_capacity) return accept_overflow(c, total);
     if (counts) {
         std::vector<unsigned long long> h((size_t)G);
         ABC_CUDA_CHECK(cudaMemcpy(h.data(), c->d_counts.p, (size_t)G * sizeof(unsigned long long), cudaMemcpyDeviceToHost));
@@ -850,11 +900,7 @@ extern "C" int abc_simulate_score(abc_ctx_t* c, int m, int64_t n, int64_t offset
     c->last.ms_simulate = ms_sim; c->last.ms_score = ms_score;
     unsigned long long total = 0;
     ABC_CUDA_CHECK(cudaMemcpy(&total, c->d_acc_count.p, sizeof(total), cudaMemcpyDeviceToHost));
-    if ((int64_t)total > c->acc_capacity) {
-        abc_set_error("accepted-tuple buffer overflow: %llu accepted pairs > capacity %lld; lower eps or score in smaller batches",
-                      total, (long long)c->acc_capacity);
-        return ABC_ERR_NOMEM;
-    }
+    if ((int64_t)total > c->acc_capacity) return accept_overflow(c, total);
     if (counts) {
         std::vector<unsigned long long> h((size_t)G);
         ABC_CUDA_CHECK(cudaMemcpy(h.data(), c->d_counts.p, (size_t)G * sizeof(unsigned long long), cudaMemcpyDeviceToHost));
@@ -868,14 +914,15 @@ extern "C" int64_t abc_accept_total(abc_ctx_t* c) {
     if (!c) return -1;
     if (cudaSetDevice(c->device) != cudaSuccess) return -1;
     unsigned long long total = 0;
-    cudaStreamSynchronize(c->stream);
+    if (sync_ctx(c) != ABC_OK) return -1;
     if (cudaMemcpy(&total, c->d_acc_count.p, sizeof(total), cudaMemcpyDeviceToHost) != cudaSuccess) return -1;
     return (int64_t)total;
 }
 
 extern "C" int abc_accept_reset(abc_ctx_t* c) {
     CTX_GUARD(c);
-    ABC_CUDA_CHECK(cudaStreamSynchronize(c->stream));
+    int rcs = sync_ctx(c);
+    if (rcs != ABC_OK) return rcs;
     ABC_CUDA_CHECK(cudaMemset(c->d_acc_count.p, 0, sizeof(unsigned long long)));
     if (c->G > 0) ABC_CUDA_CHECK(cudaMemset(c->d_counts.p, 0, (size_t)c->G * sizeof(unsigned long long)));
     c->acc_budget = 0;
@@ -883,7 +930,8 @@ extern "C" int abc_accept_reset(abc_ctx_t* c) {
 }
 
 static int fetch_tuples(abc_ctx* c, std::vector<int32_t>& g, std::vector<long long>& p, std::vector<double>& e) {
-    ABC_CUDA_CHECK(cudaStreamSynchronize(c->stream));
+    int rcs = sync_ctx(c);
+    if (rcs != ABC_OK) return rcs;
     unsigned long long total = 0;
     ABC_CUDA_CHECK(cudaMemcpy(&total, c->d_acc_count.p, sizeof(total), cudaMemcpyDeviceToHost));
     if ((int64_t)total > c->acc_capacity) { abc_set_error("accepted-tuple buffer overflowed"); return ABC_ERR_NOMEM; }
@@ -913,7 +961,8 @@ extern "C" int abc_accept_tuples(abc_ctx_t* c, int32_t* gene, int64_t* particle,
 // ascending error, ties by ascending particle index == v[sortperm(err[v])] (stable), three stable radix passes on the device
 // (abc_accept.cu).  Work is enqueued on c->stream; the caller synchronises.
 static int build_accepted_lists(abc_ctx* c, int64_t* offsets, unsigned long long* total_out, bool want_lists) {
-    ABC_CUDA_CHECK(cudaStreamSynchronize(c->stream));
+    int rcs = sync_ctx(c);
+    if (rcs != ABC_OK) return rcs;
     unsigned long long total = 0;
     ABC_CUDA_CHECK(cudaMemcpy(&total, c->d_acc_count.p, sizeof(total), cudaMemcpyDeviceToHost));
     if ((int64_t)total > c->acc_capacity) { abc_set_error("accepted-tuple buffer overflowed"); return ABC_ERR_NOMEM; }
@@ -1018,7 +1067,9 @@ extern "C" int abc_simulate_dev(abc_ctx_t* c, int m, int64_t n, int64_t offset, 
     if (rc != ABC_OK) return rc;
     if (n <= 0 || !d_theta || !d_stats) { abc_set_error("abc_simulate_dev: bad arguments"); return ABC_ERR_ARG; }
     cudaStream_t st = (cudaStream_t)stream;   // NULL = the legacy default stream (torch's default stream)
-    return simulate_device(c, m, n, offset, seed, prior_supplied, d_theta, d_stats, nullptr, st);
+    rc = simulate_device(c, m, n, offset, seed, prior_supplied, d_theta, d_stats, nullptr, st);
+    if (rc != ABC_OK) return rc;
+    return mark_user_stream(c, st);
 }
 
 extern "C" int abc_score_dev(abc_ctx_t* c, const double* d_stats, int64_t n, int64_t offset, double eps, int layout,
@@ -1026,15 +1077,18 @@ extern "C" int abc_score_dev(abc_ctx_t* c, const double* d_stats, int64_t n, int
     CTX_GUARD(c);
     if (n <= 0 || !d_stats || (layout != ABC_ERR_NONE && !d_err)) { abc_set_error("abc_score_dev: bad arguments"); return ABC_ERR_ARG; }
     cudaStream_t st = (cudaStream_t)stream;   // NULL = the legacy default stream (torch's default stream)
-    return score_device(c, d_stats, n, offset, eps, layout, d_err, st);
+    int rc = score_device(c, d_stats, n, offset, eps, layout, d_err, st);
+    if (rc != ABC_OK) return rc;
+    return mark_user_stream(c, st);
 }
 
 extern "C" int abc_counts_dev(abc_ctx_t* c, int64_t* d_counts, void* stream) {
     CTX_GUARD(c);
     if (!c->has_data || !d_counts) { abc_set_error("abc_counts_dev: bad state/arguments"); return ABC_ERR_ARG; }
     cudaStream_t st = (cudaStream_t)stream;   // NULL = the legacy default stream (torch's default stream)
+    if (c->user_pending) ABC_CUDA_CHECK(cudaStreamWaitEvent(st, c->ev_user, 0));   // scoring enqueued on another caller stream
     ABC_CUDA_CHECK(cudaMemcpyAsync(d_counts, c->d_counts.p, (size_t)c->G * sizeof(int64_t), cudaMemcpyDeviceToDevice, st));
-    return ABC_OK;
+    return mark_user_stream(c, st);
 }
 
 extern "C" int abc_accept_tuples_dev(abc_ctx_t* c, int32_t* d_gene, int64_t* d_particle, double* d_err,
@@ -1042,11 +1096,17 @@ extern "C" int abc_accept_tuples_dev(abc_ctx_t* c, int32_t* d_gene, int64_t* d_p
     CTX_GUARD(c);
     if (!d_gene || !d_particle || !d_err || capacity < 0) { abc_set_error("abc_accept_tuples_dev: bad arguments"); return ABC_ERR_ARG; }
     cudaStream_t st = (cudaStream_t)stream;   // NULL = the legacy default stream (torch's default stream)
+    int rcs = sync_ctx(c);                    // every scoring call so far, whichever stream it ran on
+    if (rcs != ABC_OK) return rcs;
     ABC_CUDA_CHECK(cudaStreamSynchronize(st));
     unsigned long long total = 0;
     ABC_CUDA_CHECK(cudaMemcpy(&total, c->d_acc_count.p, sizeof(total), cudaMemcpyDeviceToHost));
     if ((int64_t)total > c->acc_capacity) { abc_set_error("accepted-tuple buffer overflowed"); return ABC_ERR_NOMEM; }
-    size_t k = (size_t)std::min<int64_t>((int64_t)total, capacity);
+    if ((int64_t)total > capacity) {
+        abc_set_error("abc_accept_tuples_dev: %llu accepted tuples do not fit the caller's capacity %lld", total, (long long)capacity);
+        return ABC_ERR_ARG;
+    }
+    size_t k = (size_t)total;
     if (k) {
         ABC_CUDA_CHECK(cudaMemcpyAsync(d_gene, c->d_acc_gene.p, k * sizeof(int32_t), cudaMemcpyDeviceToDevice, st));
         ABC_CUDA_CHECK(cudaMemcpyAsync(d_particle, c->d_acc_particle.p, k * sizeof(long long), cudaMemcpyDeviceToDevice, st));

@@ -149,7 +149,11 @@ __device__ unsigned int integrate_piece(const OdePiece& pc, double ta, double tb
         double fac = (err > 0.0) ? 0.9 * exp2(-log2(err) / 6.0) : 4.0;
         fac = fmin(4.0, fmax(0.2, fac));
         h *= fac;
-        if (nsteps > 2000000u) break;
+        if (nsteps > 2000000u && t < tb) {      // step limit: a truncated integration must never pass for a result
+#pragma unroll
+            for (int i = 0; i < 9; ++i) y[i] = __longlong_as_double(0x7ff8000000000000ll);
+            return nsteps;
+        }
     }
     return nsteps;
 }

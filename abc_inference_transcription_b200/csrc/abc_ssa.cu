@@ -179,10 +179,12 @@ __device__ __forceinline__ bool ssa_step(Lineage& s, float& x, const Seg& sg, ui
     if (!(xn < sg.len)) return true;
     x = xn;
     const float abn = gate(g, f_fma(sg.A1, xn, sg.A0));
-    const float t32 = f_mul(f_add(base, abn), 2.3283064365386963e-10f);
+    const float tot = f_add(base, abn);
+    const float t32 = f_mul(tot, 2.3283064365386963e-10f);
     const float rs = f_mul((float)wc, t32);
     const float rb = f_mul((float)(~wc), t32);
-    const bool sw = rs < asw;
+    // (float)wc rounds the top 128 words up to 2^32 (rs == tot): when the switch is the only channel it must still fire
+    const bool sw = (rs < asw) || !(asw < tot);
     const bool death = !sw && (rb < ad);
     const bool dU = rb < f_mul(sg.gam, s.U);
     const bool birth = !sw && !death;

@@ -182,7 +182,9 @@ int  abc_score_dev(abc_ctx_t* ctx, const double* d_stats, int64_t n, int64_t par
                    int err_layout, double* d_err, void* stream);
 /* device-side exports for multi-GPU gathers (torch.distributed / NCCL work on the caller's tensors):
  * copy the per-gene accepted counts (G int64) / the unsorted accepted tuples into caller device
- * buffers on `stream`.  abc_accept_tuples_dev copies min(total, capacity) tuples. */
+ * buffers on `stream`.  abc_accept_tuples_dev fails with ABC_ERR_ARG when the
+ * accepted tuples do not fit `capacity` (nothing is truncated silently).  All accept_* entry points wait for the *_dev work
+ * enqueued on caller streams (an event recorded after every *_dev call). */
 int  abc_counts_dev(abc_ctx_t* ctx, int64_t* d_counts, void* stream);
 int  abc_accept_tuples_dev(abc_ctx_t* ctx, int32_t* d_gene, int64_t* d_particle, double* d_err, int64_t capacity,
                            void* stream);

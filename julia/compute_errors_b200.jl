@@ -1,10 +1,20 @@
 # compute_errors_b200.jl -- drop-in for compute_errors.jl + process_error_files.jl + accepted_particles.jl
-# (wrapper.jl:72-81).  Keeps `m` / `model_name`, reads the simulation files with the reference's own
-# load_s_data, writes error_<model>.txt rows, the JDF column store and data/posteriors/particles_<model>.txt.
+# (wrapper.jl:72-81).  Keeps `m` / `model_name`, reads the simulation files (own restatement of the three loaders of
+# compute_errors.jl:1-28 -- the reference script itself is NOT included: its tail, compute_errors.jl:72-81, runs the CPU
+# scoring loop), writes the JDF column store and data/posteriors/particles_<model>.txt.
 # NOT EXECUTED IN THE BUILD CONTAINER (no Julia there).
 using DelimitedFiles, DataFrames, JDF
 include(joinpath(@__DIR__, "AbcB200.jl"))
-include("scripts/compute_errors.jl")     # only for load_s_data / get_mean_subset / get_ff_subset (compute_errors.jl:1-28)
+
+# s_pulse / s_chase hold two rows per particle: odd rows the means, even rows the Fano factors (abc_simulation.jl:47-52)
+get_mean_subset(data::Matrix{Float64}) = data[1:2:end, :]                                    # compute_errors.jl:1-7
+get_ff_subset(data::Matrix{Float64}) = data[2:2:end, :]                                      # compute_errors.jl:9-15
+function load_s_data(path::String, model_name::String, ext::String)                          # compute_errors.jl:17-28
+    rd(stem) = convert(Matrix{Float64}, readdlm(path*model_name*"/"*stem*"_"*model_name*ext))
+    s_pulse, s_chase = rd("s_pulse"), rd("s_chase")
+    return get_mean_subset(s_pulse), get_ff_subset(s_pulse), get_mean_subset(s_chase), get_ff_subset(s_chase),
+           rd("s_ratios"), rd("s_mean_corr"), rd("s_corr_mean")
+end
 
 d  = permutedims(hcat(pulse_mean, pulse_ff, chase_mean, chase_ff, ratio_data, mean_corr_data, corr_mean_data))       # 53 x G
 se = permutedims(hcat(pulse_mean_se, pulse_ff_se, chase_mean_se, chase_ff_se, ratio_se, mean_corr_se, corr_mean_se))

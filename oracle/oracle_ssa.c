@@ -197,10 +197,12 @@ static int ssa_step(cell_t* s, float* x, const seg_t* sg, uint32_t wt, uint32_t 
     if (!(xn < sg->len)) return 1;
     *x = xn;
     float abn = on ? fmaf(sg->A1, xn, sg->A0) : 0.0f;
-    float t32 = (base + abn) * 2.3283064365386963e-10f;
+    float tot = base + abn;
+    float t32 = tot * 2.3283064365386963e-10f;
     float rs = (float)wc * t32;
     float rb = (float)(~wc) * t32;
-    int sw = rs < asw;
+    /* (float)wc rounds the top 128 words up to 2^32 (rs == tot): when the switch is the only channel it must still fire */
+    int sw = (rs < asw) || !(asw < tot);
     int death = !sw && (rb < ad);
     int dU = rb < sg->gam * (float)s->U;
     int birth = !sw && !death;

@@ -5,8 +5,8 @@ Run in the build container only (needs /root/reference):  python tests/golden/ma
 Outputs (all numpy, float64 unless noted):
   ref_map_sets.npz        the 2503 MAP parameter vectors  data/posterior_estimates/map_sets_<model>.txt
                           + the gene index of each row     data/model_selection/<model>_genes.txt
-  ref_recovered.npz       known answers of syntheticdata() (scripts/recover_statistics.jl:49-68) for a
-                          subset of those rows: data/recovered_statistics/<model>/<cond>/<moment>.txt
+  ref_recovered.npz       known answers of syntheticdata() (scripts/recover_statistics.jl:49-68) for ALL rows:
+                          data/recovered_statistics/<model>/<cond>/<moment>.txt
                           -> array [row, cond(11), age(5), moment(5)] + the row indices used
   ref_summary_stats.npz   data/summary_stats/*.txt  -> d[G,53], se[G,53] in the scoring order
                           pulse_mean, pulse_ff, chase_mean, chase_ff, ratio, mean_corr, corr_mean
@@ -21,7 +21,7 @@ MODELS = ["const", "const_const", "kon", "alpha", "gamma"]
 LABELS = ["pulse_15", "pulse_30", "pulse_45", "pulse_60", "pulse_120", "pulse_180",
           "chase_0", "chase_60", "chase_120", "chase_240", "chase_360"]
 MOMENTS = ["mean_u", "mean_l", "var_u", "cov_ul", "var_l"]
-MAX_ROWS = 100  # per model, evenly spaced
+MAX_ROWS = 10**9  # per model: all rows (1844 / 478 / 101 / 15 / 65 = 2503)
 
 
 def main():

@@ -101,3 +101,18 @@ def test_julia_binding_matches_the_header():
     for need in ("abc_create", "abc_set_design", "abc_set_data", "abc_fix_params", "abc_simulate", "abc_score",
                  "abc_simulate_score", "abc_accept_fetch", "abc_posterior_summary", "abc_set_option", "abc_host_alloc"):
         assert need in bound, need
+
+
+def test_julia_host_never_includes_a_reference_script():
+    """the drop-in must not pull the reference's scripts in (compute_errors.jl's tail runs the CPU scoring loop and writes
+    to an HPC path, compute_errors.jl:72-81): every include of julia/*.jl resolves inside julia/"""
+    jdir = os.path.join(ROOT, "julia")
+    for fn in sorted(os.listdir(jdir)):
+        if not fn.endswith(".jl"):
+            continue
+        for ln, line in enumerate(open(os.path.join(jdir, fn)), 1):
+            code = line.split("#", 1)[0]
+            for mt in re.finditer(r"\binclude\s*\((.*)\)", code):
+                arg = mt.group(1)
+                assert "scripts/" not in arg and "scripts\\" not in arg, f"{fn}:{ln} includes a reference script: {line.strip()}"
+                assert "@__DIR__" in arg, f"{fn}:{ln}: include outside julia/: {line.strip()}"

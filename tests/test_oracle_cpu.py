@@ -22,25 +22,38 @@ def test_philox4x32_10_known_answers(ctr, key, want):
 
 
 # ------------------------------------------------------------------ simulator vs data/recovered_statistics
-@pytest.mark.parametrize("m,name,stride", [(1, "const", 5), (2, "const_const", 5), (3, "kon", 4), (4, "alpha", 1), (5, "gamma", 3)])
-def test_moment_odes_match_reference_recovered_statistics(m, name, stride):
-    """orc_run_part_sim == run_part_sim (recover_statistics.jl:1-11) on the reference's MAP parameter sets.
-    The goldens carry CVODE reltol 1e-3 noise + the 1 % transient criterion: tolerance
-    2e-2 relative with a 1e-4 absolute floor on >= 97 % of the entries, 0.2 worst case, median < 1e-3."""
+def _pool_map(fn, items, threads=None):
+    """the oracle's C calls release the GIL: run them on all host threads"""
+    from concurrent.futures import ThreadPoolExecutor
+    with ThreadPoolExecutor(max_workers=threads or (os.cpu_count() or 1)) as ex:
+        return list(ex.map(fn, items))
+
+
+@pytest.mark.parametrize("m,name,n_rows", [(1, "const", 1844), (2, "const_const", 478), (3, "kon", 101), (4, "alpha", 15), (5, "gamma", 65)])
+def test_moment_odes_match_reference_recovered_statistics(m, name, n_rows):
+    """orc_run_part_sim == run_part_sim (recover_statistics.jl:1-11) on ALL 2503 MAP parameter sets the reference ships
+    (data/posterior_estimates/map_sets_*.txt vs data/recovered_statistics/**: 2503 x 275 = 688 325 values, SURVEY section 4
+    test 1).  The goldens carry CVODE reltol 1e-3 noise + the 1 % transient criterion: tolerance 2e-2 relative with a 1e-4
+    absolute floor on >= 97 % of the entries, 0.2 worst case, median < 1e-3."""
     maps = np.load(os.path.join(GOLD, "ref_map_sets.npz"))
     rec = np.load(os.path.join(GOLD, "ref_recovered.npz"))
-    rows, gold = rec[f"rows_{name}"][::stride], rec[f"moments_{name}"][::stride]
+    rows, gold = rec[f"rows_{name}"], rec[f"moments_{name}"]
+    assert len(rows) == n_rows == len(maps[f"theta_{name}"]) and np.array_equal(rows, np.arange(n_rows))
     theta = maps[f"theta_{name}"][rows]
     d = oracle.make_design(iv_index=0, downsampling=False, rtol=1e-7)    # recover_statistics.jl:33-34: iv[1] = 1/2
-    rel = []
-    for th, g in zip(theta, gold):
-        got, k = oracle.run_part_sim(th, m, d)
-        assert 1 <= k <= 101
-        rel.append(np.abs(got - g) / np.maximum(np.abs(g), 1e-4))
-    rel = np.array(rel)
+    oracle.lib()
+    res = _pool_map(lambda th: oracle.run_part_sim(th, m, d), theta)
+    assert all(1 <= k <= 101 for _, k in res)
+    got = np.array([g for g, _ in res])
+    rel = np.abs(got - gold) / np.maximum(np.abs(gold), 1e-4)
     assert np.median(rel) < 1e-3, np.median(rel)
     assert (rel < 2e-2).mean() > 0.97, (rel < 2e-2).mean()
     assert rel.max() < 0.2, rel.max()
+    # row by row: no single parameter set is off as a whole.  (Two gamma rows with switching times of ~130 h sit 2-3 %
+    # off uniformly: transient_phase stops at 1 % change per cycle, model.jl:116, one iteration earlier or later under
+    # CVODE noise -- hence 5e-2 here.)
+    per_row = (rel < 5e-2).reshape(len(theta), -1).mean(1)
+    assert per_row.min() > 0.95, (int(per_row.argmin()), per_row.min())
 
 
 def test_integrator_is_converged():
@@ -131,23 +144,35 @@ def test_accept_gene_order_ties_and_sentinel():
 
 
 def test_weak_end_to_end_kat_map_rows_are_accepted_by_their_gene():
-    """SURVEY 8c KAT (3): err(stats(MAP theta_i), gene_i) <= 4.8 for the reference's MAP rows.  Design constants
-    are approximated (uniform age weights, round-robin age clusters: SURVEY R10), so the bar is 'most rows'."""
+    """SURVEY 8c KAT (3) on ALL 2503 MAP rows: a MAP row is the particle with the smallest error for its gene among the
+    particles of its model (posterior_kinetics.jl:14), so (i) err(stats(MAP theta_i), gene_i) <= 4.8 and (ii) among the MAP
+    rows of the same model -- all of them particles of the same run -- row i minimises the error of gene_i
+    (data/model_selection/<model>_genes.txt maps rows to genes).  This pins downsample, the 53 statistics and the scoring
+    order end to end on reference-held data.  Design constants are approximated (uniform age weights, round-robin age
+    clusters: SURVEY R10), hence 'nearly all' rather than 'all'; measured: 99.7 % accepted, 86 % exact minima, 100 % within
+    1.25 x the minimum."""
     from abc_inference_transcription_b200.design import split_betas
     maps = np.load(os.path.join(GOLD, "ref_map_sets.npz"))
     z = np.load(os.path.join(GOLD, "ref_summary_stats.npz"))
     betas = np.load(os.path.join(GOLD, "ref_betas.npy"))
     od = oracle.make_design(iv_index=1, downsampling=True, betas=split_betas(betas), rtol=1e-5)
-    ok = tot = 0
+    oracle.lib()
+    acc = is_min = near_min = tot = 0
     for m, name in enumerate(MODELS, start=1):
         th, genes = maps[f"theta_{name}"], maps[f"genes_{name}"]
-        for i in range(0, len(th), max(1, len(th) // 12)):
-            st, _ = oracle.run_sim(th[i], m, od)
-            g = genes[i] - 1
-            e = oracle.compute_trunc_errors(st[None], z["d"][g:g + 1], z["se"][g:g + 1])[0, 0]
-            ok += e <= 4.8
-            tot += 1
-    assert ok / tot > 0.8, (ok, tot)
+        stats = np.array(_pool_map(lambda x: oracle.run_sim(x, m, od)[0], th))
+        g = genes - 1
+        E = oracle.compute_trunc_errors(stats, z["d"][g], z["se"][g])      # rows: MAP particles, columns: their genes
+        own, col_min = np.diag(E), np.nanmin(E, axis=0)
+        acc += int((own <= 4.8).sum())
+        is_min += int((own <= col_min).sum())
+        near_min += int((own <= 1.25 * col_min).sum())
+        tot += len(th)
+        assert (own <= 4.8).mean() >= 0.8, (name, (own <= 4.8).mean())
+    assert tot == 2503
+    assert acc / tot > 0.99, (acc, tot)
+    assert is_min / tot > 0.8, (is_min, tot)
+    assert near_min / tot > 0.99, (near_min, tot)
 
 
 # ------------------------------------------------------------------ oracle SSA vs the moment ODEs
