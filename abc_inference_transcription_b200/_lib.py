@@ -70,6 +70,7 @@ SYMBOLS = {
                                             _vp, _vp, ctypes.POINTER(AbcCounters)]),
     "abc_ssa_cells": (ctypes.c_int, [_vp, ctypes.c_int, _vp, ctypes.c_int64, ctypes.c_uint64, ctypes.c_int,
                                      ctypes.c_int, ctypes.c_int, _vp]),
+    "abc_ssa_window": (ctypes.c_int, [_vp, ctypes.c_int, _vp, _vp, ctypes.POINTER(ctypes.c_double)]),
     "abc_summary_stats": (ctypes.c_int, [_vp, _vp, ctypes.c_int64, _vp]),
     "abc_score": (ctypes.c_int, [_vp, _vp, ctypes.c_int64, ctypes.c_int64, ctypes.c_double, ctypes.c_int, _vp, _vp,
                                  ctypes.POINTER(AbcCounters)]),

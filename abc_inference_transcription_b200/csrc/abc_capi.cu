@@ -109,11 +109,13 @@ struct abc_ctx {
     int score_sub_batches = 0;   // sub-batches per call when overlapping; 0 = 2 below 256k particles, else 4
     int stats_guards = -1;       // -1: sample guards iff sim_kind == SSA; 0 / 1 force
     int ssa_hybrid = 2;          // exact telegraph + conditional-Poisson sampling: 1 = burn-in only, 2 = to the read-out
-    int ssa_adaptive = 1;        // burn-in cycles per particle from the decay of the discarded history (modes 1, 2)
+    int ssa_adaptive = 2;        // burn-in from the decay of the discarded history: 1 = whole cycles per particle (modes 1, 2),
+                                 // 2 = start time per (particle, read-out) from the exact mean contributions (mode 2; mode 1 uses 1)
     int64_t simscore_sub_min = 8192;   // abc_simulate_score: smallest sub-batch worth pipelining
     // simulate work buffers
     DevBuf<double> d_theta, d_stats, d_moments, d_ss_iv, d_prefix;
     DevBuf<AbcRates> d_rates;
+    DevBuf<float> d_win;         // mode 2: start time of every (particle, read-out)
     DevBuf<unsigned long long> d_sums, d_counters;
     DevBuf<unsigned int> d_work;
     DevBuf<uint32_t> d_cells;
@@ -222,7 +224,7 @@ extern "C" int abc_destroy(abc_ctx_t* c) {
     c->d_beta.release(); c->d_age_dist.release(); c->d_beta_mom.release(); c->d_d.release(); c->d_den.release(); c->d_fbw.release(); c->d_fa.release(); c->d_fstats.release(); c->d_rnan.release();
     c->d_s3_tb.release(); c->d_s3_ab.release(); c->d_s3_wt.release();
     c->d_s3_gidx.release(); c->d_s3_ok.release(); for (int l = 0; l < 2; ++l) { c->d_s3_live[l].release(); c->d_s3_nanw[l].release(); c->d_s3_qcnt[l].release(); c->d_s3_q2[l].release(); c->d_s3_fstats[l].release(); }
-    c->d_theta.release(); c->d_stats.release(); c->d_moments.release(); c->d_ss_iv.release(); c->d_prefix.release(); c->d_rates.release();
+    c->d_theta.release(); c->d_stats.release(); c->d_moments.release(); c->d_ss_iv.release(); c->d_prefix.release(); c->d_rates.release(); c->d_win.release();
     c->d_keys_in.release(); c->d_keys_out.release(); c->d_idx_in.release(); c->d_order.release(); c->d_sort_tmp.release();
     c->d_sums.release(); c->d_counters.release(); c->d_work.release(); c->d_cells.release();
     c->d_sstats.release(); c->d_err.release(); c->d_counts.release(); c->d_acc_count.release();
@@ -478,6 +480,13 @@ static int simulate_device(abc_ctx* c, int m, int64_t n, int64_t offset, uint64_
     if ((rc = abc_launch_rates(d_theta, m, n, c->d_rates.p, c->ssa_hybrid, (c->ssa_adaptive && c->ssa_hybrid) ? c->design.n_pre_cycles : 0,
                                c->design.cycle, st)) != ABC_OK) return rc;
     c->launches++;
+    AbcSsaParams prm = make_ssa_params(c, m, n, offset, seed);
+    if (c->ssa_hybrid == 2) {
+        // where every (particle, read-out) starts, and the expected work per particle (replaces the rate-based hint)
+        if ((rc = c->d_win.ensure((size_t)n * ABC_NREAD)) != ABC_OK) return rc;
+        if ((rc = abc_launch_window(c->d_rates.p, prm, c->d_win.p, n, st)) != ABC_OK) return rc;
+        c->launches++;
+    }
     // longest-processing-time-first order of the particles (scheduling only, results are order independent)
     const int* d_order = nullptr;
     if (n >= 64 && n < (1ll << 31)) {
@@ -494,10 +503,14 @@ static int simulate_device(abc_ctx* c, int m, int64_t n, int64_t offset, uint64_
     }
     ABC_CUDA_CHECK(cudaMemsetAsync(c->d_sums.p, 0, (size_t)n * ABC_NREAD * 5 * sizeof(unsigned long long), st));
     ABC_CUDA_CHECK(cudaMemsetAsync(c->d_counters.p, 0, 8 * sizeof(unsigned long long), st));
-    AbcSsaParams prm = make_ssa_params(c, m, n, offset, seed);
     ABC_CUDA_CHECK(cudaEventRecord(c->ev[0], st));
-    if ((rc = abc_launch_ssa(c->d_rates.p, prm, c->d_beta.p, c->d_sums.p, c->d_counters.p, c->d_work.p, nullptr, d_order, 0,
-                             c->sm_count, st)) != ABC_OK) return rc;
+    if (c->ssa_hybrid == 2) {
+        if ((rc = abc_launch_tele(c->d_rates.p, prm, c->d_win.p, c->d_beta.p, c->d_sums.p, c->d_counters.p, c->d_work.p, nullptr,
+                                  d_order, c->sm_count, st)) != ABC_OK) return rc;
+    } else {
+        if ((rc = abc_launch_ssa(c->d_rates.p, prm, c->d_beta.p, c->d_sums.p, c->d_counters.p, c->d_work.p, nullptr, d_order, 0,
+                                 c->sm_count, st)) != ABC_OK) return rc;
+    }
     c->launches++;
     ABC_CUDA_CHECK(cudaEventRecord(c->ev[1], st));
     if ((rc = abc_launch_moments_from_sums(c->d_sums.p, n, c->design.n_cells, d_mom, st)) != ABC_OK) return rc;
@@ -613,12 +626,44 @@ extern "C" int abc_ssa_cells(abc_ctx_t* c, int m, const double* theta, int64_t p
     ABC_CUDA_CHECK(cudaMemsetAsync(c->d_counters.p, 0, 8 * sizeof(unsigned long long), c->stream));
     AbcSsaParams prm = make_ssa_params(c, m, 1, particle_index, seed);
     prm.single_readout = cond * ABC_NAGE + age;
-    rc = abc_launch_ssa(c->d_rates.p, prm, c->d_beta.p, nullptr, c->d_counters.p, c->d_work.p, c->d_cells.p, nullptr, exact_math,
-                        c->sm_count, c->stream);
+    if (c->ssa_hybrid == 2 && !exact_math) {
+        if ((rc = c->d_win.ensure((size_t)ABC_NREAD)) != ABC_OK) return rc;
+        if ((rc = abc_launch_window(c->d_rates.p, prm, c->d_win.p, 1, c->stream)) != ABC_OK) return rc;
+        rc = abc_launch_tele(c->d_rates.p, prm, c->d_win.p, c->d_beta.p, nullptr, c->d_counters.p, c->d_work.p, c->d_cells.p, nullptr,
+                             c->sm_count, c->stream);
+        c->launches++;
+    } else {
+        rc = abc_launch_ssa(c->d_rates.p, prm, c->d_beta.p, nullptr, c->d_counters.p, c->d_work.p, c->d_cells.p, nullptr, exact_math,
+                            c->sm_count, c->stream);
+    }
     c->launches += 2;
     if (rc != ABC_OK) return rc;
     ABC_CUDA_CHECK(cudaMemcpyAsync(counts, c->d_cells.p, (size_t)4 * nc * sizeof(uint32_t), cudaMemcpyDeviceToHost, c->stream));
     ABC_CUDA_CHECK(cudaStreamSynchronize(c->stream));
+    return ABC_OK;
+}
+
+extern "C" int abc_ssa_window(abc_ctx_t* c, int m, const double* theta, float* starts, double* expected_draws) {
+    CTX_GUARD(c);
+    int rc = check_model(m);
+    if (rc != ABC_OK) return rc;
+    if (!c->has_design) { abc_set_error("abc_set_design has not been called"); return ABC_ERR_STATE; }
+    if (c->design.sim_kind != ABC_SIM_SSA) { abc_set_error("abc_ssa_window needs sim_kind == ABC_SIM_SSA"); return ABC_ERR_STATE; }
+    if (!theta || !starts) { abc_set_error("abc_ssa_window: bad arguments"); return ABC_ERR_ARG; }
+    const int P = abc_n_params(m);
+    if ((rc = c->d_theta.ensure((size_t)P)) != ABC_OK) return rc;
+    if ((rc = c->d_rates.ensure(1)) != ABC_OK) return rc;
+    if ((rc = c->d_win.ensure((size_t)ABC_NREAD)) != ABC_OK) return rc;
+    ABC_CUDA_CHECK(cudaMemcpyAsync(c->d_theta.p, theta, P * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+    if ((rc = abc_launch_rates(c->d_theta.p, m, 1, c->d_rates.p, c->ssa_hybrid, 0, c->design.cycle, c->stream)) != ABC_OK) return rc;
+    AbcSsaParams prm = make_ssa_params(c, m, 1, 0, 0);
+    if ((rc = abc_launch_window(c->d_rates.p, prm, c->d_win.p, 1, c->stream)) != ABC_OK) return rc;
+    c->launches += 2;
+    AbcRates r;
+    ABC_CUDA_CHECK(cudaMemcpyAsync(starts, c->d_win.p, ABC_NREAD * sizeof(float), cudaMemcpyDeviceToHost, c->stream));
+    ABC_CUDA_CHECK(cudaMemcpyAsync(&r, c->d_rates.p, sizeof(r), cudaMemcpyDeviceToHost, c->stream));
+    ABC_CUDA_CHECK(cudaStreamSynchronize(c->stream));
+    if (expected_draws) *expected_draws = (r.pad1 != 0.0f) ? NAN : (double)r.pad0;
     return ABC_OK;
 }
 
@@ -1125,7 +1170,7 @@ extern "C" int abc_set_option(abc_ctx_t* c, const char* name, int64_t value) {
     if (strcmp(name, "accept_capacity") == 0) { c->acc_min_capacity = value > 0 ? value : 0; return ABC_OK; }
     if (strcmp(name, "stats_sample_guards") == 0) { c->stats_guards = value < 0 ? -1 : (value ? 1 : 0); return ABC_OK; }
     if (strcmp(name, "simulate_score_sub_batch") == 0) { c->simscore_sub_min = value > 0 ? value : 8192; return ABC_OK; }
-    if (strcmp(name, "ssa_adaptive_burnin") == 0) { c->ssa_adaptive = value ? 1 : 0; return ABC_OK; }
+    if (strcmp(name, "ssa_adaptive_burnin") == 0) { c->ssa_adaptive = value <= 0 ? 0 : (value == 1 ? 1 : 2); return ABC_OK; }
     if (strcmp(name, "ssa_hybrid_burnin") == 0) { c->ssa_hybrid = value <= 0 ? 0 : (value == 1 ? 1 : 2); return ABC_OK; }
     abc_set_error("abc_set_option: unknown option '%s'", name);
     return ABC_ERR_ARG;

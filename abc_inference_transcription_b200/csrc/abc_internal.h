@@ -11,7 +11,7 @@ struct AbcRates {
     float kon[5], koff[5], alpha[5], gamma[5];
     float lam;          // labelling efficiency 10^theta_lambda clamped to [0,1]
     uint32_t pon_thr;   // floor(P_on * 2^32): initial gene state threshold
-    float pad0, pad1;   // pad0 = predicted events per hour (scheduling hint only)
+    float pad0, pad1;   // pad0 = predicted work (scheduling hint only); pad1 != 0: particle refused (abc_window_kernel)
 };
 
 struct AbcSsaParams {
@@ -27,7 +27,8 @@ struct AbcSsaParams {
     int32_t  single_readout;   // >= 0: debug mode, simulate only this read-out of particle 0
     int32_t  hybrid;           // 1: exact telegraph + Poisson burn-in before the label window; 2: to the read-out
                                // (fast-math kernel only)
-    int32_t  adaptive;         // 1: per-particle burn-in length with the truncation bias bound of n_pre cycles (modes 1, 2)
+    int32_t  adaptive;         // 1: per-particle burn-in in whole cycles with the truncation bias bound of n_pre cycles (modes 1, 2)
+                               // 2: mode 2 only, start time per (particle, read-out) from the exact mean contributions
     int32_t  pad_;
     double   cycle;
     double   agevec[5];
@@ -45,6 +46,11 @@ int abc_launch_prior(double* d_theta, int m, int64_t n, int64_t offset, uint64_t
 int abc_launch_ssa(const AbcRates* d_rates, const AbcSsaParams& prm, const uint32_t* d_beta_q32,
                    unsigned long long* d_sums, unsigned long long* d_counters, unsigned int* d_work,
                    uint32_t* d_cells_out, const int* d_order, int exact_math, int sm_count, cudaStream_t st);
+// mode 2 (abc_tele.cu): start time of every (particle, read-out) + scheduling cost, then the telegraph kernel
+int abc_launch_window(AbcRates* d_rates, const AbcSsaParams& prm, float* d_win, int64_t n, cudaStream_t st);
+int abc_launch_tele(const AbcRates* d_rates, const AbcSsaParams& prm, const float* d_win, const uint32_t* d_beta_q32,
+                    unsigned long long* d_sums, unsigned long long* d_counters, unsigned int* d_work,
+                    uint32_t* d_cells_out, const int* d_order, int sm_count, cudaStream_t st);
 size_t abc_order_temp_bytes(int n);
 int abc_launch_order(const AbcRates* d_rates, int n, unsigned int* d_keys_in, unsigned int* d_keys_out, int* d_idx_in,
                      int* d_order, void* d_temp, size_t temp_bytes, cudaStream_t st);

@@ -123,6 +123,16 @@ class AbcEngine:
                                            int(cond), int(age), int(bool(exact_math)), _lib.ptr(out)))
         return out
 
+    def ssa_window(self, m, theta):
+        """start time (hours, 0 = start of the read-out cycle) of the lineages of each read-out, (11, 5) float32, and the
+        expected switch draws of the particle (ssa_hybrid_burnin = 2)"""
+        P = n_params(_check_m(m))
+        theta = np.ascontiguousarray(theta, dtype=np.float64).reshape(P)
+        starts = np.empty((_lib.NCOND, _lib.NAGE), dtype=np.float32)
+        draws = ctypes.c_double()
+        _lib.check(self._lib.abc_ssa_window(self._ctx, m, _lib.ptr(theta), _lib.ptr(starts), ctypes.byref(draws)))
+        return starts, draws.value
+
     def summary_stats(self, moments):
         """S1 (abc_simulation.jl:23-46): (n, 11, 5, 5) moments -> (n, 53)"""
         mom = np.ascontiguousarray(moments, dtype=np.float64).reshape(-1, _lib.NCOND, _lib.NAGE, 5)

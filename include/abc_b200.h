@@ -132,6 +132,12 @@ int  abc_simulate_moments(abc_ctx_t* ctx, int m, int64_t n, int64_t particle_off
 int  abc_ssa_cells(abc_ctx_t* ctx, int m, const double* theta, int64_t particle_index, uint64_t seed,
                    int cond, int age, int exact_math, uint32_t* counts);
 
+/* SSA parity hook (ssa_hybrid_burnin = 2): where the lineages of each of the 55 read-outs of one particle start, in hours
+ * relative to the start of the read-out cycle (starts[cond*5 + age]; <= 0: before the read-out cycle), and the expected
+ * number of switch draws of the particle (nullable).  Transcripts born before the start are not simulated: their expected
+ * share of either Poisson mean at the read-out is below 2^-n_pre_cycles (option ssa_adaptive_burnin). */
+int  abc_ssa_window(abc_ctx_t* ctx, int m, const double* theta, float* starts, double* expected_draws);
+
 /* ---- S1 alone: the 53 statistics from moments  abc_simulation.jl:23-46 --------------------- */
 int  abc_summary_stats(abc_ctx_t* ctx, const double* moments, int64_t n, double* stats);
 
@@ -202,9 +208,12 @@ int  abc_accept_tuples_dev(abc_ctx_t* ctx, int32_t* d_gene, int64_t* d_particle,
  * 2 (default): simulate the gene switch to the read-out and draw U ~ Poisson(Lam_U | gene path),
  * L ~ Poisson(Lam_L | gene path) there.  All three sample the same law of (g, U, L) at the read-out;
  * the exact_math variant of abc_ssa_cells always uses 0.
- * "ssa_adaptive_burnin" = 1 (default; modes 1 and 2): n_pre_cycles is the maximum; a particle whose transcripts decay
- * fast starts k <= n_pre_cycles cycles before the read-out cycle, k the smallest number for which the discarded history
- * contributes less than 2^-n_pre_cycles of the Poisson mean (the bias bound of the full burn-in); 0 = always n_pre_cycles. */
+ * "ssa_adaptive_burnin": n_pre_cycles is the maximum burn-in and 2^-n_pre_cycles its bias bound (dilution halves the
+ * memory of the initial condition every cycle).  2 (default, mode 2): the lineages of a (particle, read-out) start at the
+ * latest time s0 for which the transcripts born before s0 contribute, in expectation, less than 2^-n_pre_cycles of the
+ * unlabelled AND of the labelled Poisson mean at the read-out -- evaluated from the exact mean contribution of every piece
+ * of the rate schedule (decay, dilution, label window), see abc_ssa_window.  1 (modes 1 and 2): whole cycles per particle
+ * by the worst-case rule k (1 + log2(e) sum gamma_s cycle/5) >= n_pre_cycles.  0 = always n_pre_cycles cycles. */
 int  abc_set_option(abc_ctx_t* ctx, const char* name, int64_t value);
 /* device counters of the last *_dev launches (synchronises the stream) */
 int  abc_counters(abc_ctx_t* ctx, abc_counters_t* counters);

@@ -1,7 +1,7 @@
 """CPU check of the sampler the GPU runs by default (SSA mode 2), independent of the GPU:
 a numpy restatement -- Gillespie on the gene switch, Poisson means of the unlabelled / labelled transcripts carried through
 the +-F(x) accumulator, halving at divisions, the (1 - lambda) : lambda split inside the label window, U ~ Poisson(Lam_U),
-L ~ Poisson(Lam_L) at the read-out, burn-in length from the adaptive rule -- against the reference's moment equations
+L ~ Poisson(Lam_L) at the read-out, start time from the adaptive rules (window_rule.py restates ssa_adaptive_burnin = 2) -- against the reference's moment equations
 (oracle/abc_oracle.c, pinned on the reference's golden vectors).  Chain of trust for the product path:
 golden vectors -> moment-ODE oracle -> (z-tests, here) -> telegraph + conditional-Poisson sampler -> (KS, GPU tests) -> kernel."""
 import math
@@ -11,40 +11,24 @@ import pytest
 
 import oracle
 from test_tseg_math_cpu import burnin_cycles
-
-CYCLE, AGES = 20.0, [2.0, 6.0, 10.0, 14.0, 18.0]
-PULSE = [0.25, 0.5, 0.75, 1, 2, 3, 22, 22, 22, 22, 22]          # scripts/abc_simulation.jl:65
-CHASE = [0, 0, 0, 0, 0, 0, 0, 1, 2, 4, 6]
+from window_rule import AGES, CHASE, CYCLE, PULSE, burnin_window, missing_share, rates_of
 
 
-def rates_of(theta, m):
-    """scripts/model.jl:1-22, 30-43: per-step linear rates (kon, koff, alpha, gamma)[5] and lambda"""
-    vary = {3: 0, 4: 2, 5: 3}.get(m, -1)
-    th, k, out = 10.0 ** np.asarray(theta, dtype=np.float64), 0, []
-    for q in range(4):
-        if q == vary:
-            out.append(th[k:k + 5].copy()); k += 5
-        else:
-            out.append(np.full(5, th[k])); k += 1
-    return out[0], out[1], out[2], out[3], min(th[k], 1.0)
-
-
-def segments(theta, m, cond, age, k_pre):
-    """[(len, kon, koff, A0, A1, gam, lam_eff, division_after)] from k_pre cycles before the read-out cycle to the read-out"""
+def segments(theta, m, cond, age, start):
+    """[(len, kon, koff, A0, A1, gam, lam_eff, division_after)] from the start time (hours, 0 = start of the read-out cycle)
+    to the read-out: cuts at every rate step, at label on/off and at the cell divisions"""
     kon, koff, alpha, gam, lam = rates_of(theta, m)
     sc = 0.0 if m == 2 else 1.0
     tl0, tl1 = age - PULSE[cond] - CHASE[cond], age - CHASE[cond]
+    grid = np.arange(math.floor(start / 4.0) + 1, math.ceil(age / 4.0)) * 4.0
+    cuts = sorted({start, age} | {float(g) for g in grid if start < g < age} | {t for t in (tl0, tl1) if start < t < age})
     segs = []
-    for c in range(-k_pre, 1):
-        end = age if c == 0 else CYCLE
-        cuts = sorted({0.0, end} | {s for s in (4.0, 8.0, 12.0, 16.0) if s < end}
-                      | {t - c * CYCLE for t in (tl0, tl1) if 0.0 < t - c * CYCLE < end})
-        for a, b in zip(cuts[:-1], cuts[1:]):
-            s = min(int(a // 4.0), 4)
-            mid = 0.5 * (a + b) + c * CYCLE
-            segs.append([b - a, kon[s], koff[s], alpha[s] * (1 + sc * a / CYCLE), alpha[s] * sc / CYCLE, gam[s],
-                         lam if tl0 <= mid <= tl1 else 0.0, False])
-        segs[-1][7] = c < 0
+    for a, b in zip(cuts[:-1], cuts[1:]):
+        mid = 0.5 * (a + b)
+        xa = a - CYCLE * math.floor(mid / CYCLE)
+        st = min(int((mid - CYCLE * math.floor(mid / CYCLE)) // 4.0), 4)
+        segs.append([b - a, kon[st], koff[st], alpha[st] * (1 + sc * xa / CYCLE), alpha[st] * sc / CYCLE, gam[st],
+                     lam if tl0 <= mid <= tl1 else 0.0, b < age and b == CYCLE * round(b / CYCLE), st])
     return segs
 
 
@@ -53,11 +37,14 @@ def F(x, ln, A0, A1, g):
     return np.exp(-g * (ln - x)) * ((A0 + A1 * x) / g - A1 / g ** 2)
 
 
-def sample_readout(theta, m, cond, age, n_cells, k_pre, rng):
+def sample_readout(theta, m, cond, age, n_cells, start, rng):
+    """start: hours relative to the start of the read-out cycle (-k * 20 for k whole pre-cycles)"""
     kon, koff, *_ = rates_of(theta, m)
-    g = (rng.random(n_cells) < kon[4] / (kon[4] + koff[4])).astype(np.int8)          # stationary start (last step's rates)
+    segs = segments(theta, m, cond, age, start)
+    st0 = segs[0][8] if segs else 0
+    g = (rng.random(n_cells) < kon[st0] / (kon[st0] + koff[st0])).astype(np.int8)    # stationary law of the step it starts in
     lam_u, lam_l = np.zeros(n_cells), np.zeros(n_cells)
-    for ln, kn, kf, A0, A1, gm, lf, div in segments(theta, m, cond, age, k_pre):
+    for ln, kn, kf, A0, A1, gm, lf, div, _ in segs:
         x = np.zeros(n_cells)
         acc = -g * F(0.0, ln, A0, A1, gm)
         live = np.ones(n_cells, dtype=bool)
@@ -91,14 +78,18 @@ CASES = [
 ]
 
 
+@pytest.mark.parametrize("rule", ["window", "cycles"])
 @pytest.mark.parametrize("m,theta,cond,age_i", CASES)
-def test_telegraph_poisson_sampler_matches_the_moment_odes(m, theta, cond, age_i):
+def test_telegraph_poisson_sampler_matches_the_moment_odes(m, theta, cond, age_i, rule):
+    """rule = "window": start time of ssa_adaptive_burnin = 2 (window_rule.burnin_window); "cycles": whole cycles (= 1)"""
     n = 40000
     rng = np.random.default_rng(100 * m + cond)
     kon, koff, _, gam, _ = rates_of(theta, m)
     tl0 = AGES[age_i] - PULSE[cond] - CHASE[cond]
     k_pre = burnin_cycles(list(gam), list(kon), list(koff), m, 10, CYCLE, tl0)
-    u, l = sample_readout(theta, m, cond, AGES[age_i], n, k_pre, rng)
+    start = burnin_window(theta, m, cond, age_i) if rule == "window" else -k_pre * CYCLE
+    assert -10 * CYCLE <= start < AGES[age_i]
+    u, l = sample_readout(theta, m, cond, AGES[age_i], n, start, rng)
     od = oracle.make_design(iv_index=1, downsampling=False, rtol=1e-9)
     mom, _ = oracle.run_part_sim(theta, m, od)
     ref = mom[cond, age_i]                                                # mean_u, mean_l, var_u, cov_ul, var_l
@@ -107,7 +98,7 @@ def test_telegraph_poisson_sampler_matches_the_moment_odes(m, theta, cond, age_i
         p = (xs - xs.mean()) * (ys - ys.mean())
         zs.append((p.sum() / (n - 1) - target) / (p.std(ddof=1) / math.sqrt(n) + 1e-12))
     # burn-in bias bound 2^-10 and the oracle's tolerance are far below the Monte-Carlo error of 40 000 cells
-    assert np.abs(zs).max() < 4.5, (k_pre, zs, ref, u.mean(), l.mean())
+    assert np.abs(zs).max() < 4.5, (rule, start, zs, ref, u.mean(), l.mean())
     assert k_pre <= 10 and ref[0] + ref[1] > 0
 
 
@@ -118,7 +109,16 @@ def test_the_comparison_has_power_a_too_short_burnin_is_detected():
     kon, koff, _, gam, _ = rates_of(theta, m)
     assert burnin_cycles(list(gam), list(kon), list(koff), m, 10, CYCLE, AGES[age_i] - PULSE[cond]) == 4
     n = 40000
-    u, l = sample_readout(theta, m, cond, AGES[age_i], n, 1, np.random.default_rng(5))
+    u, l = sample_readout(theta, m, cond, AGES[age_i], n, -1 * CYCLE, np.random.default_rng(5))
     mom, _ = oracle.run_part_sim(theta, m, oracle.make_design(iv_index=1, downsampling=False, rtol=1e-9))
+    z = (u.mean() - mom[cond, age_i][0]) / (u.std(ddof=1) / math.sqrt(n))
+    assert z < -4.5, z
+    # the start-time rule: the bound holds at its start and is violated 30 h later, which the z-test sees as well
+    start = burnin_window(theta, m, cond, age_i)
+    mu, ku, ml, kl = missing_share(theta, m, cond, age_i, start)
+    assert mu <= 2.0 ** -10 * ku * 1.01 and ml <= max(2.0 ** -10 * kl * 1.01, 2.0 ** -30)
+    mu, ku, _, _ = missing_share(theta, m, cond, age_i, start + 30.0)
+    assert mu > 0.02 * ku
+    u, l = sample_readout(theta, m, cond, AGES[age_i], n, start + 30.0, np.random.default_rng(6))
     z = (u.mean() - mom[cond, age_i][0]) / (u.std(ddof=1) / math.sqrt(n))
     assert z < -4.5, z
