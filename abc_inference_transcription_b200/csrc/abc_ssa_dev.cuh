@@ -108,16 +108,23 @@ __device__ __forceinline__ float pick(int g, float a, float b) {
     return __uint_as_float(__float_as_uint(a) + (uint32_t)g * (__float_as_uint(b) - __float_as_uint(a)));
 }
 
-// Poisson(lam): inversion by sequential search below 12, Hoermann's PTRS (1993) above; the rarely taken
-// exact acceptance test runs in FP64.
+// Poisson(lam): inversion by sequential search below 12 (binary32: the cumulative sum carries ~2^-22 of rounding, i.e. the
+// law is exact to ~1e-6 in total variation), Hoermann's PTRS (1993) above; its rarely taken exact acceptance test runs in FP64.
 static __device__ __noinline__ float poisson_draw(float lam, WordSrc& ws, Lineage& s) {
     if (!(lam > 0.0f)) return 0.0f;
     if (lam < 12.0f) {
-        const double u = ((double)next_word(ws, s) + 0.5) * 2.3283064365386963e-10;
-        double p = exp(-(double)lam), c = p;
-        int k = 0;
-        while (u > c && k < 200) { k += 1; p *= (double)lam / (double)k; c += p; }
-        return (float)k;
+        const float u = f_fma((float)next_word(ws, s), 2.3283064365386963e-10f, 1.1641532182693481e-10f);
+        float p;
+        asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(p) : "f"(f_mul(lam, -1.4426950408889634f)));
+        float c = p, k = 0.0f;
+        while (u > c && k < 96.0f) {
+            k += 1.0f;
+            float rk;
+            asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(rk) : "f"(k));
+            p = f_mul(p, f_mul(lam, rk));
+            c = f_add(c, p);
+        }
+        return k;
     }
     const float slam = sqrtf(lam);
     const float b = 0.931f + 2.53f * slam;

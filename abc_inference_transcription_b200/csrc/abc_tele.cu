@@ -44,35 +44,47 @@ struct __align__(16) TPiece {
 // The cuts of one read-out between a start time s and the read-out t_end (times in hours, 0 = start of the read-out
 // cycle): every multiple of `step` and the label window's ends tl0 < tl1 where they fall strictly inside and off a step.
 struct Cuts {
-    double s, t_end, step, tl0, tl1;
-    long long j_first;      // first multiple of step after s
+    double s, t_end, step, inv_step, tl0, tl1;
+    int j_first;            // first multiple of step after s
     int nb, ins0, ins1, r0, r1, n;   // multiples of step inside, window ends inserted (and their ranks), number of pieces
 };
 
-__device__ __forceinline__ bool on_grid(double t, double step) { return t == step * rint(t / step); }
+// floor(t / step) with the division replaced by a multiplication and two exact fix-ups
+__device__ __forceinline__ int floor_div(double t, double step, double inv_step) {
+    int j = (int)floor(t * inv_step);
+    if ((double)j * step > t) j -= 1;
+    if ((double)(j + 1) * step <= t) j += 1;
+    return j;
+}
+__device__ __forceinline__ int ceil_div(double t, double step, double inv_step) {
+    const int j = floor_div(t, step, inv_step);
+    return ((double)j * step == t) ? j : j + 1;
+}
+__device__ __forceinline__ bool on_grid(double t, double step, double inv_step) {
+    return (double)floor_div(t, step, inv_step) * step == t;
+}
 
-__device__ __forceinline__ Cuts make_cuts(double s, double t_end, double step, double tl0, double tl1, bool window) {
+__device__ __forceinline__ Cuts make_cuts(double s, double t_end, double step, double inv_step, double tl0, double tl1,
+                                          bool window) {
     Cuts c;
-    c.s = s; c.t_end = t_end; c.step = step; c.tl0 = tl0; c.tl1 = tl1;
-    c.j_first = (long long)floor(s / step) + 1;
-    long long j_end = (long long)ceil(t_end / step);          // multiples below t_end: j_first .. j_end - 1
-    c.nb = (int)((j_end > c.j_first) ? (j_end - c.j_first) : 0);
-    c.ins0 = (window && tl0 > s && tl0 < t_end && !on_grid(tl0, step)) ? 1 : 0;
-    c.ins1 = (window && tl1 > s && tl1 < t_end && !on_grid(tl1, step)) ? 1 : 0;
-    auto rank = [&](double t) {                                // multiples of step in (s, t)
-        long long r = (long long)ceil(t / step) - c.j_first;
-        return (int)(r < 0 ? 0 : (r > c.nb ? c.nb : r));
-    };
-    c.r0 = rank(tl0);
-    c.r1 = rank(tl1) + c.ins0;
+    c.s = s; c.t_end = t_end; c.step = step; c.inv_step = inv_step; c.tl0 = tl0; c.tl1 = tl1;
+    c.j_first = floor_div(s, step, inv_step) + 1;
+    const int j_end = ceil_div(t_end, step, inv_step);          // multiples below t_end: j_first .. j_end - 1
+    c.nb = (j_end > c.j_first) ? (j_end - c.j_first) : 0;
+    c.ins0 = (window && tl0 > s && tl0 < t_end && !on_grid(tl0, step, inv_step)) ? 1 : 0;
+    c.ins1 = (window && tl1 > s && tl1 < t_end && !on_grid(tl1, step, inv_step)) ? 1 : 0;
+    const int q0 = ceil_div(tl0, step, inv_step) - c.j_first, q1 = ceil_div(tl1, step, inv_step) - c.j_first;
+    c.r0 = q0 < 0 ? 0 : (q0 > c.nb ? c.nb : q0);                // multiples of step in (s, tl0)
+    c.r1 = (q1 < 0 ? 0 : (q1 > c.nb ? c.nb : q1)) + c.ins0;
     c.n = (t_end > s) ? c.nb + c.ins0 + c.ins1 + 1 : 0;
     return c;
 }
 
-// i-th interior cut, i in [0, n-1); *grid_index = multiple of step it sits on (LLONG_MIN for a window end)
-__device__ __forceinline__ double interior_cut(const Cuts& c, int i, long long* grid_index) {
-    if (c.ins0 && i == c.r0) { *grid_index = (long long)0x8000000000000000ull; return c.tl0; }
-    if (c.ins1 && i == c.r1) { *grid_index = (long long)0x8000000000000000ull; return c.tl1; }
+#define NO_GRID (-0x40000000)
+// i-th interior cut, i in [0, n-1); *grid_index = multiple of step it sits on (NO_GRID for a window end)
+__device__ __forceinline__ double interior_cut(const Cuts& c, int i, int* grid_index) {
+    if (c.ins0 && i == c.r0) { *grid_index = NO_GRID; return c.tl0; }
+    if (c.ins1 && i == c.r1) { *grid_index = NO_GRID; return c.tl1; }
     const int j = i - ((c.ins0 && i > c.r0) ? 1 : 0) - ((c.ins1 && i > c.r1) ? 1 : 0);
     *grid_index = c.j_first + j;
     return (double)(c.j_first + j) * c.step;
@@ -85,24 +97,22 @@ struct PieceDesc {
     bool labelled, div_after, last;
 };
 
-__device__ __forceinline__ PieceDesc describe_piece(const Cuts& c, int k, double cycle, int steps_per_cycle, bool window) {
+// inv_cycle, inv_step5: 1 / cycle, 5 / cycle
+__device__ __forceinline__ PieceDesc describe_piece(const Cuts& c, int k, double cycle, double inv_cycle, double inv_step5,
+                                                    int steps_per_cycle, bool window) {
     PieceDesc d;
-    long long gi = 0, gdummy = 0;
+    int gi = 0, gdummy = 0;
     d.a = (k == 0) ? c.s : interior_cut(c, k - 1, &gdummy);
     d.last = (k == c.n - 1);
     d.b = d.last ? c.t_end : interior_cut(c, k, &gi);
     const double mid = 0.5 * (d.a + d.b);
-    const double cyc0 = cycle * floor(mid / cycle);
-    int st = (int)floor((mid - cyc0) / (cycle / 5.0));
+    const double cyc0 = cycle * (double)floor_div(mid, cycle, inv_cycle);
+    int st = (int)((mid - cyc0) * inv_step5);        // mid lies strictly inside a rate step
     d.step = st < 0 ? 0 : (st > 4 ? 4 : st);
     d.xa = d.a - cyc0;
     d.labelled = window && mid >= c.tl0 && mid <= c.tl1;
     // a division follows when the piece ends on a multiple of the cycle (never the read-out itself: 0 < age < cycle)
-    d.div_after = false;
-    if (!d.last && gi != (long long)0x8000000000000000ull) {
-        long long r = gi % steps_per_cycle;
-        d.div_after = (r == 0);
-    }
+    d.div_after = !d.last && gi != NO_GRID && (steps_per_cycle == 1 || (gi % 5) == 0);
     return d;
 }
 
@@ -121,12 +131,12 @@ __device__ __forceinline__ float tp_F(float k1, float e0, float p0, float p1, fl
     return f_mul(h, x);
 }
 
-__device__ __forceinline__ TPiece make_piece(const AbcRates& r, const PieceDesc& d, double cycle, int scaling, float step_len) {
-    const double sc = scaling ? 1.0 : 0.0;
+// sc_inv_cycle = scaling / cycle (alpha(x) = alpha_step (1 + scaling x / cycle), scripts/model.jl:1-27)
+__device__ __forceinline__ TPiece make_piece(const AbcRates& r, const PieceDesc& d, float sc_inv_cycle, float step_len) {
     const float len = (float)(d.b - d.a);
     const float gam = r.gamma[d.step];
-    const float A0 = (float)((double)r.alpha[d.step] * (1.0 + sc * d.xa / cycle));
-    const float A1 = (float)((double)r.alpha[d.step] * sc / cycle);
+    const float A1 = f_mul(r.alpha[d.step], sc_inv_cycle);
+    const float A0 = f_fma(A1, (float)d.xa, r.alpha[d.step]);
     TPiece t;
     t.len = len;
     t.qon = __fdiv_rn(-0.693147182464599609375f, r.kon[d.step]);
@@ -204,7 +214,7 @@ abc_window_kernel(AbcRates* __restrict__ rates, const AbcSsaParams prm, float* _
     const long long p = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     if (p >= n) return;
     const AbcRates r = rates[p];
-    const double cycle = prm.cycle, step5 = cycle / 5.0;
+    const double cycle = prm.cycle, step5 = cycle / 5.0, inv_cycle = 1.0 / cycle, inv_step5 = 5.0 / cycle;
     const double t_min = -(double)prm.n_pre * cycle;
     const double eps = exp2(-(double)prm.n_pre), floor_abs = 9.313225746154785e-10;   // 2^-30 molecules
     double cost = 0.0;
@@ -225,12 +235,12 @@ abc_window_kernel(AbcRates* __restrict__ rates, const AbcSsaParams prm, float* _
             s0 = -(double)tele_burnin_cycles(r, prm, cond, age_i) * cycle;
         } else if (prm.adaptive >= 2) {
             // mean contribution of the births of every piece to Lam_U and Lam_L at the read-out, newest piece first
-            const Cuts c = make_cuts(t_min, age, step5, tl0, tl1, window);
+            const Cuts c = make_cuts(t_min, age, step5, inv_step5, tl0, tl1, window);
             double cu[WIN_MAX_PIECES], cl[WIN_MAX_PIECES];
             double bits_after = 0.0, TU = 0.0, TL = 0.0;
             const int np = min(c.n, WIN_MAX_PIECES);
             for (int k = np - 1; k >= 0; --k) {
-                const PieceDesc d = describe_piece(c, k, cycle, 5, window);
+                const PieceDesc d = describe_piece(c, k, cycle, inv_cycle, inv_step5, 5, window);
                 if (d.div_after) bits_after += 1.0;
                 const double L = d.b - d.a, gam = (double)r.gamma[d.step];
                 const double al = (double)r.alpha[d.step];
@@ -254,7 +264,7 @@ abc_window_kernel(AbcRates* __restrict__ rates, const AbcSsaParams prm, float* _
                 s0 = age;          // nothing to simulate: every expected count is below 2^-30
             } else {
                 // part of piece j can go as well: bisection on the cut inside it
-                const PieceDesc d = describe_piece(c, j, cycle, 5, window);
+                const PieceDesc d = describe_piece(c, j, cycle, inv_cycle, inv_step5, 5, window);
                 const double L = d.b - d.a, gam = (double)r.gamma[d.step], al = (double)r.alpha[d.step];
                 const double A0 = al * (1.0 + (prm.scaling ? d.xa / cycle : 0.0)), A1 = prm.scaling ? al / cycle : 0.0;
                 const double full = piece_integral(A0, A1, gam, L);
@@ -276,7 +286,7 @@ abc_window_kernel(AbcRates* __restrict__ rates, const AbcSsaParams prm, float* _
                     double need = 6.0, t = s0;
                     int k = j;
                     while (need > 0.0 && t > t_min) {
-                        const PieceDesc q = describe_piece(c, k, cycle, 5, window);
+                        const PieceDesc q = describe_piece(c, k, cycle, inv_cycle, inv_step5, 5, window);
                         const double rate = ((double)r.kon[q.step] + (double)r.koff[q.step]) * 1.4426950408889634;
                         const double avail = (t - q.a) * rate;
                         if (avail >= need) { t -= need / rate; need = 0.0; }
@@ -291,10 +301,10 @@ abc_window_kernel(AbcRates* __restrict__ rates, const AbcSsaParams prm, float* _
         // expected draws of one lineage: switches + one discarded draw per piece
         {
             const double stepc = (prm.m <= 2) ? cycle : step5;
-            const Cuts c = make_cuts((double)(float)s0, age, stepc, tl0, tl1, window);
+            const Cuts c = make_cuts((double)(float)s0, age, stepc, (prm.m <= 2) ? inv_cycle : inv_step5, tl0, tl1, window);
             double lineage = 0.0;
             for (int k = 0; k < c.n; ++k) {
-                const PieceDesc d = describe_piece(c, k, cycle, (prm.m <= 2) ? 1 : 5, window);
+                const PieceDesc d = describe_piece(c, k, cycle, inv_cycle, inv_step5, (prm.m <= 2) ? 1 : 5, window);
                 const double kon = (double)r.kon[d.step], koff = (double)r.koff[d.step];
                 lineage += 2.0 * kon * koff / (kon + koff) * (d.b - d.a) + 1.0;
             }
@@ -328,8 +338,9 @@ abc_tele_kernel(const AbcRates* __restrict__ rates, const AbcSsaParams prm, cons
                                          : (unsigned long long)prm.n_particles * per_particle;
     unsigned long long acc_lineages = 0, acc_events = 0, acc_draws = 0;
     const int steps_per_cycle = (prm.m <= 2) ? 1 : 5;       // models 1, 2: no rate varies, alpha is linear over the whole cycle
-    const double step_cut = prm.cycle / (double)steps_per_cycle;
-    const float step_len = (float)step_cut;
+    const double step_cut = prm.cycle / (double)steps_per_cycle, inv_step_cut = (double)steps_per_cycle / prm.cycle;
+    const double inv_cycle = 1.0 / prm.cycle, inv_step5 = 5.0 / prm.cycle;
+    const float step_len = (float)step_cut, sc_inv_cycle = prm.scaling ? (float)inv_cycle : 0.0f;
 
     for (;;) {
         unsigned int item = 0;
@@ -362,11 +373,11 @@ abc_tele_kernel(const AbcRates* __restrict__ rates, const AbcSsaParams prm, cons
         const double tl0 = age - prm.pulse[cond] - prm.chase[cond], tl1 = age - prm.chase[cond];
         const bool window = prm.pulse[cond] > 0.0;
         const double s0 = (double)win[p * ABC_NREAD + readout];
-        const Cuts cuts = make_cuts(s0, age, step_cut, tl0, tl1, window);
+        const Cuts cuts = make_cuts(s0, age, step_cut, inv_step_cut, tl0, tl1, window);
         const int n_seg = min(cuts.n, TELE_MAX_SEG);
         for (int k = lane; k < n_seg; k += 32) {
-            const PieceDesc d = describe_piece(cuts, k, prm.cycle, steps_per_cycle, window);
-            TPiece t = make_piece(srates[warp], d, prm.cycle, prm.scaling, step_len);
+            const PieceDesc d = describe_piece(cuts, k, prm.cycle, inv_cycle, inv_step5, steps_per_cycle, window);
+            TPiece t = make_piece(srates[warp], d, sc_inv_cycle, step_len);
             if (k == n_seg - 1) t.meta |= TP_LAST;
             tab[k] = t;
         }
@@ -385,7 +396,7 @@ abc_tele_kernel(const AbcRates* __restrict__ rates, const AbcSsaParams prm, cons
         // initial gene state ~ the stationary law of the rate step the lineage starts in (exact for constant kon, koff)
         {
             const double mid0 = (n_seg > 0) ? s0 + 0.5 * (double)tab[0].len : s0;
-            int st = (int)floor((mid0 - prm.cycle * floor(mid0 / prm.cycle)) / (prm.cycle / 5.0));
+            int st = (int)((mid0 - prm.cycle * (double)floor_div(mid0, prm.cycle, inv_cycle)) * inv_step5);
             st = st < 0 ? 0 : (st > 4 ? 4 : st);
             const float kon = srates[warp].kon[st], koff = srates[warp].koff[st];
             const uint4 b = next_block(s);
@@ -507,21 +518,29 @@ abc_tele_kernel(const AbcRates* __restrict__ rates, const AbcSsaParams prm, cons
             }
         }
         if (live) {
+            // Read-out.  U ~ Poisson(Lam_U), L ~ Poisson(Lam_L) given the gene path, then U' ~ Bin(U, beta), L' ~ Bin(L, beta)
+            // with the cell's capture efficiency (scripts/model.jl:221-239).  A binomially thinned Poisson variable is
+            // Poisson again and independent of the part removed, so (U', L') ~ Poisson(beta Lam_U) x Poisson(beta Lam_L)
+            // is drawn directly -- the same joint law without simulating the molecules that are thrown away; the
+            // per-cell debug output also draws the removed part and reports U = U' + U''.
             WordSrc ws; ws.avail = 0;
-            s.U = poisson_draw(lam, ws, s);
-            s.L = poisson_draw(lamL, ws, s);
-            const uint32_t Uc = (uint32_t)s.U, Lc = (uint32_t)s.L;
-            Ud = Uc; Ld = Lc;
+            float beta = 1.0f;
             if (prm.downsampling) {
-                WordSrc w2; w2.avail = 0;
                 const int grp = (cond < 6 ? 0 : ABC_NAGE) + age_i;
                 const uint32_t off = (uint32_t)prm.beta_off[grp];
                 const uint32_t cnt = (uint32_t)prm.beta_off[grp + 1] - off;
-                const uint32_t B = beta_q32[off + __umulhi(next_word(w2, s), cnt)];
-                Ud = binom_q32(Uc, B, w2, s);
-                Ld = binom_q32(Lc, B, w2, s);
+                beta = f_mul((float)beta_q32[off + __umulhi(next_word(ws, s), cnt)], 2.3283064365386963e-10f);
             }
+            const float fu = poisson_draw(f_mul(lam, beta), ws, s);
+            const float fl = poisson_draw(f_mul(lamL, beta), ws, s);
+            Ud = (uint32_t)fu; Ld = (uint32_t)fl;
             if (cells_out != nullptr) {
+                uint32_t Uc = Ud, Lc = Ld;
+                if (prm.downsampling) {
+                    const float rest = f_add(1.0f, -beta);
+                    Uc += (uint32_t)poisson_draw(f_mul(lam, rest), ws, s);
+                    Lc += (uint32_t)poisson_draw(f_mul(lamL, rest), ws, s);
+                }
                 cells_out[0 * prm.n_cells + cell] = Uc;
                 cells_out[1 * prm.n_cells + cell] = Lc;
                 cells_out[2 * prm.n_cells + cell] = Ud;

@@ -624,26 +624,33 @@ def test_ssa_hybrid_high_power(eng, m, cond, age):
         assert abs(z_cov) < 4.5, (z_cov, pa.mean(), pb.mean())
 
 
+@pytest.mark.parametrize("rule", [1, 2])
 @pytest.mark.parametrize("m,theta,cond,age", [
     (1, np.array([1.0, 1.2, 2.0, 0.0, -0.3]), 8, 1),                               # gamma = 1/h: one pre-cycle (two for the chase)
     (4, np.array([0.5, 0.0, 1.0, 1.5, 2.0, 1.5, 1.0, -0.9, -0.2]), 5, 3),          # gamma = 0.126/h: three pre-cycles
     (5, np.array([0.0, 0.5, 2.0, -2.0, -1.0, 0.0, -1.5, -0.5, -0.1]), 2, 0),       # decay steps: sum over the cycle decides
     (3, np.array([1.0, 0.5, 0.0, 1.5, 2.0, 0.7, 1.5, 0.3, -0.4]), 9, 2),           # model 3: gene memory is part of the bound
+    (4, np.array([2.5, 2.2, 2.0, 2.9, 2.4, 2.1, 2.7, 1.3, -0.05]), 6, 0),          # BASELINE configs[4] corner, 22 h pulse, lambda = 0.89
+    (5, np.array([2.1, 2.8, 2.6, 1.0, 1.9, 1.4, 1.1, 1.7, -0.6]), 10, 3),          # corner, decay steps, 6 h chase
+    (2, np.array([-1.0, -0.5, 1.5, -2.5, -0.3]), 3, 4),                            # slow gene, near-immortal mRNA: no shortening possible
 ])
-def test_ssa_adaptive_burnin_keeps_the_bias_bound(eng, m, theta, cond, age):
-    """per-particle burn-in length (ssa_adaptive_burnin = 1, default) against the full n_pre_cycles burn-in: fewer draws,
-    means / variances / covariance of U, L, U', L' within 4.5 standard errors at 262 144 cells (SE ~ 0.2-0.4 %)"""
+def test_ssa_adaptive_burnin_keeps_the_bias_bound(eng, m, theta, cond, age, rule):
+    """ssa_adaptive_burnin = 1 (whole cycles per particle) and = 2 (start time per (particle, read-out), default) against the
+    full n_pre_cycles burn-in: fewer draws, means / variances / covariance of U, L, U', L' within 4.5 standard errors at
+    262 144 cells (SE ~ 0.2-0.4 %)"""
     n = 262144
     with cells_per_readout(eng, n):
-        ada = eng.ssa_cells(m, theta, particle_index=31, cond=cond, age=age, seed=17, exact_math=False).astype(np.float64)
-        ev_ada = eng.counters()["n_events"]
-        eng.set_option("ssa_adaptive_burnin", 0)
+        eng.set_option("ssa_adaptive_burnin", rule)
         try:
+            ada = eng.ssa_cells(m, theta, particle_index=31, cond=cond, age=age, seed=17, exact_math=False).astype(np.float64)
+            ev_ada = eng.counters()["n_draws"]
+            eng.set_option("ssa_adaptive_burnin", 0)
             full = eng.ssa_cells(m, theta, particle_index=32, cond=cond, age=age, seed=17, exact_math=False).astype(np.float64)
-            ev_full = eng.counters()["n_events"]
+            ev_full = eng.counters()["n_draws"]
         finally:
-            eng.set_option("ssa_adaptive_burnin", 1)
-    assert ev_ada < 0.7 * ev_full, (ev_ada, ev_full)
+            eng.set_option("ssa_adaptive_burnin", 2)
+    if m != 2:
+        assert ev_ada < 0.7 * ev_full, (ev_ada, ev_full)
     for a, b in zip(ada, full):
         z_mean = (a.mean() - b.mean()) / np.sqrt(a.var() / n + b.var() / n + 1e-300)
         da, db = (a - a.mean()) ** 2, (b - b.mean()) ** 2
@@ -653,6 +660,60 @@ def test_ssa_adaptive_burnin_keeps_the_bias_bound(eng, m, theta, cond, age):
         pa = (ada[i] - ada[i].mean()) * (ada[j] - ada[j].mean())
         pb = (full[i] - full[i].mean()) * (full[j] - full[j].mean())
         assert abs(pa.mean() - pb.mean()) / np.sqrt(pa.var() / n + pb.var() / n + 1e-300) < 4.5
+
+
+def test_ssa_start_times_match_the_quadrature_restatement(eng):
+    """abc_window_kernel (closed forms per schedule piece + bisection) against tests/window_rule.py (quadrature on a 7 s grid)
+    on prior draws of all five models and all 55 read-outs: same start time, the bias bound 2^-n_pre holds there for the
+    unlabelled and the labelled Poisson mean, and it is tight (starting 2 % of the simulated span + 0.05 h later breaks it)"""
+    import window_rule as wr
+    rng = np.random.default_rng(11)
+    eps = 2.0 ** -10
+    n_checked = n_short = 0
+    for m in range(1, 6):
+        theta = eng.fix_params(m, 6, particle_offset=900 + m, seed=5)
+        theta[0, -1] = 0.0                                  # lambda = 1: no unlabelled births inside the window
+        for th in theta:
+            starts, draws = eng.ssa_window(m, th)
+            assert starts.shape == (11, 5) and draws > 0
+            for cond in range(11):
+                for age_i in rng.choice(5, size=2, replace=False):
+                    s_dev = float(starts[cond, age_i])
+                    age = wr.AGES[age_i]
+                    assert -200.0 <= s_dev <= age
+                    want = wr.burnin_window(th, m, cond, age_i)
+                    span = age - min(s_dev, want)
+                    assert abs(s_dev - want) <= 0.01 + 2e-3 * span, (m, cond, age_i, s_dev, want)
+                    mu, ku, ml, kl = wr.missing_share(th, m, cond, age_i, s_dev)
+                    # resolution of the two methods (grid 0.002 h, bisection 4 h / 4096): the share moves by exp(gamma ds)
+                    slack = 1.02 * np.exp(wr.rates_of(th, m)[3].max() * 0.006)
+                    assert mu <= max(eps * ku, 2.0 ** -30) * slack and ml <= max(eps * kl, 2.0 ** -30) * slack
+                    if s_dev > -200.0 + 1e-3 and m != 3:    # tight (model 3 starts earlier: gene memory)
+                        later = s_dev + 0.02 * (age - s_dev) + 0.05
+                        if later < age:
+                            mu, ku, ml, kl = wr.missing_share(th, m, cond, age_i, later)
+                            assert mu > max(eps * ku, 2.0 ** -30) or ml > max(eps * kl, 2.0 ** -30), (m, cond, age_i, s_dev)
+                        n_short += 1
+                    n_checked += 1
+    assert n_checked == 5 * 6 * 22 and n_short > 100
+
+
+def test_ssa_refuses_absurd_rates_instead_of_hanging(eng):
+    """rates far outside any prior box (10^33 switches per hour) would never finish a lineage: the particle is refused, its
+    statistics are NaN and it is never accepted; its neighbours in the batch are unaffected"""
+    theta = eng.fix_params(1, 4, particle_offset=0, seed=3)
+    want = eng.simulate(1, theta=theta, particle_offset=0, seed=3)[1]
+    bad = theta.copy()
+    bad[2, 0] = 33.0
+    bad[2, 1] = 33.0
+    _, stats, _ = eng.simulate(1, theta=bad, particle_offset=0, seed=3)
+    assert np.isnan(stats[2]).sum() >= 40            # (the sample guards turn the 11 ratios of an empty sample into 0)
+    assert oracle.same_bits(stats[[0, 1, 3]], want[[0, 1, 3]])
+    eng.accept_reset()
+    err, counts, _ = eng.score(stats, eps=4.8, err_layout=ERR_PARTICLE_MAJOR)
+    assert np.isnan(err[2]).all()                    # NaN error: neither clipped nor accepted (compute_errors.jl:62-64)
+    _, idx, _ = eng.accept_fetch()
+    assert 3 not in idx
 
 
 @pytest.mark.parametrize("layout", [ERR_PARTICLE_MAJOR, ERR_GENE_MAJOR, ERR_NONE])
