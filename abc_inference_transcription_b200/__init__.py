@@ -11,10 +11,10 @@ All arithmetic runs in libabcb200.so (hand-written CUDA, sm_100a); there is no C
 from . import _lib
 from ._lib import AbcError, ERR_GENE_MAJOR, ERR_NONE, ERR_PARTICLE_MAJOR, SIM_ODE, SIM_SSA
 from .design import Design, split_betas, synthetic_design
-from .engine import AbcEngine, PinnedArray
+from .engine import AbcEngine, AbcMulti, PinnedArray, comm_unique_id, gene_ranges
 from .model import (CONDITION_ID, ID_LABELS, MODEL_NAMES, get_vary_map, model_name, n_params, prior_bounds,
                     scaling_for, vary_map_for)
 
-__all__ = ["AbcEngine", "PinnedArray", "AbcError", "Design", "synthetic_design", "split_betas", "MODEL_NAMES", "CONDITION_ID",
+__all__ = ["AbcEngine", "AbcMulti", "PinnedArray", "comm_unique_id", "gene_ranges", "AbcError", "Design", "synthetic_design", "split_betas", "MODEL_NAMES", "CONDITION_ID",
            "ID_LABELS", "get_vary_map", "model_name", "n_params", "prior_bounds", "scaling_for", "vary_map_for",
            "ERR_NONE", "ERR_GENE_MAJOR", "ERR_PARTICLE_MAJOR", "SIM_SSA", "SIM_ODE"]

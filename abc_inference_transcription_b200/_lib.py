@@ -90,6 +90,24 @@ SYMBOLS = {
     "abc_set_option": (ctypes.c_int, [_vp, ctypes.c_char_p, ctypes.c_int64]),
     "abc_counters": (ctypes.c_int, [_vp, ctypes.POINTER(AbcCounters)]),
     "abc_launch_count": (ctypes.c_int64, [_vp]),
+    "abc_multi_create": (ctypes.c_int, [_vp, ctypes.c_int32, ctypes.POINTER(_vp)]),
+    "abc_multi_destroy": (ctypes.c_int, [_vp]),
+    "abc_multi_n_devices": (ctypes.c_int, [_vp]),
+    "abc_multi_ctx": (_vp, [_vp, ctypes.c_int32]),
+    "abc_multi_set_design": (ctypes.c_int, [_vp, ctypes.POINTER(AbcDesign)]),
+    "abc_multi_set_data": (ctypes.c_int, [_vp, _vp, _vp, ctypes.c_int32]),
+    "abc_multi_set_option": (ctypes.c_int, [_vp, ctypes.c_char_p, ctypes.c_int64]),
+    "abc_multi_simulate_score": (ctypes.c_int, [_vp, ctypes.c_int, ctypes.c_int64, ctypes.c_int64, ctypes.c_uint64, ctypes.c_int,
+                                                _vp, _vp, ctypes.c_double, ctypes.c_int, _vp, _vp, ctypes.POINTER(AbcCounters)]),
+    "abc_multi_accept_reset": (ctypes.c_int, [_vp]),
+    "abc_multi_accept_total": (ctypes.c_int64, [_vp]),
+    "abc_multi_accept_fetch": (ctypes.c_int, [_vp, _vp, _vp, _vp]),
+    "abc_comm_unique_id": (ctypes.c_int, [_vp, ctypes.c_size_t]),
+    "abc_comm_init_rank": (ctypes.c_int, [_vp, _vp, ctypes.c_size_t, ctypes.c_int32, ctypes.c_int32]),
+    "abc_comm_rank": (ctypes.c_int, [_vp, c_int32_p, c_int32_p]),
+    "abc_comm_counts": (ctypes.c_int, [_vp, _vp]),
+    "abc_comm_accept_fetch": (ctypes.c_int, [_vp, ctypes.c_int32, _vp, _vp, _vp, _vp]),
+    "abc_gene_ranges": (ctypes.c_int, [_vp, ctypes.c_int32, ctypes.c_int32, _vp]),
 }
 
 _lib = None

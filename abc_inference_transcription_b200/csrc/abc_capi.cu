@@ -10,10 +10,9 @@
 #include <utility>
 #include <vector>
 
-#include "abc_common.cuh"
-#include "abc_internal.h"
+#include "abc_ctx.h"
 
-#define ABC_VERSION 100
+#define ABC_VERSION 200
 
 static thread_local char g_err[1024] = "";
 
@@ -39,135 +38,6 @@ extern "C" const char* abc_model_name(int m) {
     static const char* names[5] = {"const", "const_const", "kon", "alpha", "gamma"};
     return (m >= 1 && m <= 5) ? names[m - 1] : nullptr;
 }
-
-// owning device buffer: freed with its owner (a context member or a local of an entry point, whatever the exit path)
-template <typename T>
-struct DevBuf {
-    T* p = nullptr;
-    size_t cap = 0;
-    DevBuf() = default;
-    DevBuf(const DevBuf&) = delete;
-    DevBuf& operator=(const DevBuf&) = delete;
-    DevBuf(DevBuf&& o) noexcept : p(o.p), cap(o.cap) { o.p = nullptr; o.cap = 0; }
-    DevBuf& operator=(DevBuf&& o) noexcept {
-        if (this != &o) { release(); p = o.p; cap = o.cap; o.p = nullptr; o.cap = 0; }
-        return *this;
-    }
-    ~DevBuf() { release(); }
-    int ensure(size_t n) {
-        if (n <= cap) return ABC_OK;
-        if (p) cudaFree(p);
-        p = nullptr; cap = 0;
-        cudaError_t e = cudaMalloc((void**)&p, n * sizeof(T));
-        if (e != cudaSuccess) {
-            abc_set_error("cudaMalloc(%zu bytes) failed: %s", n * sizeof(T), cudaGetErrorString(e));
-            cudaGetLastError();
-            return ABC_ERR_NOMEM;
-        }
-        cap = n;
-        return ABC_OK;
-    }
-    void release() { if (p) { cudaFree(p); p = nullptr; } cap = 0; }
-};
-
-struct abc_ctx {
-    int device = 0, sm_count = 0;
-    cudaStream_t stream = nullptr;
-    cudaEvent_t ev[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
-    // design
-    bool has_design = false;
-    abc_design_t design;
-    std::vector<uint32_t> beta_q32;
-    int32_t beta_off[11];
-    double beta_mean[10], beta_m2[10], beta_var[10];
-    DevBuf<uint32_t> d_beta;
-    DevBuf<double> d_age_dist;
-    DevBuf<double> d_beta_mom;   // [30]: mean, m2, var for the 10 groups
-    // data statistics
-    bool has_data = false;
-    int32_t G = 0;
-    DevBuf<double> d_d, d_den;
-    DevBuf<float2> d_fbw, d_fa;
-    DevBuf<float> d_fstats;
-    DevBuf<unsigned char> d_rnan;
-    int force_reference_score = 0;
-    int score_tile_kernel = 1;   // 1: tile-pruned scoring (abc_score3.cu); 0: three-stage kernel of abc_score.cu
-    // tile-pruned scoring tables (per data set) and work buffers
-    int32_t s3_ntiles = 0;
-    DevBuf<float4> d_s3_tb, d_s3_ab;
-    DevBuf<uint32_t> d_s3_wt;
-    DevBuf<int32_t> d_s3_gidx;
-    DevBuf<uint32_t> d_s3_ok;
-    // two lanes of work buffers: sub-batches alternate between two internal streams so that the filter kernel of one
-    // (FP32 pipe + bulk stores) overlaps the stage-3 kernel of the other (FP64 pipe + shared memory)
-    DevBuf<uint32_t> d_s3_live[2], d_s3_nanw[2], d_s3_qcnt[2];
-    DevBuf<uint16_t> d_s3_q2[2];
-    DevBuf<float> d_s3_fstats[2];
-    cudaStream_t s3_stream[2] = {nullptr, nullptr};
-    cudaEvent_t s3_ev_begin = nullptr, s3_ev_end[2] = {nullptr, nullptr};
-    int score_overlap = 1;
-    int score_sub_batches = 0;   // sub-batches per call when overlapping; 0 = 2 below 256k particles, else 4
-    int stats_guards = -1;       // -1: sample guards iff sim_kind == SSA; 0 / 1 force
-    int ssa_hybrid = 2;          // exact telegraph + conditional-Poisson sampling: 1 = burn-in only, 2 = to the read-out
-    int ssa_adaptive = 2;        // burn-in from the decay of the discarded history: 1 = whole cycles per particle (modes 1, 2),
-                                 // 2 = start time per (particle, read-out) from the exact mean contributions (mode 2; mode 1 uses 1)
-    int64_t simscore_sub_min = 8192;   // abc_simulate_score: smallest sub-batch worth pipelining
-    // simulate work buffers
-    DevBuf<double> d_theta, d_stats, d_moments, d_ss_iv, d_prefix;
-    DevBuf<AbcRates> d_rates;
-    DevBuf<float> d_win;         // mode 2: start time of every (particle, read-out)
-    DevBuf<unsigned long long> d_sums, d_counters;
-    DevBuf<unsigned int> d_work;
-    DevBuf<uint32_t> d_cells;
-    DevBuf<unsigned int> d_keys_in, d_keys_out;
-    DevBuf<int> d_idx_in, d_order;
-    DevBuf<unsigned char> d_sort_tmp;
-    // score work buffers
-    DevBuf<double> d_sstats, d_err;
-    // abc_simulate_score: two sets of output buffers, the copy stream that drains them, per-set events and a page-locked
-    // landing zone for the per-sub-batch device counters
-    DevBuf<double> d_p_theta[2], d_p_stats[2], d_p_err[2];
-    cudaStream_t copy_stream = nullptr;
-    cudaEvent_t p_done[2] = {nullptr, nullptr}, p_copied[2] = {nullptr, nullptr}, p_t0[2] = {nullptr, nullptr},
-                p_t1[2] = {nullptr, nullptr}, p_t2[2] = {nullptr, nullptr};
-    unsigned long long* h_p_counters = nullptr;      // [2][8]
-    DevBuf<unsigned long long> d_counts, d_acc_count;
-    DevBuf<int32_t> d_acc_gene;
-    DevBuf<long long> d_acc_particle;
-    DevBuf<double> d_acc_err;
-    // abc_accept_fetch: work buffers of the device sort (abc_accept.cu)
-    DevBuf<unsigned long long> d_as_k64[2];
-    DevBuf<uint32_t> d_as_k32[2], d_as_perm[2];
-    DevBuf<long long> d_as_idx;
-    DevBuf<double> d_as_err;
-    DevBuf<unsigned char> d_as_tmp;
-    int64_t acc_capacity = 0, acc_budget = 0, acc_min_capacity = 0;
-    int64_t launches = 0;
-    abc_counters_t last;
-    // the *_dev entry points enqueue on the caller's stream: an event recorded there after every such call orders the
-    // accept_* / posterior entry points (which read d_acc_count / d_counts on the host) behind that work
-    cudaEvent_t ev_user = nullptr;
-    bool user_pending = false;
-};
-
-// all work this context has enqueued -- on its own stream and on caller streams of the *_dev entry points -- is complete
-static int sync_ctx(abc_ctx* c) {
-    ABC_CUDA_CHECK(cudaStreamSynchronize(c->stream));
-    if (c->user_pending) {
-        ABC_CUDA_CHECK(cudaEventSynchronize(c->ev_user));
-        c->user_pending = false;
-    }
-    return ABC_OK;
-}
-static int mark_user_stream(abc_ctx* c, cudaStream_t st) {
-    ABC_CUDA_CHECK(cudaEventRecord(c->ev_user, st));
-    c->user_pending = true;
-    return ABC_OK;
-}
-
-#define CTX_GUARD(ctx)                                                       \
-    if (!(ctx)) { abc_set_error("null context"); return ABC_ERR_ARG; }       \
-    ABC_CUDA_CHECK(cudaSetDevice((ctx)->device))
 
 extern "C" int abc_create(int device, abc_ctx_t** out) {
     if (!out) { abc_set_error("abc_create: out is NULL"); return ABC_ERR_ARG; }
@@ -221,6 +91,7 @@ extern "C" int abc_destroy(abc_ctx_t* c) {
     cudaSetDevice(c->device);
     cudaStreamSynchronize(c->stream);
     if (c->user_pending) cudaEventSynchronize(c->ev_user);
+    abc_comm_free(c);
     c->d_beta.release(); c->d_age_dist.release(); c->d_beta_mom.release(); c->d_d.release(); c->d_den.release(); c->d_fbw.release(); c->d_fa.release(); c->d_fstats.release(); c->d_rnan.release();
     c->d_s3_tb.release(); c->d_s3_ab.release(); c->d_s3_wt.release();
     c->d_s3_gidx.release(); c->d_s3_ok.release(); for (int l = 0; l < 2; ++l) { c->d_s3_live[l].release(); c->d_s3_nanw[l].release(); c->d_s3_qcnt[l].release(); c->d_s3_q2[l].release(); c->d_s3_fstats[l].release(); }
@@ -872,6 +743,14 @@ extern "C" int abc_score(abc_ctx_t* c, const double* stats, int64_t n, int64_t o
 extern "C" int abc_simulate_score(abc_ctx_t* c, int m, int64_t n, int64_t offset, uint64_t seed, int prior_supplied,
                                   double* theta, double* stats, double eps, int layout, double* err, int64_t* counts,
                                   abc_counters_t* counters) {
+    return abc_simulate_score_impl(c, m, n, offset, seed, prior_supplied, theta, stats, eps, layout, err, n, counts, counters);
+}
+
+// gm_pitch: doubles between consecutive gene rows of a gene-major `err` (n for a stand-alone call; the whole batch when this
+// context computes one shard of a multi-GPU call)
+int abc_simulate_score_impl(abc_ctx* c, int m, int64_t n, int64_t offset, uint64_t seed, int prior_supplied, double* theta,
+                            double* stats, double eps, int layout, double* err, int64_t gm_pitch, int64_t* counts,
+                            abc_counters_t* counters) {
     CTX_GUARD(c);
     int rc = check_model(m);
     if (rc != ABC_OK) return rc;
@@ -931,7 +810,7 @@ extern "C" int abc_simulate_score(abc_ctx_t* c, int m, int64_t n, int64_t offset
         if (layout == ABC_ERR_PARTICLE_MAJOR) {
             ABC_CUDA_CHECK(cudaMemcpyAsync(err + b0 * G, c->d_p_err[l].p, (size_t)nb * G * sizeof(double), cudaMemcpyDeviceToHost, c->copy_stream));
         } else if (layout == ABC_ERR_GENE_MAJOR) {
-            ABC_CUDA_CHECK(cudaMemcpy2DAsync(err + b0, (size_t)n * sizeof(double), c->d_p_err[l].p, (size_t)nb * sizeof(double),
+            ABC_CUDA_CHECK(cudaMemcpy2DAsync(err + b0, (size_t)gm_pitch * sizeof(double), c->d_p_err[l].p, (size_t)nb * sizeof(double),
                                              (size_t)nb * sizeof(double), (size_t)G, cudaMemcpyDeviceToHost, c->copy_stream));
         }
         ABC_CUDA_CHECK(cudaEventRecord(c->p_copied[l], c->copy_stream));
@@ -1005,7 +884,7 @@ extern "C" int abc_accept_tuples(abc_ctx_t* c, int32_t* gene, int64_t* particle,
 // offsets[G+1] (host) from the per-gene counts, and -- if want_lists -- the per-gene ordered lists in c->d_as_idx / c->d_as_err:
 // ascending error, ties by ascending particle index == v[sortperm(err[v])] (stable), three stable radix passes on the device
 // (abc_accept.cu).  Work is enqueued on c->stream; the caller synchronises.
-static int build_accepted_lists(abc_ctx* c, int64_t* offsets, unsigned long long* total_out, bool want_lists) {
+int abc_build_accepted_lists(abc_ctx* c, int64_t* offsets, unsigned long long* total_out, bool want_lists) {
     int rcs = sync_ctx(c);
     if (rcs != ABC_OK) return rcs;
     unsigned long long total = 0;
@@ -1045,7 +924,7 @@ extern "C" int abc_accept_fetch(abc_ctx_t* c, int64_t* offsets, int64_t* idx, do
     CTX_GUARD(c);
     if (!c->has_data || !offsets) { abc_set_error("abc_accept_fetch: bad state/arguments"); return ABC_ERR_ARG; }
     unsigned long long total = 0;
-    int rc = build_accepted_lists(c, offsets, &total, idx || errs);
+    int rc = abc_build_accepted_lists(c, offsets, &total, idx || errs);
     if (rc != ABC_OK) return rc;
     if (total == 0 || (!idx && !errs)) return ABC_OK;
     if (idx) ABC_CUDA_CHECK(cudaMemcpyAsync(idx, c->d_as_idx.p, (size_t)total * sizeof(long long), cudaMemcpyDeviceToHost, c->stream));
@@ -1063,7 +942,7 @@ extern "C" int abc_posterior_summary(abc_ctx_t* c, const double* theta, int64_t 
     const int G = c->G;
     std::vector<int64_t> offsets((size_t)G + 1);
     unsigned long long total = 0;
-    int rc = build_accepted_lists(c, offsets.data(), &total, true);
+    int rc = abc_build_accepted_lists(c, offsets.data(), &total, true);
     if (rc != ABC_OK) return rc;
     if (n_acc) for (int g = 0; g < G; ++g) n_acc[g] = offsets[g + 1] - offsets[g];
     DevBuf<long long> d_off;
@@ -1179,8 +1058,9 @@ extern "C" int abc_set_option(abc_ctx_t* c, const char* name, int64_t value) {
 extern "C" int abc_counters(abc_ctx_t* c, abc_counters_t* out) {
     CTX_GUARD(c);
     if (!out) { abc_set_error("abc_counters: out is NULL"); return ABC_ERR_ARG; }
-    ABC_CUDA_CHECK(cudaDeviceSynchronize());
-    int rc = read_counters(c, 0, nullptr, false);
+    int rc = sync_ctx(c);          // this context's own work only (not other streams of the process, e.g. a collective in flight)
+    if (rc != ABC_OK) return rc;
+    rc = read_counters(c, 0, nullptr, false);
     if (rc != ABC_OK) return rc;
     float ms = 0.f;
     if (cudaEventElapsedTime(&ms, c->ev[3], c->ev[4]) == cudaSuccess) c->last.ms_score = ms; else cudaGetLastError();

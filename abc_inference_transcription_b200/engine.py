@@ -263,3 +263,140 @@ class AbcEngine:
 
     def launch_count(self):
         return int(self._lib.abc_launch_count(self._ctx))
+
+
+    # ---- one process per GPU: NCCL communicator owned by the library (abc_comm_*) ---------------------------------
+    def comm_init(self, unique_id, n_ranks, rank):
+        """attach this context to a communicator of n_ranks processes; unique_id: the 128 bytes rank 0 obtained from
+        comm_unique_id() and the host distributed (torch.distributed / MPI / a file)"""
+        buf = (ctypes.c_char * 128).from_buffer_copy(bytes(unique_id).ljust(128, b"\0")[:128])
+        _lib.check(self._lib.abc_comm_init_rank(self._ctx, buf, 128, int(n_ranks), int(rank)))
+
+    def comm_counts(self):
+        """per-gene acceptance counts summed over the ranks (NCCL all-reduce)"""
+        counts = np.zeros(self.n_genes, dtype=np.int64)
+        _lib.check(self._lib.abc_comm_counts(self._ctx, _lib.ptr(counts)))
+        return counts
+
+    def comm_accept_fetch(self, root=0, total_hint=None):
+        """collective: gene-range exchange + per-range ordering on every rank.  Returns (offsets, idx, errs, gene_range);
+        idx / errs are complete on `root` (None elsewhere); root < 0: every rank gets its own gene range filled in."""
+        offsets = np.zeros(self.n_genes + 1, dtype=np.int64)
+        grange = np.zeros(2, dtype=np.int64)
+        n_ranks, rank = ctypes.c_int32(), ctypes.c_int32()
+        _lib.check(self._lib.abc_comm_rank(self._ctx, ctypes.byref(n_ranks), ctypes.byref(rank)))
+        total = int(self.comm_counts().sum())
+        want = root < 0 or rank.value == root
+        idx = np.zeros(total, dtype=np.int64) if want else None
+        errs = np.zeros(total, dtype=np.float64) if want else None
+        _lib.check(self._lib.abc_comm_accept_fetch(self._ctx, int(root), _lib.ptr(offsets), _lib.ptr(idx), _lib.ptr(errs),
+                                                   _lib.ptr(grange)))
+        return offsets, idx, errs, (int(grange[0]), int(grange[1]))
+
+
+def comm_unique_id():
+    """128-byte NCCL unique id (rank 0 calls this, the host distributes it)"""
+    buf = ctypes.create_string_buffer(128)
+    _lib.check(_lib.load().abc_comm_unique_id(buf, 128))
+    return buf.raw
+
+
+def gene_ranges(counts, n_ranks):
+    """the exchange's cut: n_ranks contiguous gene ranges of equal accepted-tuple mass -> bounds (n_ranks + 1,)"""
+    counts = np.ascontiguousarray(counts, dtype=np.int64)
+    bounds = np.zeros(int(n_ranks) + 1, dtype=np.int64)
+    _lib.check(_lib.load().abc_gene_ranges(_lib.ptr(counts), len(counts), int(n_ranks), _lib.ptr(bounds)))
+    return bounds
+
+
+class AbcMulti:
+    """All GPUs of one box behind one handle in ONE host process (abc_multi_*): what the Julia host calls.  The library
+    runs one context and one host thread per device and owns the NCCL communicators."""
+
+    def __init__(self, devices=None, n_dev=None):
+        self._lib = _lib.load()
+        self._mg = ctypes.c_void_p()
+        if devices is None:
+            n = int(n_dev if n_dev is not None else self._lib.abc_device_count())
+            _lib.check(self._lib.abc_multi_create(None, n, ctypes.byref(self._mg)))
+        else:
+            dv = np.ascontiguousarray(devices, dtype=np.int32)
+            _lib.check(self._lib.abc_multi_create(_lib.ptr(dv), len(dv), ctypes.byref(self._mg)))
+        self.n_devices = int(self._lib.abc_multi_n_devices(self._mg))
+        self.design, self.n_genes = None, 0
+
+    def close(self):
+        if getattr(self, "_mg", None) is not None and self._mg:
+            self._lib.abc_multi_destroy(self._mg)
+            self._mg = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        self.close()
+
+    def set_design(self, design: Design):
+        cd, keep = design.to_c()
+        _lib.check(self._lib.abc_multi_set_design(self._mg, ctypes.byref(cd)))
+        del keep
+        self.design = design
+
+    def set_data(self, d, se):
+        d = np.ascontiguousarray(d, dtype=np.float64)
+        se = np.ascontiguousarray(se, dtype=np.float64)
+        assert d.ndim == 2 and d.shape[1] == _lib.NSTATS and d.shape == se.shape
+        _lib.check(self._lib.abc_multi_set_data(self._mg, _lib.ptr(d), _lib.ptr(se), d.shape[0]))
+        self.n_genes = d.shape[0]
+
+    def set_option(self, name, value):
+        _lib.check(self._lib.abc_multi_set_option(self._mg, name.encode(), int(value)))
+
+    def accept_reset(self):
+        _lib.check(self._lib.abc_multi_accept_reset(self._mg))
+
+    def accept_total(self):
+        t = self._lib.abc_multi_accept_total(self._mg)
+        if t < 0:
+            raise _lib.AbcError("abc_multi_accept_total failed")
+        return int(t)
+
+    def simulate_score(self, m, n_trials=None, theta=None, particle_offset=0, seed=20240229, eps=4.8,
+                       err_layout=_lib.ERR_PARTICLE_MAJOR, want_counts=True, out=None, theta_out=None, stats_out=None):
+        """AbcEngine.simulate_score sharded over the devices: the same arguments, the same results"""
+        P = n_params(_check_m(m))
+        if theta is None:
+            n = int(n_trials)
+            theta = theta_out if theta_out is not None else np.empty((n, P), dtype=np.float64)
+            supplied = 0
+        else:
+            theta = np.ascontiguousarray(theta, dtype=np.float64).reshape(-1, P)
+            n = theta.shape[0]
+            supplied = 1
+        stats = stats_out if stats_out is not None else np.empty((n, _lib.NSTATS), dtype=np.float64)
+        G = self.n_genes
+        shape = (n, G) if err_layout == _lib.ERR_PARTICLE_MAJOR else (G, n) if err_layout == _lib.ERR_GENE_MAJOR else None
+        err = None
+        if shape is not None:
+            err = out if out is not None else np.empty(shape, dtype=np.float64)
+            assert err.shape == shape and err.dtype == np.float64 and err.flags["C_CONTIGUOUS"]
+        counts = np.zeros(G, dtype=np.int64) if want_counts else None
+        cnt = _lib.AbcCounters()
+        _lib.check(self._lib.abc_multi_simulate_score(self._mg, m, n, int(particle_offset), int(seed), supplied, _lib.ptr(theta),
+                                                      _lib.ptr(stats), float(eps), int(err_layout), _lib.ptr(err),
+                                                      _lib.ptr(counts), ctypes.byref(cnt)))
+        return theta, stats, err, counts, cnt.as_dict()
+
+    def accept_fetch(self):
+        total = self.accept_total()
+        offsets = np.zeros(self.n_genes + 1, dtype=np.int64)
+        idx = np.empty(total, dtype=np.int64)
+        errs = np.empty(total, dtype=np.float64)
+        _lib.check(self._lib.abc_multi_accept_fetch(self._mg, _lib.ptr(offsets), _lib.ptr(idx), _lib.ptr(errs)))
+        return offsets, idx, errs

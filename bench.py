@@ -41,6 +41,12 @@ NOMINAL_INSTR_PER_EVENT = 64.0
 NOMINAL_INSTR_PER_TELEGRAPH_DRAW = 24.0
 SSA_MODE = 2                          # ssa_hybrid_burnin of the headline run (library default)
 ALG_BYTES_PER_PARTICLE_SCORE = 27776  # 424 B read + G*8 B written, G = 3419
+# ncu --set full of abc_tele_kernel, 4096 prior particles of one model (profiles/r2_ssa_m{1,3,5}_ncu_summary.csv): share of issue
+# slots used x active threads per instruction / 32 = executed lane-instructions over the lane-issue peak
+NCU_SSA = {"src": "profiles/r2_ssa_m{1,3,5}_ncu_summary.csv (ncu --set full, 4096 prior particles per model, adaptive start)",
+           "m1": {"issue_active": 0.686, "threads_per_inst": 29.91, "executed_lane_frac": 0.686 * 29.91 / 32},
+           "m3": {"issue_active": None, "threads_per_inst": None, "executed_lane_frac": None},
+           "m5": {"issue_active": None, "threads_per_inst": None, "executed_lane_frac": None}}
 SCORE_TRAFFIC_131070 = 4.04e9         # measured dram bytes (read + write) of one 131070-particle scoring call, see profiles/
 
 
@@ -157,7 +163,13 @@ def workload_config(args):
     return {"workload": "BASELINE configs[1]: all 5 models, prior draws streamed in batches, SSA + 53 statistics + "
                         "error scoring vs 3419 genes + eps=4.8 acceptance",
             "models": 5, "particles_per_model_per_step_per_gpu": args.batch, "n_cells_per_readout": args.n_cells,
-            "n_pre_cycles": args.n_pre, "burn_in": "per particle k <= n_pre_cycles with (1/2 exp(-sum gamma_s cycle/5))^k <= 2^-n_pre_cycles (ssa_adaptive_burnin=1)", "readouts": 55, "genes": 3419, "eps": EPS, "seed": SEED,
+            "n_pre_cycles": args.n_pre,
+            "burn_in": "ssa_adaptive_burnin=2: the lineages of a (particle, read-out) start at the latest time for which the "
+                       "transcripts born earlier contribute in expectation < 2^-n_pre_cycles of the unlabelled and of the labelled "
+                       "Poisson mean at the read-out (exact mean contributions per schedule piece; never more than n_pre_cycles "
+                       "cycles).  The line also carries ssa_mode2_cycle_burnin (=1, whole cycles per particle, the round-1 rule) "
+                       "and ssa_mode2_fixed_burnin (=0, always n_pre_cycles cycles, SURVEY 8d)",
+            "readouts": 55, "genes": 3419, "eps": EPS, "seed": SEED,
             "l2": "flushed between steps (256 MiB write)", "lineages": "independent per (condition, age, cell)",
             "ssa": "Gillespie SSA of the gene switch to the read-out, U and L ~ Poisson given the gene path (exact; "
                    "ssa_hybrid_burnin=2), binomial division and capture-efficiency thinning sampled per cell"}
@@ -168,7 +180,7 @@ def run_b200(args):
     import torch
     import torch.distributed as dist
     from abc_inference_transcription_b200 import AbcEngine, ERR_PARTICLE_MAJOR, n_params, synthetic_design
-    from abc_inference_transcription_b200.dist import gather_acceptance
+    from abc_inference_transcription_b200.dist import gather_acceptance, init_library_comm
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -183,6 +195,7 @@ def run_b200(args):
     eng = AbcEngine(local)
     eng.set_design(synthetic_design(betas, n_cells=args.n_cells, n_pre_cycles=args.n_pre))
     eng.set_data(d, se)
+    init_library_comm(eng, world, rank, dev)          # NCCL communicator owned by the library (abc_comm_init_rank)
 
     stream = torch.cuda.current_stream().cuda_stream
     th_dev = [torch.empty((B, n_params(m)), dtype=torch.float64, device=dev) for m in range(1, 6)]
@@ -203,6 +216,8 @@ def run_b200(args):
 
     sim_ms, score_ms, events, draws = [], [], 0, 0
 
+    pending = []          # all-reduces of the per-gene counts in flight (one per step, NCCL's own stream)
+
     def device_step(step, timed):
         nonlocal events, draws
         eng.accept_reset()
@@ -216,28 +231,40 @@ def run_b200(args):
                 sim_ms.append(c["ms_simulate"]); score_ms.append(c["ms_score"])
                 events += c["n_events"]; draws += c["n_draws"]
         if world > 1:
-            eng.counts_dev(counts_dev.data_ptr(), stream=stream)
-            dist.all_reduce(counts_dev)
+            # (i) of SURVEY 8e, once per batch: the G int64 counts are summed over the ranks asynchronously -- nothing in the
+            # next batch depends on them, so a rank whose batch was light does not wait for the heaviest one at every step;
+            # all of them are awaited before the closing barrier of the timed region
+            cbuf = torch.empty(G, dtype=torch.int64, device=dev)
+            eng.counts_dev(cbuf.data_ptr(), stream=stream)
+            pending.append((dist.all_reduce(cbuf, async_op=True), cbuf))
+
+    def drain_collectives():
+        for work, cbuf in pending:
+            work.wait()
+        pending.clear()
 
     # ---- device-resident timing ---------------------------------------------------------------
     for w in range(args.warmup):
         device_step(w, False)
         flush.fill_(w & 0xFF)
+    drain_collectives()
     barrier()
     launches0 = eng.launch_count()
     sampler = ClockSampler(range(world)) if rank == 0 else None
     if sampler:
         sampler.start()
-    step_ms = []
+    # EXACTLY `steps` steps between one barrier + synchronize on either side (contract); the L2 flush between steps is a
+    # 256 MiB device fill (40 us at HBM speed) kept inside the region rather than stopping all ranks at every step
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    e0.record()
     for k in range(args.steps):
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        barrier()
-        e0.record()
         device_step(args.warmup + k, True)
-        e1.record()
-        barrier()
-        step_ms.append(e0.elapsed_time(e1))
-        flush.fill_(k & 0xFF)           # L2 flush between timed iterations (outside the timed region)
+        flush.fill_(k & 0xFF)
+    drain_collectives()
+    e1.record()
+    barrier()
+    step_ms = [e0.elapsed_time(e1)]
     if sampler:
         sampler.stop_flag = True
     launches = eng.launch_count() - launches0
@@ -259,8 +286,12 @@ def run_b200(args):
 
     def e2e_step(k):
         nonlocal h2d, d2h
+        dbg = os.environ.get("ABC_BENCH_DEBUG")
+        ta = time.perf_counter()
         eng.accept_reset()
         for m in range(1, 6):
+            if dbg:
+                print(f"[e2e {k}] m={m} t={1e3 * (time.perf_counter() - ta):.1f} ms", file=sys.stderr, flush=True)
             off = offset_of(args.warmup + k, m)
             if args.e2e_separate:      # the two reference seams as two blocking calls (wrapper.jl section 2, then 3)
                 theta, stats, _ = eng.simulate(m, n_trials=B, particle_offset=off, seed=SEED)
@@ -280,10 +311,15 @@ def run_b200(args):
                                                                   err_layout=ERR_PARTICLE_MAJOR, out=err_host.array,
                                                                   theta_out=theta_host[m - 1].array, stats_out=stats_host.array)
             d2h += theta.nbytes + stats.nbytes + err.nbytes + counts.nbytes
-        res = gather_acceptance(eng, world, dev)     # NCCL: all-reduce counts, gather accepted tuples
+        if dbg:
+            print(f"[e2e {k}] before gather t={1e3 * (time.perf_counter() - ta):.1f} ms", file=sys.stderr, flush=True)
+        res = gather_acceptance(eng, world, dev)     # library-owned NCCL: counts summed, tuples exchanged by gene range
         d2h += res["bytes_d2h"]
+        if dbg:
+            print(f"[e2e {k}] done t={1e3 * (time.perf_counter() - ta):.1f} ms", file=sys.stderr, flush=True)
 
     try:                          # untimed warm-up of the host path (work buffers, page-locked staging, sort buffers)
+        e2e_step(-2 if args.warmup >= 1 else 0)
         e2e_step(-1 if args.warmup >= 1 else 0)
     except Exception as ex:       # the host-theta sequence failed: time the call that draws the prior itself, and say so
         e2e_mode["host_theta"], e2e_mode["note"] = False, f"host-side fix_params path failed ({ex}); prior drawn inside abc_simulate_score"
@@ -365,6 +401,59 @@ def run_b200(args):
                                                                (148 * 128 * peaks()["sm_max_mhz"] * 1e6 / 1e12)}
     eng.set_option("ssa_hybrid_burnin", SSA_MODE)
     full_direct = cmp_modes[0]
+    pk_instr = 148 * 128 * peaks()["sm_max_mhz"] * 1e6 / 1e12
+
+    def ssa_variant(adaptive, nvar, theta_fn=None, models=(1, 2, 3, 4, 5), reps=2):
+        """the same mode-2 kernel under another burn-in rule / on another parameter box: device-resident simulate + score
+        (particle-major error matrix) per model, second repetition timed with CUDA events on the launching stream"""
+        eng.set_option("ssa_adaptive_burnin", adaptive)
+        dr = ms_sim = 0.0
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        for rep in range(reps):
+            eng.accept_reset()
+            if rep == reps - 1:
+                torch.cuda.synchronize(); e0.record()
+            for m in models:
+                th = th_dev[m - 1][:nvar]
+                if theta_fn is not None:
+                    th.copy_(theta_fn(m, nvar, rep))
+                eng.simulate_dev(m, nvar, th.data_ptr(), st_dev.data_ptr(), particle_offset=(7 + rep) * B, seed=SEED,
+                                 prior_supplied=theta_fn is not None, stream=stream)
+                eng.score_dev(st_dev.data_ptr(), nvar, eps=EPS, particle_offset=(7 + rep) * B, err_layout=ERR_PARTICLE_MAJOR,
+                              d_err_ptr=err_dev.data_ptr(), stream=stream)
+                if rep == reps - 1:
+                    c = eng.counters()
+                    dr += c["n_draws"]; ms_sim += c["ms_simulate"]
+            if rep == reps - 1:
+                e1.record(); torch.cuda.synchronize()
+        eng.set_option("ssa_adaptive_burnin", 2)
+        t = e0.elapsed_time(e1) / 1e3
+        return {"particles_per_s": len(models) * nvar / t, "particles_per_model": nvar, "models": list(models),
+                "draws_per_particle": dr / (len(models) * nvar), "draws_per_s": dr / (ms_sim / 1e3),
+                "frac_of_issue_roofline_nominal24": dr / (ms_sim / 1e3) * NOMINAL_INSTR_PER_TELEGRAPH_DRAW / 1e12 / pk_instr,
+                "ssa_adaptive_burnin": adaptive}
+
+    nv = min(B, 4096)
+    fixed_burnin = ssa_variant(0, min(B, 2048))
+    cycle_burnin = ssa_variant(1, nv)
+
+    def corner_theta(m, n, rep):
+        # BASELINE configs[4] / SURVEY 8d: kon, koff, alpha ~ U(2, 3), gamma ~ U(1, 2) (log10), lambda from its prior
+        P = n_params(m)
+        g = torch.Generator(device=dev).manual_seed(1000 * m + rep)
+        u = torch.rand((n, P), dtype=torch.float64, device=dev, generator=g)
+        lo = torch.full((P,), 2.0, dtype=torch.float64, device=dev)
+        ngam = 5 if m == 5 else 1
+        lo[P - 1 - ngam:P - 1] = 1.0
+        th = lo + u
+        th[:, P - 1] = -0.7 + 0.7 * u[:, P - 1]
+        return th
+
+    corner = ssa_variant(2, B, theta_fn=corner_theta, models=(4, 5), reps=3)
+    corner["workload"] = ("BASELINE configs[4]: burst-size / decay-rate models (m = 4, 5) at the high-rate prior corner, kon, koff, "
+                          "alpha ~ 10^U(2,3)/h, gamma ~ 10^U(1,2)/h; simulate + score vs 3419 genes, per GPU")
+    corner["cycle_burnin"] = ssa_variant(1, min(B, 1024), theta_fn=corner_theta, models=(4, 5))
+    sweep = run_full_sweep(args, eng, dev, world, rank, barrier)
     ode = run_ode_path(args, eng_cls=AbcEngine, betas=betas, d=d, se=se, dev=dev, world=world, rank=rank, local=local,
                        barrier=barrier)
     if rank == 0:
@@ -382,19 +471,20 @@ def run_b200(args):
                 "config": workload_config(args),
                 "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d // args.steps,
                         "d2h_bytes_per_step": d2h // args.steps,
-                        "path": "abc_fix_params -> host theta (page-locked) -> abc_simulate_score -> abc_accept_fetch, one untimed "
-                                "warm-up step" if e2e_mode["host_theta"] and not args.e2e_separate else
+                        "path": "abc_fix_params -> host theta (page-locked) -> abc_simulate_score -> abc_accept_fetch, two untimed "
+                                "warm-up steps" if e2e_mode["host_theta"] and not args.e2e_separate else
                                 ("abc_simulate + abc_score" if args.e2e_separate else e2e_mode["note"])},
                 "gpu_launches": int(launches),
                 "clocks": sampler.summary(),
-                "roofline": {"kernel": "abc_ssa_kernel<false,2>", "bound": "issue", "achieved": achieved, "peak": peak_instr,
+                "roofline": {"kernel": "abc_tele_kernel", "bound": "issue", "achieved": achieved, "peak": peak_instr,
                              "unit": "Tlane-instr/s", "frac": achieved / peak_instr, "traffic": None,
-                             "traffic_note": "not memory bound: ncu dram read 6 MB, write 0.9 MB per launch (profiles/r1_ssa_mode2_ncu_summary.csv)",
+                             "traffic_note": "not memory bound: ncu dram read + write < 10 MB per launch (profiles/r2_ssa_m1_ncu_summary.csv)",
                              "events_per_s": ev_per_s, "events": int(events), "draws": int(draws),
                              "draws_per_s": draws_per_s,
                              "nominal_instr_per_draw": NOMINAL_INSTR_PER_TELEGRAPH_DRAW,
                              "work_unit": "telegraph draw (switch event or sub-interval boundary)",
                              "peak_src": f"148 SM x 128 lanes x sm_max_mhz ({pk['src']})",
+                             "ncu": NCU_SSA,
                              "share_of_step": ssa_s / t_dev if t_dev > 0 else None},
                 "roofline_score": {"kernel": "abc_score3_classify_kernel + abc_score3_tile_kernel<2> + abc_score3_exact_kernel<2>",
                                    "particles_per_launch": nb, "ms_per_launch": 1e3 * score_big_s,
@@ -408,6 +498,10 @@ def run_b200(args):
                                                    "pairs_per_s": nb * G / score_acc_s,
                                                    "note": "err_layout = ABC_ERR_NONE: fused eps-acceptance, no matrix"}}}
         line["ode_path"] = ode
+        line["ssa_mode2_fixed_burnin"] = fixed_burnin
+        line["ssa_mode2_cycle_burnin"] = cycle_burnin
+        line["corner"] = corner
+        line["full_sweep"] = sweep
         line["ssa_full_direct"] = full_direct
         line["ssa_six_channel_window"] = cmp_modes[1]
         line["roofline"]["events_per_particle"] = events / max(1, 5 * B * args.steps)
@@ -421,6 +515,56 @@ def run_b200(args):
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
+
+
+def run_full_sweep(args, eng, dev, world, rank, barrier):
+    """BASELINE configs[2] (scripts/accepted_particles.jl:13: 10^6 rows per model): all 5 models, M particles per model in
+    total, sharded over the ranks by contiguous global particle ranges (STRONG scaling: the job is fixed, N varies),
+    simulated and scored without materialising the error matrix (ABC_ERR_NONE: fused eps-acceptance), then per model the
+    counts are all-reduced and the accepted tuples gathered and ordered per gene (v[sortperm(err[v])]).  Wall clock around
+    the whole job, max over ranks."""
+    import torch
+    import torch.distributed as dist
+    from abc_inference_transcription_b200 import ERR_NONE, n_params
+    from abc_inference_transcription_b200.dist import gather_acceptance, shard_range
+    M = args.sweep_particles
+    if M <= 0:
+        return None
+    stream = torch.cuda.current_stream().cuda_stream
+    lo, hi = shard_range(M, rank, world)
+    n_chunks = max(1, -(-(hi - lo) // args.sweep_chunk))
+    chunk = max(1, -(-(hi - lo) // n_chunks))          # equal launches, no short tail
+    th = torch.empty((chunk, 9), dtype=torch.float64, device=dev)
+    st = torch.empty((chunk, 53), dtype=torch.float64, device=dev)
+    accepted, draws, t_gather = [], 0, 0.0
+    barrier()
+    t0 = time.perf_counter()
+    for m in range(1, 6):
+        eng.accept_reset()
+        for c0 in range(lo, hi, chunk):
+            nb = min(chunk, hi - c0)
+            eng.simulate_dev(m, nb, th.data_ptr(), st.data_ptr(), particle_offset=c0, seed=SEED + 1, prior_supplied=False, stream=stream)
+            eng.score_dev(st.data_ptr(), nb, eps=EPS, particle_offset=c0, err_layout=ERR_NONE, d_err_ptr=0, stream=stream)
+            draws += eng.counters()["n_draws"]
+        tg = time.perf_counter()
+        res = gather_acceptance(eng, world, dev)
+        torch.cuda.synchronize()
+        t_gather += time.perf_counter() - tg
+        accepted.append(int(res["counts"].sum()))
+    barrier()
+    t = time.perf_counter() - t0
+    tt = torch.tensor([t, t_gather], dtype=torch.float64, device=dev)
+    dd = torch.tensor([draws], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        dist.all_reduce(dd)
+    t, t_gather = float(tt[0]), float(tt[1])
+    return {"workload": "BASELINE configs[2]: full prior sweep, all 5 models, simulate + fused eps-acceptance (no error matrix) + "
+                        "per-gene ordered accepted lists; strong scaling over --gpus",
+            "particles_per_model": M, "models": 5, "n_gpus": world, "scaling": "strong", "wall_s": t,
+            "particles_per_s": 5 * M / t, "gather_and_order_s": t_gather, "accepted_pairs_per_model": accepted,
+            "draws_per_particle": float(dd[0]) / (5 * M), "chunk": chunk,
+            "extrapolated_wall_s_at_5e6_per_model": t * 5e6 / M}
 
 
 def run_ode_path(args, eng_cls, betas, d, se, dev, world, rank, local, barrier):
@@ -524,6 +668,8 @@ def main():
     ap.add_argument("--ode-batch", type=int, default=8192, help="particles per model per step for the ODE-path line")
     ap.add_argument("--score-particles", type=int, default=131072, help="particles per launch for the scoring-kernel roofline")
     ap.add_argument("--ref-particles", type=int, default=24000, help="particles per bounded CPU sample (~10 s on 16 threads)")
+    ap.add_argument("--sweep-particles", type=int, default=1000000, help="full_sweep: particles per model in total (0 = skip)")
+    ap.add_argument("--sweep-chunk", type=int, default=65536, help="full_sweep: particles per launch per rank")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--e2e-separate", action="store_true", help="e2e through abc_simulate + abc_score instead of abc_simulate_score")
     args = ap.parse_args()

@@ -220,6 +220,41 @@ int  abc_counters(abc_ctx_t* ctx, abc_counters_t* counters);
 /* how many kernels this library has launched on the context since creation */
 int64_t abc_launch_count(abc_ctx_t* ctx);
 
+/* ---- multi-GPU (the reference: independent `submit` processes + files concatenated by hand, wrapper.jl:62-63) ----------
+ * Particles shard across GPUs by contiguous ranges of the global particle index (identical bits for any partition: Philox
+ * is keyed by the global index).  NCCL is used only after a batch: per-gene counts are summed, and the accepted tuples are
+ * exchanged by gene range so that every GPU orders the lists of G / n genes (equal tuple mass).
+ *
+ * (a) one host process, n GPUs -- what a Julia host calls: one context and one host thread per device inside the library,
+ *     ncclCommInitAll.  devices == NULL: 0 .. n_dev-1.  abc_multi_simulate_score / abc_multi_accept_fetch return exactly what
+ *     abc_simulate_score / abc_accept_fetch return on one device for the same arguments. */
+typedef struct abc_multi abc_multi_t;
+int  abc_multi_create(const int32_t* devices, int32_t n_dev, abc_multi_t** out);
+int  abc_multi_destroy(abc_multi_t* mg);
+int  abc_multi_n_devices(abc_multi_t* mg);
+abc_ctx_t* abc_multi_ctx(abc_multi_t* mg, int32_t i);          /* the i-th device's context (options, counters) */
+int  abc_multi_set_design(abc_multi_t* mg, const abc_design_t* design);
+int  abc_multi_set_data(abc_multi_t* mg, const double* d, const double* se, int32_t n_genes);
+int  abc_multi_set_option(abc_multi_t* mg, const char* name, int64_t value);
+int  abc_multi_simulate_score(abc_multi_t* mg, int m, int64_t n_trials, int64_t particle_offset, uint64_t seed,
+                              int prior_supplied, double* theta, double* stats, double eps, int err_layout, double* err,
+                              int64_t* counts, abc_counters_t* counters);
+int  abc_multi_accept_reset(abc_multi_t* mg);
+int64_t abc_multi_accept_total(abc_multi_t* mg);
+int  abc_multi_accept_fetch(abc_multi_t* mg, int64_t* offsets, int64_t* idx, double* errs);
+/* (b) one process per GPU (torchrun / MPI style): rank 0 obtains a unique id (>= 128 bytes), the host distributes it, every
+ *     rank attaches a communicator to its context.  abc_comm_counts: per-gene counts summed over the ranks.
+ *     abc_comm_accept_fetch is collective: offsets[G+1] are global on every rank; root >= 0: that rank receives the complete
+ *     ordered lists; root < 0: every rank receives the lists of its own gene range gene_range[0] .. gene_range[1]-1 at their
+ *     global positions in idx / errs. */
+int  abc_comm_unique_id(void* id, size_t bytes);
+int  abc_comm_init_rank(abc_ctx_t* ctx, const void* id, size_t bytes, int32_t n_ranks, int32_t rank);
+int  abc_comm_rank(abc_ctx_t* ctx, int32_t* n_ranks, int32_t* rank);
+int  abc_comm_counts(abc_ctx_t* ctx, int64_t* counts);
+int  abc_comm_accept_fetch(abc_ctx_t* ctx, int32_t root, int64_t* offsets, int64_t* idx, double* errs, int64_t* gene_range);
+/* the cut used by the exchange: bounds[n_ranks + 1], rank k orders genes bounds[k] .. bounds[k+1]-1 (equal tuple mass) */
+int  abc_gene_ranges(const int64_t* counts, int32_t n_genes, int32_t n_ranks, int64_t* bounds);
+
 #ifdef __cplusplus
 }
 #endif

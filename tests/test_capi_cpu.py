@@ -2,6 +2,8 @@
 and refuses to compute without a CUDA device (no CPU fallback)."""
 import ctypes
 import os
+
+import numpy as np
 import re
 
 import pytest
@@ -116,3 +118,21 @@ def test_julia_host_never_includes_a_reference_script():
                 arg = mt.group(1)
                 assert "scripts/" not in arg and "scripts\\" not in arg, f"{fn}:{ln} includes a reference script: {line.strip()}"
                 assert "@__DIR__" in arg, f"{fn}:{ln}: include outside julia/: {line.strip()}"
+
+
+def test_gene_ranges_cut_equal_tuple_mass():
+    """abc_gene_ranges (host logic of the multi-GPU exchange): contiguous, covering, deterministic, balanced"""
+    from abc_inference_transcription_b200 import gene_ranges
+    rng = np.random.default_rng(0)
+    counts = (rng.pareto(1.2, 3419) * 50).astype(np.int64)
+    for n in (1, 2, 3, 8):
+        b = gene_ranges(counts, n)
+        assert b[0] == 0 and b[-1] == 3419 and np.all(np.diff(b) >= 0)
+        mass = np.array([counts[b[k]:b[k + 1]].sum() for k in range(n)])
+        assert mass.sum() == counts.sum()
+        assert mass.max() <= counts.sum() / n + counts.max()          # within one gene of the ideal share
+    z = gene_ranges(np.zeros(10, dtype=np.int64), 4)
+    assert list(z) == [0, 2, 5, 7, 10]
+    one = np.zeros(100, dtype=np.int64); one[37] = 5
+    b = gene_ranges(one, 4)
+    assert b[0] == 0 and b[-1] == 100 and sum(one[b[k]:b[k + 1]].sum() for k in range(4)) == 5

@@ -785,3 +785,42 @@ def test_posterior_summary_on_device(eng, data_stats, m, offset):
     # a theta window that does not cover the accepted indices is an error, not a silent gather
     with pytest.raises(AbcError, match="outside"):
         eng.posterior_summary(theta[:10], particle_offset=offset, q=0.95)
+
+
+# ------------------------------------------------------------------------------------------ multi-GPU behind the C ABI
+def _multi_vs_single(eng, betas, data_stats, n_dev, n, m, layout):
+    from abc_inference_transcription_b200 import AbcMulti
+    d, se = data_stats
+    with AbcMulti(n_dev=n_dev) as mg:
+        mg.set_design(synthetic_design(betas, n_cells=96, n_pre_cycles=10))
+        mg.set_data(d, se)
+        mg.accept_reset()
+        th, st, err, counts, cnt = mg.simulate_score(m, n_trials=n, particle_offset=4321, seed=7, eps=4.8, err_layout=layout)
+        off, idx, errs = mg.accept_fetch()
+    eng.accept_reset()
+    th1, st1, err1, counts1, cnt1 = eng.simulate_score(m, n_trials=n, particle_offset=4321, seed=7, eps=4.8, err_layout=layout)
+    off1, idx1, errs1 = eng.accept_fetch()
+    assert oracle.same_bits(th, th1) and oracle.same_bits(st, st1)
+    if layout != ERR_NONE:
+        assert oracle.same_bits(err, err1)
+    assert np.array_equal(counts, counts1) and cnt["n_lineages"] == cnt1["n_lineages"] and cnt["n_events"] == cnt1["n_events"]
+    assert np.array_equal(off, off1) and np.array_equal(idx, idx1) and oracle.same_bits(errs, errs1)
+    assert off[-1] > 0
+
+
+@pytest.mark.parametrize("layout", [ERR_PARTICLE_MAJOR, ERR_NONE])
+def test_multi_context_on_one_device_equals_the_engine(eng, betas, data_stats, layout):
+    """abc_multi_* with a single device (no NCCL involved): same bits as abc_simulate_score / abc_accept_fetch"""
+    _multi_vs_single(eng, betas, data_stats, 1, 301, 1, layout)
+
+
+@pytest.mark.parametrize("layout,m", [(ERR_PARTICLE_MAJOR, 1), (ERR_GENE_MAJOR, 4), (ERR_NONE, 3)])
+def test_multi_gpu_from_one_process_is_bit_identical(eng, betas, data_stats, layout, m):
+    """abc_multi_create over all GPUs of the box (one host thread + one NCCL rank per device inside the library): theta,
+    statistics, error matrix, counts and the merged per-gene lists equal the single-GPU result bit for bit (odd batch size:
+    uneven shards; the lists go through the gene-range all-to-all and the per-range merge)"""
+    import torch
+    n_dev = torch.cuda.device_count()
+    if n_dev < 2:
+        pytest.skip("needs >= 2 GPUs (run with gpurun --gpus 2)")
+    _multi_vs_single(eng, betas, data_stats, n_dev, 1501, m, layout)
