@@ -8,7 +8,7 @@ Host-side mirror of the reference's script interface (same names, argument meani
   accepted_particles.py  accepted_particles                    scripts/accepted_particles.jl
 All arithmetic runs in libabcb200.so (hand-written CUDA, sm_100a); there is no CPU fallback.
 """
-from . import _lib
+from . import _lib, io
 from ._lib import AbcError, ERR_GENE_MAJOR, ERR_NONE, ERR_PARTICLE_MAJOR, SIM_ODE, SIM_SSA
 from .design import Design, split_betas, synthetic_design
 from .engine import AbcEngine, AbcMulti, PinnedArray, comm_unique_id, gene_ranges

@@ -90,6 +90,14 @@ SYMBOLS = {
     "abc_set_option": (ctypes.c_int, [_vp, ctypes.c_char_p, ctypes.c_int64]),
     "abc_counters": (ctypes.c_int, [_vp, ctypes.POINTER(AbcCounters)]),
     "abc_launch_count": (ctypes.c_int64, [_vp]),
+    "abc_model_probs": (ctypes.c_int, [_vp, _vp, ctypes.c_int32, ctypes.c_int32, ctypes.c_int32, ctypes.c_double, ctypes.c_uint64,
+                                       _vp, _vp, _vp]),
+    "abc_format_float64": (ctypes.c_int, [ctypes.c_double, ctypes.c_char_p, ctypes.c_size_t]),
+    "abc_writedlm": (ctypes.c_int, [ctypes.c_char_p, _vp, ctypes.c_int64, ctypes.c_int64, ctypes.c_int]),
+    "abc_write_simulation": (ctypes.c_int, [ctypes.c_char_p, ctypes.c_int, ctypes.c_int32, _vp, _vp, ctypes.c_int64, ctypes.c_int64]),
+    "abc_write_accepted": (ctypes.c_int, [ctypes.c_char_p, _vp, _vp, ctypes.c_int32, ctypes.c_int]),
+    "abc_write_error_columns": (ctypes.c_int, [ctypes.c_char_p, _vp, ctypes.c_int64, ctypes.c_int64, ctypes.c_int32, ctypes.c_int]),
+    "abc_read_error_column": (ctypes.c_int, [ctypes.c_char_p, ctypes.c_int32, _vp, ctypes.c_int64, c_int64_p]),
     "abc_multi_create": (ctypes.c_int, [_vp, ctypes.c_int32, ctypes.POINTER(_vp)]),
     "abc_multi_destroy": (ctypes.c_int, [_vp]),
     "abc_multi_n_devices": (ctypes.c_int, [_vp]),

@@ -184,3 +184,95 @@ int abc_launch_posterior(const long long* d_idx, const long long* d_offsets, siz
     if (n_launches) *n_launches = launches;
     return ABC_OK;
 }
+
+// ------------------------------------------------------------------------------------------------
+// get_model_probs (scripts/model_probs.jl:1-28, constant_model_probs.jl:1-28, non_constant_model_probs.jl:1-30)
+// and the per-gene case split around it (model_probs.jl:42-54): acceptance-count ratios of K hypotheses with bootstrap
+// percentile bounds.  The reference resamples the vector of sum(l) model labels with replacement n_bootstraps times; here
+// one warp draws the sum(l) labels of one (gene, bootstrap) from Philox (64 random bits per label: index = floor(u * sum(l)),
+// class by the cumulative counts) -- the same resampling, integer arithmetic only, reproducible for a given seed.
+#define ABC_DOM_BOOT 2u
+#define BOOT_MAXK 8
+#define BOOT_MAXB 256
+
+__global__ void boot_resample_kernel(const long long* __restrict__ counts, int K, int G, int B, uint32_t k0, uint32_t k1,
+                                     double* __restrict__ stats) {
+    const long long w = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    if (w >= (long long)G * B) return;
+    const int g = (int)(w / B), b = (int)(w % B);
+    unsigned long long cum[BOOT_MAXK];
+    unsigned long long tot = 0;
+    int nz = 0;
+    for (int k = 0; k < K; ++k) {
+        const unsigned long long c = (unsigned long long)counts[(long long)k * G + g];
+        tot += c; cum[k] = tot;
+        nz += (c > 0);
+    }
+    if (nz < 2) return;            // decided without a bootstrap (model_probs.jl:42-50)
+    unsigned long long cnt[BOOT_MAXK];
+    for (int k = 0; k < K; ++k) cnt[k] = 0;
+    const unsigned long long nblk = (tot + 1) >> 1;       // one Philox block = two labels
+    for (unsigned long long j = lane; j < nblk; j += 32) {
+        const uint4 r = philox4x32_10((uint32_t)j, (uint32_t)g, (uint32_t)b, ABC_DOM_BOOT << 29, k0, k1);
+        const unsigned long long u0 = ((unsigned long long)r.x << 32) | r.y, u1 = ((unsigned long long)r.z << 32) | r.w;
+        const unsigned long long i0 = __umul64hi(u0, tot), i1 = __umul64hi(u1, tot);
+        const bool second = 2 * j + 1 < tot;
+        for (int k = 0; k < K; ++k) {
+            const bool below0 = i0 < cum[k] && (k == 0 || i0 >= cum[k - 1]);
+            const bool below1 = second && i1 < cum[k] && (k == 0 || i1 >= cum[k - 1]);
+            cnt[k] += (below0 ? 1ull : 0ull) + (below1 ? 1ull : 0ull);
+        }
+    }
+    for (int k = 0; k < K; ++k) {
+        unsigned long long c = cnt[k];
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) c += __shfl_xor_sync(0xffffffffu, c, o);
+        if (lane == 0) stats[((long long)g * K + k) * B + b] = __ddiv_rn((double)c, (double)tot);     // sample_l ./ sum(sample_l)
+    }
+}
+
+__global__ void boot_bounds_kernel(const long long* __restrict__ counts, int K, int G, int B, double alpha,
+                                   const double* __restrict__ stats, double* __restrict__ prob, double* __restrict__ lb,
+                                   double* __restrict__ ub) {
+    const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= (long long)G * K) return;
+    const int g = (int)(t / K), k = (int)(t % K);
+    unsigned long long tot = 0;
+    int nz = 0;
+    for (int q = 0; q < K; ++q) { const unsigned long long c = (unsigned long long)counts[(long long)q * G + g]; tot += c; nz += (c > 0); }
+    const unsigned long long mine = (unsigned long long)counts[(long long)k * G + g];
+    double p = 0.0, l = 0.0, u = 0.0;
+    if (nz == 1) {
+        if (mine > 0) { p = 1.0; l = 1.0; u = 1.0; }
+    } else if (nz >= 2) {
+        p = __ddiv_rn((double)mine, (double)tot);
+        double v[BOOT_MAXB];
+        const double* s = stats + ((long long)g * K + k) * B;
+        for (int b = 0; b < B; ++b) {            // insertion sort = sort(stats, dims = 1)
+            const double x = s[b];
+            int j = b;
+            while (j > 0 && v[j - 1] > x) { v[j] = v[j - 1]; --j; }
+            v[j] = x;
+        }
+        l = julia_quantile(v, B, 1.0 - alpha);
+        u = julia_quantile(v, B, alpha);
+    }
+    prob[t] = p; lb[t] = l; ub[t] = u;
+}
+
+int abc_launch_model_probs(const long long* d_counts, int K, int G, int B, double alpha, uint64_t seed, double* d_stats,
+                           double* d_prob, double* d_lb, double* d_ub, int* n_launches, cudaStream_t st) {
+    if (K < 1 || K > BOOT_MAXK || B < 1 || B > BOOT_MAXB || G < 1) {
+        abc_set_error("abc_model_probs: K in 1..%d, n_bootstraps in 1..%d", BOOT_MAXK, BOOT_MAXB);
+        return ABC_ERR_ARG;
+    }
+    const int threads = 256;
+    const long long warps = (long long)G * B;
+    boot_resample_kernel<<<(unsigned)((warps * 32 + threads - 1) / threads), threads, 0, st>>>(d_counts, K, G, B, (uint32_t)seed,
+                                                                                            (uint32_t)(seed >> 32), d_stats);
+    boot_bounds_kernel<<<(unsigned)(((long long)G * K + 127) / 128), 128, 0, st>>>(d_counts, K, G, B, alpha, d_stats, d_prob, d_lb, d_ub);
+    ABC_CUDA_CHECK(cudaGetLastError());
+    if (n_launches) *n_launches = 2;
+    return ABC_OK;
+}

@@ -983,6 +983,38 @@ extern "C" int abc_posterior_summary(abc_ctx_t* c, const double* theta, int64_t 
     return ABC_OK;
 }
 
+// SURVEY 8f-2 (model_probs.jl:1-54): per-gene model probabilities = acceptance-count ratios + bootstrap percentile bounds
+extern "C" int abc_model_probs(abc_ctx_t* c, const int64_t* counts, int32_t K, int32_t G, int32_t n_bootstraps, double alpha,
+                               uint64_t seed, double* prob, double* lb, double* ub) {
+    CTX_GUARD(c);
+    if (!counts || !prob || !lb || !ub || K < 1 || G < 1 || !(alpha >= 0.0 && alpha <= 1.0)) { abc_set_error("abc_model_probs: bad arguments"); return ABC_ERR_ARG; }
+    for (int g = 0; g < G; ++g) {
+        unsigned long long tot = 0;
+        for (int k = 0; k < K; ++k) {
+            if (counts[(size_t)k * G + g] < 0) { abc_set_error("abc_model_probs: negative count"); return ABC_ERR_ARG; }
+            tot += (unsigned long long)counts[(size_t)k * G + g];
+        }
+        if (tot >= 0xFFFFFFFFull) { abc_set_error("abc_model_probs: more than 2^32 accepted particles for gene %d", g + 1); return ABC_ERR_ARG; }
+    }
+    DevBuf<long long> d_counts;
+    DevBuf<double> d_stats, d_out;
+    int rc = d_counts.ensure((size_t)K * G);
+    if (rc == ABC_OK) rc = d_stats.ensure((size_t)G * K * (size_t)std::max(n_bootstraps, 1));
+    if (rc == ABC_OK) rc = d_out.ensure((size_t)3 * G * K);
+    if (rc != ABC_OK) return rc;
+    ABC_CUDA_CHECK(cudaMemcpyAsync(d_counts.p, counts, (size_t)K * G * sizeof(long long), cudaMemcpyHostToDevice, c->stream));
+    int nl = 0;
+    const size_t gk = (size_t)G * K;
+    rc = abc_launch_model_probs(d_counts.p, K, G, n_bootstraps, alpha, seed, d_stats.p, d_out.p, d_out.p + gk, d_out.p + 2 * gk, &nl, c->stream);
+    if (rc != ABC_OK) return rc;
+    c->launches += nl;
+    ABC_CUDA_CHECK(cudaMemcpyAsync(prob, d_out.p, gk * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+    ABC_CUDA_CHECK(cudaMemcpyAsync(lb, d_out.p + gk, gk * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+    ABC_CUDA_CHECK(cudaMemcpyAsync(ub, d_out.p + 2 * gk, gk * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+    ABC_CUDA_CHECK(cudaStreamSynchronize(c->stream));
+    return ABC_OK;
+}
+
 // ------------------------------------------------------------------------------------------------
 extern "C" int abc_simulate_dev(abc_ctx_t* c, int m, int64_t n, int64_t offset, uint64_t seed, int prior_supplied,
                                 double* d_theta, double* d_stats, void* stream) {

@@ -132,3 +132,7 @@ int abc_launch_posterior(const long long* d_idx, const long long* d_offsets, siz
                          long long n, int P, long long particle_offset, double q, double* d_vals[2], void* d_temp,
                          size_t temp_bytes, int* d_bad, double* d_map, double* d_mean, double* d_lo, double* d_hi,
                          int* n_launches, cudaStream_t st);
+
+// SURVEY 8f-2 model-probability bootstrap (abc_accept.cu)
+int abc_launch_model_probs(const long long* d_counts, int K, int G, int B, double alpha, uint64_t seed, double* d_stats,
+                           double* d_prob, double* d_lb, double* d_ub, int* n_launches, cudaStream_t st);

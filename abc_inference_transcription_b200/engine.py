@@ -226,6 +226,16 @@ class AbcEngine:
                                                    _lib.ptr(out["hi"]), _lib.ptr(out["n"])))
         return out
 
+    def model_probs(self, counts, n_bootstraps=100, alpha=0.95, seed=20240229):
+        """SURVEY 8f-2 on the device (model_probs.jl:1-54): counts (K, G) accepted particles per hypothesis and gene ->
+        (prob, l_bound, u_bound), each (G, K)"""
+        counts = np.ascontiguousarray(counts, dtype=np.int64)
+        K, G = counts.shape
+        out = [np.empty((G, K), dtype=np.float64) for _ in range(3)]
+        _lib.check(self._lib.abc_model_probs(self._ctx, _lib.ptr(counts), K, G, int(n_bootstraps), float(alpha), int(seed),
+                                             _lib.ptr(out[0]), _lib.ptr(out[1]), _lib.ptr(out[2])))
+        return tuple(out)
+
     def accept_tuples(self):
         total = self.accept_total()
         gene = np.empty(total, dtype=np.int32)

@@ -177,6 +177,15 @@ int  abc_accept_fetch(abc_ctx_t* ctx, int64_t* offsets, int64_t* idx, double* er
  * rows.  Any output may be NULL.  Lists are ordered, values gathered, sorted per gene and reduced on the device. */
 int  abc_posterior_summary(abc_ctx_t* ctx, const double* theta, int64_t n, int32_t P, int64_t particle_offset, double q,
                            double* map, double* mean, double* lo, double* hi, int64_t* n_acc);
+/* ---- next row: get_model_probs + the case split around it, model_probs.jl:1-54,
+ *      constant_model_probs.jl:1-28, non_constant_model_probs.jl:1-30 ------------------------------------------------
+ * counts: host, K x n_genes row-major: accepted particles of hypothesis k (a model, or a pooled group of models) for gene g
+ * -- the per-gene counts abc_score / abc_simulate_score return.  Per gene: no hypothesis accepted -> zeros; exactly one ->
+ * probability and both bounds 1 for it; otherwise prob = l / sum(l) and the (1 - alpha, alpha) quantiles (Julia's default
+ * quantile) over n_bootstraps resamplings of the sum(l) model labels with replacement (Philox, counter = (block, gene,
+ * bootstrap), key = seed: reproducible).  prob, lb, ub: host, n_genes x K row-major.  K <= 8, n_bootstraps <= 256. */
+int  abc_model_probs(abc_ctx_t* ctx, const int64_t* counts, int32_t K, int32_t n_genes, int32_t n_bootstraps, double alpha,
+                     uint64_t seed, double* prob, double* lb, double* ub);
 /* unsorted accepted tuples (for multi-GPU gathers): gene int32, particle int64 (1-based global), err double */
 int  abc_accept_tuples(abc_ctx_t* ctx, int32_t* gene, int64_t* particle, double* err);
 
@@ -219,6 +228,23 @@ int  abc_set_option(abc_ctx_t* ctx, const char* name, int64_t value);
 int  abc_counters(abc_ctx_t* ctx, abc_counters_t* counters);
 /* how many kernels this library has launched on the context since creation */
 int64_t abc_launch_count(abc_ctx_t* ctx);
+
+/* ---- on-disk layouts written by the library; host-side, no device needed ------------------------------
+ * abc_format_float64: Julia's print(io, ::Float64) -- what writedlm puts into every file of the pipeline (shortest
+ * round-trip digits, fixed notation for 1e-5 <= |x| < 1e6, else d.ddde[-]x, NaN / Inf / -Inf); buf >= 32 bytes, returns
+ * the length.  abc_writedlm: writedlm(io, A) of a row-major rows x cols matrix (compute_errors.jl:66-68: one 1 x G row
+ * per particle), formatted on all host threads.  abc_write_simulation: the seven files of abc_simulation.jl:47-61, 89-95
+ * for n trials (theta n x P, stats n x 53 row-major) under <dir>/<model>/.  abc_write_accepted:
+ * data/posteriors/particles_<model>.txt (accepted_particles.jl:19-30, a "0" line for a gene without accepted particles).
+ * abc_write_error_columns / abc_read_error_column: one raw little-endian Float64 file x<g>.f64 per gene column (the
+ * column-per-file layout idea of the .jdf store, process_error_files.jl:3-7; JDF.jl's own bytes are third-party). */
+int  abc_format_float64(double x, char* buf, size_t cap);
+int  abc_writedlm(const char* path, const double* a, int64_t rows, int64_t cols, int append);
+int  abc_write_simulation(const char* dir, int m, int32_t submit, const double* theta, const double* stats, int64_t n,
+                          int64_t first_trial);
+int  abc_write_accepted(const char* path, const int64_t* offsets, const int64_t* idx, int32_t n_genes, int append);
+int  abc_write_error_columns(const char* dir, const double* err_gene_major, int64_t n, int64_t pitch, int32_t n_genes, int append);
+int  abc_read_error_column(const char* dir, int32_t g, double* out, int64_t cap, int64_t* n);
 
 /* ---- multi-GPU (the reference: independent `submit` processes + files concatenated by hand, wrapper.jl:62-63) ----------
  * Particles shard across GPUs by contiguous ranges of the global particle index (identical bits for any partition: Philox

@@ -217,3 +217,66 @@ def same_bits(a, b):
     if not np.array_equal(na, nb):
         return False
     return np.array_equal(a.view(np.uint64)[~na], b.view(np.uint64)[~nb])
+
+
+def philox_np(c0, c1, c2, c3, key):
+    """Philox4x32-10 (Salmon et al. 2011) vectorised over numpy arrays of counters; returns four uint32 arrays.
+    Checked against the C restatement (philox) and Random123's known answers in tests/test_oracle_cpu.py."""
+    M0, M1, W0, W1 = np.uint64(0xD2511F53), np.uint64(0xCD9E8D57), 0x9E3779B9, 0xBB67AE85
+    c0, c1, c2, c3 = (np.asarray(c, dtype=np.uint64) & np.uint64(0xFFFFFFFF) for c in np.broadcast_arrays(c0, c1, c2, c3))
+    k0, k1 = int(key[0]) & 0xFFFFFFFF, int(key[1]) & 0xFFFFFFFF
+    mask, sh = np.uint64(0xFFFFFFFF), np.uint64(32)
+    for _ in range(10):
+        p0, p1 = M0 * c0, M1 * c2
+        hi0, lo0, hi1, lo1 = p0 >> sh, p0 & mask, p1 >> sh, p1 & mask
+        c0, c1, c2, c3 = hi1 ^ c1 ^ np.uint64(k0), lo1, hi0 ^ c3 ^ np.uint64(k1), lo0
+        k0, k1 = (k0 + W0) & 0xFFFFFFFF, (k1 + W1) & 0xFFFFFFFF
+    return tuple(c.astype(np.uint32) for c in (c0, c1, c2, c3))
+
+
+def julia_quantile(sorted_v, p):
+    """Statistics.jl quantile(v, p), default alpha = beta = 1, on sorted data"""
+    n = len(sorted_v)
+    aleph = n * p + (1.0 - p)
+    j = int(min(max(np.trunc(aleph), 1), n - 1))
+    g = min(max(aleph - j, 0.0), 1.0)
+    a, b = sorted_v[j - 1], sorted_v[j]
+    return a + g * (b - a)
+
+
+def model_probs(counts, n_bootstraps, alpha, seed):
+    """numpy restatement of abc_model_probs (model_probs.jl:1-54 with the label resampling drawn from Philox: block j of
+    (gene g, bootstrap b) = counter (j, g, b, 2 << 29), two 64-bit words -> two labels by floor(u * sum(l) / 2^64))"""
+    counts = np.asarray(counts, dtype=np.int64)
+    K, G = counts.shape
+    prob, lb, ub = (np.zeros((G, K)) for _ in range(3))
+    key = (seed & 0xFFFFFFFF, seed >> 32)
+    for g in range(G):
+        l = counts[:, g]
+        tot, nz = int(l.sum()), int((l > 0).sum())
+        if nz == 0:
+            continue
+        if nz == 1:
+            k = int(np.nonzero(l)[0][0])
+            prob[g, k] = lb[g, k] = ub[g, k] = 1.0
+            continue
+        prob[g] = l / tot
+        cum = np.cumsum(l)
+        nblk = (tot + 1) // 2
+        j = np.arange(nblk, dtype=np.uint64)
+        stats = np.zeros((n_bootstraps, K))
+        for b in range(n_bootstraps):
+            x, y, z, w = philox_np(j, g, b, 2 << 29, key)
+            u0 = (x.astype(object) << 32) | y.astype(object)
+            u1 = (z.astype(object) << 32) | w.astype(object)
+            i0 = np.array([(int(v) * tot) >> 64 for v in u0], dtype=np.int64)
+            i1 = np.array([(int(v) * tot) >> 64 for v in u1], dtype=np.int64)
+            if tot % 2 == 1:
+                i1 = i1[:-1]
+            lab = np.searchsorted(cum, np.concatenate([i0, i1]), side="right")
+            stats[b] = np.bincount(lab, minlength=K) / tot
+        s = np.sort(stats, axis=0)
+        for k in range(K):
+            lb[g, k] = julia_quantile(s[:, k], 1.0 - alpha)
+            ub[g, k] = julia_quantile(s[:, k], alpha)
+    return prob, lb, ub

@@ -85,3 +85,30 @@ def test_wrapper_cli_sections_2_and_3(tmp_path):
     assert len(lines) == 120
     for g in range(120):
         assert np.array_equal(lines[g], oracle.accept_gene(err[:, g], 4.8))
+
+
+def test_recover_statistics_writes_the_reference_layout(tmp_path):
+    """wrapper.jl:109-111 -> scripts/recover_statistics.jl:49-68 through the device moment-ODE path and the library's
+    writedlm: the 55 files of one model (11 conditions x 5 moments, one row of 5 ages per MAP row) reproduce the reference's
+    shipped data/recovered_statistics files (golden fixture) to their own CVODE noise"""
+    from abc_inference_transcription_b200 import SIM_ODE, io
+    from abc_inference_transcription_b200.model import ID_LABELS
+    betas = np.load(os.path.join(GOLD, "ref_betas.npy"))
+    maps = np.load(os.path.join(GOLD, "ref_map_sets.npz"))
+    rec = np.load(os.path.join(GOLD, "ref_recovered.npz"))
+    root = str(tmp_path)
+    with AbcEngine(0) as eng:
+        eng.set_design(synthetic_design(betas, sim_kind=SIM_ODE, downsampling=False, iv=np.array([0.5, 0, 0, 0, 0, 0, 0, 0, 0.0]),
+                                        ode_rtol=1e-7, ode_atol=1e-10))                 # recover_statistics.jl:33-42
+        for m, name in ((5, "gamma"), (4, "alpha")):
+            theta = maps[f"theta_{name}"]
+            io.recover_statistics(eng, m, theta[:7], root=root)          # appended in two batches like a resumed run
+            mom = io.recover_statistics(eng, m, theta[7:], root=root)
+            gold = rec[f"moments_{name}"]
+            for k, label in enumerate(ID_LABELS):
+                for q, stem in enumerate(io.MOMENT_FILES):
+                    got = readdlm(os.path.join(root, "data", "recovered_statistics", name, label, stem + ".txt"))
+                    assert got.shape == (len(theta), 5)
+                    assert oracle.same_bits(got[7:], mom[:, k, :, q])     # text round trip of the device result
+                    rel = np.abs(got - gold[:, k, :, q]) / np.maximum(np.abs(gold[:, k, :, q]), 1e-4)
+                    assert np.median(rel) < 5e-3 and rel.max() < 0.2, (name, label, stem, rel.max())

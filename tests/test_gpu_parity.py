@@ -824,3 +824,45 @@ def test_multi_gpu_from_one_process_is_bit_identical(eng, betas, data_stats, lay
     if n_dev < 2:
         pytest.skip("needs >= 2 GPUs (run with gpurun --gpus 2)")
     _multi_vs_single(eng, betas, data_stats, n_dev, 1501, m, layout)
+
+
+# ------------------------------------------------------------------------------------------ SURVEY 8f-2 on the device
+def test_model_probs_on_device_equal_the_restatement(eng):
+    """abc_model_probs (bootstrap of the per-gene acceptance counts, model_probs.jl:1-54) against the numpy restatement on
+    the same Philox draws: probabilities, lower and upper bounds bit for bit; K = 2 (constant vs non-constant), 3 and 5"""
+    rng = np.random.default_rng(5)
+    for K, G in ((2, 40), (3, 25), (5, 12)):
+        counts = (rng.pareto(1.0, size=(K, G)) * 20).astype(np.int64)
+        counts[:, 0] = 0                               # nothing accepted
+        counts[:, 1] = 0; counts[K - 1, 1] = 17        # a single hypothesis accepted
+        counts[:, 2] = [1] + [0] * (K - 2) + [1]       # two labels only
+        counts = np.minimum(counts, 400)
+        got = eng.model_probs(counts, n_bootstraps=100, alpha=0.95, seed=20240229)
+        want = oracle.model_probs(counts, 100, 0.95, 20240229)
+        for a, b, name in zip(got, want, ("prob", "l_bound", "u_bound")):
+            assert oracle.same_bits(a, b), (K, name, np.abs(a - b).max())
+    # reproducible, and a different seed gives different bounds
+    a = eng.model_probs(counts, seed=1)
+    b = eng.model_probs(counts, seed=1)
+    c = eng.model_probs(counts, seed=2)
+    assert oracle.same_bits(a[1], b[1]) and not oracle.same_bits(a[1], c[1]) and oracle.same_bits(a[0], c[0])
+
+
+def test_model_probs_from_scored_counts(eng, data_stats):
+    """end to end: per-gene counts of two scored 'models' -> device bootstrap; large counts (no restatement: property checks)"""
+    d, se = data_stats
+    rng = np.random.default_rng(6)
+    counts = []
+    for k in range(2):
+        eng.accept_reset()
+        _, c, _ = eng.score(synth_stats(rng, d, 3000), eps=4.8, err_layout=ERR_NONE)
+        counts.append(c)
+    counts = np.stack(counts)
+    prob, lb, ub = eng.model_probs(counts, n_bootstraps=100, alpha=0.95, seed=9)
+    tot = counts.sum(0)
+    both = (counts > 0).all(0)
+    assert both.sum() > 50
+    assert np.allclose(prob[both].sum(1), 1.0) and np.array_equal(prob[both][:, 0], (counts[0] / tot)[both])
+    assert np.all(lb[both] <= prob[both] + 0.2) and np.all(ub[both] >= prob[both] - 0.2) and np.all(lb <= ub)
+    none = tot == 0
+    assert not prob[none].any() and not ub[none].any()

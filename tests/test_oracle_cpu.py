@@ -21,6 +21,32 @@ def test_philox4x32_10_known_answers(ctr, key, want):
     assert [int(x) for x in oracle.philox(ctr, key)] == want
 
 
+def test_numpy_philox_equals_the_c_restatement():
+    rng = np.random.default_rng(0)
+    ctr = rng.integers(0, 2 ** 32, size=(50, 4), dtype=np.uint64)
+    key = [0xa4093822, 0x299f31d0]
+    got = np.stack(oracle.philox_np(ctr[:, 0], ctr[:, 1], ctr[:, 2], ctr[:, 3], key), axis=1)
+    for c, g in zip(ctr, got):
+        assert [int(x) for x in oracle.philox([int(v) for v in c], key)] == [int(x) for x in g]
+
+
+def test_model_probs_restatement_follows_the_reference_cases():
+    """model_probs.jl:42-54 + get_model_probs: no hypothesis accepted -> zeros; one -> ones; else ratios with bootstrap bounds
+    around them; compared with the host mirror posteriors.get_model_probs (multinomial) in distribution"""
+    from abc_inference_transcription_b200.posteriors import model_probs_for_genes
+    counts = np.array([[0, 5, 300, 40], [0, 0, 100, 40], [0, 0, 600, 0]], dtype=np.int64)       # K = 3 hypotheses x 4 genes
+    prob, lb, ub = oracle.model_probs(counts, 100, 0.95, 7)
+    assert not prob[0].any() and not lb[0].any() and not ub[0].any()
+    assert list(prob[1]) == [1.0, 0.0, 0.0] and list(lb[1]) == [1.0, 0.0, 0.0] and list(ub[1]) == [1.0, 0.0, 0.0]
+    assert np.allclose(prob[2], [0.3, 0.1, 0.6]) and np.all(lb[2] < prob[2]) and np.all(prob[2] < ub[2])
+    assert prob[3][2] == 0.0 and ub[3][2] == 0.0 and abs(prob[3][0] - 0.5) < 1e-12
+    p2, l2, u2 = model_probs_for_genes(counts, [[0], [1], [2]], rng=np.random.default_rng(3))
+    assert np.allclose(p2, prob) and np.abs(l2 - lb).max() < 0.05 and np.abs(u2 - ub).max() < 0.05
+    # the bootstrap spread is the binomial one: sd = sqrt(p (1 - p) / n), bounds ~ +-1.645 sd
+    sd = np.sqrt(0.3 * 0.7 / 1000)
+    assert abs((ub[2][0] - lb[2][0]) / (2 * 1.645 * sd) - 1.0) < 0.35
+
+
 # ------------------------------------------------------------------ simulator vs data/recovered_statistics
 def _pool_map(fn, items, threads=None):
     """the oracle's C calls release the GIL: run them on all host threads"""
