@@ -86,6 +86,17 @@ function simulate(ctx::Context, m, n_trials; particle_offset=0, seed=UInt64(2024
     return θ, stats, c[]
 end
 
+"""simulate_moments(ctx, m, θ) -> 5 x 5 x 11 x n array [moment, age, condition, particle] (mean_u, mean_l, var_u, cov_ul,
+var_l): run_part_sim of recover_statistics.jl:1-11 when the design has downsampling = false and sim_kind = SIM_ODE"""
+function simulate_moments(ctx::Context, m, θ::Matrix{Float64}; particle_offset=0, seed=UInt64(20240229))
+    n = size(θ, 2)
+    mom = Array{Float64}(undef, 5, 5, 11, n)
+    check(ccall((:abc_simulate_moments, LIB), Cint,
+                (Ptr{Cvoid}, Cint, Int64, Int64, UInt64, Ptr{Cdouble}, Ptr{Cdouble}, Ptr{Cvoid}),
+                ctx.ptr, m, n, particle_offset, seed, θ, mom, C_NULL))
+    return mom
+end
+
 """set_option(ctx, "ssa_hybrid_burnin" | "ssa_adaptive_burnin" | "stats_sample_guards" | "score_reference_kernel" |
 "accept_capacity", value)"""
 set_option(ctx::Context, name::AbstractString, value::Integer) =
@@ -154,6 +165,114 @@ function posterior_summary(ctx::Context, θ::Matrix{Float64}; particle_offset=0,
                 (Ptr{Cvoid}, Ptr{Cdouble}, Int64, Int32, Int64, Cdouble, Ptr{Cdouble}, Ptr{Cdouble}, Ptr{Cdouble}, Ptr{Cdouble}, Ptr{Int64}),
                 ctx.ptr, θ, n, P, particle_offset, q, out[1], out[2], out[3], out[4], nacc))
     return out[1], out[2], out[3], out[4], nacc
+end
+
+"""model_probs(ctx, counts; n_bootstraps, alpha, seed) -> (prob, l_bound, u_bound), each K x G: get_model_probs and the case
+split of model_probs.jl:1-54 on the device.  counts is G x K (column k = accepted particles per gene of hypothesis k, e.g.
+hcat(counts_const .+ counts_const_const, counts_kon .+ counts_alpha .+ counts_gamma))."""
+function model_probs(ctx::Context, counts::Matrix{Int64}; n_bootstraps=100, alpha=0.95, seed=UInt64(20240229))
+    G, K = size(counts)
+    out = [Matrix{Float64}(undef, K, G) for _ in 1:3]
+    check(ccall((:abc_model_probs, LIB), Cint,
+                (Ptr{Cvoid}, Ptr{Int64}, Int32, Int32, Int32, Cdouble, UInt64, Ptr{Cdouble}, Ptr{Cdouble}, Ptr{Cdouble}),
+                ctx.ptr, counts, K, G, n_bootstraps, alpha, seed, out[1], out[2], out[3]))
+    return out[1], out[2], out[3]
+end
+
+# ---- the reference's on-disk layouts written by the library (no 65 KB of text per particle formatted in Julia) ----------
+"""writedlm_lib(path, A; append): writedlm(io, transpose(A)) -- A is cols x rows (Julia column-major = the library's rows)"""
+writedlm_lib(path::AbstractString, A::Matrix{Float64}; append=true) =
+    check(ccall((:abc_writedlm, LIB), Cint, (Cstring, Ptr{Cdouble}, Int64, Int64, Cint), path, A, size(A, 2), size(A, 1), append))
+
+"""write_simulation(dir, m, submit, θ, stats; first_trial): the seven appends of abc_simulation.jl:47-61, 89-95 for a batch"""
+write_simulation(dir::AbstractString, m, submit, θ::Matrix{Float64}, stats::Matrix{Float64}; first_trial=1) =
+    check(ccall((:abc_write_simulation, LIB), Cint, (Cstring, Cint, Int32, Ptr{Cdouble}, Ptr{Cdouble}, Int64, Int64),
+                dir, m, submit, θ, stats, size(θ, 2), first_trial))
+
+"""write_accepted(path, offsets, idx; append): particles_<model>.txt (accepted_particles.jl:19-30)"""
+write_accepted(path::AbstractString, offsets::Vector{Int64}, idx::Vector{Int64}; append=true) =
+    check(ccall((:abc_write_accepted, LIB), Cint, (Cstring, Ptr{Int64}, Ptr{Int64}, Int32, Cint), path, offsets, idx, length(offsets) - 1, append))
+
+"""write_error_columns(dir, err; append): err is n x G (ERR_GENE_MAJOR): one raw Float64 file x<g>.f64 per gene"""
+write_error_columns(dir::AbstractString, err::Matrix{Float64}; append=true) =
+    check(ccall((:abc_write_error_columns, LIB), Cint, (Cstring, Ptr{Cdouble}, Int64, Int64, Int32, Cint),
+                dir, err, size(err, 1), size(err, 1), size(err, 2), append))
+
+"""read_error_column(dir, g) -> Vector{Float64}: f["x\$g"] of the reference's JDFFile (accepted_particles.jl:14-18)"""
+function read_error_column(dir::AbstractString, g::Integer)
+    n = Ref{Int64}(0)
+    check(ccall((:abc_read_error_column, LIB), Cint, (Cstring, Int32, Ptr{Cdouble}, Int64, Ref{Int64}), dir, g, C_NULL, 0, n))
+    v = Vector{Float64}(undef, n[])
+    check(ccall((:abc_read_error_column, LIB), Cint, (Cstring, Int32, Ptr{Cdouble}, Int64, Ref{Int64}), dir, g, v, n[], n))
+    return v
+end
+
+# ---- all GPUs of the box from this one Julia process (abc_multi_*): the library runs one host thread per device -------
+mutable struct MultiContext
+    ptr::Ptr{Cvoid}
+    n_genes::Int
+end
+
+"""MultiContext(; devices): devices = nothing uses every visible GPU"""
+function MultiContext(; devices::Union{Nothing,Vector{Int32}}=nothing)
+    p = Ref{Ptr{Cvoid}}(C_NULL)
+    n = devices === nothing ? ccall((:abc_device_count, LIB), Cint, ()) : Cint(length(devices))
+    check(ccall((:abc_multi_create, LIB), Cint, (Ptr{Int32}, Int32, Ref{Ptr{Cvoid}}), devices === nothing ? C_NULL : pointer(devices), n, p))
+    mg = MultiContext(p[], 0)
+    finalizer(c -> ccall((:abc_multi_destroy, LIB), Cint, (Ptr{Cvoid},), c.ptr), mg)
+    return mg
+end
+
+n_devices(mg::MultiContext) = Int(ccall((:abc_multi_n_devices, LIB), Cint, (Ptr{Cvoid},), mg.ptr))
+
+function set_design(mg::MultiContext; cycle=20.0, t0=-3cycle, agevec, pulsevec, chasevec, age_dist::Matrix{Float64},
+                    iv=[0.0, 0.5, 0, 0, 0, 0, 0, 0, 0], downsampling=true, betas::Vector{Float64}, age::Vector{<:Integer},
+                    pulse_idx::Vector{Int}, chase_idx::Vector{Int}, n_cells=96, n_pre_cycles=10, sim_kind=SIM_SSA,
+                    ode_rtol=1e-6, ode_atol=1e-9)
+    bp = betas[pulse_idx]; ap = Cint.(age[pulse_idx]); bc = betas[chase_idx]; ac = Cint.(age[chase_idx])
+    GC.@preserve bp ap bc ac begin
+        d = Design(cycle, t0, Tuple(agevec), Tuple(pulsevec), Tuple(chasevec), Tuple(vec(age_dist)), Tuple(iv),
+                   downsampling, n_cells, n_pre_cycles, sim_kind,
+                   pointer(bp), pointer(ap), length(bp), pointer(bc), pointer(ac), length(bc), ode_rtol, ode_atol)
+        check(ccall((:abc_multi_set_design, LIB), Cint, (Ptr{Cvoid}, Ref{Design}), mg.ptr, d))
+    end
+end
+
+function set_data(mg::MultiContext, d::Matrix{Float64}, se::Matrix{Float64})
+    @assert size(d) == size(se) && size(d, 1) == 53
+    check(ccall((:abc_multi_set_data, LIB), Cint, (Ptr{Cvoid}, Ptr{Cdouble}, Ptr{Cdouble}, Cint), mg.ptr, d, se, size(d, 2)))
+    mg.n_genes = size(d, 2)
+end
+
+set_option(mg::MultiContext, name::AbstractString, value::Integer) =
+    check(ccall((:abc_multi_set_option, LIB), Cint, (Ptr{Cvoid}, Cstring, Int64), mg.ptr, name, value))
+accept_reset(mg::MultiContext) = check(ccall((:abc_multi_accept_reset, LIB), Cint, (Ptr{Cvoid},), mg.ptr))
+
+"""simulate_score(mg, m, n_trials; ...): the particles are sharded over the GPUs by contiguous ranges; same arguments and the
+same results (bit for bit) as on one Context"""
+function simulate_score(mg::MultiContext, m, n_trials; particle_offset=0, seed=UInt64(20240229), theta=nothing, eps=4.8,
+                        layout=ERR_NONE, err=nothing)
+    θ = theta === nothing ? Matrix{Float64}(undef, n_params(m), n_trials) : theta
+    n, G = size(θ, 2), mg.n_genes
+    stats = Matrix{Float64}(undef, 53, n)
+    e = err !== nothing ? err : layout == ERR_NONE ? Matrix{Float64}(undef, 0, 0) :
+        layout == ERR_PARTICLE_MAJOR ? Matrix{Float64}(undef, G, n) : Matrix{Float64}(undef, n, G)
+    counts = Vector{Int64}(undef, G)
+    c = Ref{Counters}()
+    check(ccall((:abc_multi_simulate_score, LIB), Cint,
+                (Ptr{Cvoid}, Cint, Int64, Int64, UInt64, Cint, Ptr{Cdouble}, Ptr{Cdouble}, Cdouble, Cint, Ptr{Cdouble},
+                 Ptr{Int64}, Ref{Counters}),
+                mg.ptr, m, n, particle_offset, seed, theta === nothing ? 0 : 1, θ, stats, eps, layout,
+                layout == ERR_NONE ? C_NULL : pointer(e), counts, c))
+    return θ, stats, e, counts, c[]
+end
+
+"""accept_fetch(mg) -> (offsets, idx, errs): the merged per-gene lists of all GPUs (gene-range exchange over NCCL)"""
+function accept_fetch(mg::MultiContext)
+    total = ccall((:abc_multi_accept_total, LIB), Int64, (Ptr{Cvoid},), mg.ptr)
+    offsets = Vector{Int64}(undef, mg.n_genes + 1); idx = Vector{Int64}(undef, total); errs = Vector{Float64}(undef, total)
+    check(ccall((:abc_multi_accept_fetch, LIB), Cint, (Ptr{Cvoid}, Ptr{Int64}, Ptr{Int64}, Ptr{Cdouble}), mg.ptr, offsets, idx, errs))
+    return offsets, idx, errs
 end
 
 end # module

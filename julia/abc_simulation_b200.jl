@@ -17,23 +17,12 @@ ctx = AbcB200.Context(get(ENV, "ABCB200_DEVICE", "0") |> x -> parse(Int, x))
 AbcB200.set_design(ctx; cycle=cycle, t0=-3cycle, agevec=agevec, pulsevec=condition_id[:,1], chasevec=condition_id[:,2],
                    age_dist=age_dist, downsampling=true, betas=betas, age=age, pulse_idx=pulse_idx, chase_idx=chase_idx)
 
-dir = "data/simulations/"*model_name*"/"
-mkpath(dir)
 batch = 65536
 first_particle = (submit - 1) * n_trials          # distinct Philox streams per submit (wrapper.jl:62-63)
 @time for b0 in 0:batch:n_trials-1
     nb = min(batch, n_trials - b0)
     θ, stats, _ = AbcB200.simulate(ctx, m, nb; particle_offset=first_particle + b0)
-    open(dir*"sets_"*model_name*"_$submit.txt", "a") do io; writedlm(io, transpose(θ)); end
-    # s_pulse / s_chase: 2 rows per particle (means, Fano factors); the others 1 row of 11 (abc_simulation.jl:47-61)
-    open(dir*"s_pulse_"*model_name*"_$submit.txt", "a") do io
-        for i in 1:nb; writedlm(io, transpose(hcat(stats[1:5,i], stats[6:10,i]))); end
-    end
-    open(dir*"s_chase_"*model_name*"_$submit.txt", "a") do io
-        for i in 1:nb; writedlm(io, transpose(hcat(stats[11:15,i], stats[16:20,i]))); end
-    end
-    open(dir*"s_ratios_"*model_name*"_$submit.txt", "a") do io; writedlm(io, transpose(stats[21:31,:])); end
-    open(dir*"s_mean_corr_"*model_name*"_$submit.txt", "a") do io; writedlm(io, transpose(stats[32:42,:])); end
-    open(dir*"s_corr_mean_"*model_name*"_$submit.txt", "a") do io; writedlm(io, transpose(stats[43:53,:])); end
-    open(dir*"progress_"*model_name*"_$submit.txt", "a") do io; writedlm(io, b0 + nb); end
+    # the seven appends of abc_simulation.jl:47-61, 89-95 (sets_, s_pulse_ / s_chase_ as 2 rows x 5 per trial, s_ratios_,
+    # s_mean_corr_, s_corr_mean_, progress_), formatted like writedlm by the library: byte-identical files
+    AbcB200.write_simulation("data/simulations", m, submit, θ, stats; first_trial=b0 + 1)
 end

@@ -3,7 +3,7 @@
 # compute_errors.jl:1-28 -- the reference script itself is NOT included: its tail, compute_errors.jl:72-81, runs the CPU
 # scoring loop), writes the JDF column store and data/posteriors/particles_<model>.txt.
 # NOT EXECUTED IN THE BUILD CONTAINER (no Julia there).
-using DelimitedFiles, DataFrames, JDF
+using DelimitedFiles
 include(joinpath(@__DIR__, "AbcB200.jl"))
 
 # s_pulse / s_chase hold two rows per particle: odd rows the means, even rows the Fano factors (abc_simulation.jl:47-52)
@@ -27,11 +27,11 @@ stats = permutedims(hcat(s_pulse_mean,s_pulse_ff,s_chase_mean,s_chase_ff,s_ratio
 ε = 4.8                                                                                      # accepted_particles.jl:10
 AbcB200.accept_reset(ctx)
 @time err, counts = AbcB200.score(ctx, stats; eps=ε, layout=AbcB200.ERR_GENE_MAJOR)          # M x G, column g == x<g>
-JDF.save("data/errors/error_"*model_name*".jdf", DataFrame(err, :auto))                      # process_error_files.jl:5-6
+# process_error_files.jl:5-6: one column per gene.  With JDF.jl installed:  JDF.save("data/errors/error_"*model_name*".jdf",
+# DataFrame(err, :auto));  without it the library's own column store (one raw Float64 file per gene, AbcB200.read_error_column):
+AbcB200.write_error_columns("data/errors/error_"*model_name*".cols", err; append=false)
+# compute_errors.jl:66-68 (only if the text rows are wanted; 65 KB per particle):
+# AbcB200.writedlm_lib("data/errors/error_"*model_name*".txt", permutedims(err); append=true)
 offsets, idx, _ = AbcB200.accept_fetch(ctx)
-open("data/posteriors/particles_"*model_name*".txt", "a") do io                              # accepted_particles.jl:23-30
-    for g in 1:length(counts)
-        v = idx[offsets[g]+1:offsets[g+1]]
-        writedlm(io, isempty(v) ? [0] : reshape(v, 1, :))
-    end
-end
+mkpath("data/posteriors")
+AbcB200.write_accepted("data/posteriors/particles_"*model_name*".txt", offsets, idx; append=true)   # accepted_particles.jl:23-30
