@@ -26,7 +26,7 @@
 
 // one piece of the schedule between two consecutive cuts (rate steps, label on/off, read-out), 64 B.
 //   closed form (k1 != 0):  F(x) = 2^(k1 x + e0) (p0 + p1 x),  e0 = -k1 len, p0 = A0/gam - A1/gam^2, p1 = A1/gam, p2 = F(0)
-//   series (k1 == 0, gam len < 1/4):  F(x) = x (p0 + p1 x + ... + p5 x^5)
+//   series (k1 == 0, gam step < 1/4):  F(x) = x (p0 + p1 x + ... + p5 x^5); e0 = 1 (gam step < 1/20): F(x) = x (p0 + ... + p3 x^3)
 // F is the antiderivative of alpha(w) exp(-gam (len - w)): the Poisson mean advances by F(x2) - F(x1) over an "on"
 // stretch [x1, x2] and decays by dec = exp(-gam len) over the piece.
 struct __align__(16) TPiece {
@@ -161,7 +161,9 @@ __device__ __forceinline__ TPiece make_piece(const AbcRates& r, const PieceDesc&
 #pragma unroll
         for (int j = 7; j >= 0; --j) h = f_fma(h, len, cj[j]);
         t.Flen = f_mul(h, len);
-        t.k1 = 0.0f; t.e0 = 0.0f;
+        // gam step < 1/20: four terms reach the same 5e-8 (the fifth is (gam x)^4 / 120 of the first); flagged in e0, which the
+        // series does not use
+        t.k1 = 0.0f; t.e0 = (f_mul(gam, step_len) < 0.05f) ? 1.0f : 0.0f;
         t.p0 = cj[0]; t.p1 = cj[1]; t.p2 = cj[2]; t.p3 = cj[3]; t.p4 = cj[4]; t.p5 = cj[5];
     } else {
         const float e = __fdiv_rn(A1, gam), c = __fdiv_rn(f_add(A0, -e), gam);
@@ -175,6 +177,13 @@ __device__ __forceinline__ TPiece make_piece(const AbcRates& r, const PieceDesc&
         t.Flen = tp_F(t.k1, t.e0, c, e, 0.0f, 0.0f, 0.0f, 0.0f, len);
     }
     return t;
+}
+
+// models 1, 2: no rate varies and alpha is linear over the whole cycle: one piece per cycle (measured: cutting them into 4 h
+// pieces to use the short series costs more in boundary crossings than the two FFMAs per draw it saves)
+__device__ __forceinline__ int tele_steps_per_cycle(int m, float gam0, float cycle) {
+    (void)gam0; (void)cycle;
+    return (m <= 2) ? 1 : 5;
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -300,11 +309,12 @@ abc_window_kernel(AbcRates* __restrict__ rates, const AbcSsaParams prm, float* _
         out_start[p * ABC_NREAD + readout] = (float)s0;
         // expected draws of one lineage: switches + one discarded draw per piece
         {
-            const double stepc = (prm.m <= 2) ? cycle : step5;
-            const Cuts c = make_cuts((double)(float)s0, age, stepc, (prm.m <= 2) ? inv_cycle : inv_step5, tl0, tl1, window);
+            const int spc = tele_steps_per_cycle(prm.m, r.gamma[0], (float)cycle);
+            const double stepc = (spc == 1) ? cycle : step5;
+            const Cuts c = make_cuts((double)(float)s0, age, stepc, (spc == 1) ? inv_cycle : inv_step5, tl0, tl1, window);
             double lineage = 0.0;
             for (int k = 0; k < c.n; ++k) {
-                const PieceDesc d = describe_piece(c, k, cycle, inv_cycle, inv_step5, (prm.m <= 2) ? 1 : 5, window);
+                const PieceDesc d = describe_piece(c, k, cycle, inv_cycle, inv_step5, spc, window);
                 const double kon = (double)r.kon[d.step], koff = (double)r.koff[d.step];
                 lineage += 2.0 * kon * koff / (kon + koff) * (d.b - d.a) + 1.0;
             }
@@ -337,10 +347,8 @@ abc_tele_kernel(const AbcRates* __restrict__ rates, const AbcSsaParams prm, cons
                                          ? (unsigned long long)prm.chunks
                                          : (unsigned long long)prm.n_particles * per_particle;
     unsigned long long acc_lineages = 0, acc_events = 0, acc_draws = 0;
-    const int steps_per_cycle = (prm.m <= 2) ? 1 : 5;       // models 1, 2: no rate varies, alpha is linear over the whole cycle
-    const double step_cut = prm.cycle / (double)steps_per_cycle, inv_step_cut = (double)steps_per_cycle / prm.cycle;
-    const double inv_cycle = 1.0 / prm.cycle, inv_step5 = 5.0 / prm.cycle;
-    const float step_len = (float)step_cut, sc_inv_cycle = prm.scaling ? (float)inv_cycle : 0.0f;
+    const double inv_cycle = 1.0 / prm.cycle, inv_step5 = 5.0 / prm.cycle, step5 = prm.cycle / 5.0;
+    const float sc_inv_cycle = prm.scaling ? (float)inv_cycle : 0.0f;
 
     for (;;) {
         unsigned int item = 0;
@@ -373,6 +381,9 @@ abc_tele_kernel(const AbcRates* __restrict__ rates, const AbcSsaParams prm, cons
         const double tl0 = age - prm.pulse[cond] - prm.chase[cond], tl1 = age - prm.chase[cond];
         const bool window = prm.pulse[cond] > 0.0;
         const double s0 = (double)win[p * ABC_NREAD + readout];
+        const int steps_per_cycle = tele_steps_per_cycle(prm.m, srates[warp].gamma[0], (float)prm.cycle);
+        const double step_cut = (steps_per_cycle == 1) ? prm.cycle : step5, inv_step_cut = (steps_per_cycle == 1) ? inv_cycle : inv_step5;
+        const float step_len = (float)step_cut;
         const Cuts cuts = make_cuts(s0, age, step_cut, inv_step_cut, tl0, tl1, window);
         const int n_seg = min(cuts.n, TELE_MAX_SEG);
         for (int k = lane; k < n_seg; k += 32) {
@@ -409,7 +420,7 @@ abc_tele_kernel(const AbcRates* __restrict__ rates, const AbcSsaParams prm, cons
         float lam = 0.0f, lamL = 0.0f;      // Poisson means of U and L given the gene path
         {
             const TPiece* tp = tab;
-            bool done = !live || n_seg == 0;
+            const bool done = !live || n_seg == 0;
             float x = 0.0f, acc = 0.0f;
             float sgn = s.g ? 1.0f : -1.0f;                 // +1 while the gene is on
             float len = INFINITY, e0 = 0.0f, k1 = 0.0f, p0 = 0.0f, p1 = 0.0f;
@@ -451,6 +462,12 @@ abc_tele_kernel(const AbcRates* __restrict__ rates, const AbcSsaParams prm, cons
                     asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(d4) : "f"(f_fma(k1, x4, e0)));
                     F1 = f_mul(d1, f_fma(p1, x1, p0)); F2 = f_mul(d2, f_fma(p1, x2, p0));
                     F3 = f_mul(d3, f_fma(p1, x3, p0)); F4 = f_mul(d4, f_fma(p1, x4, p0));
+                } else if (e0 != 0.0f) {
+                    const float2 c = *reinterpret_cast<const float2*>(&tp->p2);
+                    float h1 = f_fma(c.y, x1, c.x), h2 = f_fma(c.y, x2, c.x), h3 = f_fma(c.y, x3, c.x), h4 = f_fma(c.y, x4, c.x);
+                    h1 = f_fma(h1, x1, p1); h2 = f_fma(h2, x2, p1); h3 = f_fma(h3, x3, p1); h4 = f_fma(h4, x4, p1);
+                    h1 = f_fma(h1, x1, p0); h2 = f_fma(h2, x2, p0); h3 = f_fma(h3, x3, p0); h4 = f_fma(h4, x4, p0);
+                    F1 = f_mul(h1, x1); F2 = f_mul(h2, x2); F3 = f_mul(h3, x3); F4 = f_mul(h4, x4);
                 } else {
                     const float4 c = *reinterpret_cast<const float4*>(&tp->p2);
                     float h1 = f_fma(c.w, x1, c.z), h2 = f_fma(c.w, x2, c.z), h3 = f_fma(c.w, x3, c.z), h4 = f_fma(c.w, x4, c.z);
@@ -494,7 +511,6 @@ abc_tele_kernel(const AbcRates* __restrict__ rates, const AbcSsaParams prm, cons
                         lamL = f_mul(lamL, 0.5f);
                     }
                     if (meta & TP_LAST) {
-                        done = true;
                         ctr_done = s.ctr;
                         len = INFINITY; qb = 0u; qsum = 0u;      // a finished lane idles: x stays, nothing crosses
                         k1 = 0.0f; p0 = 0.0f; p1 = 0.0f; e0 = 0.0f;
@@ -508,7 +524,7 @@ abc_tele_kernel(const AbcRates* __restrict__ rates, const AbcSsaParams prm, cons
                         acc = (k1 != 0.0f) ? f_mul(-gs, tp->p2) : 0.0f;
                     }
                 }
-                if (__all_sync(FULL, done)) break;
+                if (__all_sync(FULL, !(len < INFINITY))) break;      // every lane has finished (len = inf marks it)
             }
             if (live) {
                 // draws = switches + boundary crossings; the words discarded after a crossing are not counted

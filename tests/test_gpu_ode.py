@@ -64,15 +64,19 @@ def test_device_ode_statistics_match_oracle_run_sim(betas, m):
             assert np.allclose(stats[i][ok], want[ok], rtol=2e-3, atol=1e-6), (i, np.abs(stats[i][ok] - want[ok]).max())
 
 
-def test_accepted_posteriors_agree_between_ssa_and_moment_odes(betas):
-    """north-star part 2: on a fixed gene set the accepted posteriors of the SSA path and of the moment-ODE path
-    (what the reference computes) agree: same parameter sets, 96 cells per read-out, eps = 4.8.  Tolerances from
-    profiles/r1_equivalence_ssa_vs_ode.json (Spearman 0.99, shift 0.06 SD at 20 000 particles)."""
+@pytest.mark.parametrize("m,n,min_rich,min_rho", [(1, 20000, 1200, 0.97), (2, 20000, 1200, 0.97), (3, 20000, 1000, 0.97),
+                                                  (4, 20000, 400, 0.93), (5, 40000, 40, 0.88)])
+def test_accepted_posteriors_agree_between_ssa_and_moment_odes(betas, m, n, min_rich, min_rho):
+    """north-star part 2 (BASELINE configs[1]), all five models: on the 3419 real genes the accepted posteriors of the SSA
+    path (product sampler: telegraph SSA + conditional Poisson read-out, start time per read-out) and of the moment-ODE path
+    (what the reference computes) agree for the same fixed-seed parameter sets, 96 cells per read-out, eps = 4.8: per-gene
+    acceptance counts rank-correlate, and the posterior means of the genes with >= 20 accepted particles under both differ
+    by a fraction of the posterior SD.  (A 96-cell sample adds Monte-Carlo noise to the statistics, which lowers the
+    acceptance rate of a hard threshold: 0.4-0.8 of the ODE path's.)  Reference numbers: profiles/r2_equivalence_*.json."""
     from abc_inference_transcription_b200 import ERR_NONE
     from abc_inference_transcription_b200.posteriors import get_posterior_estimate
     z = np.load(os.path.join(GOLD, "ref_summary_stats.npz"))
     d, se = z["d"], z["se"]
-    n, m = 8000, 1
     with AbcEngine(0) as ssa, AbcEngine(0) as ode:
         ssa.set_design(synthetic_design(betas, n_cells=96, n_pre_cycles=10))
         ode.set_design(synthetic_design(betas, sim_kind=SIM_ODE))
@@ -90,10 +94,10 @@ def test_accepted_posteriors_agree_between_ssa_and_moment_odes(betas):
     c_s, c_o = acc["ssa"][0], acc["ode"][0]
     both = (c_s > 0) | (c_o > 0)
     rs, ro = np.argsort(np.argsort(c_s[both])), np.argsort(np.argsort(c_o[both]))
-    assert np.corrcoef(rs, ro)[0, 1] > 0.93
+    assert np.corrcoef(rs, ro)[0, 1] > min_rho, np.corrcoef(rs, ro)[0, 1]
     assert 0.4 < c_s.sum() / c_o.sum() < 1.1                      # MC noise of 96-cell samples lowers acceptance
     rich = np.nonzero((c_s >= 20) & (c_o >= 20))[0] + 1
-    assert len(rich) > 300
+    assert len(rich) >= min_rich, len(rich)
     pm_s = get_posterior_estimate(theta, acc["ssa"][1], acc["ssa"][2], rich, "mean")
     pm_o = get_posterior_estimate(theta, acc["ode"][1], acc["ode"][2], rich, "mean")
     sd = np.array([theta[acc["ode"][2][acc["ode"][1][g - 1]:acc["ode"][1][g]] - 1].std(0) for g in rich])

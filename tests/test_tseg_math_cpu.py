@@ -17,7 +17,7 @@ def make_tseg(len_, A0, A1, gam, step_len):
         c, flen = [], 0.0
         for j in range(1, 10):
             v = dec * (A0 * gam ** (j - 1) / math.factorial(j) + (A1 * gam ** (j - 2) / (math.factorial(j - 2) * j) if j >= 2 else 0.0))
-            if j <= 6:
+            if j <= (4 if gam * step_len < 0.05 else 6):       # short series below gam * step = 1/20 (csrc/abc_tele.cu make_piece)
                 c.append(f32(v))
             flen += v * len_ ** j
         return dict(small=True, c=c, Flen=f32(flen), F0=f32(0.0), dec=f32(dec), len=f32(len_))
@@ -31,8 +31,8 @@ def tseg_F(k, x):
     x = f32(x)
     if k["small"]:
         c = k["c"]
-        h = f32(f32(c[5] * x) + c[4])
-        for j in (3, 2, 1, 0):
+        h = c[-1]
+        for j in range(len(c) - 2, -1, -1):
             h = f32(f32(h * x) + c[j])
         return f32(h * x)
     d = f32(2.0 ** float(f32(k["k1"] * f32(x - k["len"]))))
