@@ -9,7 +9,7 @@ import os
 
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libabcb200.so")
+LIB_PATH = os.environ.get("ABCB200_LIB", os.path.join(_HERE, "libabcb200.so"))   # same override as julia/AbcB200.jl
 
 NAGE, NCOND, NSTATS, NREAD = 5, 11, 53, 55
 SIM_SSA, SIM_ODE = 0, 1

@@ -1,5 +1,7 @@
-// abc_ssa.cu -- Gillespie direct-method SSA of the 5 transcription models, capture-efficiency
-// thinning, per read-out moment sums, and the 53 summary statistics.  sm_100a.
+// abc_ssa.cu -- Gillespie direct-method SSA of the 5 transcription models over all six channels (ssa_hybrid_burnin = 0, the
+// exact-math variant that is bit-identical to the CPU oracle, and = 1 with a telegraph burn-in), capture-efficiency thinning,
+// per read-out moment sums, prior draws, rates, moments and the 53 summary statistics.  The product sampler
+// (ssa_hybrid_burnin = 2) is abc_tele.cu.  sm_100a.
 //
 // The stochastic process is the CME whose moments scripts/model.jl:74-86 (f), :98-111
 // (periodic_boundary) and :221-239 (downsample) describe -- SURVEY.md section 8a-CME:
@@ -234,7 +236,8 @@ __device__ __forceinline__ void build_table(WarpTable& tab, const AbcRates& r, c
     }
 }
 
-template <bool EXACT, int HYBRID>      // HYBRID: 0 = six-channel direct method throughout, 1 = telegraph burn-in, 2 = telegraph to the read-out
+template <bool EXACT, int HYBRID>      // HYBRID: 0 = six-channel direct method throughout, 1 = telegraph burn-in before the label
+                                       // window (mode 2, telegraph to the read-out, is abc_tele.cu)
 __global__ void __launch_bounds__(SSA_WARPS * 32, 4)
 abc_ssa_kernel(const AbcRates* __restrict__ rates, const AbcSsaParams prm, const uint32_t* __restrict__ beta_q32,
                unsigned long long* __restrict__ sums, unsigned long long* __restrict__ counters,
@@ -273,12 +276,12 @@ abc_ssa_kernel(const AbcRates* __restrict__ rates, const AbcSsaParams prm, const
         __syncwarp();
         if (lane == 0) { tab.c_star = -1; tab.e_star = 0; }
         __syncwarp();
-        const int n_steps = (HYBRID == 2 && prm.m <= 2) ? 1 : 5;
+        const int n_steps = 5;
         const int c0 = (HYBRID && prm.adaptive) ? prm.n_pre - burnin_cycles(srates[warp], prm, cond, age_i) : 0;   // first simulated cycle
         build_table(tab, srates[warp], prm, cond, age_i, lane, n_steps, c0);
         __syncwarp();
-        if (lane == 0 && (tab.c_star < 0 || HYBRID == 2)) {
-            // empty window, or hybrid mode 2: the telegraph phase runs to the read-out
+        if (lane == 0 && tab.c_star < 0) {
+            // empty window: the telegraph phase runs to the read-out
             tab.c_star = prm.n_pre; tab.e_star = tab.n_ent[prm.n_pre];
         }
         __syncwarp();
@@ -346,14 +349,17 @@ abc_ssa_kernel(const AbcRates* __restrict__ rates, const AbcSsaParams prm, const
                     }
                     // fast path: all four draws of every lane of the warp are switches inside the current sub-interval
                     // (the waiting-time factor alternates between the two gene states); same arithmetic as the
-                    // draw-by-draw path below for the event times, F enters as sgn ((F1 - F2) + (F3 - F4))
+                    // draw-by-draw path below
                     const float qc = __uint_as_float(qb), qo = __uint_as_float(qsum - qb);
                     const float x1 = f_fma(l4[0], qc, x), x2 = f_fma(l4[1], qo, x1);
                     const float x3 = f_fma(l4[2], qc, x2), x4 = f_fma(l4[3], qo, x3);
                     if (__all_sync(__activemask(), x4 < len)) {
-                        const float t = f_add(f_add(tseg_F(tp, len, k1, p0, p1, x1), -tseg_F(tp, len, k1, p0, p1, x2)),
-                                              f_add(tseg_F(tp, len, k1, p0, p1, x3), -tseg_F(tp, len, k1, p0, p1, x4)));
-                        acc = f_fma(sgn, t, acc);
+                        // the same four sequential FMAs as the draw-by-draw path below: a lineage's result does not depend
+                        // on which lanes happen to be converged at the vote
+                        acc = f_fma(sgn, tseg_F(tp, len, k1, p0, p1, x1), acc);
+                        acc = f_fma(-sgn, tseg_F(tp, len, k1, p0, p1, x2), acc);
+                        acc = f_fma(sgn, tseg_F(tp, len, k1, p0, p1, x3), acc);
+                        acc = f_fma(-sgn, tseg_F(tp, len, k1, p0, p1, x4), acc);
                         x = x4;
                         continue;
                     }
@@ -398,7 +404,6 @@ abc_ssa_kernel(const AbcRates* __restrict__ rates, const AbcSsaParams prm, const
                 s.L = poisson_draw(lamL, ws, s);
                 c_first = tab.c_star; e_first = tab.e_star;
             }
-            if (HYBRID != 2)
             for (int c = c_first; c <= prm.n_pre; ++c) {
                 const int n_ent = tab.n_ent[c];
                 int e = (c == c_first) ? e_first : 0;

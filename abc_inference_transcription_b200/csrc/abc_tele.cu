@@ -20,6 +20,10 @@
 //                      rest of their block is discarded: the waiting times are memoryless and the words independent).
 #include "abc_ssa_dev.cuh"
 
+#ifndef TELE_MIN_CTAS
+#define TELE_MIN_CTAS 3      // 24 warps x 80 registers per SM: measured best (4 x 64: -4 %, 2 x 100: -8 %; computing the next
+                             // Philox block one iteration ahead for more ILP: -8 %, the loop is bound by issue slots, not latency)
+#endif
 #define TELE_WARPS 8
 #define TELE_MAX_SEG 80      // 5 rate steps x (n_pre_cycles + 1 <= 14 cycles) + label on/off + the cut at the start + slack
 #define FULL 0xffffffffu
@@ -226,7 +230,10 @@ abc_window_kernel(AbcRates* __restrict__ rates, const AbcSsaParams prm, float* _
     const double cycle = prm.cycle, step5 = cycle / 5.0, inv_cycle = 1.0 / cycle, inv_step5 = 5.0 / cycle;
     const double t_min = -(double)prm.n_pre * cycle;
     const double eps = exp2(-(double)prm.n_pre), floor_abs = 9.313225746154785e-10;   // 2^-30 molecules
-    double cost = 0.0;
+    double cost = 0.0, rate_max = 0.0;      // rate_max >= alpha(t) P_on(t) at any time
+#pragma unroll
+    for (int j = 0; j < 5; ++j)
+        rate_max = fmax(rate_max, 2.0 * (double)r.alpha[j] * (double)r.kon[j] / ((double)r.kon[j] + (double)r.koff[j]));
     bool bad = false;
 #pragma unroll
     for (int j = 0; j < 5; ++j) {
@@ -248,6 +255,7 @@ abc_window_kernel(AbcRates* __restrict__ rates, const AbcSsaParams prm, float* _
             double cu[WIN_MAX_PIECES], cl[WIN_MAX_PIECES];
             double bits_after = 0.0, TU = 0.0, TL = 0.0;
             const int np = min(c.n, WIN_MAX_PIECES);
+            int k_old = 0;          // pieces older than this one are not evaluated: their sum is provably negligible
             for (int k = np - 1; k >= 0; --k) {
                 const PieceDesc d = describe_piece(c, k, cycle, inv_cycle, inv_step5, 5, window);
                 if (d.div_after) bits_after += 1.0;
@@ -260,10 +268,19 @@ abc_window_kernel(AbcRates* __restrict__ rates, const AbcSsaParams prm, float* _
                 cu[k] = I * (1.0 - lf); cl[k] = I * lf;
                 TU += cu[k]; TL += cl[k];
                 bits_after += gam * L * 1.4426950408889634;
+                // Everything older than this piece is born before the label window (unlabelled only) and has decayed by at
+                // least 2^-bits_after: once even the largest possible birth rate over the remaining time stays below
+                // 2^-20 of the bound itself, the older pieces cannot move the start time and the walk stops.
+                if (k > 0 && (!window || d.a <= tl0) &&
+                    rate_max * (d.a - t_min) * exp2(-fmin(bits_after, 1020.0)) <= 9.5367431640625e-7 * fmax(eps * TU, floor_abs)) {
+                    k_old = k;
+                    break;
+                }
             }
+            for (int k = 0; k < k_old; ++k) { cu[k] = 0.0; cl[k] = 0.0; }
             // drop the oldest pieces while their sum stays below the bound for both species
             double MU = 0.0, ML = 0.0;
-            int j = 0;
+            int j = k_old;
             for (; j < np; ++j) {
                 const double mu = MU + cu[j], ml = ML + cl[j];
                 if (!(mu <= fmax(eps * (TU - mu), floor_abs) && ml <= fmax(eps * (TL - ml), floor_abs))) break;
@@ -333,7 +350,7 @@ abc_window_kernel(AbcRates* __restrict__ rates, const AbcSsaParams prm, float* _
 }
 
 // ------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(TELE_WARPS * 32, 4)
+__global__ void __launch_bounds__(TELE_WARPS * 32, TELE_MIN_CTAS)
 abc_tele_kernel(const AbcRates* __restrict__ rates, const AbcSsaParams prm, const float* __restrict__ win,
                 const uint32_t* __restrict__ beta_q32, unsigned long long* __restrict__ sums,
                 unsigned long long* __restrict__ counters, unsigned int* __restrict__ work, uint32_t* __restrict__ cells_out,
