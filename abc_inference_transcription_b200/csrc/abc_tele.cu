@@ -234,6 +234,16 @@ abc_window_kernel(AbcRates* __restrict__ rates, const AbcSsaParams prm, float* _
 #pragma unroll
     for (int j = 0; j < 5; ++j)
         rate_max = fmax(rate_max, 2.0 * (double)r.alpha[j] * (double)r.kon[j] / ((double)r.kon[j] + (double)r.koff[j]));
+    // a whole rate step (4 h) contributes the same in every cycle: P_on x integral of alpha(w) exp(-gam (end - w)), and exp(-gam step)
+    double step_int[5], step_dec[5], pon_step[5];
+#pragma unroll
+    for (int j = 0; j < 5; ++j) {
+        const double gam = (double)r.gamma[j], al = (double)r.alpha[j];
+        const double A0 = al * (1.0 + (prm.scaling ? (double)j * 0.2 : 0.0)), A1 = prm.scaling ? al / cycle : 0.0;
+        pon_step[j] = (double)r.kon[j] / ((double)r.kon[j] + (double)r.koff[j]);
+        step_int[j] = pon_step[j] * piece_integral(A0, A1, gam, step5);
+        step_dec[j] = exp(-gam * step5);
+    }
     bool bad = false;
 #pragma unroll
     for (int j = 0; j < 5; ++j) {
@@ -253,26 +263,32 @@ abc_window_kernel(AbcRates* __restrict__ rates, const AbcSsaParams prm, float* _
             // mean contribution of the births of every piece to Lam_U and Lam_L at the read-out, newest piece first
             const Cuts c = make_cuts(t_min, age, step5, inv_step5, tl0, tl1, window);
             double cu[WIN_MAX_PIECES], cl[WIN_MAX_PIECES];
-            double bits_after = 0.0, TU = 0.0, TL = 0.0;
+            double surv = 1.0, TU = 0.0, TL = 0.0;      // surv = 2^-B: survival from the newer end of the piece to the read-out
             const int np = min(c.n, WIN_MAX_PIECES);
             int k_old = 0;          // pieces older than this one are not evaluated: their sum is provably negligible
             for (int k = np - 1; k >= 0; --k) {
                 const PieceDesc d = describe_piece(c, k, cycle, inv_cycle, inv_step5, 5, window);
-                if (d.div_after) bits_after += 1.0;
-                const double L = d.b - d.a, gam = (double)r.gamma[d.step];
-                const double al = (double)r.alpha[d.step];
-                const double A0 = al * (1.0 + (prm.scaling ? d.xa / cycle : 0.0)), A1 = prm.scaling ? al / cycle : 0.0;
-                const double pon = (double)r.kon[d.step] / ((double)r.kon[d.step] + (double)r.koff[d.step]);
-                const double I = pon * exp2(-fmin(bits_after, 1020.0)) * piece_integral(A0, A1, gam, L);
+                if (d.div_after) surv *= 0.5;
+                const double L = d.b - d.a;
+                double integral, decay;
+                if (L == step5) {       // a whole rate step: the same integral and decay in every cycle (per-particle tables)
+                    integral = step_int[d.step]; decay = step_dec[d.step];
+                } else {
+                    const double gam = (double)r.gamma[d.step], al = (double)r.alpha[d.step];
+                    const double A0 = al * (1.0 + (prm.scaling ? d.xa / cycle : 0.0)), A1 = prm.scaling ? al / cycle : 0.0;
+                    integral = pon_step[d.step] * piece_integral(A0, A1, gam, L);
+                    decay = exp(-gam * L);
+                }
+                const double I = surv * integral;
                 const double lf = d.labelled ? (double)r.lam : 0.0;
                 cu[k] = I * (1.0 - lf); cl[k] = I * lf;
                 TU += cu[k]; TL += cl[k];
-                bits_after += gam * L * 1.4426950408889634;
-                // Everything older than this piece is born before the label window (unlabelled only) and has decayed by at
-                // least 2^-bits_after: once even the largest possible birth rate over the remaining time stays below
-                // 2^-20 of the bound itself, the older pieces cannot move the start time and the walk stops.
+                surv *= decay;
+                // Everything older than this piece is born before the label window (unlabelled only) and survives with at
+                // most `surv`: once even the largest possible birth rate over the remaining time stays below 2^-20 of the
+                // bound itself, the older pieces cannot move the start time and the walk stops.
                 if (k > 0 && (!window || d.a <= tl0) &&
-                    rate_max * (d.a - t_min) * exp2(-fmin(bits_after, 1020.0)) <= 9.5367431640625e-7 * fmax(eps * TU, floor_abs)) {
+                    rate_max * (d.a - t_min) * surv <= 9.5367431640625e-7 * fmax(eps * TU, floor_abs)) {
                     k_old = k;
                     break;
                 }
