@@ -43,10 +43,13 @@ SSA_MODE = 2                          # ssa_hybrid_burnin of the headline run (l
 ALG_BYTES_PER_PARTICLE_SCORE = 27776  # 424 B read + G*8 B written, G = 3419
 # ncu --set full of abc_tele_kernel, 4096 prior particles of one model (profiles/r2_ssa_m{1,3,5}_ncu_summary.csv): share of issue
 # slots used x active threads per instruction / 32 = executed lane-instructions over the lane-issue peak
-NCU_SSA = {"src": "profiles/r2_ssa_m{1,3,5}_ncu_summary.csv (ncu --set full, 4096 prior particles per model, adaptive start)",
-           "m1": {"issue_active": 0.686, "threads_per_inst": 29.91, "executed_lane_frac": 0.686 * 29.91 / 32},
-           "m3": {"issue_active": None, "threads_per_inst": None, "executed_lane_frac": None},
-           "m5": {"issue_active": None, "threads_per_inst": None, "executed_lane_frac": None}}
+NCU_SSA = {"src": "profiles/r2_ssa_m{1,3,5}_ncu_summary.csv (ncu --set full --clock-control none of abc_tele_kernel, 4096 prior "
+                  "particles of one model, start-time rule)",
+           "m1": {"issue_active": 0.690, "threads_per_inst": 29.85, "executed_lane_frac": 0.690 * 29.85 / 32,
+                  "warp_inst_per_warp_draw": 28.2},
+           "m3": {"issue_active": 0.717, "threads_per_inst": 27.87, "executed_lane_frac": 0.717 * 27.87 / 32},
+           "m5": {"issue_active": 0.695, "threads_per_inst": 26.32, "executed_lane_frac": 0.695 * 26.32 / 32},
+           "pipes_m1_pct_of_own_peak": {"alu": 41.6, "fma": 36.0, "xu": 30.4}, "dram_bytes_per_launch": 11.0e6}
 SCORE_TRAFFIC_131070 = 4.04e9         # measured dram bytes (read + write) of one 131070-particle scoring call, see profiles/
 
 
