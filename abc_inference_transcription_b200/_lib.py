@@ -92,6 +92,8 @@ SYMBOLS = {
     "abc_launch_count": (ctypes.c_int64, [_vp]),
     "abc_model_probs": (ctypes.c_int, [_vp, _vp, ctypes.c_int32, ctypes.c_int32, ctypes.c_int32, ctypes.c_double, ctypes.c_uint64,
                                        _vp, _vp, _vp]),
+    "abc_data_summary_stats": (ctypes.c_int, [_vp, _vp, _vp, ctypes.c_int32, ctypes.c_int32, _vp, _vp, _vp, _vp, ctypes.c_int32, _vp,
+                                              ctypes.c_int32, _vp, ctypes.c_int32, ctypes.c_uint64, _vp, _vp]),
     "abc_format_float64": (ctypes.c_int, [ctypes.c_double, ctypes.c_char_p, ctypes.c_size_t]),
     "abc_writedlm": (ctypes.c_int, [ctypes.c_char_p, _vp, ctypes.c_int64, ctypes.c_int64, ctypes.c_int]),
     "abc_write_simulation": (ctypes.c_int, [ctypes.c_char_p, ctypes.c_int, ctypes.c_int32, _vp, _vp, ctypes.c_int64, ctypes.c_int64]),

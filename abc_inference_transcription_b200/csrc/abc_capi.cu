@@ -983,6 +983,16 @@ extern "C" int abc_posterior_summary(abc_ctx_t* c, const double* theta, int64_t 
     return ABC_OK;
 }
 
+// SURVEY 8f-4 (data_summary_statistics.jl:183-194 get_summary_stats for every gene)
+extern "C" int abc_data_summary_stats(abc_ctx_t* c, const double* u, const double* l, int32_t n_cells, int32_t n_genes,
+                                      const int32_t* age, const int32_t* experiment, const int32_t* cond_vec,
+                                      const int32_t* pulse_idx, int32_t n_pulse, const int32_t* chase_idx, int32_t n_chase,
+                                      const double* age_id_dist, int32_t n_bootstraps, uint64_t seed, double* d, double* se) {
+    CTX_GUARD(c);
+    return abc_run_data_summary_stats(u, l, n_cells, n_genes, age, experiment, cond_vec, pulse_idx, n_pulse, chase_idx, n_chase,
+                                      age_id_dist, n_bootstraps, seed, d, se, &c->launches, c->stream);
+}
+
 // SURVEY 8f-2 (model_probs.jl:1-54): per-gene model probabilities = acceptance-count ratios + bootstrap percentile bounds
 extern "C" int abc_model_probs(abc_ctx_t* c, const int64_t* counts, int32_t K, int32_t G, int32_t n_bootstraps, double alpha,
                                uint64_t seed, double* prob, double* lb, double* ub) {

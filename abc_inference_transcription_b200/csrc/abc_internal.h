@@ -136,3 +136,9 @@ int abc_launch_posterior(const long long* d_idx, const long long* d_offsets, siz
 // SURVEY 8f-2 model-probability bootstrap (abc_accept.cu)
 int abc_launch_model_probs(const long long* d_counts, int K, int G, int B, double alpha, uint64_t seed, double* d_stats,
                            double* d_prob, double* d_lb, double* d_ub, int* n_launches, cudaStream_t st);
+
+// data-side summary statistics with bootstrap standard errors (abc_datastats.cu)
+int abc_run_data_summary_stats(const double* u, const double* l, int n_cells, int G, const int32_t* age, const int32_t* experiment,
+                               const int32_t* cond_vec, const int32_t* pulse_idx, int n_pulse, const int32_t* chase_idx, int n_chase,
+                               const double* age_id_dist, int B, uint64_t seed, double* d_out, double* se_out, int64_t* launches,
+                               cudaStream_t st);

@@ -236,6 +236,26 @@ class AbcEngine:
                                              _lib.ptr(out[0]), _lib.ptr(out[1]), _lib.ptr(out[2])))
         return tuple(out)
 
+    def data_summary_stats(self, u, l, age, experiment, cond_vec, pulse_idx, chase_idx, age_id_dist, n_bootstraps=100,
+                           seed=20240229):
+        """get_summary_stats of scripts/data_summary_statistics.jl:183-194 for every gene on the device: u, l (G, n_cells)
+        integer-valued counts; age (n_cells,) clusters 1..5; experiment (n_cells,) condition ids; cond_vec (11,); pulse_idx /
+        chase_idx 1-based cell indices; age_id_dist (5, 11).  Returns (d, se), each (G, 53): the inputs of set_data."""
+        u = np.ascontiguousarray(u, dtype=np.float64)
+        l = np.ascontiguousarray(l, dtype=np.float64)
+        G, n_cells = u.shape
+        assert l.shape == u.shape
+        i32 = lambda a: np.ascontiguousarray(a, dtype=np.int32)
+        age, experiment, cond_vec, pulse_idx, chase_idx = i32(age), i32(experiment), i32(cond_vec), i32(pulse_idx), i32(chase_idx)
+        assert len(age) == n_cells == len(experiment) and len(cond_vec) == _lib.NCOND
+        ad = np.ascontiguousarray(np.asarray(age_id_dist, dtype=np.float64).T.reshape(-1))     # 5 x 11 column-major
+        d = np.empty((G, _lib.NSTATS), dtype=np.float64)
+        se = np.empty((G, _lib.NSTATS), dtype=np.float64)
+        _lib.check(self._lib.abc_data_summary_stats(self._ctx, _lib.ptr(u), _lib.ptr(l), n_cells, G, _lib.ptr(age), _lib.ptr(experiment),
+                                                    _lib.ptr(cond_vec), _lib.ptr(pulse_idx), len(pulse_idx), _lib.ptr(chase_idx),
+                                                    len(chase_idx), _lib.ptr(ad), int(n_bootstraps), int(seed), _lib.ptr(d), _lib.ptr(se)))
+        return d, se
+
     def accept_tuples(self):
         total = self.accept_total()
         gene = np.empty(total, dtype=np.int32)

@@ -229,6 +229,21 @@ int  abc_counters(abc_ctx_t* ctx, abc_counters_t* counters);
 /* how many kernels this library has launched on the context since creation */
 int64_t abc_launch_count(abc_ctx_t* ctx);
 
+/* ---- data side: get_summary_stats of scripts/data_summary_statistics.jl:183-194 for every gene -----------------
+ * The 53 data statistics d and their bootstrap standard errors se -- the inputs of abc_set_data -- from the per-cell UMI counts.
+ * u, l: host, Julia n_cells x n_genes column-major (one gene's cells contiguous), integer-valued (gene_selection.jl:36-38);
+ * age[n_cells]: age cluster 1..5 (load_process_data.jl:68-69); experiment[n_cells]: labelling condition id of the cell;
+ * cond_vec[11]: the ids of the 11 conditions in statistic order; pulse_idx / chase_idx: 1-based cell indices
+ * (load_process_data.jl:72-73); age_id_dist: 5 x 11 column-major, used as given for the data correlations (R12).
+ * Point estimates: :2-38 (mean, Fano of u+l per age cluster over the pulse / chase cells), :61-79 (ratios), :100-147
+ * (mean_corr, corr_mean).  Standard errors: :40-58, :81-97, :149-177 -- n_bootstraps (<= 128) resamples of the cells with
+ * replacement per statistic family, drawn from Philox (counter = (block, bootstrap, family), key = seed) and shared by all
+ * genes; the correlation bootstrap uses the resample's own per-condition age distribution (:160-164).  d, se: 53 x n_genes. */
+int  abc_data_summary_stats(abc_ctx_t* ctx, const double* u, const double* l, int32_t n_cells, int32_t n_genes,
+                            const int32_t* age, const int32_t* experiment, const int32_t* cond_vec,
+                            const int32_t* pulse_idx, int32_t n_pulse, const int32_t* chase_idx, int32_t n_chase,
+                            const double* age_id_dist, int32_t n_bootstraps, uint64_t seed, double* d, double* se);
+
 /* ---- on-disk layouts written by the library; host-side, no device needed ------------------------------
  * abc_format_float64: Julia's print(io, ::Float64) -- what writedlm puts into every file of the pipeline (shortest
  * round-trip digits, fixed notation for 1e-5 <= |x| < 1e6, else d.ddde[-]x, NaN / Inf / -Inf); buf >= 32 bytes, returns

@@ -179,6 +179,22 @@ function model_probs(ctx::Context, counts::Matrix{Int64}; n_bootstraps=100, alph
     return out[1], out[2], out[3]
 end
 
+"""data_summary_stats(ctx, u_data, l_data, age, experiment, cond_vec, pulse_idx, chase_idx, age_id_distribution) -> (d, se), each
+53 x G: get_summary_stats of scripts/data_summary_statistics.jl:183-194 for every gene on the device (bootstrap SEs from seeded
+Philox resamples).  u_data, l_data: n_cells x G count matrices (gene_selection.jl:36-38)."""
+function data_summary_stats(ctx::Context, u_data::Matrix{Float64}, l_data::Matrix{Float64}, age::Vector{<:Integer},
+                            experiment::Vector{<:Integer}, cond_vec::Vector{<:Integer}, pulse_idx::Vector{<:Integer},
+                            chase_idx::Vector{<:Integer}, age_id_dist::Matrix{Float64}; n_bootstraps=100, seed=UInt64(20240229))
+    n_cells, G = size(u_data)
+    d = Matrix{Float64}(undef, 53, G); se = Matrix{Float64}(undef, 53, G)
+    a, e, cv, pi, ci = Int32.(age), Int32.(experiment), Int32.(cond_vec), Int32.(pulse_idx), Int32.(chase_idx)
+    check(ccall((:abc_data_summary_stats, LIB), Cint,
+                (Ptr{Cvoid}, Ptr{Cdouble}, Ptr{Cdouble}, Int32, Int32, Ptr{Int32}, Ptr{Int32}, Ptr{Int32}, Ptr{Int32}, Int32,
+                 Ptr{Int32}, Int32, Ptr{Cdouble}, Int32, UInt64, Ptr{Cdouble}, Ptr{Cdouble}),
+                ctx.ptr, u_data, l_data, n_cells, G, a, e, cv, pi, length(pi), ci, length(ci), age_id_dist, n_bootstraps, seed, d, se))
+    return d, se
+end
+
 # ---- the reference's on-disk layouts written by the library (no 65 KB of text per particle formatted in Julia) ----------
 """writedlm_lib(path, A; append): writedlm(io, transpose(A)) -- A is cols x rows (Julia column-major = the library's rows)"""
 writedlm_lib(path::AbstractString, A::Matrix{Float64}; append=true) =

@@ -280,3 +280,110 @@ def model_probs(counts, n_bootstraps, alpha, seed):
             lb[g, k] = julia_quantile(s[:, k], 1.0 - alpha)
             ub[g, k] = julia_quantile(s[:, k], alpha)
     return prob, lb, ub
+
+
+def data_summary_stats(u, l, age, experiment, cond_vec, pulse_idx, chase_idx, age_id_dist, n_bootstraps, seed):
+    """numpy restatement of abc_data_summary_stats = get_summary_stats (scripts/data_summary_statistics.jl:2-194) for every
+    gene, with the resamples drawn from Philox as the library draws them (counter (block j, bootstrap b, family f, 3 << 29):
+    two 64-bit words -> two cell positions floor(u64 * n_pop / 2^64) of the family's population: 0 pulse_idx, 1 chase_idx,
+    2 and 3 all cells).  u, l: (G, n_cells) integer counts.  Exact integer sums, then the reference's FP64 formulas."""
+    u = np.asarray(u).astype(np.int64); l = np.asarray(l).astype(np.int64)
+    G, n_cells = u.shape
+    age = np.asarray(age); experiment = np.asarray(experiment)
+    ad = np.asarray(age_id_dist, dtype=np.float64)                      # (5, 11)
+    key = (seed & 0xFFFFFFFF, seed >> 32)
+    pops = [np.asarray(pulse_idx) - 1, np.asarray(chase_idx) - 1, np.arange(n_cells), np.arange(n_cells)]
+    cond_of = np.full(n_cells, -1)
+    for j, e in enumerate(cond_vec):
+        cond_of[experiment == e] = j
+
+    def resample(f, b):
+        n = len(pops[f])
+        j = np.arange((n + 1) // 2, dtype=np.uint64)
+        x, y, z, w = philox_np(j, b, f, 3 << 29, key)
+        u0 = [(int(a) << 32 | int(c)) * n >> 64 for a, c in zip(x, y)]
+        u1 = [(int(a) << 32 | int(c)) * n >> 64 for a, c in zip(z, w)]
+        if n % 2 == 1:
+            u1 = u1[:-1]
+        return pops[f][np.array(u0 + u1, dtype=np.int64)]
+
+    def cov(n, sxy, sx, sy):
+        if n < 2:
+            return np.nan
+        num = int(n) * int(sxy) - int(sx) * int(sy)
+        return float(abs(num)) / (float(n) * float(n - 1)) * (1.0 if num >= 0 else -1.0)
+
+    def wsum(w, x):
+        s = 0.0
+        for a, b in zip(w, x):
+            s = s + a * b
+        return s
+
+    def wcov(x, y, w):
+        mx, my = wsum(w, x), wsum(w, y)
+        s = 0.0
+        for i in range(5):
+            s = s + w[i] * ((x[i] - mx) * (y[i] - my))
+        return s
+
+    def stats(g, cells4, boot):
+        out = np.zeros(53)
+        for f in range(2):
+            c_ = cells4[f]
+            t = u[g, c_] + l[g, c_]
+            a_ = age[c_]
+            for c in range(5):
+                x = t[a_ == c + 1]
+                n = len(x)
+                if n > 0:
+                    st, stt = int(x.sum()), int((x * x).sum())
+                    mean = float(st) / float(n)
+                    out[10 * f + c] = mean
+                    out[10 * f + 5 + c] = cov(n, stt, st, st) / (mean + (0.0001 if mean == 0.0 else 0.0))
+        c_ = cells4[2]
+        cj = cond_of[c_]
+        for j in range(11):
+            sel = c_[cj == j]
+            if len(sel) > 0:
+                mu, ml = float(int(u[g, sel].sum())) / len(sel), float(int(l[g, sel].sum())) / len(sel)
+                if mu + ml > 0.0:
+                    out[20 + j] = ml / (mu + ml)
+        c_ = cells4[3]
+        cj, ca = cond_of[c_], age[c_]
+        for j in range(11):
+            m1, m2, v1, v2, c12, nc = ([0.0] * 5 for _ in range(6))
+            for c in range(5):
+                sel = c_[(cj == j) & (ca == c + 1)]
+                n = len(sel)
+                nc[c] = n
+                if n > 0:
+                    x, y = u[g, sel], l[g, sel]
+                    sx, sy = int(x.sum()), int(y.sum())
+                    m1[c], m2[c] = float(sx) / n, float(sy) / n
+                    v1[c], v2[c] = cov(n, int((x * x).sum()), sx, sx), cov(n, int((y * y).sum()), sy, sy)
+                    c12[c] = cov(n, int((x * y).sum()), sx, sy)
+            ntot = sum(nc)
+            w = [(float(k) / float(ntot) if ntot > 0 else 0.0) for k in nc] if boot else list(ad[:, j])
+            tv1, tv2 = wsum(w, v1) + wcov(m1, m1, w), wsum(w, v2) + wcov(m2, m2, w)
+            with np.errstate(invalid="ignore", divide="ignore"):
+                sd = np.sqrt(np.abs(np.float64(tv1) * np.float64(tv2)))
+                if any(c != 0.0 for c in c12) and tv1 != 0.0 and tv2 != 0.0:
+                    out[31 + j] = np.float64(wsum(w, c12)) / sd
+                if tv1 != 0.0 and tv2 != 0.0:
+                    out[42 + j] = np.float64(wcov(m1, m2, w)) / sd
+        return out
+
+    d = np.array([stats(g, pops, False) for g in range(G)])
+    samples = [[resample(f, b) for f in range(4)] for b in range(n_bootstraps)]
+    boots = np.array([[stats(g, samples[b], True) for b in range(n_bootstraps)] for g in range(G)])     # (G, B, 53)
+    with np.errstate(invalid="ignore"):
+        s = np.zeros((G, 53))
+        for b in range(n_bootstraps):
+            s = s + boots[:, b]
+        mean = s / float(n_bootstraps)
+        q = np.zeros((G, 53))
+        for b in range(n_bootstraps):
+            dl = boots[:, b] - mean
+            q = q + dl * dl
+        se = np.sqrt((1.0 / float(n_bootstraps - 1)) * q)
+    return d, se

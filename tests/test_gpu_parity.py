@@ -866,3 +866,58 @@ def test_model_probs_from_scored_counts(eng, data_stats):
     assert np.all(lb[both] <= prob[both] + 0.2) and np.all(ub[both] >= prob[both] - 0.2) and np.all(lb <= ub)
     none = tot == 0
     assert not prob[none].any() and not ub[none].any()
+
+
+# ------------------------------------------------------------------------------------------ data-side statistics
+def _synthetic_cells(rng, n_cells, G):
+    """per-cell counts shaped like the experiment: 12 experiment ids (0 = unused control, 1..6 pulse, 7..11 chase)"""
+    experiment = rng.integers(0, 12, n_cells).astype(np.int32)
+    age = rng.integers(1, 6, n_cells).astype(np.int32)
+    lam = rng.lognormal(0.0, 1.0, size=(G, 1))
+    u = rng.poisson(lam * (1.0 + 0.2 * age), size=(G, n_cells)).astype(np.float64)
+    l = rng.poisson(lam * 0.3 * (experiment > 0), size=(G, n_cells)).astype(np.float64)
+    u[0] = 0; l[0] = 0                               # a silent gene: every guard of the formulas
+    l[1] = 0
+    cond_vec = np.arange(1, 12, dtype=np.int32)
+    pulse_idx = (np.nonzero((experiment >= 0) & (experiment <= 6))[0] + 1).astype(np.int32)      # load_process_data.jl:72
+    chase_idx = (np.nonzero(experiment >= 7)[0] + 1).astype(np.int32)
+    age_id_dist = rng.dirichlet(np.ones(5), size=11).T / 11.0                                     # columns sum to 1/11 (R12)
+    return u, l, age, experiment, cond_vec, pulse_idx, chase_idx, age_id_dist
+
+
+def test_data_summary_stats_equal_the_restatement(eng):
+    """abc_data_summary_stats (get_summary_stats of data_summary_statistics.jl for every gene, bootstrap SEs from Philox
+    resamples) against the numpy restatement on the same draws: d and se bit for bit, incl. a silent gene, a gene without
+    labelled counts, an unused experiment id and clusters that run empty in small resamples"""
+    rng = np.random.default_rng(8)
+    u, l, age, experiment, cond_vec, pulse_idx, chase_idx, ad = _synthetic_cells(rng, 150, 7)
+    d, se = eng.data_summary_stats(u, l, age, experiment, cond_vec, pulse_idx, chase_idx, ad, n_bootstraps=12, seed=77)
+    wd, wse = oracle.data_summary_stats(u, l, age, experiment, cond_vec, pulse_idx, chase_idx, ad, 12, 77)
+    assert oracle.same_bits(d, wd), np.nonzero(bits(d) != bits(wd))
+    assert oracle.same_bits(se, wse), np.nonzero(bits(se) != bits(wse))
+    # the silent gene: zeros, except the correlations of a (condition, age) bin with a single cell (Julia's var of one value is NaN)
+    assert not np.nan_to_num(d[0]).any() and not np.nan_to_num(se[0]).any() and not np.isnan(d[0][:31]).any()
+
+
+def test_data_summary_stats_at_the_experiments_size(eng):
+    """5422 cells x 64 genes x 100 bootstraps: point estimates against plain numpy means / variances, SEs against the
+    textbook sigma / sqrt(n), and the result feeds abc_set_data"""
+    rng = np.random.default_rng(9)
+    u, l, age, experiment, cond_vec, pulse_idx, chase_idx, ad = _synthetic_cells(rng, 5422, 64)
+    d, se = eng.data_summary_stats(u, l, age, experiment, cond_vec, pulse_idx, chase_idx, ad, n_bootstraps=100, seed=3)
+    t = u + l
+    for g in (2, 17, 63):
+        for f, idx in ((0, pulse_idx), (1, chase_idx)):
+            for c in range(5):
+                x = t[g, idx - 1][age[idx - 1] == c + 1]
+                assert d[g, 10 * f + c] == pytest.approx(x.mean(), rel=1e-13)
+                assert d[g, 10 * f + 5 + c] == pytest.approx(x.var(ddof=1) / x.mean(), rel=1e-11)
+                assert se[g, 10 * f + c] == pytest.approx(x.std(ddof=1) / np.sqrt(len(x)), rel=0.35)
+        for j in range(11):
+            sel = experiment == cond_vec[j]
+            assert d[g, 20 + j] == pytest.approx(l[g, sel].mean() / (u[g, sel].mean() + l[g, sel].mean()), rel=1e-13)
+    assert np.isfinite(d).all() and np.isfinite(se).all() and (se[2:] >= 0).all()
+    from abc_inference_transcription_b200 import AbcEngine
+    with AbcEngine(0) as e2:
+        e2.set_data(d, se)                             # the scoring kernel accepts it as its data statistics
+        assert e2.n_genes == 64
