@@ -19,6 +19,7 @@
 //                      draws beyond the boundary masked, and only the lanes that cross run the boundary code (the
 //                      rest of their block is discarded: the waiting times are memoryless and the words independent).
 #include "abc_ssa_dev.cuh"
+#include <type_traits>
 
 #ifndef TELE_MIN_CTAS
 #define TELE_MIN_CTAS 3      // 24 warps x 80 registers per SM: measured best (4 x 64: -4 %, 2 x 100: -8 %; computing the next
@@ -419,12 +420,15 @@ abc_tele_kernel(const AbcRates* __restrict__ rates, const AbcSsaParams prm, cons
         const float step_len = (float)step_cut;
         const Cuts cuts = make_cuts(s0, age, step_cut, inv_step_cut, tl0, tl1, window);
         const int n_seg = min(cuts.n, TELE_MAX_SEG);
+        unsigned int kinds = 0u;         // forms of F among the pieces: bit 1 closed form, bit 2 six-term series, bit 3 four-term
         for (int k = lane; k < n_seg; k += 32) {
             const PieceDesc d = describe_piece(cuts, k, prm.cycle, inv_cycle, inv_step5, steps_per_cycle, window);
             TPiece t = make_piece(srates[warp], d, sc_inv_cycle, step_len);
             if (k == n_seg - 1) t.meta |= TP_LAST;
             tab[k] = t;
+            kinds |= (t.k1 != 0.0f) ? 2u : ((t.e0 != 0.0f) ? 8u : 4u);
         }
+        kinds = __reduce_or_sync(FULL, kinds);
         __syncwarp();
 
         const int cell = chunk * 32 + lane;
@@ -468,7 +472,12 @@ abc_tele_kernel(const AbcRates* __restrict__ rates, const AbcSsaParams prm, cons
             }
             uint32_t invalid = 0u, ctr_done = s.ctr;
             const uint32_t ctr0 = s.ctr;
-            if (!__all_sync(FULL, done))
+            // The loop, instantiated per form of F: when every piece of the read-out has the same form (always for models 1-4,
+            // where the decay rate is constant along the lineage) the loop body carries no branch on it (KIND 1 closed form,
+            // 2 six-term series, 3 four-term series); mixed schedules (model 5 with decay steps on both sides of a split) take
+            // the generic body (KIND 0), which selects per lane and block.
+            auto telegraph = [&](auto kind_tag) {
+            constexpr int KIND = decltype(kind_tag)::value;
             for (;;) {
                 const uint4 b = next_block(s);
                 float l0, l1, l2, l3;
@@ -487,7 +496,7 @@ abc_tele_kernel(const AbcRates* __restrict__ rates, const AbcSsaParams prm, cons
                 const float x1 = f_fma(l0, qc, x), x2 = f_fma(l1, qo, x1);
                 const float x3 = f_fma(l2, qc, x2), x4 = f_fma(l3, qo, x3);
                 float F1, F2, F3, F4;
-                if (k1 != 0.0f) {
+                if (KIND == 1 || (KIND == 0 && k1 != 0.0f)) {
                     float d1, d2, d3, d4;
                     asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(d1) : "f"(f_fma(k1, x1, e0)));
                     asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(d2) : "f"(f_fma(k1, x2, e0)));
@@ -495,7 +504,7 @@ abc_tele_kernel(const AbcRates* __restrict__ rates, const AbcSsaParams prm, cons
                     asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(d4) : "f"(f_fma(k1, x4, e0)));
                     F1 = f_mul(d1, f_fma(p1, x1, p0)); F2 = f_mul(d2, f_fma(p1, x2, p0));
                     F3 = f_mul(d3, f_fma(p1, x3, p0)); F4 = f_mul(d4, f_fma(p1, x4, p0));
-                } else if (e0 != 0.0f) {
+                } else if (KIND == 3 || (KIND == 0 && e0 != 0.0f)) {
                     const float2 c = *reinterpret_cast<const float2*>(&tp->p2);
                     float h1 = f_fma(c.y, x1, c.x), h2 = f_fma(c.y, x2, c.x), h3 = f_fma(c.y, x3, c.x), h4 = f_fma(c.y, x4, c.x);
                     h1 = f_fma(h1, x1, p1); h2 = f_fma(h2, x2, p1); h3 = f_fma(h3, x3, p1); h4 = f_fma(h4, x4, p1);
@@ -558,6 +567,14 @@ abc_tele_kernel(const AbcRates* __restrict__ rates, const AbcSsaParams prm, cons
                     }
                 }
                 if (__all_sync(FULL, !(len < INFINITY))) break;      // every lane has finished (len = inf marks it)
+            }
+            };
+            if (!__all_sync(FULL, done)) {
+                const int kind = (kinds == 2u) ? 1 : (kinds == 4u) ? 2 : (kinds == 8u) ? 3 : 0;    // warp uniform
+                if (kind == 1) telegraph(std::integral_constant<int, 1>{});
+                else if (kind == 2) telegraph(std::integral_constant<int, 2>{});
+                else if (kind == 3) telegraph(std::integral_constant<int, 3>{});
+                else telegraph(std::integral_constant<int, 0>{});
             }
             if (live) {
                 // draws = switches + boundary crossings; the words discarded after a crossing are not counted
