@@ -45,11 +45,11 @@ ALG_BYTES_PER_PARTICLE_SCORE = 27776  # 424 B read + G*8 B written, G
 # slots used x active threads per instruction / 32 = executed lane-instructions over the lane-issue peak
 NCU_SSA = {"src": "profiles/r2_ssa_m{1,3,5}_ncu_summary.csv (ncu --set full --clock-control none of abc_tele_kernel, 4096 prior "
                   "particles of one model, start-time rule)",
-           "m1": {"issue_active": 0.690, "threads_per_inst": 29.85, "executed_lane_frac": 0.690 * 29.85 / 32,
-                  "warp_inst_per_warp_draw": 28.2},
-           "m3": {"issue_active": 0.717, "threads_per_inst": 27.87, "executed_lane_frac": 0.717 * 27.87 / 32},
-           "m5": {"issue_active": 0.695, "threads_per_inst": 26.32, "executed_lane_frac": 0.695 * 26.32 / 32},
-           "pipes_m1_pct_of_own_peak": {"alu": 41.6, "fma": 36.0, "xu": 30.4}, "dram_bytes_per_launch": 11.0e6}
+           "m1": {"issue_active": 0.662, "threads_per_inst": 29.93, "executed_lane_frac": 0.662 * 29.93 / 32,
+                  "warp_inst_per_warp_draw": 25.9},
+           "m3": {"issue_active": 0.692, "threads_per_inst": 27.93, "executed_lane_frac": 0.692 * 27.93 / 32},
+           "m5": {"issue_active": 0.657, "threads_per_inst": 26.34, "executed_lane_frac": 0.657 * 26.34 / 32},
+           "pipes_m1_pct_of_own_peak": {"alu": 42.3, "fma": 36.6, "xu": 31.2}, "dram_bytes_per_launch": 11.0e6}
 SCORE_TRAFFIC_131070 = 4.04e9         # measured dram bytes (read + write) of one 131070-particle scoring call, see profiles/
 
 
