@@ -76,6 +76,9 @@ SYMBOLS = {
                                  ctypes.POINTER(AbcCounters)]),
     "abc_simulate_score": (ctypes.c_int, [_vp, ctypes.c_int, ctypes.c_int64, ctypes.c_int64, ctypes.c_uint64, ctypes.c_int,
                                           _vp, _vp, ctypes.c_double, ctypes.c_int, _vp, _vp, ctypes.POINTER(AbcCounters)]),
+    "abc_simulate_score_async": (ctypes.c_int, [_vp, ctypes.c_int, ctypes.c_int64, ctypes.c_int64, ctypes.c_uint64, ctypes.c_int,
+                                                _vp, _vp, ctypes.c_double, ctypes.c_int, _vp]),
+    "abc_wait": (ctypes.c_int, [_vp, _vp, ctypes.POINTER(AbcCounters)]),
     "abc_accept_total": (ctypes.c_int64, [_vp]),
     "abc_accept_reset": (ctypes.c_int, [_vp]),
     "abc_accept_fetch": (ctypes.c_int, [_vp, _vp, _vp, _vp]),

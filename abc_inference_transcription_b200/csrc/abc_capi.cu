@@ -91,6 +91,7 @@ extern "C" int abc_destroy(abc_ctx_t* c) {
     cudaSetDevice(c->device);
     cudaStreamSynchronize(c->stream);
     if (c->user_pending) cudaEventSynchronize(c->ev_user);
+    if (c->copy_stream) cudaStreamSynchronize(c->copy_stream);      // asynchronous batches still travelling to the host
     abc_comm_free(c);
     c->d_beta.release(); c->d_age_dist.release(); c->d_beta_mom.release(); c->d_d.release(); c->d_den.release(); c->d_fbw.release(); c->d_fa.release(); c->d_fstats.release(); c->d_rnan.release();
     c->d_s3_tb.release(); c->d_s3_ab.release(); c->d_s3_wt.release();
@@ -746,6 +747,100 @@ extern "C" int abc_simulate_score(abc_ctx_t* c, int m, int64_t n, int64_t offset
     return abc_simulate_score_impl(c, m, n, offset, seed, prior_supplied, theta, stats, eps, layout, err, n, counts, counters);
 }
 
+// ---- asynchronous batches: abc_simulate_score_async enqueues one batch and returns; abc_wait completes all of them ---------
+static int async_drain_set(abc_ctx* c, int l) {
+    if (c->async_nb[l] == 0) return ABC_OK;
+    ABC_CUDA_CHECK(cudaEventSynchronize(c->p_copied[l]));
+    const unsigned long long* h = c->h_p_counters + 8 * l;
+    c->last.n_particles += (uint64_t)c->async_nb[l]; c->last.n_lineages += h[0]; c->last.n_events += h[1];
+    c->last.n_draws += h[2]; c->last.n_ode_steps += h[4];
+    float a = 0.f, b = 0.f;
+    if (cudaEventElapsedTime(&a, c->p_t0[l], c->p_t1[l]) != cudaSuccess) cudaGetLastError();
+    if (cudaEventElapsedTime(&b, c->p_t1[l], c->p_t2[l]) != cudaSuccess) cudaGetLastError();
+    c->async_ms_sim += a; c->async_ms_score += b;
+    c->async_nb[l] = 0;
+    return ABC_OK;
+}
+
+extern "C" int abc_wait(abc_ctx_t* c, int64_t* counts, abc_counters_t* counters) {
+    CTX_GUARD(c);
+    int rc;
+    for (int k = 0; k < 2; ++k)          // oldest first
+        if ((rc = async_drain_set(c, (c->async_next + k) & 1)) != ABC_OK) return rc;
+    ABC_CUDA_CHECK(cudaStreamSynchronize(c->stream));
+    if (c->async_open) {
+        c->last.ms_simulate = c->async_ms_sim; c->last.ms_score = c->async_ms_score;
+        c->async_open = false;
+    }
+    if (c->has_data) {
+        unsigned long long total = 0;
+        ABC_CUDA_CHECK(cudaMemcpy(&total, c->d_acc_count.p, sizeof(total), cudaMemcpyDeviceToHost));
+        if ((int64_t)total > c->acc_capacity) return accept_overflow(c, total);
+        if (counts) {
+            std::vector<unsigned long long> h((size_t)c->G);
+            ABC_CUDA_CHECK(cudaMemcpy(h.data(), c->d_counts.p, (size_t)c->G * sizeof(unsigned long long), cudaMemcpyDeviceToHost));
+            for (int g = 0; g < c->G; ++g) counts[g] = (int64_t)h[g];
+        }
+    }
+    if (counters) *counters = c->last;
+    return ABC_OK;
+}
+
+// One batch, enqueued: the same work and results as abc_simulate_score.  Up to two batches may be in flight (two sets of
+// device output buffers): the outputs of one travel to the host while the next one is simulated; a third call first waits
+// for the oldest.  theta / stats / err belong to the library until abc_wait returns (page-locked memory from abc_host_alloc
+// keeps the copies asynchronous).  A batch too large for one launch is run by the blocking path.
+extern "C" int abc_simulate_score_async(abc_ctx_t* c, int m, int64_t n, int64_t offset, uint64_t seed, int prior_supplied,
+                                        double* theta, double* stats, double eps, int layout, double* err) {
+    CTX_GUARD(c);
+    int rc = check_model(m);
+    if (rc != ABC_OK) return rc;
+    if (!c->has_data) { abc_set_error("abc_set_data has not been called"); return ABC_ERR_STATE; }
+    if (n < 0 || (n > 0 && (!theta || !stats)) || (layout != ABC_ERR_NONE && n > 0 && !err)) {
+        abc_set_error("abc_simulate_score_async: bad arguments");
+        return ABC_ERR_ARG;
+    }
+    if (n == 0) return ABC_OK;
+    const int P = abc_n_params(m), G = c->G;
+    const int64_t limit = std::min<int64_t>(sim_chunk(c), layout != ABC_ERR_NONE ? std::max<int64_t>(1024, (int64_t)(2.0e9 / (8.0 * G))) : (1ll << 40));
+    if (n > limit) {
+        if ((rc = abc_wait(c, nullptr, nullptr)) != ABC_OK) return rc;
+        return abc_simulate_score_impl(c, m, n, offset, seed, prior_supplied, theta, stats, eps, layout, err, n, nullptr, nullptr);
+    }
+    if (!c->async_open) {
+        memset(&c->last, 0, sizeof(c->last));
+        c->async_ms_sim = c->async_ms_score = 0.0;
+        c->async_open = true;
+    }
+    const int l = c->async_next;
+    if ((rc = async_drain_set(c, l)) != ABC_OK) return rc;      // the batch that used this set two calls ago
+    if ((rc = c->d_p_theta[l].ensure((size_t)n * P)) != ABC_OK) return rc;
+    if ((rc = c->d_p_stats[l].ensure((size_t)n * ABC_NSTATS)) != ABC_OK) return rc;
+    if (layout != ABC_ERR_NONE && (rc = c->d_p_err[l].ensure((size_t)n * G)) != ABC_OK) return rc;
+    if (prior_supplied)
+        ABC_CUDA_CHECK(cudaMemcpyAsync(c->d_p_theta[l].p, theta, (size_t)n * P * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+    ABC_CUDA_CHECK(cudaEventRecord(c->p_t0[l], c->stream));
+    if ((rc = simulate_device(c, m, n, offset, seed, prior_supplied, c->d_p_theta[l].p, c->d_p_stats[l].p, nullptr, c->stream)) != ABC_OK) return rc;
+    ABC_CUDA_CHECK(cudaMemcpyAsync(c->h_p_counters + 8 * l, c->d_counters.p, 8 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, c->stream));
+    ABC_CUDA_CHECK(cudaEventRecord(c->p_t1[l], c->stream));
+    if ((rc = score_device(c, c->d_p_stats[l].p, n, offset, eps, layout, c->d_p_err[l].p, c->stream)) != ABC_OK) return rc;
+    ABC_CUDA_CHECK(cudaEventRecord(c->p_t2[l], c->stream));
+    ABC_CUDA_CHECK(cudaEventRecord(c->p_done[l], c->stream));
+    ABC_CUDA_CHECK(cudaStreamWaitEvent(c->copy_stream, c->p_done[l], 0));
+    if (!prior_supplied)
+        ABC_CUDA_CHECK(cudaMemcpyAsync(theta, c->d_p_theta[l].p, (size_t)n * P * sizeof(double), cudaMemcpyDeviceToHost, c->copy_stream));
+    ABC_CUDA_CHECK(cudaMemcpyAsync(stats, c->d_p_stats[l].p, (size_t)n * ABC_NSTATS * sizeof(double), cudaMemcpyDeviceToHost, c->copy_stream));
+    if (layout == ABC_ERR_PARTICLE_MAJOR) {
+        ABC_CUDA_CHECK(cudaMemcpyAsync(err, c->d_p_err[l].p, (size_t)n * G * sizeof(double), cudaMemcpyDeviceToHost, c->copy_stream));
+    } else if (layout == ABC_ERR_GENE_MAJOR) {
+        ABC_CUDA_CHECK(cudaMemcpyAsync(err, c->d_p_err[l].p, (size_t)n * G * sizeof(double), cudaMemcpyDeviceToHost, c->copy_stream));
+    }
+    ABC_CUDA_CHECK(cudaEventRecord(c->p_copied[l], c->copy_stream));
+    c->async_nb[l] = n;
+    c->async_next = l ^ 1;
+    return ABC_OK;
+}
+
 // gm_pitch: doubles between consecutive gene rows of a gene-major `err` (n for a stand-alone call; the whole batch when this
 // context computes one shard of a multi-GPU call)
 int abc_simulate_score_impl(abc_ctx* c, int m, int64_t n, int64_t offset, uint64_t seed, int prior_supplied, double* theta,
@@ -758,6 +853,9 @@ int abc_simulate_score_impl(abc_ctx* c, int m, int64_t n, int64_t offset, uint64
     if (n < 0 || (n > 0 && (!theta || !stats)) || (layout != ABC_ERR_NONE && n > 0 && !err)) {
         abc_set_error("abc_simulate_score: bad arguments");
         return ABC_ERR_ARG;
+    }
+    if (c->async_nb[0] != 0 || c->async_nb[1] != 0 || c->async_open) {       // asynchronous batches share the buffer sets
+        if ((rc = abc_wait(c, nullptr, nullptr)) != ABC_OK) return rc;
     }
     const int P = abc_n_params(m), G = c->G;
     memset(&c->last, 0, sizeof(c->last));

@@ -101,6 +101,12 @@ struct abc_ctx {
     cudaEvent_t p_done[2] = {nullptr, nullptr}, p_copied[2] = {nullptr, nullptr}, p_t0[2] = {nullptr, nullptr},
                 p_t1[2] = {nullptr, nullptr}, p_t2[2] = {nullptr, nullptr};
     unsigned long long* h_p_counters = nullptr;      // [2][8]
+    // abc_simulate_score_async: batches in flight per output buffer set (0 = none), the set the next call uses, and the
+    // device times accumulated for abc_wait
+    int64_t async_nb[2] = {0, 0};
+    int async_next = 0;
+    double async_ms_sim = 0.0, async_ms_score = 0.0;
+    bool async_open = false;
     DevBuf<unsigned long long> d_counts, d_acc_count;
     DevBuf<int32_t> d_acc_gene;
     DevBuf<long long> d_acc_particle;

@@ -197,6 +197,28 @@ class AbcEngine:
                                                 ctypes.byref(cnt)))
         return theta, stats, err, counts, cnt.as_dict()
 
+    def simulate_score_async(self, m, theta, stats, err=None, prior_supplied=True, particle_offset=0, seed=20240229, eps=4.8,
+                             err_layout=_lib.ERR_PARTICLE_MAJOR):
+        """abc_simulate_score_async: enqueue one batch and return.  theta (n, P), stats (n, 53) and err are the caller's
+        (page-locked) output arrays -- theta is the input when prior_supplied -- and must stay alive and untouched until
+        wait().  Up to two batches are in flight."""
+        P = n_params(_check_m(m))
+        n = theta.shape[0]
+        assert theta.shape == (n, P) and theta.dtype == np.float64 and theta.flags["C_CONTIGUOUS"]
+        assert stats.shape == (n, _lib.NSTATS) and stats.dtype == np.float64 and stats.flags["C_CONTIGUOUS"]
+        if err_layout != _lib.ERR_NONE:
+            shape = (n, self.n_genes) if err_layout == _lib.ERR_PARTICLE_MAJOR else (self.n_genes, n)
+            assert err is not None and err.shape == shape and err.dtype == np.float64 and err.flags["C_CONTIGUOUS"]
+        _lib.check(self._lib.abc_simulate_score_async(self._ctx, m, n, int(particle_offset), int(seed), int(bool(prior_supplied)),
+                                                      _lib.ptr(theta), _lib.ptr(stats), float(eps), int(err_layout), _lib.ptr(err)))
+
+    def wait(self, want_counts=True):
+        """abc_wait: every asynchronous batch is complete.  Returns (counts or None, counters)."""
+        counts = np.zeros(self.n_genes, dtype=np.int64) if want_counts and self.n_genes else None
+        cnt = _lib.AbcCounters()
+        _lib.check(self._lib.abc_wait(self._ctx, _lib.ptr(counts), ctypes.byref(cnt)))
+        return counts, cnt.as_dict()
+
     def accept_total(self):
         t = self._lib.abc_accept_total(self._ctx)
         if t < 0:

@@ -282,10 +282,13 @@ def run_b200(args):
     # ---- end to end through the host-buffer C ABI ----------------------------------------------
     h2d = d2h = 0
     from abc_inference_transcription_b200 import PinnedArray
-    err_host = PinnedArray((B, G))            # page-locked host buffers (abc_host_alloc) for the error matrix, statistics, theta
-    stats_host = PinnedArray((B, 53))
+    # page-locked host buffers (abc_host_alloc), one set per model: theta, statistics, error matrix (224 MB each)
+    err_hosts = [PinnedArray((B, G)) for _ in range(5)]
+    stats_hosts = [PinnedArray((B, 53)) for _ in range(5)]
+    err_host, stats_host = err_hosts[0], stats_hosts[0]
     theta_host = [PinnedArray((B, n_params(m))) for m in range(1, 6)]
     e2e_mode = {"host_theta": True, "note": None}
+    counts_dev_host = np.zeros(G, dtype=np.int64)
 
     def e2e_step(k):
         nonlocal h2d, d2h
@@ -300,10 +303,18 @@ def run_b200(args):
                 theta, stats, _ = eng.simulate(m, n_trials=B, particle_offset=off, seed=SEED)
                 err, counts, _ = eng.score(stats, eps=EPS, particle_offset=off, err_layout=ERR_PARTICLE_MAJOR, out=err_host.array)
                 h2d += stats.nbytes
-            elif e2e_mode["host_theta"]:
+            elif e2e_mode["host_theta"] and not args.e2e_blocking:
                 # the reference's sequence: theta = fix_params(...) on the host side of the boundary (abc_simulation.jl:92),
                 # then abc_sim(theta, ...) + scoring as one call per (model, batch); theta travels host -> device from
-                # page-locked memory inside the timed region
+                # page-locked memory inside the timed region.  The calls are the asynchronous ones: the outputs of model m
+                # travel to the host while model m + 1 is simulated; abc_wait below completes the step.
+                th_in = eng.fix_params(m, B, particle_offset=off, seed=SEED, out=theta_host[m - 1].array)
+                eng.simulate_score_async(m, th_in, stats_hosts[m - 1].array, err_hosts[m - 1].array, prior_supplied=True,
+                                         particle_offset=off, seed=SEED, eps=EPS, err_layout=ERR_PARTICLE_MAJOR)
+                h2d += th_in.nbytes
+                theta, stats, err = th_in, stats_hosts[m - 1].array, err_hosts[m - 1].array
+                counts = counts_dev_host
+            elif e2e_mode["host_theta"]:
                 th_in = eng.fix_params(m, B, particle_offset=off, seed=SEED, out=theta_host[m - 1].array)
                 theta, stats, err, counts, _ = eng.simulate_score(m, theta=th_in, particle_offset=off, seed=SEED, eps=EPS,
                                                                   err_layout=ERR_PARTICLE_MAJOR, out=err_host.array,
@@ -314,6 +325,10 @@ def run_b200(args):
                                                                   err_layout=ERR_PARTICLE_MAJOR, out=err_host.array,
                                                                   theta_out=theta_host[m - 1].array, stats_out=stats_host.array)
             d2h += theta.nbytes + stats.nbytes + err.nbytes + counts.nbytes
+        if e2e_mode["host_theta"] and not args.e2e_blocking and not args.e2e_separate:
+            _, wc = eng.wait()                           # every model's theta / statistics / error matrix is on the host
+            if dbg:
+                print(f"[e2e {k}] device ms: simulate {wc['ms_simulate']:.1f} score {wc['ms_score']:.1f}", file=sys.stderr, flush=True)
         if dbg:
             print(f"[e2e {k}] before gather t={1e3 * (time.perf_counter() - ta):.1f} ms", file=sys.stderr, flush=True)
         res = gather_acceptance(eng, world, dev)     # library-owned NCCL: counts summed, tuples exchanged by gene range
@@ -474,7 +489,8 @@ def run_b200(args):
                 "config": workload_config(args),
                 "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d // args.steps,
                         "d2h_bytes_per_step": d2h // args.steps,
-                        "path": "abc_fix_params -> host theta (page-locked) -> abc_simulate_score -> abc_accept_fetch, two untimed "
+                        "path": "abc_fix_params -> host theta (page-locked) -> abc_simulate_score_async per model -> abc_wait -> "
+                                "abc_accept_fetch (--e2e-blocking: abc_simulate_score per model), two untimed "
                                 "warm-up steps" if e2e_mode["host_theta"] and not args.e2e_separate else
                                 ("abc_simulate + abc_score" if args.e2e_separate else e2e_mode["note"])},
                 "gpu_launches": int(launches),
@@ -674,6 +690,7 @@ def main():
     ap.add_argument("--sweep-particles", type=int, default=1000000, help="full_sweep: particles per model in total (0 = skip)")
     ap.add_argument("--sweep-chunk", type=int, default=65536, help="full_sweep: particles per launch per rank")
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--e2e-blocking", action="store_true", help="e2e through the blocking abc_simulate_score (one call per model)")
     ap.add_argument("--e2e-separate", action="store_true", help="e2e through abc_simulate + abc_score instead of abc_simulate_score")
     args = ap.parse_args()
     if args.impl == "reference":

@@ -157,6 +157,15 @@ int  abc_score(abc_ctx_t* ctx, const double* stats, int64_t n, int64_t particle_
 int  abc_simulate_score(abc_ctx_t* ctx, int m, int64_t n_trials, int64_t particle_offset, uint64_t seed,
                         int prior_supplied, double* theta, double* stats, double eps, int err_layout, double* err,
                         int64_t* counts, abc_counters_t* counters);
+/* The same batch, enqueued: abc_simulate_score_async returns as soon as the work is queued, abc_wait returns when every batch
+ * in flight is complete (outputs on the host; counts = running per-gene counts since abc_accept_reset, counters = sums over the
+ * batches since the previous abc_wait; both nullable).  Up to two batches are in flight: while the 27 KB per particle of one
+ * travel to the host, the next one is simulated -- a host that loops over the five models (wrapper.jl:59-81) pays for the
+ * copies of the last batch only.  theta / stats / err must stay untouched until abc_wait; use abc_host_alloc memory (pageable
+ * memory makes the copies synchronous).  Results are identical to abc_simulate_score. */
+int  abc_simulate_score_async(abc_ctx_t* ctx, int m, int64_t n_trials, int64_t particle_offset, uint64_t seed,
+                              int prior_supplied, double* theta, double* stats, double eps, int err_layout, double* err);
+int  abc_wait(abc_ctx_t* ctx, int64_t* counts, abc_counters_t* counters);
 /* number of accepted (gene, particle) pairs of the last abc_score call(s) since abc_accept_reset */
 int64_t abc_accept_total(abc_ctx_t* ctx);
 int  abc_accept_reset(abc_ctx_t* ctx);

@@ -146,6 +146,24 @@ function simulate_score(ctx::Context, m, n_trials; particle_offset=0, seed=UInt6
     return θ, stats, e, counts, c[]
 end
 
+"""simulate_score_async!(ctx, m, θ, stats, err; ...): enqueue one batch (abc_simulate_score_async) and return; θ (P x n, input
+when prior_supplied), stats (53 x n) and err are caller-owned page-locked arrays (pinned_matrix) that stay untouched until
+wait(ctx).  Two batches may be in flight: the copies of one overlap the simulation of the next."""
+function simulate_score_async!(ctx::Context, m, θ::Matrix{Float64}, stats::Matrix{Float64}, err::Matrix{Float64};
+                               prior_supplied=false, particle_offset=0, seed=UInt64(20240229), eps=4.8, layout=ERR_PARTICLE_MAJOR)
+    check(ccall((:abc_simulate_score_async, LIB), Cint,
+                (Ptr{Cvoid}, Cint, Int64, Int64, UInt64, Cint, Ptr{Cdouble}, Ptr{Cdouble}, Cdouble, Cint, Ptr{Cdouble}),
+                ctx.ptr, m, size(θ, 2), particle_offset, seed, prior_supplied ? 1 : 0, θ, stats, eps, layout,
+                layout == ERR_NONE ? C_NULL : pointer(err)))
+end
+
+"""wait(ctx) -> (counts, counters): every asynchronous batch is complete"""
+function wait(ctx::Context)
+    counts = Vector{Int64}(undef, ctx.n_genes); c = Ref{Counters}()
+    check(ccall((:abc_wait, LIB), Cint, (Ptr{Cvoid}, Ptr{Int64}, Ref{Counters}), ctx.ptr, counts, c))
+    return counts, c[]
+end
+
 """accept_fetch(ctx) -> (offsets G+1, idx): idx[offsets[g]+1 : offsets[g+1]] == v[sortperm(err[v])] of gene g"""
 function accept_fetch(ctx::Context)
     total = ccall((:abc_accept_total, LIB), Int64, (Ptr{Cvoid},), ctx.ptr)

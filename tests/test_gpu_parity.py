@@ -921,3 +921,45 @@ def test_data_summary_stats_at_the_experiments_size(eng):
     with AbcEngine(0) as e2:
         e2.set_data(d, se)                             # the scoring kernel accepts it as its data statistics
         assert e2.n_genes == 64
+
+
+@pytest.mark.parametrize("layout", [ERR_PARTICLE_MAJOR, ERR_GENE_MAJOR, ERR_NONE])
+def test_simulate_score_async_equals_the_blocking_call(eng, data_stats, layout):
+    """abc_simulate_score_async + abc_wait over the five models with three batches in flight in turn (two buffer sets: the
+    third call waits for the first) == abc_simulate_score per model: theta, statistics, error matrices, counts, accepted
+    lists bit for bit; a blocking call issued while batches are in flight completes them first"""
+    from abc_inference_transcription_b200 import PinnedArray
+    G, n = eng.n_genes, 700
+    shape = None if layout == ERR_NONE else ((n, G) if layout == ERR_PARTICLE_MAJOR else (G, n))
+    eng.accept_reset()
+    want = []
+    for m in range(1, 6):
+        th, st, err, counts, _ = eng.simulate_score(m, n_trials=n, particle_offset=100 * m, seed=5, eps=4.8, err_layout=layout)
+        want.append((th, st, None if err is None else err.copy()))
+    off_w, idx_w, errs_w = eng.accept_fetch()
+    counts_w = counts
+    eng.accept_reset()
+    bufs = [(PinnedArray((n, n_params(m))), PinnedArray((n, 53)), PinnedArray(shape) if shape else None) for m in range(1, 6)]
+    for m in range(1, 6):
+        th, st, er = bufs[m - 1]
+        eng.simulate_score_async(m, th.array, st.array, None if er is None else er.array, prior_supplied=False,
+                                 particle_offset=100 * m, seed=5, eps=4.8, err_layout=layout)
+    counts, cnt = eng.wait()
+    assert cnt["n_particles"] == 5 * n and cnt["n_lineages"] == 5 * n * 55 * 96
+    for m in range(1, 6):
+        th, st, er = bufs[m - 1]
+        assert oracle.same_bits(th.array, want[m - 1][0]) and oracle.same_bits(st.array, want[m - 1][1])
+        if er is not None:
+            assert oracle.same_bits(er.array, want[m - 1][2])
+    off, idx, errs = eng.accept_fetch()
+    assert np.array_equal(counts, counts_w) and np.array_equal(off, off_w) and np.array_equal(idx, idx_w) and oracle.same_bits(errs, errs_w)
+    # theta supplied, and a blocking call while one batch is in flight
+    eng.accept_reset()
+    th, st, er = bufs[0]
+    th.array[:] = want[0][0]
+    st.array[:] = 0.0
+    eng.simulate_score_async(1, th.array, st.array, None if er is None else er.array, prior_supplied=True, particle_offset=100,
+                             seed=5, eps=4.8, err_layout=layout)
+    th2, st2, _, _, _ = eng.simulate_score(2, n_trials=n, particle_offset=200, seed=5, eps=4.8, err_layout=ERR_NONE)
+    assert oracle.same_bits(st.array, want[0][1]) and oracle.same_bits(st2, want[1][1])
+    eng.wait()

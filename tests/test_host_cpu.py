@@ -149,4 +149,13 @@ def test_engine_argument_plumbing_with_stub_library():
     assert theta2 is th_host and calls[-1][1][5] == 0
     with pytest.raises(AssertionError):
         e.fix_params(m, B, out=np.empty((B, 5)))
+    # the asynchronous pair bench.py's end-to-end loop uses: buffers passed through untouched, wait() returns counts
+    e.simulate_score_async(m, th_host, st, err, prior_supplied=True, particle_offset=5, seed=1, eps=4.8, err_layout=2)
+    name, a = calls[-1]
+    assert name == "abc_simulate_score_async" and a[1] == m and a[2] == B and a[3] == 5 and a[5] == 1 and a[9] == 2
+    assert a[6].value == th_host.ctypes.data and a[7].value == st.ctypes.data and a[10].value == err.ctypes.data
+    with pytest.raises(AssertionError):
+        e.simulate_score_async(m, th_host, st, np.empty((7, B)), err_layout=2)       # wrong orientation of the error matrix
+    counts, cnt = e.wait()
+    assert calls[-1][0] == "abc_wait" and counts.shape == (7,)
     e._ctx = None
