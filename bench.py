@@ -684,7 +684,7 @@ def main():
     ap.add_argument("--batch", type=int, default=8192, help="particles per model per step per GPU")
     ap.add_argument("--n-cells", type=int, default=96)
     ap.add_argument("--n-pre", type=int, default=10)
-    ap.add_argument("--ode-batch", type=int, default=8192, help="particles per model per step for the ODE-path line")
+    ap.add_argument("--ode-batch", type=int, default=32768, help="particles per model per step for the ODE-path line")
     ap.add_argument("--score-particles", type=int, default=131072, help="particles per launch for the scoring-kernel roofline")
     ap.add_argument("--ref-particles", type=int, default=24000, help="particles per bounded CPU sample (~10 s on 16 threads)")
     ap.add_argument("--sweep-particles", type=int, default=1000000, help="full_sweep: particles per model in total (0 = skip)")
