@@ -74,6 +74,8 @@ SYMBOLS = {
     "abc_summary_stats": (ctypes.c_int, [_vp, _vp, ctypes.c_int64, _vp]),
     "abc_score": (ctypes.c_int, [_vp, _vp, ctypes.c_int64, ctypes.c_int64, ctypes.c_double, ctypes.c_int, _vp, _vp,
                                  ctypes.POINTER(AbcCounters)]),
+    "abc_score_mma_columns": (ctypes.c_int, [_vp]),
+    "abc_score_mma_debug": (ctypes.c_int, [_vp, _vp, ctypes.c_int64, _vp, _vp]),
     "abc_simulate_score": (ctypes.c_int, [_vp, ctypes.c_int, ctypes.c_int64, ctypes.c_int64, ctypes.c_uint64, ctypes.c_int,
                                           _vp, _vp, ctypes.c_double, ctypes.c_int, _vp, _vp, ctypes.POINTER(AbcCounters)]),
     "abc_simulate_score_async": (ctypes.c_int, [_vp, ctypes.c_int, ctypes.c_int64, ctypes.c_int64, ctypes.c_uint64, ctypes.c_int,

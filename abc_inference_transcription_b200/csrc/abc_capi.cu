@@ -260,6 +260,10 @@ extern "C" int abc_set_data(abc_ctx_t* c, const double* d, const double* se, int
         ABC_CUDA_CHECK(cudaMemcpy(c->d_s3_gidx.p, h.gidx.data(), h.gidx.size() * sizeof(int32_t), cudaMemcpyHostToDevice));
         ABC_CUDA_CHECK(cudaMemcpy(c->d_s3_ok.p, h.okmask.data(), h.okmask.size() * sizeof(uint32_t), cudaMemcpyHostToDevice));
         c->s3_ntiles = h.ntiles;
+        std::vector<float> bblob;
+        abc_score_mma_build(d, h_den.data(), h, bblob, &c->mf_max_slack);
+        if ((rc = c->d_mf_b.ensure(bblob.size())) != ABC_OK) return rc;
+        ABC_CUDA_CHECK(cudaMemcpy(c->d_mf_b.p, bblob.data(), bblob.size() * sizeof(float), cudaMemcpyHostToDevice));
     }
     ABC_CUDA_CHECK(cudaMemset(c->d_counts.p, 0, (size_t)G * sizeof(unsigned long long)));
     ABC_CUDA_CHECK(cudaMemset(c->d_acc_count.p, 0, sizeof(unsigned long long)));
@@ -656,6 +660,7 @@ static int score_device(abc_ctx* c, const double* d_stats, int64_t n, int64_t of
             if ((rc = c->d_s3_nanw[l].ensure((size_t)((sub + 31) / 32))) != ABC_OK) return rc;
             if ((rc = c->d_s3_qcnt[l].ensure(nblocks * (size_t)x.ntiles)) != ABC_OK) return rc;
             if ((rc = c->d_s3_q2[l].ensure(abc_score3_queue_entries(sub, x.ntiles))) != ABC_OK) return rc;
+            if (c->score_mma_filter && (rc = c->d_mf_a[l].ensure((size_t)((sub + 127) / 128) * 128 * 128)) != ABC_OK) return rc;
         }
         if (overlap) {
             ABC_CUDA_CHECK(cudaEventRecord(c->s3_ev_begin, st));
@@ -672,7 +677,8 @@ static int score_device(abc_ctx* c, const double* d_stats, int64_t n, int64_t of
             if (b.err != nullptr) b.err = (layout == ABC_ERR_GENE_MAJOR) ? d_err + s0 : d_err + s0 * (int64_t)c->G;
             x.live = c->d_s3_live[l].p; x.nanw = c->d_s3_nanw[l].p; x.q2 = c->d_s3_q2[l].p; x.qcnt = c->d_s3_qcnt[l].p;
             x.W = (b.n + 31) / 32;
-            rc = abc_launch_score3(b, x, overlap ? c->s3_stream[l] : st);
+            if (c->score_mma_filter && layout != ABC_ERR_NONE) rc = abc_launch_score_mma(b, x, c->d_mf_a[l].p, c->d_mf_b.p, nullptr, overlap ? c->s3_stream[l] : st);
+            else rc = abc_launch_score3(b, x, overlap ? c->s3_stream[l] : st);
             c->launches += 3;
         }
         if (overlap) {
@@ -695,6 +701,40 @@ static int score_device(abc_ctx* c, const double* d_stats, int64_t n, int64_t of
     c->launches++;
     ABC_CUDA_CHECK(cudaEventRecord(c->ev[4], st));
     return rc;
+}
+
+// diagnostic: the raw accumulators of the tensor-core filter, V[i][column] (column = tile * 32 + slot), for device-resident
+// statistics; d_out has ceil(n / 128) * 128 rows of abc_score_mma_columns() floats.  No matrix, no acceptance.
+extern "C" int abc_score_mma_columns(abc_ctx_t* c) {
+    if (!c || !c->has_data) return 0;
+    return abc_score_mma_tiles(c->s3_ntiles) * 128;
+}
+extern "C" int abc_score_mma_debug(abc_ctx_t* c, const double* d_stats, int64_t n, float* d_out, int32_t* gene_of_column) {
+    CTX_GUARD(c);
+    if (!c->has_data) { abc_set_error("abc_set_data has not been called"); return ABC_ERR_STATE; }
+    if (n <= 0 || !d_stats || !d_out) { abc_set_error("abc_score_mma_debug: bad arguments"); return ABC_ERR_ARG; }
+    int rc;
+    AbcScoreArgs a{};
+    a.stats = d_stats; a.n = n; a.G = c->G; a.eps = 0.0; a.err = nullptr; a.err_layout = ABC_ERR_NONE; a.gm_stride = n;
+    a.counts = c->d_counts.p; a.acc_count = c->d_acc_count.p; a.acc_capacity = 0;
+    AbcScore3Tables x{};
+    x.ntiles = c->s3_ntiles; x.tb = c->d_s3_tb.p; x.ab = c->d_s3_ab.p; x.wt = c->d_s3_wt.p; x.gidx = c->d_s3_gidx.p; x.okmask = c->d_s3_ok.p;
+    const size_t nblocks = abc_score3_blocks(n);
+    if ((rc = c->d_s3_nanw[0].ensure((size_t)((n + 31) / 32))) != ABC_OK) return rc;
+    if ((rc = c->d_s3_qcnt[0].ensure(nblocks * (size_t)x.ntiles)) != ABC_OK) return rc;
+    if ((rc = c->d_s3_q2[0].ensure(abc_score3_queue_entries(n, x.ntiles))) != ABC_OK) return rc;
+    if ((rc = c->d_mf_a[0].ensure((size_t)((n + 127) / 128) * 128 * 128)) != ABC_OK) return rc;
+    x.nanw = c->d_s3_nanw[0].p; x.q2 = c->d_s3_q2[0].p; x.qcnt = c->d_s3_qcnt[0].p; x.W = (n + 31) / 32;
+    a.eps = -1.0;                                        // nothing is accepted
+    rc = abc_launch_score_mma(a, x, c->d_mf_a[0].p, c->d_mf_b.p, d_out, c->stream);
+    if (rc != ABC_OK) return rc;
+    ABC_CUDA_CHECK(cudaStreamSynchronize(c->stream));
+    if (gene_of_column) {
+        const int cols = abc_score_mma_columns(c);
+        for (int k = 0; k < cols; ++k) gene_of_column[k] = -1;
+        ABC_CUDA_CHECK(cudaMemcpy(gene_of_column, c->d_s3_gidx.p, (size_t)x.ntiles * 32 * sizeof(int32_t), cudaMemcpyDeviceToHost));
+    }
+    return ABC_OK;
 }
 
 extern "C" int abc_score(abc_ctx_t* c, const double* stats, int64_t n, int64_t offset, double eps, int layout,
@@ -1185,6 +1225,7 @@ extern "C" int abc_set_option(abc_ctx_t* c, const char* name, int64_t value) {
     if (strcmp(name, "score_reference_kernel") == 0) { c->force_reference_score = value ? 1 : 0; return ABC_OK; }
     if (strcmp(name, "score_tile_kernel") == 0) { c->score_tile_kernel = value ? 1 : 0; return ABC_OK; }
     if (strcmp(name, "score_overlap") == 0) { c->score_overlap = value ? 1 : 0; return ABC_OK; }
+    if (strcmp(name, "score_mma_filter") == 0) { c->score_mma_filter = value ? 1 : 0; return ABC_OK; }
     if (strcmp(name, "score_sub_batches") == 0) { c->score_sub_batches = (int)std::min<int64_t>(std::max<int64_t>(value, 0), 64); return ABC_OK; }
     if (strcmp(name, "accept_capacity") == 0) { c->acc_min_capacity = value > 0 ? value : 0; return ABC_OK; }
     if (strcmp(name, "stats_sample_guards") == 0) { c->stats_guards = value < 0 ? -1 : (value ? 1 : 0); return ABC_OK; }

@@ -73,6 +73,9 @@ struct abc_ctx {
     DevBuf<uint32_t> d_s3_live[2], d_s3_nanw[2], d_s3_qcnt[2];
     DevBuf<uint16_t> d_s3_q2[2];
     DevBuf<float> d_s3_fstats[2];
+    DevBuf<float> d_mf_b, d_mf_a[2];   // tensor-core filter: gene operand (per data set), particle operand (per sub-batch)
+    int score_mma_filter = 0;    // 1: TF32 tcgen05 GEMM decides which pairs reach stage 3 (abc_score3.cu, tensor-core filter)
+    double mf_max_slack = 0.0;
     cudaStream_t s3_stream[2] = {nullptr, nullptr};
     cudaEvent_t s3_ev_begin = nullptr, s3_ev_end[2] = {nullptr, nullptr};
     int score_overlap = 1;

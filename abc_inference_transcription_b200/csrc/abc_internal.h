@@ -118,6 +118,13 @@ void abc_score3_build(const double* d, const double* den, int G, AbcScore3Host& 
 size_t abc_score3_blocks(int64_t n);
 size_t abc_score3_queue_entries(int64_t n, int ntiles);
 int abc_launch_score3(const AbcScoreArgs& a, const AbcScore3Tables& x, cudaStream_t st);
+// tensor-core filter (TF32 tcgen05 GEMM) in front of the same stage 3: abc_score3.cu
+#ifdef __cplusplus
+void abc_score_mma_build(const double* d, const double* den, const AbcScore3Host& h, std::vector<float>& bblob, double* max_slack);
+#endif
+int abc_score_mma_tiles(int ntiles);
+int abc_launch_score_mma(const AbcScoreArgs& a, const AbcScore3Tables& x, float* d_ablob, const float* d_bblob, float* d_dbg,
+                         cudaStream_t st);
 int abc_launch_score_prep(const double* d_stats, int64_t n, float* d_fstats, unsigned char* d_rnan, cudaStream_t st);
 
 // A1 ordering on the device (abc_accept.cu)

@@ -604,6 +604,348 @@ abc_score3_exact_kernel(const AbcScoreArgs a, const AbcScore3Tables x) {
     }
 }
 
+// ------------------------------------------------------------------------------------------------ tensor-core filter
+// The same decision as classification + filter -- "can this pair be <= 10?" -- taken by one TF32 GEMM on the 5th-generation
+// tensor cores (tcgen05.mma, accumulators in tensor memory) instead of FP32 FMAs on the SM:
+//
+//     sum_t w_t (d_t - s_t)^2  =  sum_t a_t^2  -  2 sum_t (a_t b_t) s_t  +  sum_t b_t^2 s_t^2 ,     a = sqrt(w) d, b = sqrt(w),
+//
+// i.e. V[i][g] = A[i][:] . B[g][:] with  A[i] = (s_0..s_52, s_0^2..s_52^2, 1, 0/1 row-invalid flag, 0...)  per particle and
+// B[g] = (-2 a_t b_t, b_t^2, sum a^2 - thr_g, 1, 0...) per gene, all rounded to TF32 beforehand (the low 13 mantissa bits are
+// zero, so whatever the hardware does with them does not matter).  A pair is queued for stage 3 iff V < 0 (sign bit).
+//
+// Soundness (true error <= 10  =>  queued).  Write R = sum a_t^2 and Q = sum b_t^2 s_t^2.  If the true error is <= 10 then
+// sqrt(Q) <= sqrt(10) + sqrt(R) (triangle inequality), sum |2 a_t b_t s_t| <= 2 sqrt(R Q) (Cauchy-Schwarz), every operand
+// carries a relative rounding error <= 2^-11 (+2^-24 for the double rounding through binary32), so each product is off by at
+// most 2^-10 (1 + 2^-9) of its size, and the FP32 accumulation of K = 128 products adds at most K 2^-21 of the sum of the
+// magnitudes (two ulps per addition: covers truncating adders).  Hence V + thr_g - 10 <= slack_g with
+//     slack_g = 1.002 2^-10 (2 sqrt(R Qmax) + Qmax) + 2^-14 (R + 2 sqrt(R Qmax) + Qmax),   Qmax = (sqrt(10) + sqrt(R))^2,
+// and thr_g = 10 + slack_g + 0.002 (the constant is rounded towards -inf).  R <= 100 because den >= 0.01 d^2, so
+// slack_g <= 0.45; on the shipped data the median is 0.22 and 6 % more pairs are queued than are truly <= 10.
+// Elements that are not finite in binary32 (|s| > 1.8e19 or Inf) enter as 0: such a statistic puts the true error of every
+// gene with usable constants above 10, so any decision is sound.  Rows with a NaN statistic (all errors NaN) and rows past
+// the end of the batch are all-zero with the invalid flag set: V = +1.  Genes whose constants cannot use the fast division
+// have B = (0, ..., -1, 1): always queued for valid rows.  Padding slots have B = (0, ..., +1, 1): never queued.
+//
+// Operand layout: the canonical K-major, no-swizzle UMMA layout -- 8 rows x 16 bytes "core matrices" stored contiguously
+// (128 B); element (row r, k) of a 128 x 128 tile sits at byte (k/4) 2048 + (r/8) 128 + (r%8) 16 + (k%4) 4, so the stride
+// between the two 16-byte K-chunks of one MMA (K = 8) is LBO = 2048 and between 8-row groups SBO = 128.  Both operands are
+// written in exactly this image to global memory (B once per data set on the host, A by abc_score_mma_prep_kernel) and
+// arrive in shared memory by plain bulk copies.
+#define MF_M 128                          // particles per CTA (= MMA M, one TMEM lane each)
+#define MF_N 128                          // genes per accumulator tile: four tiles of 32
+#define MF_K 128
+#define MF_KSTEPS (MF_K / 8)
+#define MF_TILE_FLOATS (MF_N * MF_K)      // 64 KB
+#define MF_EPI_WARPS 8
+#define MF_THREADS (32 * (3 + MF_EPI_WARPS)) // warp 0 loads, warp 1 issues the MMAs, warps 2-9 read the accumulators, warp 10 fills
+#define MF_COL_ONE 106
+#define MF_COL_INVALID 107
+
+static float tf32_rn(double x) {
+    float f = (float)x;
+    uint32_t u;
+    memcpy(&u, &f, 4);
+    if ((u & 0x7f800000u) == 0x7f800000u) return f;
+    u = (u + 0x0fffu + ((u >> 13) & 1u)) & 0xffffe000u;
+    memcpy(&f, &u, 4);
+    return f;
+}
+static float tf32_down(double x) {
+    float f = f32_down(x);
+    uint32_t u;
+    memcpy(&u, &f, 4);
+    if ((u & 0x7f800000u) == 0x7f800000u) return f;
+    if (u & 0x1fffu) {
+        if (f > 0.f) u &= 0xffffe000u;                    // towards zero = down
+        else u = (u | 0x1fffu) + 1u;                       // away from zero = down
+    }
+    memcpy(&f, &u, 4);
+    return f;
+}
+static inline size_t mf_off(int r, int k) { return (size_t)(k / 4) * 512 + (size_t)(r / 8) * 32 + (size_t)(r % 8) * 4 + (size_t)(k % 4); }
+
+int abc_score_mma_tiles(int ntiles) { return (ntiles * S3_TG + MF_N - 1) / MF_N; }
+
+void abc_score_mma_build(const double* d, const double* den, const AbcScore3Host& h, std::vector<float>& bblob, double* max_slack) {
+    const int ntn = abc_score_mma_tiles(h.ntiles);
+    bblob.assign((size_t)ntn * MF_TILE_FLOATS, 0.f);
+    double worst = 0.0;
+    for (int col = 0; col < ntn * MF_N; ++col) {
+        float* tile = &bblob[(size_t)(col / MF_N) * MF_TILE_FLOATS];
+        const int r = col % MF_N, T = col / S3_TG, l = col % S3_TG;
+        const int g = (T < h.ntiles) ? h.gidx[(size_t)T * S3_TG + l] : -1;
+        tile[mf_off(r, MF_COL_INVALID)] = 1.f;
+        if (g < 0) { tile[mf_off(r, MF_COL_ONE)] = 1.f; continue; }
+        if (!((h.okmask[T] >> l) & 1u)) { tile[mf_off(r, MF_COL_ONE)] = -1.f; continue; }
+        double R = 0.0;
+        for (int t = 0; t < ABC_NSTATS; ++t) {
+            const double w = 1.0 / (53.0 * den[(size_t)g * ABC_NSTATS + t]), dv = d[(size_t)g * ABC_NSTATS + t];
+            R += w * dv * dv;
+            tile[mf_off(r, t)] = tf32_rn(-2.0 * w * dv);
+            tile[mf_off(r, ABC_NSTATS + t)] = tf32_rn(w);
+        }
+        const double sq = std::sqrt(10.0) + std::sqrt(R), Q = sq * sq, X = 2.0 * std::sqrt(R * Q);
+        const double slack = 1.002 * std::ldexp(X + Q, -10) + std::ldexp(R + X + Q, -14);
+        worst = std::max(worst, slack);
+        tile[mf_off(r, MF_COL_ONE)] = tf32_down(R - (10.0 + slack + 0.002));
+    }
+    if (max_slack) *max_slack = worst;
+}
+
+// statistics -> the A operand (one 64 KB image per 128 particles) and the per-particle NaN bits.  One thread per particle.
+__global__ void __launch_bounds__(128)
+abc_score_mma_prep_kernel(const double* __restrict__ stats, long long n, float* __restrict__ ablob, unsigned int* __restrict__ nanw, long long W) {
+    const long long i = (long long)blockIdx.x * 128 + threadIdx.x;
+    const int r = threadIdx.x, lane = r & 31;
+    const bool in = i < n;
+    const double* sp = stats + (in ? i : 0) * ABC_NSTATS;
+    bool nn = false;
+#pragma unroll 1
+    for (int t = 0; t < ABC_NSTATS; ++t) { const double v = sp[t]; nn = nn || (v != v); }
+    const unsigned int nb = __ballot_sync(0xffffffffu, in && nn);
+    const long long word = i >> 5;
+    if (lane == 0 && word < W) nanw[word] = nb;
+    const bool valid = in && !nn;
+    float4* dst = reinterpret_cast<float4*>(ablob + (size_t)blockIdx.x * MF_TILE_FLOATS) + (r >> 3) * 8 + (r & 7);
+    auto elem = [&](int k) -> float {
+        if (k == MF_COL_ONE) return valid ? 1.f : 0.f;
+        if (k == MF_COL_INVALID) return valid ? 0.f : 1.f;
+        if (k > MF_COL_INVALID || !valid) return 0.f;
+        const double s = sp[k < ABC_NSTATS ? k : k - ABC_NSTATS];
+        float f = (float)(k < ABC_NSTATS ? s : s * s);
+        unsigned int u;
+        asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(u) : "f"(f));
+        f = __uint_as_float(u);
+        return (fabsf(f) <= 3.0e38f) ? f : 0.f;            // Inf / NaN -> 0 (see the header)
+    };
+#pragma unroll
+    for (int c = 0; c < MF_K / 4; ++c) dst[(size_t)c * 128] = make_float4(elem(4 * c), elem(4 * c + 1), elem(4 * c + 2), elem(4 * c + 3));
+}
+
+struct MfSmem {
+    alignas(1024) float a[MF_TILE_FLOATS];
+    alignas(1024) float b[2][MF_TILE_FLOATS];
+    alignas(16) double tens[S3_FILL_DOUBLES];
+    unsigned long long a_full, b_full[2], b_empty[2], acc_full[2], acc_empty[2];
+    unsigned int tmem_base;
+};
+
+__device__ __forceinline__ void mf_mbar_arrive(unsigned long long* mbar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(s3_saddr(mbar)) : "memory");
+}
+__device__ __forceinline__ void mf_tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void mf_tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void mf_commit(unsigned long long* mbar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(s3_saddr(mbar)) : "memory");
+}
+__device__ __forceinline__ unsigned long long mf_desc(unsigned int saddr) {
+    // start address, LBO = 2048 B (K direction), SBO = 128 B (8-row groups), descriptor version 1, no swizzle
+    return (unsigned long long)((saddr >> 4) & 0x3fffu) | ((unsigned long long)(2048u >> 4) << 16) |
+           ((unsigned long long)(128u >> 4) << 32) | (1ull << 46);
+}
+__device__ __forceinline__ void mf_mma(unsigned int tmem_d, unsigned long long adesc, unsigned long long bdesc, unsigned int idesc, unsigned int acc) {
+    asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+                 "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
+                 ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(acc) : "memory");
+}
+__device__ __forceinline__ void mf_tmem_ld32(unsigned int taddr, unsigned int (&v)[32]) {
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+                 "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+                 "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+                 : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
+                   "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]),
+                   "=r"(v[16]), "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]),
+                   "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+                 : "r"(taddr) : "memory");
+}
+
+// One CTA per 128 particles: V = A B^T tile by tile over all genes (double-buffered gene tiles in shared memory and
+// accumulators in tensor memory), sign bits -> stage-3 queue segments of (tile of 32 genes, block of 2048 particles); the
+// service warp writes the CTA's share of the matrix with 10.0 (NaN rows for NaN particles) meanwhile.
+template <int LAYOUT>
+__global__ void __launch_bounds__(MF_THREADS, 1)
+abc_score_mma_filter_kernel(const AbcScoreArgs a, const AbcScore3Tables x, const float* __restrict__ ablob,
+                            const float* __restrict__ bblob, int ntn, float* __restrict__ dbg) {
+    extern __shared__ unsigned char mf_raw[];
+    // the operand tiles want their natural alignment whatever the base of the dynamic window is
+    MfSmem& sm = *reinterpret_cast<MfSmem*>(mf_raw + ((1024u - (s3_saddr(mf_raw) & 1023u)) & 1023u));
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const long long i0 = (long long)blockIdx.x * MF_M;
+    if (tid == 0) {
+        s3_mbar_init(&sm.a_full, 1);
+        for (int s = 0; s < 2; ++s) {
+            s3_mbar_init(&sm.b_full[s], 1);
+            s3_mbar_init(&sm.b_empty[s], 1);
+            s3_mbar_init(&sm.acc_full[s], 1);
+            s3_mbar_init(&sm.acc_empty[s], MF_EPI_WARPS);
+        }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        s3_fence_proxy_async();
+    }
+    if (warp == 1) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 256;" ::"r"(s3_saddr(&sm.tmem_base)) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    if (warp == 2 + MF_EPI_WARPS) {
+        for (int j = lane; j < S3_FILL_DOUBLES; j += 32) sm.tens[j] = 10.0;
+        s3_fence_proxy_async();
+    }
+    mf_tc_fence_before();
+    __syncthreads();
+    mf_tc_fence_after();
+    const unsigned int tmem = *(volatile unsigned int*)&sm.tmem_base;
+
+    if (warp == 0) {
+        // ================= loads: the particle tile once, the gene tiles through a two-slot ring
+        if (lane == 0) {
+            s3_mbar_expect_tx(&sm.a_full, MF_TILE_FLOATS * 4);
+            for (int c = 0; c < 4; ++c)
+                s3_bulk_g2s(sm.a + c * (MF_TILE_FLOATS / 4), ablob + (size_t)blockIdx.x * MF_TILE_FLOATS + c * (MF_TILE_FLOATS / 4),
+                            (MF_TILE_FLOATS / 4) * 4, &sm.a_full);
+            for (int j = 0; j < ntn; ++j) {
+                const int s = j & 1;
+                if (j >= 2) s3_mbar_wait(&sm.b_empty[s], (unsigned int)(((j >> 1) - 1) & 1));
+                s3_mbar_expect_tx(&sm.b_full[s], MF_TILE_FLOATS * 4);
+                for (int c = 0; c < 4; ++c)
+                    s3_bulk_g2s(sm.b[s] + c * (MF_TILE_FLOATS / 4), bblob + (size_t)j * MF_TILE_FLOATS + c * (MF_TILE_FLOATS / 4),
+                                (MF_TILE_FLOATS / 4) * 4, &sm.b_full[s]);
+            }
+        }
+    } else if (warp == 1) {
+        // ================= MMA issue: one thread
+        if (lane == 0) {
+            // instruction descriptor: D = F32, A = B = TF32, both K-major, N = 128, M = 128
+            const unsigned int idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((unsigned int)(MF_N >> 3) << 17) | ((unsigned int)(MF_M >> 4) << 24);
+            const unsigned long long adesc = mf_desc(s3_saddr(sm.a));
+            s3_mbar_wait(&sm.a_full, 0);
+            for (int j = 0; j < ntn; ++j) {
+                const int s = j & 1;
+                if (j >= 2) s3_mbar_wait(&sm.acc_empty[s], (unsigned int)(((j >> 1) - 1) & 1));
+                s3_mbar_wait(&sm.b_full[s], (unsigned int)((j >> 1) & 1));
+                mf_tc_fence_after();
+                const unsigned long long bdesc = mf_desc(s3_saddr(sm.b[s]));
+#pragma unroll
+                for (int kk = 0; kk < MF_KSTEPS; ++kk)       // two 16-byte chunks (2 x 2048 B) per K step
+                    mf_mma(tmem + (unsigned int)(s * MF_N), adesc + (unsigned long long)(kk * (4096 >> 4)),
+                           bdesc + (unsigned long long)(kk * (4096 >> 4)), idesc, kk > 0 ? 1u : 0u);
+                mf_commit(&sm.b_empty[s]);
+                mf_commit(&sm.acc_full[s]);
+            }
+        }
+    } else if (warp < 2 + MF_EPI_WARPS) {
+        // ================= accumulators -> sign bits -> queue.  Warp w may read TMEM lanes 32 (w % 4) .. + 31; the two
+        // warps of a lane group take two of the four 32-gene tiles each.  Everything with a long latency is issued for
+        // both tiles before it is waited for (TMEM loads, the scan, the queue reservations).
+        const int lg = warp & 3, half = (warp - 2) >> 2;
+        const long long i = i0 + lg * 32 + lane;
+        const unsigned int pl = (unsigned int)(i & (S3_PB - 1));
+        const long long kblk = i >> 11;
+        for (int j = 0; j < ntn; ++j) {
+            const int s = j & 1;
+            s3_mbar_wait(&sm.acc_full[s], (unsigned int)((j >> 1) & 1));
+            mf_tc_fence_after();
+            unsigned int v[2][32];
+            const unsigned int taddr = tmem + ((unsigned int)(lg * 32) << 16) + (unsigned int)(s * MF_N + half * 64);
+            mf_tmem_ld32(taddr, v[0]);
+            mf_tmem_ld32(taddr + 32u, v[1]);
+            asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+            unsigned int m0 = 0u, m1 = 0u;
+#pragma unroll
+            for (int c = 31; c >= 0; --c) {
+                m0 = __funnelshift_l(v[0][c], m0, 1);
+                m1 = __funnelshift_l(v[1][c], m1, 1);
+            }
+            if (dbg != nullptr) {
+#pragma unroll
+                for (int c = 0; c < 64; ++c)
+                    dbg[(size_t)i * (size_t)(ntn * MF_N) + (size_t)(j * MF_N + half * 64 + c)] = __uint_as_float(v[c >> 5][c & 31]);
+            }
+            mf_tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mf_mbar_arrive(&sm.acc_empty[s]);
+            if (!__any_sync(0xffffffffu, (m0 | m1) != 0u)) continue;
+            // both counts in one scan: 16 bits each (<= 32 x 32)
+            const unsigned int cnt = (unsigned int)__popc(m0) | ((unsigned int)__popc(m1) << 16);
+            unsigned int incl = cnt;
+#pragma unroll
+            for (int dd = 1; dd < 32; dd <<= 1) {
+                const unsigned int t = __shfl_up_sync(0xffffffffu, incl, dd);
+                if (lane >= dd) incl += t;
+            }
+            const unsigned int total = __shfl_sync(0xffffffffu, incl, 31);
+            const int T0 = 4 * j + 2 * half;
+            unsigned int base = 0u;
+            if (lane < 2) {                                  // lane q reserves room in the segment of tile T0 + q
+                const unsigned int tq = (total >> (16 * lane)) & 0xffffu;
+                if (tq > 0u && T0 + lane < x.ntiles) base = atomicAdd(&x.qcnt[(size_t)kblk * (size_t)x.ntiles + (size_t)(T0 + lane)], tq);
+            }
+            const unsigned int base0 = __shfl_sync(0xffffffffu, base, 0), base1 = __shfl_sync(0xffffffffu, base, 1);
+            const unsigned int excl = incl - cnt;
+            if (T0 < x.ntiles) {
+                unsigned short* seg = x.q2 + ((size_t)kblk * (size_t)x.ntiles + (size_t)T0) * (size_t)(S3_PB * S3_TG);
+                unsigned int pos = base0 + (excl & 0xffffu);
+                while (m0) {
+                    const int b = __ffs(m0) - 1;
+                    m0 &= m0 - 1u;
+                    seg[pos++] = (unsigned short)((pl << 5) | (unsigned int)b);
+                }
+            }
+            if (T0 + 1 < x.ntiles) {
+                unsigned short* seg = x.q2 + ((size_t)kblk * (size_t)x.ntiles + (size_t)(T0 + 1)) * (size_t)(S3_PB * S3_TG);
+                unsigned int pos = base1 + (excl >> 16);
+                while (m1) {
+                    const int b = __ffs(m1) - 1;
+                    m1 &= m1 - 1u;
+                    seg[pos++] = (unsigned short)((pl << 5) | (unsigned int)b);
+                }
+            }
+        }
+    } else {
+        // ================= service warp: this CTA's 128 rows (particle-major) or 128-particle columns (gene-major)
+        if (LAYOUT != ABC_ERR_NONE) {
+            const int rows = (int)max(0ll, min((long long)MF_M, a.n - i0));
+            bool nn = false;
+            if (lane < MF_M / 32) {
+                const long long wi = (i0 >> 5) + lane;
+                nn = wi < x.W && x.nanw[wi] != 0u;
+            }
+            const bool any_nan = __any_sync(0xffffffffu, nn);
+            const double qnan = __longlong_as_double(0x7ff8000000000000ll);
+            if (LAYOUT == ABC_ERR_GENE_MAJOR) {
+                for (int g = lane; g < a.G && rows > 0; g += 32) {      // one gene row (<= 1 KB) per lane and step
+                    double* p = a.err + (long long)g * a.gm_stride + i0;
+                    if (!any_nan) {
+                        const int head = (int)((reinterpret_cast<unsigned long long>(p) >> 3) & 1ull);
+                        if (head) p[0] = 10.0;
+                        const int mid = (rows - head) & ~1;
+                        if (mid > 0) s3_bulk_s2g(p + head, sm.tens, (unsigned int)(mid * 8));
+                        if (head + mid < rows) p[rows - 1] = 10.0;
+                    } else {
+                        for (int r = 0; r < rows; ++r)
+                            p[r] = ((x.nanw[(i0 >> 5) + (r >> 5)] >> (r & 31)) & 1u) ? qnan : 10.0;
+                    }
+                }
+            } else if (rows > 0) {
+                double* base = a.err + i0 * (long long)a.G;
+                const long long L = (long long)rows * a.G;
+                if (!any_nan) {
+                    s3_fill_tma(base, L, sm.tens, lane);
+                } else {
+                    for (long long j = lane; j < L; j += 32) {
+                        const int r = (int)(j / a.G);
+                        base[j] = ((x.nanw[(i0 >> 5) + (r >> 5)] >> (r & 31)) & 1u) ? qnan : 10.0;
+                    }
+                }
+            }
+            s3_bulk_commit_wait();
+        }
+    }
+    mf_tc_fence_before();
+    __syncthreads();
+    if (warp == 1) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 256;" ::"r"(tmem) : "memory");
+}
+
 // ------------------------------------------------------------------------------------------------ launcher
 size_t abc_score3_blocks(int64_t n) { return (size_t)((n + S3_PB - 1) / S3_PB); }
 size_t abc_score3_queue_entries(int64_t n, int ntiles) { return abc_score3_blocks(n) * (size_t)ntiles * (size_t)(S3_PB * S3_TG); }
@@ -637,6 +979,36 @@ int abc_launch_score3(const AbcScoreArgs& a, const AbcScore3Tables& x_in, cudaSt
     } else {
         abc_score3_tile_kernel<ABC_ERR_PARTICLE_MAJOR><<<grid, S3_THREADS, smem, st>>>(a, x);
         abc_score3_exact_kernel<ABC_ERR_PARTICLE_MAJOR><<<grid, S3E_THREADS, 0, st>>>(a, x);
+    }
+    ABC_CUDA_CHECK(cudaGetLastError());
+    return ABC_OK;
+}
+
+int abc_launch_score_mma(const AbcScoreArgs& a, const AbcScore3Tables& x_in, float* d_ablob, const float* d_bblob, float* d_dbg,
+                         cudaStream_t st) {
+    if (a.n <= 0 || a.G <= 0) return ABC_OK;
+    const long long nblocks = (a.n + S3_PB - 1) / S3_PB;
+    if (nblocks * x_in.ntiles > 0x7fffffffll) { abc_set_error("abc_score: batch too large for one launch"); return ABC_ERR_ARG; }
+    const int lay = (a.err == nullptr) ? ABC_ERR_NONE : a.err_layout;
+    const int smem = (int)sizeof(MfSmem) + 1024;
+    const int ntn = abc_score_mma_tiles(x_in.ntiles);
+    const unsigned int grid128 = (unsigned int)((a.n + MF_M - 1) / MF_M);
+    ABC_CUDA_CHECK(cudaFuncSetAttribute(abc_score_mma_filter_kernel<ABC_ERR_NONE>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    ABC_CUDA_CHECK(cudaFuncSetAttribute(abc_score_mma_filter_kernel<ABC_ERR_GENE_MAJOR>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    ABC_CUDA_CHECK(cudaFuncSetAttribute(abc_score_mma_filter_kernel<ABC_ERR_PARTICLE_MAJOR>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    ABC_CUDA_CHECK(cudaMemsetAsync(x_in.qcnt, 0, (size_t)nblocks * (size_t)x_in.ntiles * sizeof(uint32_t), st));
+    abc_score_mma_prep_kernel<<<grid128, 128, 0, st>>>(a.stats, (long long)a.n, d_ablob, x_in.nanw, (long long)x_in.W);
+    ABC_CUDA_CHECK(cudaGetLastError());
+    const unsigned int grid = (unsigned int)(nblocks * x_in.ntiles);
+    if (lay == ABC_ERR_NONE) {
+        abc_score_mma_filter_kernel<ABC_ERR_NONE><<<grid128, MF_THREADS, smem, st>>>(a, x_in, d_ablob, d_bblob, ntn, d_dbg);
+        abc_score3_exact_kernel<ABC_ERR_NONE><<<grid, S3E_THREADS, 0, st>>>(a, x_in);
+    } else if (lay == ABC_ERR_GENE_MAJOR) {
+        abc_score_mma_filter_kernel<ABC_ERR_GENE_MAJOR><<<grid128, MF_THREADS, smem, st>>>(a, x_in, d_ablob, d_bblob, ntn, d_dbg);
+        abc_score3_exact_kernel<ABC_ERR_GENE_MAJOR><<<grid, S3E_THREADS, 0, st>>>(a, x_in);
+    } else {
+        abc_score_mma_filter_kernel<ABC_ERR_PARTICLE_MAJOR><<<grid128, MF_THREADS, smem, st>>>(a, x_in, d_ablob, d_bblob, ntn, d_dbg);
+        abc_score3_exact_kernel<ABC_ERR_PARTICLE_MAJOR><<<grid, S3E_THREADS, 0, st>>>(a, x_in);
     }
     ABC_CUDA_CHECK(cudaGetLastError());
     return ABC_OK;

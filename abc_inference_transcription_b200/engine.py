@@ -298,6 +298,18 @@ class AbcEngine:
                                            float(eps), int(err_layout), ctypes.c_void_p(d_err_ptr or 0),
                                            ctypes.c_void_p(stream or 0)))
 
+    def score_mma_debug(self, d_stats_ptr, n, d_out_ptr):
+        """diagnostic: raw accumulators of the tensor-core filter into a device float array of ceil(n/128)*128 rows x
+        score_mma_columns(); returns the gene index of every column (-1 = padding)"""
+        cols = int(self._lib.abc_score_mma_columns(self._ctx))
+        gene = np.empty(cols, dtype=np.int32)
+        _lib.check(self._lib.abc_score_mma_debug(self._ctx, ctypes.c_void_p(d_stats_ptr), int(n), ctypes.c_void_p(d_out_ptr),
+                                                 gene.ctypes.data_as(ctypes.c_void_p)))
+        return gene
+
+    def score_mma_columns(self):
+        return int(self._lib.abc_score_mma_columns(self._ctx))
+
     def counts_dev(self, d_counts_ptr, stream=None):
         _lib.check(self._lib.abc_counts_dev(self._ctx, ctypes.c_void_p(d_counts_ptr), ctypes.c_void_p(stream or 0)))
 

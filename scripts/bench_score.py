@@ -1,6 +1,6 @@
 """Scoring-kernel micro-benchmark: realistic statistics (prior draws through the device ODE path), one large
 resident batch, CUDA events.
-Usage: python scripts/bench_score.py [n_particles] [layout 0|1|2] [reference_kernel 0|1] [tile_kernel 1|0] [overlap 1|0]"""
+Usage: python scripts/bench_score.py [n_particles] [layout 0|1|2] [reference_kernel 0|1] [tile_kernel 1|0] [overlap 1|0] [sub_batches] [mma_filter 0|1]"""
 import os
 import sys
 
@@ -17,6 +17,7 @@ refk = int(sys.argv[3]) if len(sys.argv) > 3 else 0
 tilek = int(sys.argv[4]) if len(sys.argv) > 4 else 1
 overlap = int(sys.argv[5]) if len(sys.argv) > 5 else 1
 nsb = int(sys.argv[6]) if len(sys.argv) > 6 else 0
+mma = int(sys.argv[7]) if len(sys.argv) > 7 else 0
 gold = os.path.join(ROOT, "tests", "golden")
 betas = np.load(os.path.join(gold, "ref_betas.npy"))
 z = np.load(os.path.join(gold, "ref_summary_stats.npz"))
@@ -27,6 +28,7 @@ eng.set_option("score_reference_kernel", refk)
 eng.set_option("score_tile_kernel", tilek)
 eng.set_option("score_overlap", overlap)
 eng.set_option("score_sub_batches", nsb)
+eng.set_option("score_mma_filter", mma)
 G = z["d"].shape[0]
 dev = torch.device("cuda", 0)
 per = n // 5
@@ -50,5 +52,5 @@ for it in range(5):
     torch.cuda.synchronize()
     ms.append(e0.elapsed_time(e1))
 t = float(np.median(ms[1:])) / 1e3
-print(f"n={n} layout={layout} ref_kernel={refk} tile_kernel={tilek} overlap={overlap} sub_batches={nsb}: {t*1e3:.3f} ms  {n*27776/t/1e9:.1f} GB/s algorithmic  "
+print(f"n={n} layout={layout} ref_kernel={refk} tile_kernel={tilek} overlap={overlap} sub_batches={nsb} mma_filter={mma}: {t*1e3:.3f} ms  {n*27776/t/1e9:.1f} GB/s algorithmic  "
       f"{n*G/t/1e9:.2f} Gpairs/s  accepted={eng.accept_total()}  frac<10={(err < 10).float().mean().item():.4f}")
