@@ -96,6 +96,7 @@ extern "C" int abc_destroy(abc_ctx_t* c) {
     c->d_beta.release(); c->d_age_dist.release(); c->d_beta_mom.release(); c->d_d.release(); c->d_den.release(); c->d_fbw.release(); c->d_fa.release(); c->d_fstats.release(); c->d_rnan.release();
     c->d_s3_tb.release(); c->d_s3_ab.release(); c->d_s3_wt.release();
     c->d_s3_gidx.release(); c->d_s3_ok.release(); for (int l = 0; l < 2; ++l) { c->d_s3_live[l].release(); c->d_s3_nanw[l].release(); c->d_s3_qcnt[l].release(); c->d_s3_q2[l].release(); c->d_s3_fstats[l].release(); }
+    c->d_mf_b.release(); c->d_mf_done.release(); for (int l = 0; l < 2; ++l) { c->d_mf_a[l].release(); c->d_mf_mask[l].release(); }
     c->d_theta.release(); c->d_stats.release(); c->d_moments.release(); c->d_ss_iv.release(); c->d_prefix.release(); c->d_rates.release(); c->d_win.release();
     c->d_keys_in.release(); c->d_keys_out.release(); c->d_idx_in.release(); c->d_order.release(); c->d_sort_tmp.release();
     c->d_sums.release(); c->d_counters.release(); c->d_work.release(); c->d_cells.release();
@@ -645,6 +646,28 @@ static int score_device(abc_ctx* c, const double* d_stats, int64_t n, int64_t of
         x.ntiles = c->s3_ntiles;
         x.tb = c->d_s3_tb.p; x.ab = c->d_s3_ab.p; x.wt = c->d_s3_wt.p;
         x.gidx = c->d_s3_gidx.p; x.okmask = c->d_s3_ok.p;
+        if (c->score_mma_filter && layout != ABC_ERR_NONE) {
+            // tensor-core filter: statistics -> TF32 operand, GEMM -> sign-bit words, stage 3 on the flagged pairs; the matrix's
+            // background is written on a side stream meanwhile.  Chunks of <= 2^19 particles (1 KB of work space each).
+            const int64_t chunk = std::min<int64_t>((n + 2047) / 2048 * 2048, 1ll << 19);
+            if ((rc = c->d_s3_nanw[0].ensure((size_t)((chunk + 31) / 32))) != ABC_OK) return rc;
+            if ((rc = c->d_mf_a[0].ensure((size_t)chunk * 128)) != ABC_OK) return rc;
+            if ((rc = c->d_mf_mask[0].ensure((size_t)abc_score_mma_tiles(x.ntiles) * 8 * (size_t)chunk)) != ABC_OK) return rc;
+            if ((rc = c->d_mf_done.ensure((size_t)(chunk / 2048 + 2))) != ABC_OK) return rc;
+            for (int64_t s0 = 0; s0 < n && rc == ABC_OK; s0 += chunk) {
+                AbcScoreArgs b = a;
+                b.n = std::min<int64_t>(chunk, n - s0);
+                b.stats = d_stats + s0 * ABC_NSTATS;
+                b.particle_offset = offset + s0;
+                if (b.err != nullptr) b.err = (layout == ABC_ERR_GENE_MAJOR) ? d_err + s0 : d_err + s0 * (int64_t)c->G;
+                x.nanw = c->d_s3_nanw[0].p; x.W = (b.n + 31) / 32;
+                x.gmask = c->d_mf_mask[0].p; x.n_pad = (b.n + 127) / 128 * 128; x.n_rows = x.n_pad; x.fill_done = c->d_mf_done.p;
+                rc = abc_launch_score_mma(b, x, c->d_mf_a[0].p, c->d_mf_b.p, nullptr, c->sm_count, st);
+                c->launches += 3;
+            }
+            ABC_CUDA_CHECK(cudaEventRecord(c->ev[4], st));
+            return rc;
+        }
         const int64_t per_particle = (int64_t)x.ntiles * 32 * 2;
         int64_t sub = std::max<int64_t>(2048, ((int64_t)2000000000 / per_particle) / 2048 * 2048);
         // at least four sub-batches of >= 16 particle blocks when the batch is large enough to pipeline
@@ -660,7 +683,6 @@ static int score_device(abc_ctx* c, const double* d_stats, int64_t n, int64_t of
             if ((rc = c->d_s3_nanw[l].ensure((size_t)((sub + 31) / 32))) != ABC_OK) return rc;
             if ((rc = c->d_s3_qcnt[l].ensure(nblocks * (size_t)x.ntiles)) != ABC_OK) return rc;
             if ((rc = c->d_s3_q2[l].ensure(abc_score3_queue_entries(sub, x.ntiles))) != ABC_OK) return rc;
-            if (c->score_mma_filter && (rc = c->d_mf_a[l].ensure((size_t)((sub + 127) / 128) * 128 * 128)) != ABC_OK) return rc;
         }
         if (overlap) {
             ABC_CUDA_CHECK(cudaEventRecord(c->s3_ev_begin, st));
@@ -677,8 +699,7 @@ static int score_device(abc_ctx* c, const double* d_stats, int64_t n, int64_t of
             if (b.err != nullptr) b.err = (layout == ABC_ERR_GENE_MAJOR) ? d_err + s0 : d_err + s0 * (int64_t)c->G;
             x.live = c->d_s3_live[l].p; x.nanw = c->d_s3_nanw[l].p; x.q2 = c->d_s3_q2[l].p; x.qcnt = c->d_s3_qcnt[l].p;
             x.W = (b.n + 31) / 32;
-            if (c->score_mma_filter && layout != ABC_ERR_NONE) rc = abc_launch_score_mma(b, x, c->d_mf_a[l].p, c->d_mf_b.p, nullptr, overlap ? c->s3_stream[l] : st);
-            else rc = abc_launch_score3(b, x, overlap ? c->s3_stream[l] : st);
+            rc = abc_launch_score3(b, x, overlap ? c->s3_stream[l] : st);
             c->launches += 3;
         }
         if (overlap) {
@@ -707,7 +728,7 @@ static int score_device(abc_ctx* c, const double* d_stats, int64_t n, int64_t of
 // statistics; d_out has ceil(n / 128) * 128 rows of abc_score_mma_columns() floats.  No matrix, no acceptance.
 extern "C" int abc_score_mma_columns(abc_ctx_t* c) {
     if (!c || !c->has_data) return 0;
-    return abc_score_mma_tiles(c->s3_ntiles) * 128;
+    return abc_score_mma_tiles(c->s3_ntiles) * 256;
 }
 extern "C" int abc_score_mma_debug(abc_ctx_t* c, const double* d_stats, int64_t n, float* d_out, int32_t* gene_of_column) {
     CTX_GUARD(c);
@@ -719,14 +740,16 @@ extern "C" int abc_score_mma_debug(abc_ctx_t* c, const double* d_stats, int64_t 
     a.counts = c->d_counts.p; a.acc_count = c->d_acc_count.p; a.acc_capacity = 0;
     AbcScore3Tables x{};
     x.ntiles = c->s3_ntiles; x.tb = c->d_s3_tb.p; x.ab = c->d_s3_ab.p; x.wt = c->d_s3_wt.p; x.gidx = c->d_s3_gidx.p; x.okmask = c->d_s3_ok.p;
-    const size_t nblocks = abc_score3_blocks(n);
     if ((rc = c->d_s3_nanw[0].ensure((size_t)((n + 31) / 32))) != ABC_OK) return rc;
-    if ((rc = c->d_s3_qcnt[0].ensure(nblocks * (size_t)x.ntiles)) != ABC_OK) return rc;
-    if ((rc = c->d_s3_q2[0].ensure(abc_score3_queue_entries(n, x.ntiles))) != ABC_OK) return rc;
-    if ((rc = c->d_mf_a[0].ensure((size_t)((n + 127) / 128) * 128 * 128)) != ABC_OK) return rc;
-    x.nanw = c->d_s3_nanw[0].p; x.q2 = c->d_s3_q2[0].p; x.qcnt = c->d_s3_qcnt[0].p; x.W = (n + 31) / 32;
+    const size_t n_pad = (size_t)((n + 127) / 128) * 128;
+    if ((rc = c->d_mf_a[0].ensure(n_pad * 128)) != ABC_OK) return rc;
+    if ((rc = c->d_mf_mask[0].ensure((size_t)abc_score_mma_tiles(x.ntiles) * 8 * n_pad)) != ABC_OK) return rc;
+    if ((rc = c->d_mf_done.ensure(n_pad / 2048 + 2)) != ABC_OK) return rc;
+    x.fill_done = c->d_mf_done.p;
+    x.nanw = c->d_s3_nanw[0].p; x.W = (n + 31) / 32; x.gmask = c->d_mf_mask[0].p; x.n_pad = (int64_t)n_pad;
     a.eps = -1.0;                                        // nothing is accepted
-    rc = abc_launch_score_mma(a, x, c->d_mf_a[0].p, c->d_mf_b.p, d_out, c->stream);
+    x.n_rows = x.n_pad;
+    rc = abc_launch_score_mma(a, x, c->d_mf_a[0].p, c->d_mf_b.p, d_out, c->sm_count, c->stream);
     if (rc != ABC_OK) return rc;
     ABC_CUDA_CHECK(cudaStreamSynchronize(c->stream));
     if (gene_of_column) {

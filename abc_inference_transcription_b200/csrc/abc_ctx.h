@@ -74,6 +74,8 @@ struct abc_ctx {
     DevBuf<uint16_t> d_s3_q2[2];
     DevBuf<float> d_s3_fstats[2];
     DevBuf<float> d_mf_b, d_mf_a[2];   // tensor-core filter: gene operand (per data set), particle operand (per sub-batch)
+    DevBuf<uint32_t> d_mf_mask[2];     // its output: sign-bit words [tile of 32 genes][particle]
+    DevBuf<uint32_t> d_mf_done;        // per particle block: CTAs that have written their slice of the background
     int score_mma_filter = 0;    // 1: TF32 tcgen05 GEMM decides which pairs reach stage 3 (abc_score3.cu, tensor-core filter)
     double mf_max_slack = 0.0;
     cudaStream_t s3_stream[2] = {nullptr, nullptr};

@@ -103,6 +103,11 @@ struct AbcScore3Tables {
     uint32_t* qcnt;          // [blocks*ntiles] work: fill of each segment
     int64_t W;               // ceil(n / 32)
     float sure;              // FP32 bounds above this prove that a pair is not needed (set by the launcher)
+    uint32_t* gmask;         // [8 * mma tiles][n_pad] work (tensor-core filter): bit l = (particle, slot l of the tile) reaches stage 3
+    int64_t n_pad;           // its row pitch: particles of the launch rounded up to 128
+    int64_t n_rows;          // rows readable from gmask (stage 3 may be launched on a row range)
+    uint32_t* fill_done;     // [blocks + 1] work: CTAs that have written their slice of a particle block's background
+    int32_t fill_b0, fill_d; // background: blocks < fill_b0 by the filter kernel, block j >= fill_b0 by stage 3 of block j - fill_d
 };
 #ifdef __cplusplus
 #include <vector>
@@ -124,7 +129,7 @@ void abc_score_mma_build(const double* d, const double* den, const AbcScore3Host
 #endif
 int abc_score_mma_tiles(int ntiles);
 int abc_launch_score_mma(const AbcScoreArgs& a, const AbcScore3Tables& x, float* d_ablob, const float* d_bblob, float* d_dbg,
-                         cudaStream_t st);
+                         int sm_count, cudaStream_t st);
 int abc_launch_score_prep(const double* d_stats, int64_t n, float* d_fstats, unsigned char* d_rnan, cudaStream_t st);
 
 // A1 ordering on the device (abc_accept.cu)

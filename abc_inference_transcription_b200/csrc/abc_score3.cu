@@ -39,6 +39,9 @@
 #include <cstring>
 #include <vector>
 
+#ifndef S3_FILL_EVICT_FIRST
+#define S3_FILL_EVICT_FIRST 1
+#endif
 #define S3_TG 32
 #define S3_NN 31          // statistics used by the tile bound: means, Fano factors, ratios (non-negative)
 #define S3_WARPS 5                       // compute warps
@@ -261,12 +264,32 @@ __device__ __forceinline__ void s3_mbar_wait(unsigned long long* mbar, unsigned 
                      : "=r"(ok) : "r"(s3_saddr(mbar)), "r"(phase) : "memory");
     } while (!ok);
 }
+// The background is written once and not read again on the device: evict-first keeps 3.6 GB of streaming stores from
+// displacing the statistics, tables and operands that the kernels running beside them re-read from L2.
 __device__ __forceinline__ void s3_bulk_s2g(void* dst, const void* src, unsigned int bytes) {
+#if S3_FILL_EVICT_FIRST
+    unsigned long long pol;
+    asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
+    asm volatile("cp.async.bulk.global.shared::cta.bulk_group.L2::cache_hint [%0], [%1], %2, %3;"
+                 ::"l"(dst), "r"(s3_saddr(src)), "r"(bytes), "l"(pol) : "memory");
+#else
     asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst), "r"(s3_saddr(src)), "r"(bytes) : "memory");
+#endif
 }
 __device__ __forceinline__ void s3_bulk_commit_wait() {
     asm volatile("cp.async.bulk.commit_group;" ::: "memory");
     asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+}
+// read-once data (tables, sign-bit words): do not displace the statistics rows that stage 3 re-reads from L1
+__device__ __forceinline__ uint4 s3_ldg_stream(const uint4* p) {
+    uint4 v;
+    asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p));
+    return v;
+}
+__device__ __forceinline__ unsigned int s3_ld_acquire(const unsigned int* p) {
+    unsigned int v;
+    asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
 }
 __device__ __forceinline__ unsigned int s3_ld_relaxed(const unsigned int* p) {
     unsigned int v;
@@ -612,31 +635,38 @@ abc_score3_exact_kernel(const AbcScoreArgs a, const AbcScore3Tables x) {
 //
 // i.e. V[i][g] = A[i][:] . B[g][:] with  A[i] = (s_0..s_52, s_0^2..s_52^2, 1, 0/1 row-invalid flag, 0...)  per particle and
 // B[g] = (-2 a_t b_t, b_t^2, sum a^2 - thr_g, 1, 0...) per gene, all rounded to TF32 beforehand (the low 13 mantissa bits are
-// zero, so whatever the hardware does with them does not matter).  A pair is queued for stage 3 iff V < 0 (sign bit).
+// zero, so whatever the hardware does with them does not matter).  A pair goes to stage 3 iff V < 0 (sign bit).
 //
-// Soundness (true error <= 10  =>  queued).  Write R = sum a_t^2 and Q = sum b_t^2 s_t^2.  If the true error is <= 10 then
+// Soundness (true error <= 10  =>  V < 0).  Write R = sum a_t^2 and Q = sum b_t^2 s_t^2.  If the true error is <= 10 then
 // sqrt(Q) <= sqrt(10) + sqrt(R) (triangle inequality), sum |2 a_t b_t s_t| <= 2 sqrt(R Q) (Cauchy-Schwarz), every operand
 // carries a relative rounding error <= 2^-11 (+2^-24 for the double rounding through binary32), so each product is off by at
 // most 2^-10 (1 + 2^-9) of its size, and the FP32 accumulation of K = 128 products adds at most K 2^-21 of the sum of the
 // magnitudes (two ulps per addition: covers truncating adders).  Hence V + thr_g - 10 <= slack_g with
 //     slack_g = 1.002 2^-10 (2 sqrt(R Qmax) + Qmax) + 2^-14 (R + 2 sqrt(R Qmax) + Qmax),   Qmax = (sqrt(10) + sqrt(R))^2,
 // and thr_g = 10 + slack_g + 0.002 (the constant is rounded towards -inf).  R <= 100 because den >= 0.01 d^2, so
-// slack_g <= 0.45; on the shipped data the median is 0.22 and 6 % more pairs are queued than are truly <= 10.
+// slack_g <= 0.45; on the shipped data the median is 0.22 and 6 % more pairs reach stage 3 than are truly <= 10.
 // Elements that are not finite in binary32 (|s| > 1.8e19 or Inf) enter as 0: such a statistic puts the true error of every
 // gene with usable constants above 10, so any decision is sound.  Rows with a NaN statistic (all errors NaN) and rows past
 // the end of the batch are all-zero with the invalid flag set: V = +1.  Genes whose constants cannot use the fast division
-// have B = (0, ..., -1, 1): always queued for valid rows.  Padding slots have B = (0, ..., +1, 1): never queued.
+// have B = (0, ..., -1, 1): V = -1 for valid rows.  Padding slots have B = (0, ..., +1, 1): V = +1.
 //
-// Operand layout: the canonical K-major, no-swizzle UMMA layout -- 8 rows x 16 bytes "core matrices" stored contiguously
-// (128 B); element (row r, k) of a 128 x 128 tile sits at byte (k/4) 2048 + (r/8) 128 + (r%8) 16 + (k%4) 4, so the stride
-// between the two 16-byte K-chunks of one MMA (K = 8) is LBO = 2048 and between 8-row groups SBO = 128.  Both operands are
-// written in exactly this image to global memory (B once per data set on the host, A by abc_score_mma_prep_kernel) and
-// arrive in shared memory by plain bulk copies.
-#define MF_M 128                          // particles per CTA (= MMA M, one TMEM lane each)
-#define MF_N 128                          // genes per accumulator tile: four tiles of 32
+// Operand layout: the canonical K-major UMMA layout with the 128-byte swizzle.  A K slice of 32 values is one 128-byte row per
+// particle (gene); eight rows form a 1024-byte atom in which the 16-byte chunk c of row r sits at chunk position c ^ (r % 8);
+// atoms of consecutive row groups follow each other (SBO = 1024).  One MMA consumes K = 8 = 32 bytes of every row, so the
+// descriptor's start address advances by 32 bytes per step inside a slice.  (The un-swizzled "interleaved" layout with
+// LBO / SBO strides gives the same results and was the first version.)  Both operands are written in exactly this image to global memory (B once per data set on the host, in K slices of 256
+// genes x 32; A by abc_score_mma_prep_kernel, four slices of 128 particles x 32) and arrive in shared memory by plain bulk
+// copies -- no tensor maps.
+#define MF_M 128                          // particles per work item (= MMA M, one TMEM lane each)
+#define MF_N 256                          // genes per accumulator tile: eight tiles of 32.  At N = 256 one MMA (K = 8) reads
+                                          // 4 KB of A and 8 KB of B in its 128 cycles (96 B/clk); at N = 64 it would be
+                                          // 4 + 2 KB in 32 cycles (192 B/clk, above the shared-memory rate)
 #define MF_K 128
-#define MF_KSTEPS (MF_K / 8)
-#define MF_TILE_FLOATS (MF_N * MF_K)      // 64 KB
+#define MF_KSTAGE 32                      // K per ring slot: the gene operand arrives in slices of 256 genes x 32 K (32 KB)
+#define MF_NKS (MF_K / MF_KSTAGE)
+#define MF_RING 3
+#define MF_A_FLOATS (MF_M * MF_K)         // 64 KB
+#define MF_B_FLOATS (MF_N * MF_KSTAGE)    // 32 KB
 #define MF_EPI_WARPS 8
 #define MF_THREADS (32 * (3 + MF_EPI_WARPS)) // warp 0 loads, warp 1 issues the MMAs, warps 2-9 read the accumulators, warp 10 fills
 #define MF_COL_ONE 106
@@ -663,32 +693,37 @@ static float tf32_down(double x) {
     memcpy(&f, &u, 4);
     return f;
 }
-static inline size_t mf_off(int r, int k) { return (size_t)(k / 4) * 512 + (size_t)(r / 8) * 32 + (size_t)(r % 8) * 4 + (size_t)(k % 4); }
+// float index of element (row r, kk) in the image of a K slice (32 K = one 128-byte row per particle / gene): 8-row atoms of
+// 1024 B, the 16-byte chunk c of row r stored at chunk position c ^ (r % 8) (128-byte swizzle)
+static inline size_t mf_off(int r, int kk) { return (size_t)(r / 8) * 256 + (size_t)(r % 8) * 32 + (size_t)(((kk / 4) ^ (r % 8)) * 4) + (size_t)(kk % 4); }
 
 int abc_score_mma_tiles(int ntiles) { return (ntiles * S3_TG + MF_N - 1) / MF_N; }
 
 void abc_score_mma_build(const double* d, const double* den, const AbcScore3Host& h, std::vector<float>& bblob, double* max_slack) {
     const int ntn = abc_score_mma_tiles(h.ntiles);
-    bblob.assign((size_t)ntn * MF_TILE_FLOATS, 0.f);
+    bblob.assign((size_t)ntn * MF_NKS * MF_B_FLOATS, 0.f);
     double worst = 0.0;
     for (int col = 0; col < ntn * MF_N; ++col) {
-        float* tile = &bblob[(size_t)(col / MF_N) * MF_TILE_FLOATS];
         const int r = col % MF_N, T = col / S3_TG, l = col % S3_TG;
+        // element (column r of tile col / 256, k): K slice k / 32, image of a 256-row operand inside the slice
+        auto at = [&](int k) -> float& {
+            return bblob[((size_t)(col / MF_N) * MF_NKS + (size_t)(k / MF_KSTAGE)) * MF_B_FLOATS + mf_off(r, k % MF_KSTAGE)];
+        };
         const int g = (T < h.ntiles) ? h.gidx[(size_t)T * S3_TG + l] : -1;
-        tile[mf_off(r, MF_COL_INVALID)] = 1.f;
-        if (g < 0) { tile[mf_off(r, MF_COL_ONE)] = 1.f; continue; }
-        if (!((h.okmask[T] >> l) & 1u)) { tile[mf_off(r, MF_COL_ONE)] = -1.f; continue; }
+        at(MF_COL_INVALID) = 1.f;
+        if (g < 0) { at(MF_COL_ONE) = 1.f; continue; }
+        if (!((h.okmask[T] >> l) & 1u)) { at(MF_COL_ONE) = -1.f; continue; }
         double R = 0.0;
         for (int t = 0; t < ABC_NSTATS; ++t) {
             const double w = 1.0 / (53.0 * den[(size_t)g * ABC_NSTATS + t]), dv = d[(size_t)g * ABC_NSTATS + t];
             R += w * dv * dv;
-            tile[mf_off(r, t)] = tf32_rn(-2.0 * w * dv);
-            tile[mf_off(r, ABC_NSTATS + t)] = tf32_rn(w);
+            at(t) = tf32_rn(-2.0 * w * dv);
+            at(ABC_NSTATS + t) = tf32_rn(w);
         }
         const double sq = std::sqrt(10.0) + std::sqrt(R), Q = sq * sq, X = 2.0 * std::sqrt(R * Q);
         const double slack = 1.002 * std::ldexp(X + Q, -10) + std::ldexp(R + X + Q, -14);
         worst = std::max(worst, slack);
-        tile[mf_off(r, MF_COL_ONE)] = tf32_down(R - (10.0 + slack + 0.002));
+        at(MF_COL_ONE) = tf32_down(R - (10.0 + slack + 0.002));
     }
     if (max_slack) *max_slack = worst;
 }
@@ -707,7 +742,7 @@ abc_score_mma_prep_kernel(const double* __restrict__ stats, long long n, float* 
     const long long word = i >> 5;
     if (lane == 0 && word < W) nanw[word] = nb;
     const bool valid = in && !nn;
-    float4* dst = reinterpret_cast<float4*>(ablob + (size_t)blockIdx.x * MF_TILE_FLOATS) + (r >> 3) * 8 + (r & 7);
+    float4* dst = reinterpret_cast<float4*>(ablob + (size_t)blockIdx.x * MF_A_FLOATS) + (r >> 3) * 64 + (r & 7) * 8;
     auto elem = [&](int k) -> float {
         if (k == MF_COL_ONE) return valid ? 1.f : 0.f;
         if (k == MF_COL_INVALID) return valid ? 0.f : 1.f;
@@ -720,14 +755,15 @@ abc_score_mma_prep_kernel(const double* __restrict__ stats, long long n, float* 
         return (fabsf(f) <= 3.0e38f) ? f : 0.f;            // Inf / NaN -> 0 (see the header)
     };
 #pragma unroll
-    for (int c = 0; c < MF_K / 4; ++c) dst[(size_t)c * 128] = make_float4(elem(4 * c), elem(4 * c + 1), elem(4 * c + 2), elem(4 * c + 3));
+    for (int c = 0; c < MF_K / 4; ++c)           // K slice c / 8 (16 KB each), chunk c % 8 of the row, swizzled
+        dst[(size_t)(c >> 3) * 1024 + (size_t)((c & 7) ^ (r & 7))] = make_float4(elem(4 * c), elem(4 * c + 1), elem(4 * c + 2), elem(4 * c + 3));
 }
 
 struct MfSmem {
-    alignas(1024) float a[MF_TILE_FLOATS];
-    alignas(1024) float b[2][MF_TILE_FLOATS];
+    alignas(1024) float a[MF_A_FLOATS];
+    alignas(1024) float b[MF_RING][MF_B_FLOATS];
     alignas(16) double tens[S3_FILL_DOUBLES];
-    unsigned long long a_full, b_full[2], b_empty[2], acc_full[2], acc_empty[2];
+    unsigned long long a_full, a_empty, b_full[MF_RING], b_empty[MF_RING], acc_full[2], acc_empty[2];
     unsigned int tmem_base;
 };
 
@@ -740,9 +776,8 @@ __device__ __forceinline__ void mf_commit(unsigned long long* mbar) {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(s3_saddr(mbar)) : "memory");
 }
 __device__ __forceinline__ unsigned long long mf_desc(unsigned int saddr) {
-    // start address, LBO = 2048 B (K direction), SBO = 128 B (8-row groups), descriptor version 1, no swizzle
-    return (unsigned long long)((saddr >> 4) & 0x3fffu) | ((unsigned long long)(2048u >> 4) << 16) |
-           ((unsigned long long)(128u >> 4) << 32) | (1ull << 46);
+    // K-major, 128-byte swizzle: start address, LBO = 1 (unused), SBO = 1024 B (8-row atoms), descriptor version 1, layout 2
+    return (unsigned long long)((saddr >> 4) & 0x3fffu) | (1ull << 16) | ((unsigned long long)(1024u >> 4) << 32) | (1ull << 46) | (2ull << 61);
 }
 __device__ __forceinline__ void mf_mma(unsigned int tmem_d, unsigned long long adesc, unsigned long long bdesc, unsigned int idesc, unsigned int acc) {
     asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
@@ -760,23 +795,29 @@ __device__ __forceinline__ void mf_tmem_ld32(unsigned int taddr, unsigned int (&
                  : "r"(taddr) : "memory");
 }
 
-// One CTA per 128 particles: V = A B^T tile by tile over all genes (double-buffered gene tiles in shared memory and
-// accumulators in tensor memory), sign bits -> stage-3 queue segments of (tile of 32 genes, block of 2048 particles); the
-// service warp writes the CTA's share of the matrix with 10.0 (NaN rows for NaN particles) meanwhile.
+// Persistent: one CTA per SM.  Work item = (128 particles, one of `ks` ranges of gene tiles): V = A B^T tile by tile -- the
+// particle operand stays in shared memory for the item (64 KB), the gene operand streams through a three-slot ring of
+// 256 genes x 32 K slices (32 KB each) by bulk copies, accumulators are double-buffered in tensor memory (2 x 256 columns) --
+// and the sign bits of every (tile of 32 genes, particle) go to gmask as one 32-bit word.  Warp 0 loads, warp 1 (one thread)
+// issues the MMAs and commits them to the ring's and the accumulators' mbarriers, warps 2-9 read the accumulators
+// (tcgen05.ld, 32 columns per load), warp 10 writes the background of the first fill_b0 particle blocks.
 template <int LAYOUT>
 __global__ void __launch_bounds__(MF_THREADS, 1)
 abc_score_mma_filter_kernel(const AbcScoreArgs a, const AbcScore3Tables x, const float* __restrict__ ablob,
-                            const float* __restrict__ bblob, int ntn, float* __restrict__ dbg) {
+                            const float* __restrict__ bblob, int ntn, int ks, float* __restrict__ dbg) {
     extern __shared__ unsigned char mf_raw[];
     // the operand tiles want their natural alignment whatever the base of the dynamic window is
     MfSmem& sm = *reinterpret_cast<MfSmem*>(mf_raw + ((1024u - (s3_saddr(mf_raw) & 1023u)) & 1023u));
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const long long i0 = (long long)blockIdx.x * MF_M;
+    const int n_items = (int)((a.n + MF_M - 1) / MF_M) * ks;
     if (tid == 0) {
         s3_mbar_init(&sm.a_full, 1);
-        for (int s = 0; s < 2; ++s) {
+        s3_mbar_init(&sm.a_empty, 1);
+        for (int s = 0; s < MF_RING; ++s) {
             s3_mbar_init(&sm.b_full[s], 1);
             s3_mbar_init(&sm.b_empty[s], 1);
+        }
+        for (int s = 0; s < 2; ++s) {
             s3_mbar_init(&sm.acc_full[s], 1);
             s3_mbar_init(&sm.acc_empty[s], MF_EPI_WARPS);
         }
@@ -784,7 +825,7 @@ abc_score_mma_filter_kernel(const AbcScoreArgs a, const AbcScore3Tables x, const
         s3_fence_proxy_async();
     }
     if (warp == 1) {
-        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 256;" ::"r"(s3_saddr(&sm.tmem_base)) : "memory");
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 512;" ::"r"(s3_saddr(&sm.tmem_base)) : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
     }
     if (warp == 2 + MF_EPI_WARPS) {
@@ -797,153 +838,402 @@ abc_score_mma_filter_kernel(const AbcScoreArgs a, const AbcScore3Tables x, const
     const unsigned int tmem = *(volatile unsigned int*)&sm.tmem_base;
 
     if (warp == 0) {
-        // ================= loads: the particle tile once, the gene tiles through a two-slot ring
+        // ================= loads: the particle tile of the item, its gene tiles through the ring
         if (lane == 0) {
-            s3_mbar_expect_tx(&sm.a_full, MF_TILE_FLOATS * 4);
-            for (int c = 0; c < 4; ++c)
-                s3_bulk_g2s(sm.a + c * (MF_TILE_FLOATS / 4), ablob + (size_t)blockIdx.x * MF_TILE_FLOATS + c * (MF_TILE_FLOATS / 4),
-                            (MF_TILE_FLOATS / 4) * 4, &sm.a_full);
-            for (int j = 0; j < ntn; ++j) {
-                const int s = j & 1;
-                if (j >= 2) s3_mbar_wait(&sm.b_empty[s], (unsigned int)(((j >> 1) - 1) & 1));
-                s3_mbar_expect_tx(&sm.b_full[s], MF_TILE_FLOATS * 4);
+            int g = 0, iter = 0;
+            for (int it = blockIdx.x; it < n_items; it += gridDim.x, ++iter) {
+                const int blk = it / ks, part = it - blk * ks;
+                const int t0 = part * ntn / ks, t1 = (part + 1) * ntn / ks;
+                if (iter >= 1) s3_mbar_wait(&sm.a_empty, (unsigned int)((iter - 1) & 1));
+                s3_mbar_expect_tx(&sm.a_full, MF_A_FLOATS * 4);
                 for (int c = 0; c < 4; ++c)
-                    s3_bulk_g2s(sm.b[s] + c * (MF_TILE_FLOATS / 4), bblob + (size_t)j * MF_TILE_FLOATS + c * (MF_TILE_FLOATS / 4),
-                                (MF_TILE_FLOATS / 4) * 4, &sm.b_full[s]);
+                    s3_bulk_g2s(sm.a + c * (MF_A_FLOATS / 4), ablob + (size_t)blk * MF_A_FLOATS + c * (MF_A_FLOATS / 4), MF_A_FLOATS, &sm.a_full);
+                for (int j = t0; j < t1; ++j) {
+                    for (int q = 0; q < MF_NKS; ++q, ++g) {
+                        const int s = g % MF_RING, u = g / MF_RING;
+                        if (u >= 1) s3_mbar_wait(&sm.b_empty[s], (unsigned int)((u - 1) & 1));
+                        s3_mbar_expect_tx(&sm.b_full[s], MF_B_FLOATS * 4);
+                        const float* src = bblob + ((size_t)j * MF_NKS + (size_t)q) * MF_B_FLOATS;
+                        for (int c = 0; c < 2; ++c)
+                            s3_bulk_g2s(sm.b[s] + c * (MF_B_FLOATS / 2), src + c * (MF_B_FLOATS / 2), MF_B_FLOATS * 2, &sm.b_full[s]);
+                    }
+                }
             }
         }
     } else if (warp == 1) {
         // ================= MMA issue: one thread
         if (lane == 0) {
-            // instruction descriptor: D = F32, A = B = TF32, both K-major, N = 128, M = 128
+            // instruction descriptor: D = F32, A = B = TF32, both K-major, N = 256, M = 128
             const unsigned int idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((unsigned int)(MF_N >> 3) << 17) | ((unsigned int)(MF_M >> 4) << 24);
             const unsigned long long adesc = mf_desc(s3_saddr(sm.a));
-            s3_mbar_wait(&sm.a_full, 0);
-            for (int j = 0; j < ntn; ++j) {
-                const int s = j & 1;
-                if (j >= 2) s3_mbar_wait(&sm.acc_empty[s], (unsigned int)(((j >> 1) - 1) & 1));
-                s3_mbar_wait(&sm.b_full[s], (unsigned int)((j >> 1) & 1));
-                mf_tc_fence_after();
-                const unsigned long long bdesc = mf_desc(s3_saddr(sm.b[s]));
+            int g = 0, iter = 0, tc = 0;
+            for (int it = blockIdx.x; it < n_items; it += gridDim.x, ++iter) {
+                const int blk = it / ks, part = it - blk * ks;
+                const int t0 = part * ntn / ks, t1 = (part + 1) * ntn / ks;
+                s3_mbar_wait(&sm.a_full, (unsigned int)(iter & 1));
+                for (int j = t0; j < t1; ++j, ++tc) {
+                    const int as = tc & 1;
+                    if (tc >= 2) s3_mbar_wait(&sm.acc_empty[as], (unsigned int)(((tc >> 1) - 1) & 1));
+                    for (int q = 0; q < MF_NKS; ++q, ++g) {
+                        const int s = g % MF_RING, u = g / MF_RING;
+                        s3_mbar_wait(&sm.b_full[s], (unsigned int)(u & 1));
+                        mf_tc_fence_after();
+                        const unsigned long long bdesc = mf_desc(s3_saddr(sm.b[s]));
 #pragma unroll
-                for (int kk = 0; kk < MF_KSTEPS; ++kk)       // two 16-byte chunks (2 x 2048 B) per K step
-                    mf_mma(tmem + (unsigned int)(s * MF_N), adesc + (unsigned long long)(kk * (4096 >> 4)),
-                           bdesc + (unsigned long long)(kk * (4096 >> 4)), idesc, kk > 0 ? 1u : 0u);
-                mf_commit(&sm.b_empty[s]);
-                mf_commit(&sm.acc_full[s]);
+                        for (int kk = 0; kk < MF_KSTAGE / 8; ++kk)       // K slice q of A (16 KB each), 32 bytes along the row per step
+                            mf_mma(tmem + (unsigned int)(as * MF_N),
+                                   adesc + (unsigned long long)((q * (MF_M * MF_KSTAGE * 4) + kk * 32) >> 4),
+                                   bdesc + (unsigned long long)((kk * 32) >> 4), idesc, (q | kk) > 0 ? 1u : 0u);
+                        mf_commit(&sm.b_empty[s]);
+                    }
+                    mf_commit(&sm.acc_full[as]);
+                }
+                mf_commit(&sm.a_empty);
             }
+            // every commit has landed before the CTA may exit (they complete in issue order)
+            if (iter > 0) s3_mbar_wait(&sm.a_empty, (unsigned int)((iter - 1) & 1));
         }
     } else if (warp < 2 + MF_EPI_WARPS) {
-        // ================= accumulators -> sign bits -> queue.  Warp w may read TMEM lanes 32 (w % 4) .. + 31; the two
-        // warps of a lane group take two of the four 32-gene tiles each.  Everything with a long latency is issued for
-        // both tiles before it is waited for (TMEM loads, the scan, the queue reservations).
+        // ================= accumulators -> sign bits.  Warp w may read TMEM lanes 32 (w % 4) .. + 31; the two warps of a
+        // lane group take four of the eight 32-gene tiles each.  The 32 sign bits of (tile of 32 genes, particle) go to
+        // gmask[tile][particle] (128 bytes per warp and store); stage 3 builds its work list from them.
         const int lg = warp & 3, half = (warp - 2) >> 2;
-        const long long i = i0 + lg * 32 + lane;
-        const unsigned int pl = (unsigned int)(i & (S3_PB - 1));
-        const long long kblk = i >> 11;
-        for (int j = 0; j < ntn; ++j) {
-            const int s = j & 1;
-            s3_mbar_wait(&sm.acc_full[s], (unsigned int)((j >> 1) & 1));
-            mf_tc_fence_after();
-            unsigned int v[2][32];
-            const unsigned int taddr = tmem + ((unsigned int)(lg * 32) << 16) + (unsigned int)(s * MF_N + half * 64);
-            mf_tmem_ld32(taddr, v[0]);
-            mf_tmem_ld32(taddr + 32u, v[1]);
-            asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-            unsigned int m0 = 0u, m1 = 0u;
+        int tc = 0;
+        for (int it = blockIdx.x; it < n_items; it += gridDim.x) {
+            const int blk = it / ks, part = it - blk * ks;
+            const int t0 = part * ntn / ks, t1 = (part + 1) * ntn / ks;
+            const long long ib = (long long)blk * MF_M;
+            for (int j = t0; j < t1; ++j, ++tc) {
+                const int as = tc & 1;
+                s3_mbar_wait(&sm.acc_full[as], (unsigned int)((tc >> 1) & 1));
+                mf_tc_fence_after();
+#pragma unroll 1
+                for (int q = 0; q < 4; ++q) {                  // this warp: columns half * 128 + 32 q .. + 31 of the tile
+                    unsigned int v[32];
+                    const int col = half * 128 + q * 32;
+                    mf_tmem_ld32(tmem + ((unsigned int)(lg * 32) << 16) + (unsigned int)(as * MF_N + col), v);
+                    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+                    unsigned int mm = 0u;
 #pragma unroll
-            for (int c = 31; c >= 0; --c) {
-                m0 = __funnelshift_l(v[0][c], m0, 1);
-                m1 = __funnelshift_l(v[1][c], m1, 1);
-            }
-            if (dbg != nullptr) {
+                    for (int c = 31; c >= 0; --c) mm = __funnelshift_l(v[c], mm, 1);
+                    x.gmask[(size_t)(8 * j + half * 4 + q) * (size_t)x.n_pad + (size_t)(ib + lg * 32 + lane)] = mm;
+                    if (dbg != nullptr) {
 #pragma unroll
-                for (int c = 0; c < 64; ++c)
-                    dbg[(size_t)i * (size_t)(ntn * MF_N) + (size_t)(j * MF_N + half * 64 + c)] = __uint_as_float(v[c >> 5][c & 31]);
-            }
-            mf_tc_fence_before();
-            __syncwarp();
-            if (lane == 0) mf_mbar_arrive(&sm.acc_empty[s]);
-            if (!__any_sync(0xffffffffu, (m0 | m1) != 0u)) continue;
-            // both counts in one scan: 16 bits each (<= 32 x 32)
-            const unsigned int cnt = (unsigned int)__popc(m0) | ((unsigned int)__popc(m1) << 16);
-            unsigned int incl = cnt;
-#pragma unroll
-            for (int dd = 1; dd < 32; dd <<= 1) {
-                const unsigned int t = __shfl_up_sync(0xffffffffu, incl, dd);
-                if (lane >= dd) incl += t;
-            }
-            const unsigned int total = __shfl_sync(0xffffffffu, incl, 31);
-            const int T0 = 4 * j + 2 * half;
-            unsigned int base = 0u;
-            if (lane < 2) {                                  // lane q reserves room in the segment of tile T0 + q
-                const unsigned int tq = (total >> (16 * lane)) & 0xffffu;
-                if (tq > 0u && T0 + lane < x.ntiles) base = atomicAdd(&x.qcnt[(size_t)kblk * (size_t)x.ntiles + (size_t)(T0 + lane)], tq);
-            }
-            const unsigned int base0 = __shfl_sync(0xffffffffu, base, 0), base1 = __shfl_sync(0xffffffffu, base, 1);
-            const unsigned int excl = incl - cnt;
-            if (T0 < x.ntiles) {
-                unsigned short* seg = x.q2 + ((size_t)kblk * (size_t)x.ntiles + (size_t)T0) * (size_t)(S3_PB * S3_TG);
-                unsigned int pos = base0 + (excl & 0xffffu);
-                while (m0) {
-                    const int b = __ffs(m0) - 1;
-                    m0 &= m0 - 1u;
-                    seg[pos++] = (unsigned short)((pl << 5) | (unsigned int)b);
-                }
-            }
-            if (T0 + 1 < x.ntiles) {
-                unsigned short* seg = x.q2 + ((size_t)kblk * (size_t)x.ntiles + (size_t)(T0 + 1)) * (size_t)(S3_PB * S3_TG);
-                unsigned int pos = base1 + (excl >> 16);
-                while (m1) {
-                    const int b = __ffs(m1) - 1;
-                    m1 &= m1 - 1u;
-                    seg[pos++] = (unsigned short)((pl << 5) | (unsigned int)b);
-                }
-            }
-        }
-    } else {
-        // ================= service warp: this CTA's 128 rows (particle-major) or 128-particle columns (gene-major)
-        if (LAYOUT != ABC_ERR_NONE) {
-            const int rows = (int)max(0ll, min((long long)MF_M, a.n - i0));
-            bool nn = false;
-            if (lane < MF_M / 32) {
-                const long long wi = (i0 >> 5) + lane;
-                nn = wi < x.W && x.nanw[wi] != 0u;
-            }
-            const bool any_nan = __any_sync(0xffffffffu, nn);
-            const double qnan = __longlong_as_double(0x7ff8000000000000ll);
-            if (LAYOUT == ABC_ERR_GENE_MAJOR) {
-                for (int g = lane; g < a.G && rows > 0; g += 32) {      // one gene row (<= 1 KB) per lane and step
-                    double* p = a.err + (long long)g * a.gm_stride + i0;
-                    if (!any_nan) {
-                        const int head = (int)((reinterpret_cast<unsigned long long>(p) >> 3) & 1ull);
-                        if (head) p[0] = 10.0;
-                        const int mid = (rows - head) & ~1;
-                        if (mid > 0) s3_bulk_s2g(p + head, sm.tens, (unsigned int)(mid * 8));
-                        if (head + mid < rows) p[rows - 1] = 10.0;
-                    } else {
-                        for (int r = 0; r < rows; ++r)
-                            p[r] = ((x.nanw[(i0 >> 5) + (r >> 5)] >> (r & 31)) & 1u) ? qnan : 10.0;
+                        for (int c = 0; c < 32; ++c)
+                            dbg[(size_t)(ib + lg * 32 + lane) * (size_t)(ntn * MF_N) + (size_t)(j * MF_N + col + c)] = __uint_as_float(v[c]);
                     }
                 }
-            } else if (rows > 0) {
-                double* base = a.err + i0 * (long long)a.G;
-                const long long L = (long long)rows * a.G;
-                if (!any_nan) {
-                    s3_fill_tma(base, L, sm.tens, lane);
+                mf_tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mf_mbar_arrive(&sm.acc_empty[as]);
+            }
+        }
+    }
+    if (LAYOUT != ABC_ERR_NONE && warp == 2 + MF_EPI_WARPS) {
+        // ================= service warp: the background of the first fill_b0 particle blocks (the memory system is idle
+        // under the GEMM); the stage-3 kernel writes the rest while it computes
+        const double qnan = __longlong_as_double(0x7ff8000000000000ll);
+        const long long R0 = min((long long)a.n, (long long)x.fill_b0 * S3_PB);
+        if (LAYOUT == ABC_ERR_PARTICLE_MAJOR) {
+            const long long L = R0 * a.G;
+            long long chunk = (L + gridDim.x - 1) / gridDim.x;
+            chunk += chunk & 1;
+            const long long lo = min(L, (long long)blockIdx.x * chunk), hi = min(L, lo + chunk);
+            if (hi > lo) {
+                const long long w0 = (lo / a.G) >> 5, w1 = ((hi - 1) / a.G) >> 5;
+                bool nn = false;
+                for (long long wi = w0 + lane; wi <= w1; wi += 32) nn = nn || (wi < x.W && x.nanw[wi] != 0u);
+                if (!__any_sync(0xffffffffu, nn)) {
+                    s3_fill_tma(a.err + lo, hi - lo, sm.tens, lane);
                 } else {
-                    for (long long j = lane; j < L; j += 32) {
-                        const int r = (int)(j / a.G);
-                        base[j] = ((x.nanw[(i0 >> 5) + (r >> 5)] >> (r & 31)) & 1u) ? qnan : 10.0;
+                    for (long long j = lo + lane; j < hi; j += 32) {
+                        const long long r = j / a.G;
+                        a.err[j] = ((x.nanw[r >> 5] >> (int)(r & 31)) & 1u) ? qnan : 10.0;
                     }
                 }
             }
-            s3_bulk_commit_wait();
+        } else if (R0 > 0) {
+            bool nn = false;
+            for (long long wi = lane; wi < ((R0 + 31) >> 5); wi += 32) nn = nn || (wi < x.W && x.nanw[wi] != 0u);
+            const bool any_nan = __any_sync(0xffffffffu, nn);
+            const int g0 = (int)((long long)blockIdx.x * a.G / gridDim.x), g1 = (int)((long long)(blockIdx.x + 1) * a.G / gridDim.x);
+            for (int g = g0; g < g1; ++g) {
+                double* p = a.err + (long long)g * a.gm_stride;
+                if (!any_nan) {
+                    s3_fill_tma(p, R0, sm.tens, lane);
+                } else {
+                    for (long long r = lane; r < R0; r += 32) p[r] = ((x.nanw[r >> 5] >> (int)(r & 31)) & 1u) ? qnan : 10.0;
+                }
+            }
         }
+        s3_bulk_commit_wait();
     }
     mf_tc_fence_before();
     __syncthreads();
-    if (warp == 1) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 256;" ::"r"(tmem) : "memory");
+    if (warp == 1) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 512;" ::"r"(tmem) : "memory");
+}
+
+// Stage 3 behind the tensor-core filter: one CTA per (tile of 32 genes, block of 2048 particles).  The work list is built
+// from the filter's sign-bit words, 256 particles at a time: popcount, block-wide exclusive scan, entries
+// (particle << 5 | gene slot) into a ring in shared memory; whenever the ring holds >= 256 pairs, one pair per thread goes
+// through the reference's FP64 arithmetic (same code as abc_score3_exact_kernel).  A chunk whose pairs would not fit the
+// ring (every particle close to every gene of the tile) is appended warp by warp (<= 1024 pairs) with drains in between.
+#define MX_CAP 2048
+struct MxSmem {
+    S3ExactSmem t;
+    alignas(16) double tens[S3_FILL_DOUBLES];     // 10.0: source of the background's bulk stores
+    unsigned short ring[MX_CAP];
+    int wtot[S3E_THREADS / 32];
+};
+
+// The matrix's background (10.0; NaN rows for particles with a NaN statistic).  The first fill_b0 particle blocks are written
+// by the service warp of the filter kernel (which leaves the memory system idle otherwise); block j >= fill_b0 is written by
+// the stage-3 CTAs of block j - fill_d while they compute: CTA (k, T) writes, of block k + fill_d, slice T of its rows
+// (particle-major) or the 32 gene rows of tile T (gene-major), and publishes that through a per-block counter when it is
+// done.  The CTAs of block j wait for fill_done[j] == ntiles before their first store.  fill_d particle blocks are more CTAs
+// than fit the GPU at once and CTAs are dispatched in blockIdx order, so the writers of a block have normally left the GPU
+// before its readers arrive; a CTA never waits for a later block, and the wait is bounded (trap).
+template <int LAYOUT>
+__device__ __forceinline__ void mx_fill_block(const AbcScoreArgs& a, const AbcScore3Tables& x, const int* gidx, const double* tens,
+                                              int T, long long kt, int lane) {
+    const double qnan = __longlong_as_double(0x7ff8000000000000ll);
+    const long long i0 = kt * S3_PB;
+    const int rows = (int)max(0ll, min((long long)S3_PB, a.n - i0));
+    if (rows <= 0) return;
+    bool nn = false;
+    for (int j = lane; j < S3_PB / 32; j += 32) {
+        const long long wi = (i0 >> 5) + j;
+        nn = nn || (wi < x.W && x.nanw[wi] != 0u);
+    }
+    const bool any_nan = __any_sync(0xffffffffu, nn);
+    if (LAYOUT == ABC_ERR_GENE_MAJOR) {
+        const int g = gidx[lane];
+        if (g >= 0) {
+            double* p = a.err + (long long)g * a.gm_stride + i0;
+            if (!any_nan) {
+                const int head = (int)((reinterpret_cast<unsigned long long>(p) >> 3) & 1ull);
+                if (head) p[0] = 10.0;
+                const int mid = (rows - head) & ~1;
+                for (int c = 0; c < mid; c += S3_FILL_DOUBLES) s3_bulk_s2g(p + head + c, tens, (unsigned int)(min(S3_FILL_DOUBLES, mid - c) * 8));
+                if (head + mid < rows) p[rows - 1] = 10.0;
+            } else {
+                for (int r = 0; r < rows; ++r) p[r] = ((x.nanw[(i0 >> 5) + (r >> 5)] >> (r & 31)) & 1u) ? qnan : 10.0;
+            }
+        }
+    } else if (LAYOUT == ABC_ERR_PARTICLE_MAJOR) {
+        const long long L = (long long)rows * a.G;
+        long long chunk = (L + x.ntiles - 1) / x.ntiles;
+        chunk += chunk & 1;
+        const long long lo = min(L, (long long)T * chunk), hi = min(L, lo + chunk);
+        double* base = a.err + i0 * (long long)a.G;
+        if (!any_nan) {
+            s3_fill_tma(base + lo, hi - lo, tens, lane);
+        } else {
+            for (long long j = lo + lane; j < hi; j += 32) {
+                const int r = (int)(j / a.G);
+                base[j] = ((x.nanw[(i0 >> 5) + (r >> 5)] >> (r & 31)) & 1u) ? qnan : 10.0;
+            }
+        }
+    }
+}
+
+// by the issuing warp: the stores have completed -> publish them
+__device__ __forceinline__ void mx_fill_publish(const AbcScore3Tables& x, long long kt, int lane) {
+    asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+    asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+    s3_fence_proxy_async();
+    __threadfence();
+    __syncwarp();
+    if (lane == 0) atomicAdd(&x.fill_done[kt], 1u);
+}
+
+// by one thread before the CTA's first store: the background of this block's rows is in place
+__device__ __forceinline__ void mx_wait_block(const AbcScore3Tables& x, long long kblk) {
+    unsigned int spins = 0u;
+    while (s3_ld_acquire(&x.fill_done[kblk]) < (unsigned int)x.ntiles) {
+        __nanosleep(100);
+        if (++spins > (1u << 25)) __trap();       // > 3 s: the dispatch-order assumption failed; fail loudly
+    }
+}
+
+template <int LAYOUT>
+__device__ __forceinline__ void mx_process(const AbcScoreArgs& a, const MxSmem& sm, unsigned int okmask, long long i0, int head, int tail,
+                                           int tid, int lane) {
+    const int e = head + tid;
+    bool acc = false;
+    double err = 0.0;
+    long long i = 0;
+    int g = 0;
+    if (e < tail) {
+        const unsigned int ent = sm.ring[e & (MX_CAP - 1)];
+        const int gl = (int)(ent & 31u);
+        i = i0 + (long long)(ent >> 5);
+        g = sm.t.gidx[gl];
+        err = s3_exact(a.stats + i * ABC_NSTATS, sm.t, gl, ((okmask >> gl) & 1u) != 0u);
+        if (LAYOUT == ABC_ERR_GENE_MAJOR) a.err[(long long)g * a.gm_stride + i] = err;
+        else if (LAYOUT == ABC_ERR_PARTICLE_MAJOR) a.err[i * (long long)a.G + g] = err;
+        acc = err <= a.eps;                       // NaN is never accepted
+    }
+    const unsigned int mask = __ballot_sync(0xffffffffu, acc);
+    if (mask != 0u) {
+        const int leader = __ffs(mask) - 1;
+        unsigned long long slot = 0;
+        if (lane == leader) slot = atomicAdd(a.acc_count, (unsigned long long)__popc(mask));
+        slot = __shfl_sync(0xffffffffu, slot, leader) + (unsigned long long)__popc(mask & ((1u << lane) - 1u));
+        if (acc) {
+            atomicAdd(a.counts + g, 1ull);
+            if ((long long)slot < a.acc_capacity) {
+                a.acc_gene[slot] = g;
+                a.acc_particle[slot] = a.particle_offset + i + 1;     // 1-based like Julia
+                a.acc_err[slot] = err;
+            }
+        }
+    }
+}
+
+template <int LAYOUT>
+__global__ void __launch_bounds__(S3E_THREADS, 4)
+abc_score_mask_exact_kernel(const AbcScoreArgs a, const AbcScore3Tables x) {
+    __shared__ __align__(128) MxSmem sm;
+    constexpr bool FILL = LAYOUT != ABC_ERR_NONE;
+    constexpr int FW = S3E_THREADS / 32 - 1;       // the warp that also writes the background
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int T = (int)(blockIdx.x % (unsigned int)x.ntiles);
+    const long long kblk = (long long)(blockIdx.x / (unsigned int)x.ntiles);
+    const long long i0 = kblk * S3_PB;
+    const unsigned int* mrow = x.gmask + (size_t)T * (size_t)x.n_pad + (size_t)i0;
+    const int nrows = (int)min((long long)S3_PB, x.n_rows - i0);
+    if (tid < S3_TG) sm.t.gidx[tid] = x.gidx[T * S3_TG + tid];
+    if (FILL) {
+        for (int j = tid; j < S3_FILL_DOUBLES; j += S3E_THREADS) sm.tens[j] = 10.0;
+        s3_fence_proxy_async();
+    }
+    __syncthreads();
+    const long long kt = kblk + x.fill_d;          // the block whose background this CTA writes
+    const bool writer = FILL && kt >= x.fill_b0 && kt * S3_PB < a.n;
+    if (writer && warp == FW) mx_fill_block<LAYOUT>(a, x, sm.t.gidx, sm.tens, T, kt, lane);
+    const bool waiter = FILL && kblk >= x.fill_b0;
+    // the gene constants of the tile: plain loads (a bulk copy would queue behind the SM's background stores)
+    {
+        const uint4* src = reinterpret_cast<const uint4*>(x.wt + (long long)T * 6 * ABC_NSTATS * S3_TG);
+        uint4* dst = reinterpret_cast<uint4*>(&sm.t.wt[0][0][0]);
+        for (int j = tid; j < (int)(sizeof(sm.t.wt) / 16); j += S3E_THREADS) dst[j] = s3_ldg_stream(src + j);
+    }
+    const unsigned int okmask = x.okmask[T];
+    // the whole block at once, eight consecutive particles per thread: popcounts, one block-wide scan
+    unsigned int m8[8];
+    int cnt = 0;
+    const int r0 = 8 * tid;
+    if (r0 + 8 <= nrows) {
+        const uint4 lo = s3_ldg_stream(reinterpret_cast<const uint4*>(mrow + r0)), hi = s3_ldg_stream(reinterpret_cast<const uint4*>(mrow + r0 + 4));
+        m8[0] = lo.x; m8[1] = lo.y; m8[2] = lo.z; m8[3] = lo.w; m8[4] = hi.x; m8[5] = hi.y; m8[6] = hi.z; m8[7] = hi.w;
+    } else {
+#pragma unroll
+        for (int k = 0; k < 8; ++k) m8[k] = (r0 + k < nrows) ? mrow[r0 + k] : 0u;
+    }
+#pragma unroll
+    for (int k = 0; k < 8; ++k) cnt += __popc(m8[k]);
+    int incl = cnt;
+#pragma unroll
+    for (int dd = 1; dd < 32; dd <<= 1) {
+        const int t = __shfl_up_sync(0xffffffffu, incl, dd);
+        if (lane >= dd) incl += t;
+    }
+    if (lane == 31) sm.wtot[warp] = incl;
+    __syncthreads();
+    int total = 0, woff = 0;
+#pragma unroll
+    for (int w = 0; w < S3E_THREADS / 32; ++w) {
+        const int t = sm.wtot[w];
+        woff += (w < warp) ? t : 0;
+        total += t;
+    }
+    if (total == 0) {
+        if (writer && warp == FW) mx_fill_publish(x, kt, lane);
+        return;
+    }
+    if (total <= MX_CAP) {
+        // ---- the usual case: all pairs of the block fit the ring
+        int pos = woff + incl - cnt;
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+            unsigned int m = m8[k];
+            while (m) {
+                const int b = __ffs(m) - 1;
+                m &= m - 1u;
+                sm.ring[pos++] = (unsigned short)(((unsigned int)(r0 + k) << 5) | (unsigned int)b);
+            }
+        }
+        __syncthreads();
+        if (waiter) {
+            if (tid == 0) mx_wait_block(x, kblk);
+            __syncthreads();
+        }
+        for (int head = 0; head < total; head += S3E_THREADS) mx_process<LAYOUT>(a, sm, okmask, i0, head, total, tid, lane);
+        if (writer && warp == FW) mx_fill_publish(x, kt, lane);
+        return;
+    }
+    // ---- dense block (every particle close to every gene of the tile): the background first, then 256 particles at a time
+    if (waiter && tid == 0) mx_wait_block(x, kblk);
+    __syncthreads();
+    int head = 0, tail = 0;                        // the same in every thread
+    for (int c0 = 0; c0 < nrows; c0 += S3E_THREADS) {
+        const int r = c0 + tid;
+        unsigned int m = (r < nrows) ? mrow[r] : 0u;
+        const int c1 = __popc(m);
+        int in1 = c1;
+#pragma unroll
+        for (int dd = 1; dd < 32; dd <<= 1) {
+            const int t = __shfl_up_sync(0xffffffffu, in1, dd);
+            if (lane >= dd) in1 += t;
+        }
+        if (lane == 31) sm.wtot[warp] = in1;
+        __syncthreads();
+        int tot1 = 0, wo1 = 0;
+#pragma unroll
+        for (int w = 0; w < S3E_THREADS / 32; ++w) {
+            const int t = sm.wtot[w];
+            wo1 += (w < warp) ? t : 0;
+            tot1 += t;
+        }
+        if (tot1 == 0) { __syncthreads(); continue; }
+        if (tail - head + tot1 <= MX_CAP) {
+            int pos = tail + wo1 + in1 - c1;
+            while (m) {
+                const int b = __ffs(m) - 1;
+                m &= m - 1u;
+                sm.ring[(pos++) & (MX_CAP - 1)] = (unsigned short)(((unsigned int)r << 5) | (unsigned int)b);
+            }
+            tail += tot1;
+            __syncthreads();
+            while (tail - head >= S3E_THREADS) {
+                mx_process<LAYOUT>(a, sm, okmask, i0, head, tail, tid, lane);
+                head += S3E_THREADS;
+            }
+            __syncthreads();
+        } else {
+            for (int w = 0; w < S3E_THREADS / 32; ++w) {
+                const int wt = sm.wtot[w];
+                if (warp == w) {
+                    int pos = tail + in1 - c1;
+                    while (m) {
+                        const int b = __ffs(m) - 1;
+                        m &= m - 1u;
+                        sm.ring[(pos++) & (MX_CAP - 1)] = (unsigned short)(((unsigned int)r << 5) | (unsigned int)b);
+                    }
+                }
+                tail += wt;
+                __syncthreads();
+                while (tail - head >= S3E_THREADS) {
+                    mx_process<LAYOUT>(a, sm, okmask, i0, head, tail, tid, lane);
+                    head += S3E_THREADS;
+                }
+                __syncthreads();
+            }
+        }
+    }
+    if (tail > head) mx_process<LAYOUT>(a, sm, okmask, i0, head, tail, tid, lane);
+    if (writer && warp == FW) mx_fill_publish(x, kt, lane);
 }
 
 // ------------------------------------------------------------------------------------------------ launcher
@@ -985,31 +1275,38 @@ int abc_launch_score3(const AbcScoreArgs& a, const AbcScore3Tables& x_in, cudaSt
 }
 
 int abc_launch_score_mma(const AbcScoreArgs& a, const AbcScore3Tables& x_in, float* d_ablob, const float* d_bblob, float* d_dbg,
-                         cudaStream_t st) {
+                         int sm_count, cudaStream_t st) {
     if (a.n <= 0 || a.G <= 0) return ABC_OK;
     const long long nblocks = (a.n + S3_PB - 1) / S3_PB;
     if (nblocks * x_in.ntiles > 0x7fffffffll) { abc_set_error("abc_score: batch too large for one launch"); return ABC_ERR_ARG; }
     const int lay = (a.err == nullptr) ? ABC_ERR_NONE : a.err_layout;
     const int smem = (int)sizeof(MfSmem) + 1024;
     const int ntn = abc_score_mma_tiles(x_in.ntiles);
-    const unsigned int grid128 = (unsigned int)((a.n + MF_M - 1) / MF_M);
+    const int nblk128 = (int)((a.n + MF_M - 1) / MF_M);
+    // one persistent CTA per SM; items are split over gene-tile ranges until there are >= ~6 per CTA (wave quantisation)
+    int ks = 1;
+    while (ks < 8 && ks * 2 <= ntn && (long long)nblk128 * ks < 6ll * sm_count) ks *= 2;
+    const unsigned int pgrid = (unsigned int)std::min<long long>((long long)nblk128 * ks, sm_count);
     ABC_CUDA_CHECK(cudaFuncSetAttribute(abc_score_mma_filter_kernel<ABC_ERR_NONE>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     ABC_CUDA_CHECK(cudaFuncSetAttribute(abc_score_mma_filter_kernel<ABC_ERR_GENE_MAJOR>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     ABC_CUDA_CHECK(cudaFuncSetAttribute(abc_score_mma_filter_kernel<ABC_ERR_PARTICLE_MAJOR>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-    ABC_CUDA_CHECK(cudaMemsetAsync(x_in.qcnt, 0, (size_t)nblocks * (size_t)x_in.ntiles * sizeof(uint32_t), st));
-    abc_score_mma_prep_kernel<<<grid128, 128, 0, st>>>(a.stats, (long long)a.n, d_ablob, x_in.nanw, (long long)x_in.W);
+    // background: the first fill_b0 particle blocks by the filter kernel (about what fits its duration, at least the
+    // look-ahead), block j >= fill_b0 by the stage-3 CTAs of block j - fill_d (more blocks than are resident at once)
+    AbcScore3Tables x = x_in;
+    const long long resident = 4ll * sm_count / std::max(1, x.ntiles) + 2;
+    x.fill_d = (int32_t)resident;
+    x.fill_b0 = (int32_t)std::min<long long>(nblocks, std::max<long long>(resident, (nblocks * 3 + 5) / 10));
+    if (lay != ABC_ERR_NONE) ABC_CUDA_CHECK(cudaMemsetAsync(x.fill_done, 0, (size_t)(nblocks + 1) * sizeof(uint32_t), st));
+    abc_score_mma_prep_kernel<<<(unsigned int)nblk128, 128, 0, st>>>(a.stats, (long long)a.n, d_ablob, x.nanw, (long long)x.W);
     ABC_CUDA_CHECK(cudaGetLastError());
-    const unsigned int grid = (unsigned int)(nblocks * x_in.ntiles);
-    if (lay == ABC_ERR_NONE) {
-        abc_score_mma_filter_kernel<ABC_ERR_NONE><<<grid128, MF_THREADS, smem, st>>>(a, x_in, d_ablob, d_bblob, ntn, d_dbg);
-        abc_score3_exact_kernel<ABC_ERR_NONE><<<grid, S3E_THREADS, 0, st>>>(a, x_in);
-    } else if (lay == ABC_ERR_GENE_MAJOR) {
-        abc_score_mma_filter_kernel<ABC_ERR_GENE_MAJOR><<<grid128, MF_THREADS, smem, st>>>(a, x_in, d_ablob, d_bblob, ntn, d_dbg);
-        abc_score3_exact_kernel<ABC_ERR_GENE_MAJOR><<<grid, S3E_THREADS, 0, st>>>(a, x_in);
-    } else {
-        abc_score_mma_filter_kernel<ABC_ERR_PARTICLE_MAJOR><<<grid128, MF_THREADS, smem, st>>>(a, x_in, d_ablob, d_bblob, ntn, d_dbg);
-        abc_score3_exact_kernel<ABC_ERR_PARTICLE_MAJOR><<<grid, S3E_THREADS, 0, st>>>(a, x_in);
-    }
+    if (lay == ABC_ERR_NONE) abc_score_mma_filter_kernel<ABC_ERR_NONE><<<pgrid, MF_THREADS, smem, st>>>(a, x, d_ablob, d_bblob, ntn, ks, d_dbg);
+    else if (lay == ABC_ERR_GENE_MAJOR) abc_score_mma_filter_kernel<ABC_ERR_GENE_MAJOR><<<pgrid, MF_THREADS, smem, st>>>(a, x, d_ablob, d_bblob, ntn, ks, d_dbg);
+    else abc_score_mma_filter_kernel<ABC_ERR_PARTICLE_MAJOR><<<pgrid, MF_THREADS, smem, st>>>(a, x, d_ablob, d_bblob, ntn, ks, d_dbg);
+    ABC_CUDA_CHECK(cudaGetLastError());
+    const unsigned int grid = (unsigned int)(nblocks * x.ntiles);
+    if (lay == ABC_ERR_NONE) abc_score_mask_exact_kernel<ABC_ERR_NONE><<<grid, S3E_THREADS, 0, st>>>(a, x);
+    else if (lay == ABC_ERR_GENE_MAJOR) abc_score_mask_exact_kernel<ABC_ERR_GENE_MAJOR><<<grid, S3E_THREADS, 0, st>>>(a, x);
+    else abc_score_mask_exact_kernel<ABC_ERR_PARTICLE_MAJOR><<<grid, S3E_THREADS, 0, st>>>(a, x);
     ABC_CUDA_CHECK(cudaGetLastError());
     return ABC_OK;
 }

@@ -153,7 +153,7 @@ int  abc_score(abc_ctx_t* ctx, const double* stats, int64_t n, int64_t particle_
                int err_layout, double* err, int64_t* counts, abc_counters_t* counters);
 /* Diagnostics of the tensor-core filter (option "score_mma_filter": a TF32 tcgen05 GEMM decides which pairs can be <= 10 and
  * reach the FP64 stage; results are identical either way).  abc_score_mma_columns: padded gene columns of the GEMM (multiple of
- * 128).  abc_score_mma_debug: V[i][column] for DEVICE-resident statistics (53 x n column-major) into d_out, a device array of
+ * 64).  abc_score_mma_debug: V[i][column] for DEVICE-resident statistics (53 x n column-major) into d_out, a device array of
  * ceil(n/128)*128 rows x columns floats; V < 0 <=> the pair is queued.  gene_of_column: NULL or columns int32 (host), the
  * gene index of every column, -1 for padding.  No reference counterpart. */
 int  abc_score_mma_columns(abc_ctx_t* ctx);

@@ -11,7 +11,8 @@ KEEP = ("gpu__time_duration.sum", "dram__bytes_read.sum", "dram__bytes_write.sum
         "sm__inst_executed_pipe_xu.avg.pct_of_peak_sustained_active", "l1tex__data_pipe_lsu_wavefronts.avg.pct_of_peak_sustained_elapsed",
         "l1tex__data_pipe_lsu_wavefronts_mem_shared.sum", "l1tex__t_sector_pipe_lsu_mem_global_op_ld_hit_rate.pct",
         "lts__throughput.avg.pct_of_peak_sustained_elapsed", "smsp__average_warps_issue_stalled", "sm__throughput.avg.pct_of_peak_sustained_elapsed",
-        "dram__throughput.avg.pct_of_peak_sustained_elapsed")
+        "dram__throughput.avg.pct_of_peak_sustained_elapsed", "sm__inst_executed_pipe_tc", "sm__pipe_tc", "sm__inst_executed_pipe_uniform",
+        "sm__inst_executed_pipe_tmem", "smsp__inst_executed_pipe_tmem", "sm__pipe_tensor", "sm__inst_executed_pipe_tensor")
 raw = subprocess.run(["ncu", "-i", sys.argv[1], "--page", "raw", "--csv"], capture_output=True, text=True).stdout
 rows = list(csv.reader(raw.splitlines()))
 hdr, units, vals = rows[0], rows[1], rows[2]

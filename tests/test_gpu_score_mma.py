@@ -86,7 +86,7 @@ def test_accumulators_match_the_tf32_restatement_and_are_sound(eng_mma, data_sta
     dev = torch.device("cuda", 0)
     st = torch.from_numpy(np.ascontiguousarray(s)).to(dev)
     cols = eng_mma.score_mma_columns()
-    assert cols % 128 == 0 and cols >= d.shape[0]
+    assert cols % 64 == 0 and cols >= d.shape[0]
     out = torch.full((384, cols), 7.0, dtype=torch.float32, device=dev)
     gene = eng_mma.score_mma_debug(st.data_ptr(), n, out.data_ptr())
     V = out.cpu().numpy().astype(np.float64)
