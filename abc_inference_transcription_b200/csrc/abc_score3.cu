@@ -1049,11 +1049,14 @@ __device__ __forceinline__ void mx_fill_publish(const AbcScore3Tables& x, long l
 
 // by one thread before the CTA's first store: the background of this block's rows is in place
 __device__ __forceinline__ void mx_wait_block(const AbcScore3Tables& x, long long kblk) {
+    // relaxed polls (an acquire load invalidates the SM's L1 on every poll: the statistics rows the other warps re-read);
+    // one acquire once the count is there
     unsigned int spins = 0u;
-    while (s3_ld_acquire(&x.fill_done[kblk]) < (unsigned int)x.ntiles) {
-        __nanosleep(100);
-        if (++spins > (1u << 25)) __trap();       // > 3 s: the dispatch-order assumption failed; fail loudly
+    while (s3_ld_relaxed(&x.fill_done[kblk]) < (unsigned int)x.ntiles) {
+        __nanosleep(200);
+        if (++spins > (1u << 24)) __trap();       // > 3 s: the dispatch-order assumption failed; fail loudly
     }
+    (void)s3_ld_acquire(&x.fill_done[kblk]);
 }
 
 template <int LAYOUT>
