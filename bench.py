@@ -258,16 +258,23 @@ def run_b200(args):
         sampler.start()
     # EXACTLY `steps` steps between one barrier + synchronize on either side (contract); the L2 flush between steps is a
     # 256 MiB device fill (40 us at HBM speed) kept inside the region rather than stopping all ranks at every step
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0, e1, eb = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
     e0.record()
     for k in range(args.steps):
         device_step(args.warmup + k, True)
         flush.fill_(k & 0xFF)
+    eb.record()                      # this rank's own work is done; what follows waits for the slowest rank
     drain_collectives()
     e1.record()
     barrier()
     step_ms = [e0.elapsed_time(e1)]
+    busy_by_rank = None
+    if world > 1:
+        tb = torch.tensor([e0.elapsed_time(eb)], dtype=torch.float64, device=dev)
+        allb = [torch.zeros_like(tb) for _ in range(world)]
+        dist.all_gather(allb, tb)
+        busy_by_rank = [round(float(x.item()) / args.steps, 3) for x in allb]
     if sampler:
         sampler.stop_flag = True
     launches = eng.launch_count() - launches0
@@ -485,6 +492,7 @@ def run_b200(args):
         sc_gbs = nb * ALG_BYTES_PER_PARTICLE_SCORE / score_big_s / 1e9
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
                 "ms_per_step": 1e3 * t_dev / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+                "ms_busy_per_step_by_rank": busy_by_rank,
                 "dtype": "f32 (SSA propensities/times) + u32 counts + f64 (statistics, scoring)", "data": "synthetic",
                 "config": workload_config(args),
                 "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d // args.steps,
