@@ -391,6 +391,24 @@ def run_b200(args):
         if it > 0:
             score_big_ms.append(e0.elapsed_time(e1))
     score_big_s = sum(score_big_ms) / len(score_big_ms) / 1e3
+    # the same call with the tensor-core filter (TF32 tcgen05 GEMM decides which pairs reach the FP64 stage)
+    score_mma_ms = []
+    eng.set_option("score_mma_filter", 1)
+    try:
+        for it in range(4):
+            eng.accept_reset()
+            flush.fill_(it)
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            eng.score_dev(big_stats.data_ptr(), nb, eps=EPS, particle_offset=0, err_layout=ERR_PARTICLE_MAJOR,
+                          d_err_ptr=big_err.data_ptr(), stream=stream)
+            e1.record()
+            torch.cuda.synchronize()
+            if it > 0:
+                score_mma_ms.append(e0.elapsed_time(e1))
+    finally:
+        eng.set_option("score_mma_filter", 0)
+    score_mma_s = sum(score_mma_ms) / len(score_mma_ms) / 1e3
     # acceptance only (no matrix: what a full prior sweep uses, the matrix of 5e6 x 3419 doubles is 137 GB per model)
     from abc_inference_transcription_b200 import ERR_NONE
     score_acc_ms = []
@@ -521,6 +539,12 @@ def run_b200(args):
                                    "traffic_src": "ncu --set full dram read+write of the three kernels of one 131070-particle "
                                                   "call (profiles/r1_score3_*_ncu_summary.csv), scaled to this launch size",
                                    "peak_src": pk["src"], "share_of_step": sc_s / t_dev if t_dev > 0 else None,
+                                   "tensor_core_filter": {"option": "score_mma_filter = 1 (opt-in, bit-identical results)",
+                                                          "kernel": "abc_score_mma_prep_kernel + abc_score_mma_filter_kernel<2> (tcgen05 "
+                                                                    "TF32 GEMM, TMEM accumulators) + abc_score_mask_exact_kernel<2>",
+                                                          "ms_per_launch": 1e3 * score_mma_s,
+                                                          "achieved": nb * ALG_BYTES_PER_PARTICLE_SCORE / score_mma_s / 1e9,
+                                                          "frac": nb * ALG_BYTES_PER_PARTICLE_SCORE / score_mma_s / 1e9 / pk["hbm_gbs"]},
                                    "accept_only": {"ms_per_launch": 1e3 * score_acc_s, "particles_per_s": nb / score_acc_s,
                                                    "pairs_per_s": nb * G / score_acc_s,
                                                    "note": "err_layout = ABC_ERR_NONE: fused eps-acceptance, no matrix"}}}
