@@ -299,13 +299,14 @@ __device__ __forceinline__ unsigned int s3_ld_relaxed(const unsigned int* p) {
 
 // fill p[0 .. len) with 10.0 by one warp: bulk stores (shared -> global) of up to 8 KB from sm.tens, at most one
 // plain store at either end for 16-byte alignment.  Returns after the lane has ISSUED its stores.
+template <int CH = S3_FILL_DOUBLES>
 __device__ __forceinline__ void s3_fill_tma(double* __restrict__ p, long long len, const double* tens, int lane) {
     if (len <= 0) return;
     const long long head = (long long)((reinterpret_cast<unsigned long long>(p) >> 3) & 1ull);
     if (head && lane == 0) p[0] = 10.0;
     const long long mid = (len - head) & ~1ll;
-    for (long long c = (long long)lane * S3_FILL_DOUBLES; c < mid; c += 32ll * S3_FILL_DOUBLES) {
-        const long long m = min((long long)S3_FILL_DOUBLES, mid - c);
+    for (long long c = (long long)lane * CH; c < mid; c += 32ll * CH) {
+        const long long m = min((long long)CH, mid - c);
         s3_bulk_s2g(p + head + c, tens, (unsigned int)(m * 8));
     }
     if (head + mid < len && lane == 0) p[len - 1] = 10.0;
@@ -979,9 +980,11 @@ abc_score_mma_filter_kernel(const AbcScoreArgs a, const AbcScore3Tables x, const
 // through the reference's FP64 arithmetic (same code as abc_score3_exact_kernel).  A chunk whose pairs would not fit the
 // ring (every particle close to every gene of the tile) is appended warp by warp (<= 1024 pairs) with drains in between.
 #define MX_CAP 2048
+#define MX_FILL_DOUBLES 256                    // 2 KB: with the tables (40.7 KB) and the ring (4 KB) a CTA stays below 48 KB, so four
+                                           // of them fit the 196 KB carve-out and leave the SM 60 KB of L1 for the statistics rows
 struct MxSmem {
     S3ExactSmem t;
-    alignas(16) double tens[S3_FILL_DOUBLES];     // 10.0: source of the background's bulk stores
+    alignas(16) double tens[MX_FILL_DOUBLES];     // 10.0: source of the background's bulk stores
     unsigned short ring[MX_CAP];
     int wtot[S3E_THREADS / 32];
 };
@@ -1014,7 +1017,7 @@ __device__ __forceinline__ void mx_fill_block(const AbcScoreArgs& a, const AbcSc
                 const int head = (int)((reinterpret_cast<unsigned long long>(p) >> 3) & 1ull);
                 if (head) p[0] = 10.0;
                 const int mid = (rows - head) & ~1;
-                for (int c = 0; c < mid; c += S3_FILL_DOUBLES) s3_bulk_s2g(p + head + c, tens, (unsigned int)(min(S3_FILL_DOUBLES, mid - c) * 8));
+                for (int c = 0; c < mid; c += MX_FILL_DOUBLES) s3_bulk_s2g(p + head + c, tens, (unsigned int)(min(MX_FILL_DOUBLES, mid - c) * 8));
                 if (head + mid < rows) p[rows - 1] = 10.0;
             } else {
                 for (int r = 0; r < rows; ++r) p[r] = ((x.nanw[(i0 >> 5) + (r >> 5)] >> (r & 31)) & 1u) ? qnan : 10.0;
@@ -1027,7 +1030,7 @@ __device__ __forceinline__ void mx_fill_block(const AbcScoreArgs& a, const AbcSc
         const long long lo = min(L, (long long)T * chunk), hi = min(L, lo + chunk);
         double* base = a.err + i0 * (long long)a.G;
         if (!any_nan) {
-            s3_fill_tma(base + lo, hi - lo, tens, lane);
+            s3_fill_tma<MX_FILL_DOUBLES>(base + lo, hi - lo, tens, lane);
         } else {
             for (long long j = lo + lane; j < hi; j += 32) {
                 const int r = (int)(j / a.G);
@@ -1108,7 +1111,7 @@ abc_score_mask_exact_kernel(const AbcScoreArgs a, const AbcScore3Tables x) {
     const int nrows = (int)min((long long)S3_PB, x.n_rows - i0);
     if (tid < S3_TG) sm.t.gidx[tid] = x.gidx[T * S3_TG + tid];
     if (FILL) {
-        for (int j = tid; j < S3_FILL_DOUBLES; j += S3E_THREADS) sm.tens[j] = 10.0;
+        for (int j = tid; j < MX_FILL_DOUBLES; j += S3E_THREADS) sm.tens[j] = 10.0;
         s3_fence_proxy_async();
     }
     __syncthreads();
