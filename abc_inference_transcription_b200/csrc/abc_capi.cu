@@ -649,11 +649,21 @@ static int score_device(abc_ctx* c, const double* d_stats, int64_t n, int64_t of
         if (c->score_mma_filter && layout != ABC_ERR_NONE) {
             // tensor-core filter: statistics -> TF32 operand, GEMM -> sign-bit words, stage 3 on the flagged pairs; the matrix's
             // background is written on a side stream meanwhile.  Chunks of <= 2^19 particles (1 KB of work space each).
-            const int64_t chunk = std::min<int64_t>((n + 2047) / 2048 * 2048, 1ll << 19);
+            // mode 1: sign-bit words + mask-driven stage 3 (background split between the filter kernel and stage 3);
+            // mode 2: the filter kernel writes the whole background and the stage-3 queue, then the queue-driven stage 3
+            const bool queue = c->score_mma_filter == 2;
+            const int64_t per_particle_q = (int64_t)x.ntiles * 32 * 2;
+            int64_t chunk = std::min<int64_t>((n + 2047) / 2048 * 2048, 1ll << 19);
+            if (queue) chunk = std::min<int64_t>(chunk, std::max<int64_t>(2048, ((int64_t)2000000000 / per_particle_q) / 2048 * 2048));
             if ((rc = c->d_s3_nanw[0].ensure((size_t)((chunk + 31) / 32))) != ABC_OK) return rc;
             if ((rc = c->d_mf_a[0].ensure((size_t)chunk * 128)) != ABC_OK) return rc;
-            if ((rc = c->d_mf_mask[0].ensure((size_t)abc_score_mma_tiles(x.ntiles) * 8 * (size_t)chunk)) != ABC_OK) return rc;
-            if ((rc = c->d_mf_done.ensure((size_t)(chunk / 2048 + 2))) != ABC_OK) return rc;
+            if (queue) {
+                if ((rc = c->d_s3_qcnt[0].ensure(abc_score3_blocks(chunk) * (size_t)x.ntiles)) != ABC_OK) return rc;
+                if ((rc = c->d_s3_q2[0].ensure(abc_score3_queue_entries(chunk, x.ntiles))) != ABC_OK) return rc;
+            } else {
+                if ((rc = c->d_mf_mask[0].ensure((size_t)abc_score_mma_tiles(x.ntiles) * 8 * (size_t)chunk)) != ABC_OK) return rc;
+                if ((rc = c->d_mf_done.ensure((size_t)(chunk / 2048 + 2))) != ABC_OK) return rc;
+            }
             for (int64_t s0 = 0; s0 < n && rc == ABC_OK; s0 += chunk) {
                 AbcScoreArgs b = a;
                 b.n = std::min<int64_t>(chunk, n - s0);
@@ -662,6 +672,7 @@ static int score_device(abc_ctx* c, const double* d_stats, int64_t n, int64_t of
                 if (b.err != nullptr) b.err = (layout == ABC_ERR_GENE_MAJOR) ? d_err + s0 : d_err + s0 * (int64_t)c->G;
                 x.nanw = c->d_s3_nanw[0].p; x.W = (b.n + 31) / 32;
                 x.gmask = c->d_mf_mask[0].p; x.n_pad = (b.n + 127) / 128 * 128; x.n_rows = x.n_pad; x.fill_done = c->d_mf_done.p;
+                x.q2 = queue ? c->d_s3_q2[0].p : nullptr; x.qcnt = queue ? c->d_s3_qcnt[0].p : nullptr;
                 rc = abc_launch_score_mma(b, x, c->d_mf_a[0].p, c->d_mf_b.p, nullptr, c->sm_count, st);
                 c->launches += 3;
             }
@@ -748,7 +759,7 @@ extern "C" int abc_score_mma_debug(abc_ctx_t* c, const double* d_stats, int64_t 
     x.fill_done = c->d_mf_done.p;
     x.nanw = c->d_s3_nanw[0].p; x.W = (n + 31) / 32; x.gmask = c->d_mf_mask[0].p; x.n_pad = (int64_t)n_pad;
     a.eps = -1.0;                                        // nothing is accepted
-    x.n_rows = x.n_pad;
+    x.n_rows = x.n_pad; x.q2 = nullptr; x.qcnt = nullptr;
     rc = abc_launch_score_mma(a, x, c->d_mf_a[0].p, c->d_mf_b.p, d_out, c->sm_count, c->stream);
     if (rc != ABC_OK) return rc;
     ABC_CUDA_CHECK(cudaStreamSynchronize(c->stream));
@@ -1248,7 +1259,7 @@ extern "C" int abc_set_option(abc_ctx_t* c, const char* name, int64_t value) {
     if (strcmp(name, "score_reference_kernel") == 0) { c->force_reference_score = value ? 1 : 0; return ABC_OK; }
     if (strcmp(name, "score_tile_kernel") == 0) { c->score_tile_kernel = value ? 1 : 0; return ABC_OK; }
     if (strcmp(name, "score_overlap") == 0) { c->score_overlap = value ? 1 : 0; return ABC_OK; }
-    if (strcmp(name, "score_mma_filter") == 0) { c->score_mma_filter = value ? 1 : 0; return ABC_OK; }
+    if (strcmp(name, "score_mma_filter") == 0) { c->score_mma_filter = (value == 2) ? 2 : (value ? 1 : 0); return ABC_OK; }
     if (strcmp(name, "score_sub_batches") == 0) { c->score_sub_batches = (int)std::min<int64_t>(std::max<int64_t>(value, 0), 64); return ABC_OK; }
     if (strcmp(name, "accept_capacity") == 0) { c->acc_min_capacity = value > 0 ? value : 0; return ABC_OK; }
     if (strcmp(name, "stats_sample_guards") == 0) { c->stats_guards = value < 0 ? -1 : (value ? 1 : 0); return ABC_OK; }

@@ -670,6 +670,7 @@ abc_score3_exact_kernel(const AbcScoreArgs a, const AbcScore3Tables x) {
 #define MF_B_FLOATS (MF_N * MF_KSTAGE)    // 32 KB
 #define MF_EPI_WARPS 8
 #define MF_THREADS (32 * (3 + MF_EPI_WARPS)) // warp 0 loads, warp 1 issues the MMAs, warps 2-9 read the accumulators, warp 10 fills
+#define MF_MAXT 112                       // tiles of 32 genes per item (14 x 256 genes)
 #define MF_COL_ONE 106
 #define MF_COL_INVALID 107
 
@@ -764,6 +765,8 @@ struct MfSmem {
     alignas(1024) float a[MF_A_FLOATS];
     alignas(1024) float b[MF_RING][MF_B_FLOATS];
     alignas(16) double tens[S3_FILL_DOUBLES];
+    unsigned int mask[MF_MAXT][MF_M];          // queue mode: sign bits of the item, [tile of 32 genes][particle]
+    unsigned int qbase[MF_MAXT];               // queue mode: reserved position in the segment of every tile
     unsigned long long a_full, a_empty, b_full[MF_RING], b_empty[MF_RING], acc_full[2], acc_empty[2];
     unsigned int tmem_base;
 };
@@ -802,7 +805,7 @@ __device__ __forceinline__ void mf_tmem_ld32(unsigned int taddr, unsigned int (&
 // and the sign bits of every (tile of 32 genes, particle) go to gmask as one 32-bit word.  Warp 0 loads, warp 1 (one thread)
 // issues the MMAs and commits them to the ring's and the accumulators' mbarriers, warps 2-9 read the accumulators
 // (tcgen05.ld, 32 columns per load), warp 10 writes the background of the first fill_b0 particle blocks.
-template <int LAYOUT>
+template <int LAYOUT, bool QUEUE>
 __global__ void __launch_bounds__(MF_THREADS, 1)
 abc_score_mma_filter_kernel(const AbcScoreArgs a, const AbcScore3Tables x, const float* __restrict__ ablob,
                             const float* __restrict__ bblob, int ntn, int ks, float* __restrict__ dbg) {
@@ -917,7 +920,8 @@ abc_score_mma_filter_kernel(const AbcScoreArgs a, const AbcScore3Tables x, const
                     unsigned int mm = 0u;
 #pragma unroll
                     for (int c = 31; c >= 0; --c) mm = __funnelshift_l(v[c], mm, 1);
-                    x.gmask[(size_t)(8 * j + half * 4 + q) * (size_t)x.n_pad + (size_t)(ib + lg * 32 + lane)] = mm;
+                    if (QUEUE) sm.mask[8 * (j - t0) + half * 4 + q][lg * 32 + lane] = mm;
+                    else x.gmask[(size_t)(8 * j + half * 4 + q) * (size_t)x.n_pad + (size_t)(ib + lg * 32 + lane)] = mm;
                     if (dbg != nullptr) {
 #pragma unroll
                         for (int c = 0; c < 32; ++c)
@@ -927,6 +931,55 @@ abc_score_mma_filter_kernel(const AbcScoreArgs a, const AbcScore3Tables x, const
                 mf_tc_fence_before();
                 __syncwarp();
                 if (lane == 0) mf_mbar_arrive(&sm.acc_empty[as]);
+            }
+            if (QUEUE) {
+                // the item's sign bits -> entries (particle << 5 | gene slot) in the stage-3 queue segments of
+                // (tile, block of 2048 particles): epilogue warp ew takes the tiles ew, ew + 8, ...; one round of atomics
+                // reserves room in all of them, then every lane writes the entries of its four particles
+                asm volatile("bar.sync 1, %0;" ::"n"(MF_EPI_WARPS * 32) : "memory");
+                const int ew = warp - 2, nT = 8 * (t1 - t0), Tg0 = 8 * t0;
+                const size_t seg0 = (size_t)(ib >> 11) * (size_t)x.ntiles;
+                unsigned int mytot = 0u;
+                for (int k = 0; k < 32; ++k) {
+                    const int tt = ew + MF_EPI_WARPS * k;
+                    if (tt >= nT) break;
+                    unsigned int c = (unsigned int)(__popc(sm.mask[tt][lane]) + __popc(sm.mask[tt][lane + 32]) +
+                                                    __popc(sm.mask[tt][lane + 64]) + __popc(sm.mask[tt][lane + 96]));
+                    c = __reduce_add_sync(0xffffffffu, c);
+                    if (lane == k) mytot = c;
+                }
+                const int myT = Tg0 + ew + MF_EPI_WARPS * lane;
+                if (mytot > 0u && myT < x.ntiles) sm.qbase[ew + MF_EPI_WARPS * lane] = atomicAdd(&x.qcnt[seg0 + (size_t)myT], mytot);
+                __syncwarp();
+                for (int k = 0; k < 32; ++k) {
+                    const int tt = ew + MF_EPI_WARPS * k;
+                    if (tt >= nT) break;
+                    if (Tg0 + tt >= x.ntiles) continue;
+                    unsigned int mk[4];
+                    int c = 0;
+#pragma unroll
+                    for (int r = 0; r < 4; ++r) { mk[r] = sm.mask[tt][lane + 32 * r]; c += __popc(mk[r]); }
+                    if (!__any_sync(0xffffffffu, c != 0)) continue;
+                    int incl = c;
+#pragma unroll
+                    for (int dd = 1; dd < 32; dd <<= 1) {
+                        const int t = __shfl_up_sync(0xffffffffu, incl, dd);
+                        if (lane >= dd) incl += t;
+                    }
+                    unsigned short* seg = x.q2 + (seg0 + (size_t)(Tg0 + tt)) * (size_t)(S3_PB * S3_TG);
+                    unsigned int pos = sm.qbase[tt] + (unsigned int)(incl - c);
+#pragma unroll
+                    for (int r = 0; r < 4; ++r) {
+                        const unsigned int pl = (unsigned int)((ib + lane + 32 * r) & (S3_PB - 1));
+                        unsigned int mm = mk[r];
+                        while (mm) {
+                            const int b = __ffs(mm) - 1;
+                            mm &= mm - 1u;
+                            seg[pos++] = (unsigned short)((pl << 5) | (unsigned int)b);
+                        }
+                    }
+                }
+                asm volatile("bar.sync 1, %0;" ::"n"(MF_EPI_WARPS * 32) : "memory");
             }
         }
     }
@@ -1292,27 +1345,39 @@ int abc_launch_score_mma(const AbcScoreArgs& a, const AbcScore3Tables& x_in, flo
     // one persistent CTA per SM; items are split over gene-tile ranges until there are >= ~6 per CTA (wave quantisation)
     int ks = 1;
     while (ks < 8 && ks * 2 <= ntn && (long long)nblk128 * ks < 6ll * sm_count) ks *= 2;
+    AbcScore3Tables x = x_in;
+    const bool queue = x.q2 != nullptr;            // queue mode: the filter kernel writes the whole background and the stage-3 queue
+    while (queue && (ntn + ks - 1) / ks > MF_MAXT / 8) ks *= 2;      // the item's sign bits must fit the shared-memory array
     const unsigned int pgrid = (unsigned int)std::min<long long>((long long)nblk128 * ks, sm_count);
-    ABC_CUDA_CHECK(cudaFuncSetAttribute(abc_score_mma_filter_kernel<ABC_ERR_NONE>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-    ABC_CUDA_CHECK(cudaFuncSetAttribute(abc_score_mma_filter_kernel<ABC_ERR_GENE_MAJOR>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-    ABC_CUDA_CHECK(cudaFuncSetAttribute(abc_score_mma_filter_kernel<ABC_ERR_PARTICLE_MAJOR>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     // background: the first fill_b0 particle blocks by the filter kernel (about what fits its duration, at least the
     // look-ahead), block j >= fill_b0 by the stage-3 CTAs of block j - fill_d (more blocks than are resident at once)
-    AbcScore3Tables x = x_in;
     const long long resident = 4ll * sm_count / std::max(1, x.ntiles) + 2;
     x.fill_d = (int32_t)resident;
-    x.fill_b0 = (int32_t)std::min<long long>(nblocks, std::max<long long>(resident, (nblocks * 3 + 5) / 10));
-    if (lay != ABC_ERR_NONE) ABC_CUDA_CHECK(cudaMemsetAsync(x.fill_done, 0, (size_t)(nblocks + 1) * sizeof(uint32_t), st));
+    x.fill_b0 = queue ? (int32_t)nblocks : (int32_t)std::min<long long>(nblocks, std::max<long long>(resident, (nblocks * 3 + 5) / 10));
+    if (queue) ABC_CUDA_CHECK(cudaMemsetAsync(x.qcnt, 0, (size_t)nblocks * (size_t)x.ntiles * sizeof(uint32_t), st));
+    else if (lay != ABC_ERR_NONE) ABC_CUDA_CHECK(cudaMemsetAsync(x.fill_done, 0, (size_t)(nblocks + 1) * sizeof(uint32_t), st));
     abc_score_mma_prep_kernel<<<(unsigned int)nblk128, 128, 0, st>>>(a.stats, (long long)a.n, d_ablob, x.nanw, (long long)x.W);
     ABC_CUDA_CHECK(cudaGetLastError());
-    if (lay == ABC_ERR_NONE) abc_score_mma_filter_kernel<ABC_ERR_NONE><<<pgrid, MF_THREADS, smem, st>>>(a, x, d_ablob, d_bblob, ntn, ks, d_dbg);
-    else if (lay == ABC_ERR_GENE_MAJOR) abc_score_mma_filter_kernel<ABC_ERR_GENE_MAJOR><<<pgrid, MF_THREADS, smem, st>>>(a, x, d_ablob, d_bblob, ntn, ks, d_dbg);
-    else abc_score_mma_filter_kernel<ABC_ERR_PARTICLE_MAJOR><<<pgrid, MF_THREADS, smem, st>>>(a, x, d_ablob, d_bblob, ntn, ks, d_dbg);
+#define MF_LAUNCH(LAY, Q)                                                                                                   \
+    do {                                                                                                                    \
+        ABC_CUDA_CHECK(cudaFuncSetAttribute(abc_score_mma_filter_kernel<LAY, Q>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem)); \
+        abc_score_mma_filter_kernel<LAY, Q><<<pgrid, MF_THREADS, smem, st>>>(a, x, d_ablob, d_bblob, ntn, ks, d_dbg);       \
+    } while (0)
+    if (lay == ABC_ERR_NONE) { if (queue) MF_LAUNCH(ABC_ERR_NONE, true); else MF_LAUNCH(ABC_ERR_NONE, false); }
+    else if (lay == ABC_ERR_GENE_MAJOR) { if (queue) MF_LAUNCH(ABC_ERR_GENE_MAJOR, true); else MF_LAUNCH(ABC_ERR_GENE_MAJOR, false); }
+    else { if (queue) MF_LAUNCH(ABC_ERR_PARTICLE_MAJOR, true); else MF_LAUNCH(ABC_ERR_PARTICLE_MAJOR, false); }
+#undef MF_LAUNCH
     ABC_CUDA_CHECK(cudaGetLastError());
     const unsigned int grid = (unsigned int)(nblocks * x.ntiles);
-    if (lay == ABC_ERR_NONE) abc_score_mask_exact_kernel<ABC_ERR_NONE><<<grid, S3E_THREADS, 0, st>>>(a, x);
-    else if (lay == ABC_ERR_GENE_MAJOR) abc_score_mask_exact_kernel<ABC_ERR_GENE_MAJOR><<<grid, S3E_THREADS, 0, st>>>(a, x);
-    else abc_score_mask_exact_kernel<ABC_ERR_PARTICLE_MAJOR><<<grid, S3E_THREADS, 0, st>>>(a, x);
+    if (queue) {
+        if (lay == ABC_ERR_NONE) abc_score3_exact_kernel<ABC_ERR_NONE><<<grid, S3E_THREADS, 0, st>>>(a, x);
+        else if (lay == ABC_ERR_GENE_MAJOR) abc_score3_exact_kernel<ABC_ERR_GENE_MAJOR><<<grid, S3E_THREADS, 0, st>>>(a, x);
+        else abc_score3_exact_kernel<ABC_ERR_PARTICLE_MAJOR><<<grid, S3E_THREADS, 0, st>>>(a, x);
+    } else {
+        if (lay == ABC_ERR_NONE) abc_score_mask_exact_kernel<ABC_ERR_NONE><<<grid, S3E_THREADS, 0, st>>>(a, x);
+        else if (lay == ABC_ERR_GENE_MAJOR) abc_score_mask_exact_kernel<ABC_ERR_GENE_MAJOR><<<grid, S3E_THREADS, 0, st>>>(a, x);
+        else abc_score_mask_exact_kernel<ABC_ERR_PARTICLE_MAJOR><<<grid, S3E_THREADS, 0, st>>>(a, x);
+    }
     ABC_CUDA_CHECK(cudaGetLastError());
     return ABC_OK;
 }

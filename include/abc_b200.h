@@ -221,8 +221,9 @@ int  abc_accept_tuples_dev(abc_ctx_t* ctx, int32_t* d_gene, int64_t* d_particle,
                            void* stream);
 /* tuning / diagnostics switches.  "score_reference_kernel" = 1: score with the plain FP64 kernel (every pair
  * evaluated in full) instead of the three-stage kernel; results are bit-identical either way.
- * "score_mma_filter" = 1 (default 0): for err_layout != ABC_ERR_NONE, decide which pairs can be <= 10 with a TF32 GEMM on the
- * tensor cores (tcgen05) instead of the FP32 tile filter; results are bit-identical either way.
+ * "score_mma_filter" = 1 or 2 (default 0): for err_layout != ABC_ERR_NONE, decide which pairs can be <= 10 with a TF32 GEMM on
+ * the tensor cores (tcgen05) instead of the FP32 tile filter; 1 hands sign-bit words to the FP64 stage, 2 writes its queue;
+ * results are bit-identical in all three cases.
  * "accept_capacity" = N: reserve room for at least N accepted tuples (20 bytes each); by default the buffer grows by
  * 2 % of the pairs of every abc_score call since the last abc_accept_reset (a call whose acceptance rate exceeds
  * that fails with ABC_ERR_NOMEM instead of dropping tuples).

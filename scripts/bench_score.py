@@ -1,6 +1,6 @@
 """Scoring-kernel micro-benchmark: realistic statistics (prior draws through the device ODE path), one large
 resident batch, CUDA events.
-Usage: python scripts/bench_score.py [n_particles] [layout 0|1|2] [reference_kernel 0|1] [tile_kernel 1|0] [overlap 1|0] [sub_batches] [mma_filter 0|1]"""
+Usage: python scripts/bench_score.py [n_particles] [layout 0|1|2] [reference_kernel 0|1] [tile_kernel 1|0] [overlap 1|0] [sub_batches] [mma_filter 0|1|2]"""
 import os
 import sys
 

@@ -32,12 +32,14 @@ def data_stats():
     return z["d"], z["se"]
 
 
-@pytest.fixture(scope="module")
-def eng_mma(betas, data_stats):
+@pytest.fixture(scope="module", params=[1, 2], ids=["sign_bit_words", "queue"])
+def eng_mma(request, betas, data_stats):
+    """score_mma_filter = 1: sign-bit words + mask-driven stage 3; 2: the filter kernel writes the stage-3 queue"""
     e = AbcEngine(0)
     e.set_design(synthetic_design(betas, n_cells=96, n_pre_cycles=10))
     e.set_data(*data_stats)
-    e.set_option("score_mma_filter", 1)
+    e.set_option("score_mma_filter", request.param)
+    e.mma_mode = request.param
     yield e
     e.close()
 
@@ -144,14 +146,14 @@ def test_filter_on_and_off_agree_bit_for_bit(eng_mma, data_stats):
     s = P.synth_stats(rng, d, 9000)
     s[100, 3] = np.nan
     res = []
-    for on in (1, 0):
+    for on in (eng_mma.mma_mode, 0):
         eng_mma.set_option("score_mma_filter", on)
         try:
             eng_mma.accept_reset()
             err, counts, _ = eng_mma.score(s, eps=4.8, err_layout=ERR_PARTICLE_MAJOR)
             res.append((err, counts, eng_mma.accept_fetch()))
         finally:
-            eng_mma.set_option("score_mma_filter", 1)
+            eng_mma.set_option("score_mma_filter", eng_mma.mma_mode)
     assert oracle.same_bits(res[0][0], res[1][0]) and np.array_equal(res[0][1], res[1][1])
     for x, y in zip(res[0][2], res[1][2]):
         assert np.array_equal(np.asarray(x).view(np.uint64) if np.asarray(x).dtype == np.float64 else x,
