@@ -29,8 +29,10 @@
 // non-finite or extreme data use div.rn.f64.
 //
 // Particle-major output: the 32 genes of a tile are scattered over a row, so the fill is done on contiguous
-// slices of the block's rows instead and a per-block counter (release/acquire) orders "all slices filled" before
-// the first stage-3 store of the block.  CTAs of one block are adjacent in launch order and fill before they wait.
+// slices of the block's rows instead; stage 3 runs as the next kernel on the stream, which orders its stores after the fill.
+//
+// Second half of the file ("tensor-core filter"): the same decision taken by a TF32 GEMM on the tensor cores
+// (tcgen05.mma, accumulators in tensor memory) in front of the same FP64 stage; option score_mma_filter, DESIGN.md 6.2.
 #include "abc_common.cuh"
 #include "abc_internal.h"
 
